@@ -1,0 +1,352 @@
+"""ctypes binding of the CPU oracle (oracle/phnsw_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(parallel_hnsw_b200) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libphnsw_oracle.so")
+
+EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
+FLT_MAX = np.float32(3.4028235e38)
+
+COS_HALF, ONE_MINUS_DOT, L2_SQRT, COS_CLAMP = 0, 1, 2, 3
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc, seconds)."""
+    src = os.path.join(_HERE, "phnsw_oracle.c")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", _HERE], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("number_of_candidates", C.c_uint64),
+                ("upper_layer_candidate_count", C.c_uint64),
+                ("probe_depth", C.c_uint64)]
+
+
+class OptimizationParams(C.Structure):
+    _fields_ = [("promotion_threshold", C.c_float),
+                ("neighborhood_threshold", C.c_float),
+                ("recall_proportion", C.c_float),
+                ("promotion_proportion", C.c_float),
+                ("search", SearchParams)]
+
+
+class BuildParams(C.Structure):
+    _fields_ = [("order", C.c_uint64),
+                ("zero_layer_neighborhood_size", C.c_uint64),
+                ("neighborhood_size", C.c_uint64),
+                ("optimization", OptimizationParams),
+                ("initial_partition_search", SearchParams)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    u64p, f32p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    L.orc_pq_len.restype = C.c_uint64
+    L.orc_pq_len.argtypes = [f32p, C.c_uint64]
+    L.orc_pq_insert.restype = C.c_uint64
+    L.orc_pq_insert.argtypes = [u64p, f32p, C.c_uint64, C.c_uint64, C.c_float]
+    L.orc_pq_merge.restype = C.c_int
+    L.orc_pq_merge.argtypes = [u64p, f32p, C.c_uint64, u64p, f32p, C.c_uint64]
+    L.orc_pq_merge_flag_closed_form.restype = C.c_int
+    L.orc_pq_merge_flag_closed_form.argtypes = [u64p, f32p, C.c_uint64, u64p, f32p, C.c_uint64]
+    L.orc_get_final_neighbor_idx.restype = C.c_uint64
+    L.orc_get_final_neighbor_idx.argtypes = [C.c_uint64, u64p, C.c_uint64]
+    L.orc_calculate_partitions.restype = C.c_uint64
+    L.orc_calculate_partitions.argtypes = [C.c_uint64, C.c_uint64, u64p, C.c_uint64]
+    L.orc_calculate_partitions_for_additions.restype = C.c_uint64
+    L.orc_calculate_partitions_for_additions.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                         u64p, C.c_uint64]
+    L.orc_distance.restype = C.c_float
+    L.orc_distance.argtypes = [C.c_int, C.c_uint64, f32p, f32p]
+    L.orc_hnsw_new.restype = C.c_void_p
+    L.orc_hnsw_new.argtypes = [C.c_int, C.c_uint64, C.c_uint64, f32p]
+    L.orc_hnsw_free.argtypes = [C.c_void_p]
+    L.orc_hnsw_push_layer.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u64p]
+    L.orc_hnsw_layer_count.restype = C.c_uint64
+    L.orc_hnsw_layer_count.argtypes = [C.c_void_p]
+    L.orc_hnsw_layer_info.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p, C.POINTER(u64p),
+                                      C.POINTER(u64p)]
+    L.orc_hnsw_set_build_params.argtypes = [C.c_void_p, C.POINTER(BuildParams)]
+    L.orc_hnsw_get_build_params.argtypes = [C.c_void_p, C.POINTER(BuildParams)]
+    L.orc_search_batch.restype = C.c_int
+    L.orc_search_batch.argtypes = [C.c_void_p, f32p, u64p, C.c_uint64, C.POINTER(SearchParams),
+                                   C.c_uint64, u64p, C.c_uint64, u64p, f32p, u32p, u64p, u64p,
+                                   u64p, C.c_int]
+    L.orc_knn.restype = C.c_int
+    L.orc_knn.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u64p, f32p, u32p, C.c_int]
+    L.orc_threshold_nn.restype = C.c_int
+    L.orc_threshold_nn.argtypes = [C.c_void_p, C.c_float, C.c_uint64, C.c_uint64, C.POINTER(u64p),
+                                   C.POINTER(u64p), C.POINTER(f32p), C.c_int]
+    L.orc_free.argtypes = [C.c_void_p]
+    L.orc_compare_all.restype = C.c_int
+    L.orc_compare_all.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_uint64, u64p, f32p]
+    L.orc_generate.restype = C.c_void_p
+    L.orc_generate.argtypes = [C.c_int, C.c_uint64, C.c_uint64, f32p, u64p, C.c_uint64,
+                               C.POINTER(BuildParams), C.c_uint64, C.c_int, C.c_int]
+    L.orc_improve_index.restype = C.c_float
+    L.orc_improve_index.argtypes = [C.c_void_p, C.POINTER(BuildParams), C.c_int]
+    L.orc_stochastic_recall.restype = C.c_float
+    L.orc_stochastic_recall.argtypes = [C.c_void_p, C.POINTER(OptimizationParams), C.c_int]
+    L.orc_serialize.restype = C.c_int
+    L.orc_serialize.argtypes = [C.c_void_p, C.c_char_p]
+    L.orc_deserialize.restype = C.c_void_p
+    L.orc_deserialize.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.orc_num_threads.restype = C.c_int
+    L.orc_default_search_params.argtypes = [C.POINTER(SearchParams)]
+    L.orc_default_build_params.argtypes = [C.POINTER(BuildParams)]
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def default_search_params():
+    sp = SearchParams()
+    lib().orc_default_search_params(C.byref(sp))
+    return sp
+
+
+def default_build_params():
+    bp = BuildParams()
+    lib().orc_default_build_params(C.byref(bp))
+    return bp
+
+
+def search_params(ef=300, upper=300, probe=2):
+    return SearchParams(ef, upper, probe)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+# ---- queue helpers (operate in place on numpy arrays) ----
+def pq_insert(data, pri, elt, priority):
+    return int(lib().orc_pq_insert(_p(data, C.c_uint64), _p(pri, C.c_float), len(pri),
+                                   int(elt), float(priority)))
+
+
+def pq_merge(data, pri, ids, prs):
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    prs = np.ascontiguousarray(prs, dtype=np.float32)
+    return bool(lib().orc_pq_merge(_p(data, C.c_uint64), _p(pri, C.c_float), len(pri),
+                                   _p(ids, C.c_uint64), _p(prs, C.c_float), len(prs)))
+
+
+def pq_merge_flag_closed_form(data, pri, ids, prs):
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    prs = np.ascontiguousarray(prs, dtype=np.float32)
+    return bool(lib().orc_pq_merge_flag_closed_form(_p(data, C.c_uint64), _p(pri, C.c_float),
+                                                    len(pri), _p(ids, C.c_uint64),
+                                                    _p(prs, C.c_float), len(prs)))
+
+
+def pq_len(pri):
+    return int(lib().orc_pq_len(_p(pri, C.c_float), len(pri)))
+
+
+def final_neighbor_idx(M, neighbors, n):
+    neighbors = np.ascontiguousarray(neighbors, dtype=np.uint64)
+    return int(lib().orc_get_final_neighbor_idx(M, _p(neighbors, C.c_uint64), n))
+
+
+def calculate_partitions(total, order):
+    out = np.zeros(64, dtype=np.uint64)
+    n = lib().orc_calculate_partitions(total, order, _p(out, C.c_uint64), 64)
+    return [int(x) for x in out[:n]]
+
+
+def calculate_partitions_for_additions(sizes_from_bottom, new_vecs, order):
+    s = np.ascontiguousarray(sizes_from_bottom, dtype=np.uint64)
+    out = np.zeros(64, dtype=np.uint64)
+    n = lib().orc_calculate_partitions_for_additions(_p(s, C.c_uint64), len(s), new_vecs, order,
+                                                     _p(out, C.c_uint64), 64)
+    return [int(x) for x in out[:n]]
+
+
+def distance(metric, a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return np.float32(lib().orc_distance(metric, len(a), _p(a, C.c_float), _p(b, C.c_float)))
+
+
+class Hnsw:
+    """Handle on an oracle index; mirrors the reference's Hnsw surface (lib.rs:585-1699)."""
+
+    def __init__(self, handle, rows=None):
+        self._h = handle
+        self._rows = rows  # keep the borrowed vectors alive
+
+    @classmethod
+    def from_layers(cls, metric, rows, layers, bp=None):
+        """layers: list of (nodes u64[n], neighbors u64[n*M], M), top layer first."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        h = lib().orc_hnsw_new(metric, rows.shape[1], rows.shape[0], _p(rows, C.c_float))
+        self = cls(h, rows)
+        for nodes, neighbors, M in layers:
+            nodes = np.ascontiguousarray(nodes, dtype=np.uint64)
+            neighbors = np.ascontiguousarray(neighbors, dtype=np.uint64).reshape(-1)
+            assert neighbors.size == nodes.size * M
+            lib().orc_hnsw_push_layer(h, nodes.size, M, _p(nodes, C.c_uint64),
+                                      _p(neighbors, C.c_uint64))
+        if bp is not None:
+            lib().orc_hnsw_set_build_params(h, C.byref(bp))
+        return self
+
+    @classmethod
+    def generate(cls, metric, rows, vs=None, bp=None, seed=1, improve=True, nthreads=0):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if vs is None:
+            vs = np.arange(rows.shape[0], dtype=np.uint64)
+        vs = np.ascontiguousarray(vs, dtype=np.uint64)
+        bp = bp or default_build_params()
+        h = lib().orc_generate(metric, rows.shape[1], rows.shape[0], _p(rows, C.c_float),
+                               _p(vs, C.c_uint64), vs.size, C.byref(bp), seed,
+                               1 if improve else 0, nthreads)
+        if not h:
+            raise ValueError("generate: empty vector list")
+        return cls(h, rows)
+
+    @classmethod
+    def deserialize(cls, path):
+        err = C.c_int(0)
+        h = lib().orc_deserialize(os.fsencode(path), C.byref(err))
+        if not h:
+            raise {-3: FileNotFoundError("IndexNotFound"), -2: ValueError("serde")}.get(
+                err.value, OSError("io error %d" % err.value))
+        return cls(h)
+
+    def serialize(self, path):
+        rc = lib().orc_serialize(self._h, os.fsencode(path))
+        if rc:
+            raise OSError("serialize failed: %d" % rc)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_hnsw_free(self._h)
+            self._h = None
+
+    @property
+    def layer_count(self):
+        return int(lib().orc_hnsw_layer_count(self._h))
+
+    @property
+    def build_parameters(self):
+        bp = BuildParams()
+        lib().orc_hnsw_get_build_params(self._h, C.byref(bp))
+        return bp
+
+    def layer(self, i_from_top):
+        nc, M = C.c_uint64(), C.c_uint64()
+        nodes, neigh = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+        rc = lib().orc_hnsw_layer_info(self._h, i_from_top, C.byref(nc), C.byref(M),
+                                       C.byref(nodes), C.byref(neigh))
+        if rc:
+            raise IndexError(i_from_top)
+        n, m = nc.value, M.value
+        nodes_a = np.ctypeslib.as_array(nodes, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        neigh_a = (np.ctypeslib.as_array(neigh, shape=(n * m,)).copy() if n * m
+                   else np.zeros(0, np.uint64))
+        return nodes_a, neigh_a.reshape(n, m), m
+
+    def layers(self):
+        return [self.layer(i) for i in range(self.layer_count)]
+
+    def search(self, queries=None, stored_ids=None, sp=None, upto_layers=0, exclude=None,
+               max_out=None, nthreads=0, stats=False):
+        sp = sp or default_search_params()
+        L = self.layer_count
+        if queries is not None:
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+            if queries.ndim == 1:
+                queries = queries[None, :]
+            nq = queries.shape[0]
+            qp, sidp = _p(queries, C.c_float), None
+        else:
+            stored_ids = np.ascontiguousarray(stored_ids, dtype=np.uint64)
+            nq = stored_ids.size
+            qp, sidp = None, _p(stored_ids, C.c_uint64)
+        max_out = max_out or int(sp.number_of_candidates)
+        ids = np.empty((nq, max_out), dtype=np.uint64)
+        ds = np.empty((nq, max_out), dtype=np.float32)
+        cnt = np.empty(nq, dtype=np.uint32)
+        nd = np.zeros((nq, L), dtype=np.uint64)
+        ne = np.zeros((nq, L), dtype=np.uint64)
+        idist = np.zeros(nq, dtype=np.uint64)
+        exp = None
+        if exclude is not None:
+            exclude = np.ascontiguousarray(exclude, dtype=np.uint64)
+            exp = _p(exclude, C.c_uint64)
+        rc = lib().orc_search_batch(self._h, qp, sidp, nq, C.byref(sp), upto_layers, exp, max_out,
+                                    _p(ids, C.c_uint64), _p(ds, C.c_float), _p(cnt, C.c_uint32),
+                                    _p(nd, C.c_uint64), _p(ne, C.c_uint64), _p(idist, C.c_uint64),
+                                    nthreads)
+        if rc:
+            raise RuntimeError("oracle search hit a reference panic condition")
+        if stats:
+            return ids, ds, cnt, nd, ne
+        return ids, ds, cnt
+
+    def knn(self, k, probe_depth, nthreads=0):
+        n = self.layer(self.layer_count - 1)[0].size
+        ids = np.empty((n, k), dtype=np.uint64)
+        ds = np.empty((n, k), dtype=np.float32)
+        cnt = np.empty(n, dtype=np.uint32)
+        rc = lib().orc_knn(self._h, k, probe_depth, _p(ids, C.c_uint64), _p(ds, C.c_float),
+                           _p(cnt, C.c_uint32), nthreads)
+        if rc:
+            raise RuntimeError("oracle knn failed")
+        return ids, ds, cnt
+
+    def threshold_nn(self, threshold, probe_depth, initial_search_depth, nthreads=0):
+        n = self.layer(self.layer_count - 1)[0].size
+        off, ids, ds = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_float)()
+        rc = lib().orc_threshold_nn(self._h, threshold, probe_depth, initial_search_depth,
+                                    C.byref(off), C.byref(ids), C.byref(ds), nthreads)
+        if rc:
+            raise RuntimeError("oracle threshold_nn failed")
+        offsets = np.ctypeslib.as_array(off, shape=(n + 1,)).copy()
+        total = int(offsets[-1])
+        ids_a = np.ctypeslib.as_array(ids, shape=(max(total, 1),)).copy()[:total]
+        ds_a = np.ctypeslib.as_array(ds, shape=(max(total, 1),)).copy()[:total]
+        for p in (off, ids, ds):
+            lib().orc_free(C.cast(p, C.c_void_p))
+        return offsets, ids_a, ds_a
+
+    def compare_all(self, v, vs):
+        vs = np.ascontiguousarray(vs, dtype=np.uint64)
+        ids = np.empty(vs.size, dtype=np.uint64)
+        ds = np.empty(vs.size, dtype=np.float32)
+        c = lib().orc_compare_all(self._h, v, _p(vs, C.c_uint64), vs.size, _p(ids, C.c_uint64),
+                                  _p(ds, C.c_float))
+        return ids[:c], ds[:c]
+
+    def improve_index(self, bp=None, nthreads=0):
+        bp = bp or self.build_parameters
+        return float(lib().orc_improve_index(self._h, C.byref(bp), nthreads))
+
+    def stochastic_recall(self, op=None, nthreads=0):
+        op = op or self.build_parameters.optimization
+        return float(lib().orc_stochastic_recall(self._h, C.byref(op), nthreads))

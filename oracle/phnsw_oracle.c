@@ -1,0 +1,1577 @@
+/*
+ * phnsw_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY; see phnsw_oracle.h).
+ *
+ * A restatement, not a translation: data lives in flat C arrays, but every
+ * decision the reference makes on the hot path (queue tie rules, the merge
+ * return flag, trailing-sentinel trimming, the cumulative probe budget, the
+ * unbounded frontier) is reproduced step for step.  Build with
+ *   gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp
+ * so that f32 sums stay strictly sequential and unfused, as rustc emits them.
+ */
+#include "phnsw_oracle.h"
+
+#include <errno.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ params */
+
+void orc_default_search_params(orc_search_params *sp) { /* parameters.rs:10-18 */
+  sp->number_of_candidates = 300;
+  sp->upper_layer_candidate_count = 300;
+  sp->probe_depth = 2;
+}
+
+void orc_default_build_params(orc_build_params *bp) { /* parameters.rs:30-64 */
+  bp->order = 12;
+  bp->zero_layer_neighborhood_size = 48;
+  bp->neighborhood_size = 24;
+  bp->optimization.promotion_threshold = 0.01f;
+  bp->optimization.neighborhood_threshold = 0.01f;
+  bp->optimization.recall_proportion = 0.1f;
+  bp->optimization.promotion_proportion = 1.0f;
+  orc_default_search_params(&bp->optimization.search);
+  bp->initial_partition_search.number_of_candidates = 6;
+  bp->initial_partition_search.upper_layer_candidate_count = 6;
+  bp->initial_partition_search.probe_depth = 2;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static int pick_threads(int nthreads) {
+  int m = orc_num_threads();
+  if (nthreads <= 0 || nthreads > m) return m;
+  return nthreads;
+}
+
+/* ------------------------------------------------- queue: priority_queue.rs */
+
+typedef struct {
+  uint64_t *data;
+  float *pri;
+  uint64_t cap;
+} pq_t;
+
+/* priority_queue.rs:56-59  len = partition_point(d != f32::MAX) */
+static uint64_t pq_len(const pq_t *q) {
+  uint64_t lo = 0, hi = q->cap;
+  while (lo < hi) {
+    uint64_t mid = lo + (hi - lo) / 2;
+    if (q->pri[mid] != FLT_MAX) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+/* priority_queue.rs:70-100.  Returns the slot the element ended up in, or cap
+ * when it walked off the end of a run of equal priorities without being stored. */
+static uint64_t pq_insert_at(pq_t *q, uint64_t idx, uint64_t elt, float priority) {
+  if (idx < q->cap && q->data[idx] != elt) {
+    while (q->pri[idx] == priority && q->data[idx] <= elt) {
+      if (q->data[idx] == elt) return idx; /* already present */
+      idx++;
+      if (idx == q->cap) return idx;
+    }
+    uint64_t filled = pq_len(q);
+    for (uint64_t i = filled; i > idx; i--) { /* (idx+1..filled+1).rev() */
+      if (i == q->cap) continue;              /* the last element falls off */
+      q->data[i] = q->data[i - 1];
+      q->pri[i] = q->pri[i - 1];
+    }
+    q->data[idx] = elt;
+    q->pri[idx] = priority;
+  }
+  return idx;
+}
+
+/* priority_queue.rs:102-107 */
+static uint64_t pq_insert(pq_t *q, uint64_t elt, float priority) {
+  uint64_t lo = 0, hi = q->cap;
+  while (lo < hi) { /* partition_point(d < priority) */
+    uint64_t mid = lo + (hi - lo) / 2;
+    if (q->pri[mid] < priority) lo = mid + 1;
+    else hi = mid;
+  }
+  return pq_insert_at(q, lo, elt, priority);
+}
+
+/* priority_queue.rs:109-144.  `other` must be ascending by (priority, id). */
+static int pq_merge(pq_t *q, const uint64_t *ids, const float *prs, uint64_t n) {
+  int did_something = 0;
+  uint64_t last_idx = 0;
+  for (uint64_t k = 0; k < n; k++) {
+    float od = prs[k];
+    if (last_idx > q->cap) break;
+    /* binary search of od in pri[last_idx..] */
+    uint64_t lo = last_idx, hi = q->cap;
+    while (lo < hi) {
+      uint64_t mid = lo + (hi - lo) / 2;
+      if (q->pri[mid] < od) lo = mid + 1;
+      else hi = mid;
+    }
+    int found = (lo < q->cap && q->pri[lo] == od);
+    if (found) {
+      uint64_t start = lo; /* walk to the start of the run, even below last_idx (:121-128) */
+      while (start != 0 && q->pri[start - 1] == od) start--;
+      last_idx = pq_insert_at(q, start, ids[k], od);
+      did_something |= (last_idx != q->cap);
+    } else {
+      uint64_t i = lo - last_idx; /* insertion point RELATIVE to last_idx, compared to cap (:133) */
+      if (i >= q->cap) break;
+      last_idx = pq_insert_at(q, i + last_idx, ids[k], od);
+      did_something = 1; /* set even when insert_at(cap) was a no-op (:136-138) */
+    }
+  }
+  return did_something;
+}
+
+uint64_t orc_pq_len(const float *pri, uint64_t cap) {
+  pq_t q = {NULL, (float *)pri, cap};
+  return pq_len(&q);
+}
+uint64_t orc_pq_insert(uint64_t *data, float *pri, uint64_t cap, uint64_t elt, float priority) {
+  pq_t q = {data, pri, cap};
+  return pq_insert(&q, elt, priority);
+}
+int orc_pq_merge(uint64_t *data, float *pri, uint64_t cap, const uint64_t *ids,
+                 const float *prs, uint64_t n) {
+  pq_t q = {data, pri, cap};
+  return pq_merge(&q, ids, prs, n);
+}
+
+/*
+ * What merge's flag boils down to when (a) `other` is ascending by (priority,id)
+ * and (b) no incoming id is already in the queue (closest_nodes guarantees (b)
+ * through its visited set).  The CUDA kernel evaluates this expression instead of
+ * replaying the loop; tests/test_oracle_golden.py fuzzes it against pq_merge.
+ */
+int orc_pq_merge_flag_closed_form(const uint64_t *data, const float *pri, uint64_t cap,
+                                  const uint64_t *ids, const float *prs, uint64_t n) {
+  if (n == 0 || cap == 0) return 0;
+  pq_t q = {(uint64_t *)data, (float *)pri, cap};
+  if (pq_len(&q) < cap) return 1; /* a free slot: the head of the batch always lands */
+  float tp = pri[cap - 1];
+  uint64_t tid = data[cap - 1];
+  if (prs[0] < tp || (prs[0] == tp && ids[0] < tid)) return 1; /* real insertion */
+  /* nothing can be inserted; the flag is still raised when the head ties the tail
+   * priority (walks off the end, last_idx = cap) and another element follows */
+  return (prs[0] == tp && n >= 2) ? 1 : 0;
+}
+
+/* ------------------------------------------------------------ layer helpers */
+
+uint64_t orc_get_final_neighbor_idx(uint64_t M, const uint64_t *neighbors, uint64_t n) {
+  uint64_t final_idx = M * (n + 1); /* lib.rs:114-125: trims TRAILING !0 only */
+  uint64_t cur = final_idx;
+  for (uint64_t off = 1; off <= M; off++) {
+    if (neighbors[final_idx - off] == ORC_EMPTY) cur--;
+    else break;
+  }
+  return cur;
+}
+
+uint64_t orc_calculate_partitions(uint64_t total, uint64_t order, uint64_t *out, uint64_t cap) {
+  /* lib.rs:1883-1899: layer_count = max(1, ceil(log_order(total))) evaluated in f32 */
+  float l = logf((float)total) / logf((float)order); /* f32::log(self, base) = ln(self)/ln(base) */
+  float c = ceilf(l);
+  uint64_t layer_count = 1;
+  if (c > 1.0f) layer_count = (uint64_t)c;
+  uint64_t size = total;
+  uint64_t tmp[64];
+  if (layer_count > 64) layer_count = 64;
+  for (uint64_t i = 0; i < layer_count; i++) {
+    tmp[i] = size;
+    size /= order;
+  }
+  for (uint64_t i = 0; i < layer_count && i < cap; i++) out[i] = tmp[layer_count - 1 - i];
+  return layer_count;
+}
+
+
+/* calculate_partitions_for_additions (lib.rs:1901-1958, unused helper; golden at lib.rs:2353) */
+uint64_t orc_calculate_partitions_for_additions(const uint64_t *sizes_from_bottom, uint64_t n_sizes,
+                                                uint64_t new_vecs, uint64_t order, uint64_t *out,
+                                                uint64_t out_cap) {
+  uint64_t top_first[64], np_[64];
+  uint64_t n = orc_calculate_partitions(sizes_from_bottom[0] + new_vecs, order, top_first, 64);
+  for (uint64_t i = 0; i < n; i++) np_[i] = top_first[n - 1 - i]; /* from bottom */
+  while (n < n_sizes && n < 64) np_[n++] = 0;
+  for (uint64_t i = 0; i < n; i++)
+    if (i < n_sizes && sizes_from_bottom[i] > np_[i]) np_[i] = sizes_from_bottom[i];
+  uint64_t last = 0;
+  for (uint64_t i = n; i-- > 0;) { /* monotone layer stack */
+    if (last > np_[i]) np_[i] = last;
+    last = np_[i];
+  }
+  for (uint64_t i = 0; i < n; i++)
+    if (i < n_sizes) np_[i] -= sizes_from_bottom[i];
+  last = 0;
+  for (uint64_t i = n; i-- > 0;) { /* promotions reverse monotone */
+    if (last > np_[i]) np_[i] = last;
+    last = np_[i];
+  }
+  for (uint64_t i = 0; i < n && i < out_cap; i++) out[i] = np_[i];
+  return n;
+}
+
+/* ---------------------------------------------------------------- distances */
+
+float orc_distance(int metric, uint64_t dim, const float *a, const float *b) {
+  float r = 0.0f;
+  switch (metric) {
+    case ORC_L2_SQRT: /* lib.rs:2431-2437, pq.rs:499-505 */
+      for (uint64_t i = 0; i < dim; i++) {
+        float d = a[i] - b[i];
+        r += d * d; /* powi(2) == x*x */
+      }
+      return powf(r, 0.5f);
+    case ORC_COS_HALF: /* bigvec.rs:41-53 */
+      for (uint64_t i = 0; i < dim; i++) r += a[i] * b[i];
+      return (1.0f - r) / 2.0f;
+    case ORC_ONE_MINUS_DOT: /* lib.rs:1985-1991, benches/bench.rs:24-30 */
+      for (uint64_t i = 0; i < dim; i++) r += a[i] * b[i];
+      return 1.0f - r;
+    case ORC_COS_CLAMP: { /* pq.rs:481-497 */
+      for (uint64_t i = 0; i < dim; i++) r += a[i] * b[i];
+      float x = (r - 1.0f) / -2.0f;
+      if (x < 0.0f) x = 0.0f;
+      if (x > 1.0f) x = 1.0f;
+      return x;
+    }
+  }
+  return NAN;
+}
+
+/* -------------------------------------------------------------------- index */
+
+typedef struct {
+  uint64_t node_count, M;
+  uint64_t *nodes;     /* ascending VectorIds */
+  uint64_t *neighbors; /* node_count * M NodeIds, !0 padded */
+} layer_t;
+
+struct orc_hnsw {
+  int metric;
+  uint64_t dim, n_vectors;
+  const float *rows;
+  float *owned_rows;
+  uint64_t layer_count, layer_cap;
+  layer_t *layers; /* top first */
+  orc_build_params bp;
+};
+
+orc_hnsw *orc_hnsw_new(int metric, uint64_t dim, uint64_t n, const float *rows) {
+  orc_hnsw *h = (orc_hnsw *)calloc(1, sizeof(*h));
+  h->metric = metric;
+  h->dim = dim;
+  h->n_vectors = n;
+  h->rows = rows;
+  orc_default_build_params(&h->bp);
+  return h;
+}
+
+void orc_hnsw_free(orc_hnsw *h) {
+  if (!h) return;
+  for (uint64_t i = 0; i < h->layer_count; i++) {
+    free(h->layers[i].nodes);
+    free(h->layers[i].neighbors);
+  }
+  free(h->layers);
+  free(h->owned_rows);
+  free(h);
+}
+
+static layer_t *push_layer_raw(orc_hnsw *h, uint64_t node_count, uint64_t M) {
+  if (h->layer_count == h->layer_cap) {
+    h->layer_cap = h->layer_cap ? h->layer_cap * 2 : 8;
+    h->layers = (layer_t *)realloc(h->layers, h->layer_cap * sizeof(layer_t));
+  }
+  layer_t *l = &h->layers[h->layer_count++];
+  l->node_count = node_count;
+  l->M = M;
+  l->nodes = (uint64_t *)malloc((node_count ? node_count : 1) * sizeof(uint64_t));
+  l->neighbors = (uint64_t *)malloc((node_count * M ? node_count * M : 1) * sizeof(uint64_t));
+  return l;
+}
+
+int orc_hnsw_push_layer(orc_hnsw *h, uint64_t node_count, uint64_t M, const uint64_t *nodes,
+                        const uint64_t *neighbors) {
+  layer_t *l = push_layer_raw(h, node_count, M);
+  memcpy(l->nodes, nodes, node_count * sizeof(uint64_t));
+  memcpy(l->neighbors, neighbors, node_count * M * sizeof(uint64_t));
+  return 0;
+}
+
+uint64_t orc_hnsw_layer_count(const orc_hnsw *h) { return h->layer_count; }
+
+int orc_hnsw_layer_info(const orc_hnsw *h, uint64_t i, uint64_t *node_count, uint64_t *M,
+                        const uint64_t **nodes, const uint64_t **neighbors) {
+  if (i >= h->layer_count) return -1;
+  if (node_count) *node_count = h->layers[i].node_count;
+  if (M) *M = h->layers[i].M;
+  if (nodes) *nodes = h->layers[i].nodes;
+  if (neighbors) *neighbors = h->layers[i].neighbors;
+  return 0;
+}
+
+void orc_hnsw_set_build_params(orc_hnsw *h, const orc_build_params *bp) { h->bp = *bp; }
+void orc_hnsw_get_build_params(const orc_hnsw *h, orc_build_params *bp) { *bp = h->bp; }
+
+/* lib.rs:129-131 get_node: binary search of a VectorId in the ascending nodes array */
+static int64_t layer_get_node(const layer_t *l, uint64_t v) {
+  uint64_t lo = 0, hi = l->node_count;
+  while (lo < hi) {
+    uint64_t mid = lo + (hi - lo) / 2;
+    if (l->nodes[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo < l->node_count && l->nodes[lo] == v) return (int64_t)lo;
+  return -1;
+}
+
+/* Comparator::compare_vec (lib.rs:69-73) with the query either stored or caller supplied */
+typedef struct {
+  const orc_hnsw *h;
+  const float *qvec;
+} query_t;
+
+static inline float dist_to_stored(const query_t *q, uint64_t vid) {
+  return orc_distance(q->h->metric, q->h->dim, q->qvec, q->h->rows + vid * q->h->dim);
+}
+
+/* ---------------------------------------------------- visited set (HashSet) */
+
+typedef struct {
+  uint64_t *slots;
+  uint64_t cap, count;
+} set_t;
+
+static void set_init(set_t *s, uint64_t hint) {
+  uint64_t c = 64;
+  while (c < hint * 2) c <<= 1;
+  s->cap = c;
+  s->count = 0;
+  s->slots = (uint64_t *)malloc(c * sizeof(uint64_t));
+  memset(s->slots, 0xff, c * sizeof(uint64_t));
+}
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+static int set_contains(const set_t *s, uint64_t k) {
+  uint64_t i = mix64(k) & (s->cap - 1);
+  while (s->slots[i] != ORC_EMPTY) {
+    if (s->slots[i] == k) return 1;
+    i = (i + 1) & (s->cap - 1);
+  }
+  return 0;
+}
+static void set_insert(set_t *s, uint64_t k);
+static void set_grow(set_t *s) {
+  set_t n;
+  n.cap = s->cap * 2;
+  n.count = 0;
+  n.slots = (uint64_t *)malloc(n.cap * sizeof(uint64_t));
+  memset(n.slots, 0xff, n.cap * sizeof(uint64_t));
+  for (uint64_t i = 0; i < s->cap; i++)
+    if (s->slots[i] != ORC_EMPTY) set_insert(&n, s->slots[i]);
+  free(s->slots);
+  *s = n;
+}
+static void set_insert(set_t *s, uint64_t k) {
+  if ((s->count + 1) * 2 > s->cap) set_grow(s);
+  uint64_t i = mix64(k) & (s->cap - 1);
+  while (s->slots[i] != ORC_EMPTY) {
+    if (s->slots[i] == k) return;
+    i = (i + 1) & (s->cap - 1);
+  }
+  s->slots[i] = k;
+  s->count++;
+}
+static void set_free(set_t *s) { free(s->slots); }
+
+/* ------------------------------------------- closest_nodes (lib.rs:175-248) */
+
+typedef struct {
+  uint64_t node;
+  float dist;
+  uint64_t hops, index_sum; /* NodeDistance, instrumentation only (lib.rs:568-583) */
+} frontier_t;
+
+typedef struct {
+  uint64_t id;
+  float d;
+} pair_t;
+
+static int pair_cmp(const void *a, const void *b) { /* (OrderedFloat(d), id) */
+  const pair_t *x = (const pair_t *)a, *y = (const pair_t *)b;
+  if (x->d < y->d) return -1;
+  if (x->d > y->d) return 1;
+  if (x->id < y->id) return -1;
+  if (x->id > y->id) return 1;
+  return 0;
+}
+
+/* key of lib.rs:243-244: (OrderedFloat(-d), usize::MAX - n); a <= b in that key */
+static inline int frontier_le(const frontier_t *a, const frontier_t *b) {
+  float ka = -a->dist, kb = -b->dist;
+  if (ka < kb) return 1;
+  if (ka > kb) return 0;
+  return (UINT64_MAX - a->node) <= (UINT64_MAX - b->node);
+}
+
+/* Stable sort of the frontier by that key.  The input is always "one sorted run
+ * followed by freshly appended elements", so a stable insertion of the tail into the
+ * sorted prefix (binary search for the upper bound, then one memmove per block) is
+ * both exact and linear-ish -- the same work Rust's run-detecting merge sort does. */
+static void frontier_sort(frontier_t *f, uint64_t sorted_prefix, uint64_t n, frontier_t *tmp) {
+  if (n - sorted_prefix == 0) return;
+  /* sort the tail on its own with a stable insertion sort (tail <= neighborhood size) */
+  for (uint64_t i = sorted_prefix + 1; i < n; i++) {
+    frontier_t x = f[i];
+    uint64_t j = i;
+    while (j > sorted_prefix && !frontier_le(&f[j - 1], &x)) {
+      f[j] = f[j - 1];
+      j--;
+    }
+    f[j] = x;
+  }
+  /* stable two-run merge: on ties the prefix element goes first */
+  uint64_t a = 0, b = sorted_prefix, o = 0;
+  while (a < sorted_prefix && b < n) {
+    if (frontier_le(&f[a], &f[b])) tmp[o++] = f[a++];
+    else tmp[o++] = f[b++];
+  }
+  while (a < sorted_prefix) tmp[o++] = f[a++];
+  while (b < n) tmp[o++] = f[b++];
+  memcpy(f, tmp, n * sizeof(frontier_t));
+}
+
+typedef struct {
+  frontier_t *f, *tmp;
+  uint64_t cap;
+  pair_t *nd;
+  uint64_t *ids;
+  float *prs;
+  uint64_t nd_cap;
+} scratch_t;
+
+static void scratch_init(scratch_t *s) { memset(s, 0, sizeof(*s)); }
+static void scratch_free(scratch_t *s) {
+  free(s->f);
+  free(s->tmp);
+  free(s->nd);
+  free(s->ids);
+  free(s->prs);
+}
+static void scratch_reserve_frontier(scratch_t *s, uint64_t n) {
+  if (n <= s->cap) return;
+  uint64_t c = s->cap ? s->cap : 1024;
+  while (c < n) c *= 2;
+  s->f = (frontier_t *)realloc(s->f, c * sizeof(frontier_t));
+  s->tmp = (frontier_t *)realloc(s->tmp, c * sizeof(frontier_t));
+  s->cap = c;
+}
+static void scratch_reserve_nd(scratch_t *s, uint64_t n) {
+  if (n <= s->nd_cap) return;
+  s->nd = (pair_t *)realloc(s->nd, n * sizeof(pair_t));
+  s->ids = (uint64_t *)realloc(s->ids, n * sizeof(uint64_t));
+  s->prs = (float *)realloc(s->prs, n * sizeof(float));
+  s->nd_cap = n;
+}
+
+static uint64_t closest_nodes(const layer_t *layer, const query_t *q, pq_t *cand,
+                              uint64_t probe_depth, scratch_t *s, uint64_t *n_dist,
+                              uint64_t *n_exp) {
+  uint64_t len = pq_len(cand);
+  /* visit_queue = candidates reversed, so that pop() yields the smallest (d,id) (:182-186) */
+  scratch_reserve_frontier(s, len + layer->M);
+  scratch_reserve_nd(s, layer->M);
+  uint64_t fn = 0;
+  /* PriorityQueueIter stops at the first empty id (priority_queue.rs:207-222) */
+  uint64_t it_len = 0;
+  while (it_len < cand->cap && cand->data[it_len] != ORC_EMPTY) it_len++;
+  for (uint64_t i = 0; i < it_len; i++) {
+    frontier_t *e = &s->f[fn++];
+    e->node = cand->data[it_len - 1 - i];
+    e->dist = cand->pri[it_len - 1 - i];
+    e->hops = 0;
+    e->index_sum = 0;
+  }
+  (void)len;
+  set_t visited;
+  set_init(&visited, it_len + 64);
+  for (uint64_t i = 0; i < it_len; i++) set_insert(&visited, cand->data[i]);
+  uint64_t highest_improvement = 0;
+
+  while (fn > 0) {
+    frontier_t next = s->f[--fn]; /* pop() */
+    if (n_exp) (*n_exp)++;
+    uint64_t first = layer->M * next.node;
+    uint64_t last = orc_get_final_neighbor_idx(layer->M, layer->neighbors, next.node);
+    uint64_t nn = 0;
+    for (uint64_t j = first; j < last; j++) {
+      uint64_t n = layer->neighbors[j];
+      if (set_contains(&visited, n)) continue; /* :198; duplicates inside one row both pass */
+      s->nd[nn].id = n;
+      s->nd[nn].d = dist_to_stored(q, layer->nodes[n]);
+      nn++;
+    }
+    if (n_dist) (*n_dist) += nn;
+    /* :206 stable sort by (d, n); qsort is fine: equal keys are identical pairs */
+    qsort(s->nd, nn, sizeof(pair_t), pair_cmp);
+    for (uint64_t j = 0; j < nn; j++) set_insert(&visited, s->nd[j].id);
+    scratch_reserve_frontier(s, fn + nn + 1);
+    uint64_t sorted_prefix = fn;
+    for (uint64_t j = 0; j < nn; j++) { /* :211-220 every one of them, no bound */
+      frontier_t *e = &s->f[fn++];
+      e->node = s->nd[j].id;
+      e->dist = s->nd[j].d;
+      e->hops = next.hops + 1;
+      e->index_sum = next.index_sum + j + 1;
+      s->ids[j] = s->nd[j].id;
+      s->prs[j] = s->nd[j].d;
+    }
+    uint64_t best_id = cand->data[0];
+    float best_pr = cand->pri[0];
+    int did_something = pq_merge(cand, s->ids, s->prs, nn);
+    if (best_id != cand->data[0] || best_pr != cand->pri[0]) highest_improvement = next.index_sum;
+    if (!did_something) { /* :233-238 cumulative, never reset */
+      probe_depth--;
+      if (probe_depth == 0) break;
+    }
+    frontier_sort(s->f, sorted_prefix, fn, s->tmp); /* :243-244 */
+  }
+  set_free(&visited);
+  return highest_improvement;
+}
+
+/* closest_vectors (lib.rs:250-277).  `cand_v` holds VectorIds; the result is appended
+ * to out (VectorId, d) and its length returned; -1 when a candidate is not a node of
+ * this layer (the reference unwrap()s, lib.rs:261). */
+static int64_t closest_vectors(const layer_t *layer, const query_t *q, const pq_t *cand_v,
+                               uint64_t candidate_count, uint64_t probe_depth, uint64_t exclude,
+                               pair_t *out, scratch_t *s, uint64_t *idx_dist, uint64_t *n_dist,
+                               uint64_t *n_exp) {
+  uint64_t cap = cand_v->cap;
+  uint64_t *ids = (uint64_t *)malloc(cap * sizeof(uint64_t));
+  float *prs = (float *)malloc(cap * sizeof(float));
+  uint64_t n = 0;
+  while (n < cap && cand_v->data[n] != ORC_EMPTY) {
+    int64_t node = layer_get_node(layer, cand_v->data[n]);
+    if (node < 0) {
+      free(ids);
+      free(prs);
+      return -1;
+    }
+    ids[n] = (uint64_t)node;
+    prs[n] = cand_v->pri[n];
+    n++;
+  }
+  pq_t queue; /* capacity = candidates.capacity(), NOT candidate_count (:264) */
+  queue.cap = cap;
+  queue.data = (uint64_t *)malloc(cap * sizeof(uint64_t));
+  queue.pri = (float *)malloc(cap * sizeof(float));
+  for (uint64_t i = 0; i < cap; i++) {
+    queue.data[i] = ORC_EMPTY;
+    queue.pri[i] = FLT_MAX;
+  }
+  pq_merge(&queue, ids, prs, n);
+  int64_t produced = 0;
+  if (queue.data[0] == ORC_EMPTY) { /* assert!(!candidates.is_empty()) lib.rs:181 */
+    produced = -1;
+  } else {
+    uint64_t id = closest_nodes(layer, q, &queue, probe_depth, s, n_dist, n_exp);
+    if (idx_dist) *idx_dist = id;
+    for (uint64_t i = 0; i < cap && queue.data[i] != ORC_EMPTY; i++) {
+      uint64_t v = layer->nodes[queue.data[i]];
+      if (v == exclude) continue; /* include = |v| Some(v) != exclude (search.rs:133) */
+      if ((uint64_t)produced == candidate_count) break;
+      out[produced].id = v;
+      out[produced].d = queue.pri[i];
+      produced++;
+    }
+  }
+  free(ids);
+  free(prs);
+  free(queue.data);
+  free(queue.pri);
+  return produced;
+}
+
+/* search_layers_instrumented (search.rs:93-140).  exclude = ORC_EMPTY for None. */
+static int64_t search_layers(const orc_hnsw *h, const layer_t *layers, uint64_t n_layers,
+                             const query_t *q, const orc_search_params *sp, uint64_t exclude,
+                             pq_t *cand /* cap = ef, initialised empty */, scratch_t *s,
+                             uint64_t *idx_dist, uint64_t *n_dist, uint64_t *n_exp) {
+  (void)h;
+  if (n_layers == 0) return -1;
+  uint64_t entry = layers[0].nodes[0]; /* search.rs:9-11 */
+  float d0 = dist_to_stored(q, entry);
+  if (n_dist) n_dist[0]++;
+  pq_insert(cand, entry, d0);
+  uint64_t last_index_distance = UINT64_MAX;
+  pair_t *closest = (pair_t *)malloc((cand->cap ? cand->cap : 1) * sizeof(pair_t));
+  uint64_t *ids = (uint64_t *)malloc((cand->cap ? cand->cap : 1) * sizeof(uint64_t));
+  float *prs = (float *)malloc((cand->cap ? cand->cap : 1) * sizeof(float));
+  int64_t rc = 0;
+  for (uint64_t i = 0; i < n_layers; i++) {
+    /* sortedness sanity fold (search.rs:114-121): panic if a distance decreases */
+    float lastd = -FLT_MAX;
+    for (uint64_t k = 0; k < cand->cap && cand->data[k] != ORC_EMPTY; k++) {
+      if (cand->pri[k] < lastd) {
+        rc = -1;
+        goto done;
+      }
+      lastd = cand->pri[k];
+    }
+    uint64_t candidate_count = (n_layers == 1 || i == n_layers - 1)
+                                   ? sp->number_of_candidates
+                                   : sp->upper_layer_candidate_count;
+    int64_t n = closest_vectors(&layers[i], q, cand, candidate_count, sp->probe_depth, exclude,
+                                closest, s, &last_index_distance, n_dist ? &n_dist[i] : NULL,
+                                n_exp ? &n_exp[i] : NULL);
+    if (n < 0) {
+      rc = -1;
+      goto done;
+    }
+    for (int64_t k = 0; k < n; k++) {
+      ids[k] = closest[k].id;
+      prs[k] = closest[k].d;
+    }
+    pq_merge(cand, ids, prs, (uint64_t)n); /* search.rs:136 */
+  }
+  if (idx_dist) *idx_dist = last_index_distance;
+done:
+  free(closest);
+  free(ids);
+  free(prs);
+  return rc;
+}
+
+int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *stored_ids,
+                     uint64_t nq, const orc_search_params *sp, uint64_t upto_layers,
+                     const uint64_t *exclude, uint64_t max_out, uint64_t *out_ids,
+                     float *out_dists, uint32_t *out_counts, uint64_t *out_ndist,
+                     uint64_t *out_nexp, uint64_t *out_index_distance, int nthreads) {
+  uint64_t L = (upto_layers == 0 || upto_layers > h->layer_count) ? h->layer_count : upto_layers;
+  uint64_t ef = sp->number_of_candidates;
+  int failed = 0;
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel num_threads(nt)
+  {
+    scratch_t s;
+    scratch_init(&s);
+    pq_t cand;
+    cand.cap = ef;
+    cand.data = (uint64_t *)malloc((ef ? ef : 1) * sizeof(uint64_t));
+    cand.pri = (float *)malloc((ef ? ef : 1) * sizeof(float));
+    uint64_t *nd = (uint64_t *)calloc(h->layer_count + 1, sizeof(uint64_t));
+    uint64_t *ne = (uint64_t *)calloc(h->layer_count + 1, sizeof(uint64_t));
+#pragma omp for schedule(dynamic, 8)
+    for (int64_t qi = 0; qi < (int64_t)nq; qi++) {
+      for (uint64_t i = 0; i < ef; i++) {
+        cand.data[i] = ORC_EMPTY;
+        cand.pri[i] = FLT_MAX;
+      }
+      memset(nd, 0, (h->layer_count + 1) * sizeof(uint64_t));
+      memset(ne, 0, (h->layer_count + 1) * sizeof(uint64_t));
+      query_t q;
+      q.h = h;
+      q.qvec = queries ? queries + (uint64_t)qi * h->dim : h->rows + stored_ids[qi] * h->dim;
+      uint64_t idx_dist = UINT64_MAX;
+      int64_t rc = search_layers(h, h->layers, L, &q, sp, exclude ? exclude[qi] : ORC_EMPTY,
+                                 &cand, &s, &idx_dist, nd, ne);
+      if (rc < 0) {
+#pragma omp atomic write
+        failed = 1;
+      }
+      uint64_t cnt = 0;
+      while (cnt < ef && cnt < max_out && cand.data[cnt] != ORC_EMPTY) {
+        out_ids[(uint64_t)qi * max_out + cnt] = cand.data[cnt];
+        out_dists[(uint64_t)qi * max_out + cnt] = cand.pri[cnt];
+        cnt++;
+      }
+      for (uint64_t k = cnt; k < max_out; k++) {
+        out_ids[(uint64_t)qi * max_out + k] = ORC_EMPTY;
+        out_dists[(uint64_t)qi * max_out + k] = FLT_MAX;
+      }
+      if (out_counts) out_counts[qi] = (uint32_t)cnt;
+      if (out_ndist)
+        for (uint64_t l = 0; l < h->layer_count; l++) out_ndist[(uint64_t)qi * h->layer_count + l] = nd[l];
+      if (out_nexp)
+        for (uint64_t l = 0; l < h->layer_count; l++) out_nexp[(uint64_t)qi * h->layer_count + l] = ne[l];
+      if (out_index_distance) out_index_distance[qi] = idx_dist;
+    }
+    free(nd);
+    free(ne);
+    free(cand.data);
+    free(cand.pri);
+    scratch_free(&s);
+  }
+  return failed ? -1 : 0;
+}
+
+/* ------------------------------------------------ knn / threshold_nn / brute */
+
+int orc_knn(const orc_hnsw *h, uint64_t k, uint64_t probe_depth, uint64_t *out_ids,
+            float *out_dists, uint32_t *out_counts, int nthreads) {
+  if (h->layer_count == 0) return -1;
+  const layer_t *layer = &h->layers[h->layer_count - 1];
+  uint64_t cap = k * 3; /* eff_factor = 3, lib.rs:916-917 */
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel num_threads(nt)
+  {
+    scratch_t s;
+    scratch_init(&s);
+    pq_t pq;
+    pq.cap = cap;
+    pq.data = (uint64_t *)malloc((cap ? cap : 1) * sizeof(uint64_t));
+    pq.pri = (float *)malloc((cap ? cap : 1) * sizeof(float));
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)layer->node_count; i++) {
+      for (uint64_t j = 0; j < cap; j++) {
+        pq.data[j] = ORC_EMPTY;
+        pq.pri[j] = FLT_MAX;
+      }
+      uint64_t node = (uint64_t)i;
+      float zero = 0.0f;
+      pq_merge(&pq, &node, &zero, 1); /* seeded with (self, 0.0) lib.rs:918 */
+      query_t q;
+      q.h = h;
+      q.qvec = h->rows + layer->nodes[i] * h->dim;
+      closest_nodes(layer, &q, &pq, probe_depth, &s, NULL, NULL);
+      uint64_t cnt = 0;
+      for (uint64_t j = 0; j < cap && pq.data[j] != ORC_EMPTY && cnt < k; j++) {
+        if (pq.data[j] == node) continue;
+        out_ids[(uint64_t)i * k + cnt] = layer->nodes[pq.data[j]];
+        out_dists[(uint64_t)i * k + cnt] = pq.pri[j];
+        cnt++;
+      }
+      for (uint64_t j = cnt; j < k; j++) {
+        out_ids[(uint64_t)i * k + j] = ORC_EMPTY;
+        out_dists[(uint64_t)i * k + j] = FLT_MAX;
+      }
+      if (out_counts) out_counts[i] = (uint32_t)cnt;
+    }
+    free(pq.data);
+    free(pq.pri);
+    scratch_free(&s);
+  }
+  return 0;
+}
+
+int orc_threshold_nn(const orc_hnsw *h, float threshold, uint64_t probe_depth,
+                     uint64_t initial_search_depth, uint64_t **out_offsets, uint64_t **out_ids,
+                     float **out_dists, int nthreads) {
+  if (h->layer_count == 0) return -1;
+  const layer_t *layer = &h->layers[h->layer_count - 1];
+  uint64_t n = layer->node_count;
+  pair_t **res = (pair_t **)calloc(n ? n : 1, sizeof(pair_t *));
+  uint64_t *cnt = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel num_threads(nt)
+  {
+    scratch_t s;
+    scratch_init(&s);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+      pq_t pq;
+      pq.cap = initial_search_depth;
+      pq.data = (uint64_t *)malloc((pq.cap ? pq.cap : 1) * sizeof(uint64_t));
+      pq.pri = (float *)malloc((pq.cap ? pq.cap : 1) * sizeof(float));
+      for (uint64_t j = 0; j < pq.cap; j++) {
+        pq.data[j] = ORC_EMPTY;
+        pq.pri[j] = FLT_MAX;
+      }
+      uint64_t node = (uint64_t)i;
+      float zero = 0.0f;
+      pq_merge(&pq, &node, &zero, 1);
+      query_t q;
+      q.h = h;
+      q.qvec = h->rows + layer->nodes[i] * h->dim;
+      float last = 0.0f;
+      uint64_t last_size = 0;
+      while (last < threshold && pq_len(&pq) > last_size) { /* lib.rs:946-953 */
+        last_size = pq_len(&pq);
+        closest_nodes(layer, &q, &pq, probe_depth, &s, NULL, NULL);
+        uint64_t len = pq_len(&pq);
+        last = pq.pri[len - 1];
+        if (last < threshold && len == pq.cap) { /* resize_capacity(cap*2) */
+          uint64_t nc = pq.cap * 2;
+          pq.data = (uint64_t *)realloc(pq.data, nc * sizeof(uint64_t));
+          pq.pri = (float *)realloc(pq.pri, nc * sizeof(float));
+          for (uint64_t j = pq.cap; j < nc; j++) {
+            pq.data[j] = ORC_EMPTY;
+            pq.pri[j] = FLT_MAX;
+          }
+          pq.cap = nc;
+        }
+      }
+      pair_t *r = (pair_t *)malloc((pq.cap ? pq.cap : 1) * sizeof(pair_t));
+      uint64_t c = 0;
+      for (uint64_t j = 0; j < pq.cap && pq.data[j] != ORC_EMPTY; j++) {
+        if (pq.data[j] == node) continue;       /* filter, then ... */
+        if (!(pq.pri[j] < threshold)) break;    /* ... take_while(d < threshold) */
+        r[c].id = layer->nodes[pq.data[j]];
+        r[c].d = pq.pri[j];
+        c++;
+      }
+      res[i] = r;
+      cnt[i + 1] = c;
+      free(pq.data);
+      free(pq.pri);
+    }
+    scratch_free(&s);
+  }
+  for (uint64_t i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+  uint64_t total = cnt[n];
+  uint64_t *ids = (uint64_t *)malloc((total ? total : 1) * sizeof(uint64_t));
+  float *ds = (float *)malloc((total ? total : 1) * sizeof(float));
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t c = cnt[i + 1] - cnt[i];
+    for (uint64_t j = 0; j < c; j++) {
+      ids[cnt[i] + j] = res[i][j].id;
+      ds[cnt[i] + j] = res[i][j].d;
+    }
+    free(res[i]);
+  }
+  free(res);
+  *out_offsets = cnt;
+  *out_ids = ids;
+  *out_dists = ds;
+  return 0;
+}
+
+void orc_free(void *p) { free(p); }
+
+int orc_compare_all(const orc_hnsw *h, uint64_t v, const uint64_t *vs, uint64_t n_vs,
+                    uint64_t *out_ids, float *out_dists) {
+  pair_t *r = (pair_t *)malloc((n_vs ? n_vs : 1) * sizeof(pair_t));
+  uint64_t c = 0;
+  for (uint64_t i = 0; i < n_vs; i++) {
+    if (vs[i] == v) continue;
+    r[c].id = vs[i];
+    r[c].d = orc_distance(h->metric, h->dim, h->rows + v * h->dim, h->rows + vs[i] * h->dim);
+    c++;
+  }
+  qsort(r, c, sizeof(pair_t), pair_cmp);
+  for (uint64_t i = 0; i < c; i++) {
+    out_ids[i] = r[i].id;
+    out_dists[i] = r[i].d;
+  }
+  free(r);
+  return (int)c;
+}
+
+/* ---------------------------------------------------------------- RNG (ours) */
+
+typedef struct {
+  uint64_t s;
+} rng_t;
+static inline uint64_t rng_next(rng_t *r) { /* splitmix64 */
+  uint64_t z = (r->s += 0x9e3779b97f4a7c15ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+static inline uint64_t rng_below(rng_t *r, uint64_t n) { return n ? rng_next(r) % n : 0; }
+static inline float rng_unit(rng_t *r) { return (float)((rng_next(r) >> 40) + 1) / 16777217.0f; }
+static void shuffle_u64(uint64_t *a, uint64_t n, rng_t *r) {
+  for (uint64_t i = n; i > 1; i--) {
+    uint64_t j = rng_below(r, i);
+    uint64_t t = a[i - 1];
+    a[i - 1] = a[j];
+    a[j] = t;
+  }
+}
+
+/* ------------------------------------------------ build: lib.rs:675-893 etc. */
+
+static int u64_cmp(const void *a, const void *b) {
+  uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+typedef struct {
+  uint64_t node, vec;
+  uint64_t n_d;
+  pair_t d[8]; /* initial distances as (NodeId in this layer, d); <= ef of the seed search */
+  pair_t *dl;  /* used instead of d[] when n_d > 8 (top layer brute force) */
+} ipart_t;
+
+static int ipart_cmp(const void *a, const void *b) {
+  /* par_sort_unstable_by_key(first distance as Option): None < Some (search.rs:67-69) */
+  const ipart_t *x = (const ipart_t *)a, *y = (const ipart_t *)b;
+  const pair_t *dx = x->dl ? x->dl : x->d, *dy = y->dl ? y->dl : y->d;
+  if (x->n_d == 0 || y->n_d == 0) {
+    if (x->n_d == y->n_d) return x->node < y->node ? -1 : (x->node > y->node);
+    return x->n_d == 0 ? -1 : 1;
+  }
+  if (dx[0].d < dy[0].d) return -1;
+  if (dx[0].d > dy[0].d) return 1;
+  return x->node < y->node ? -1 : (x->node > y->node); /* unstable in the reference; fixed here */
+}
+
+/* choose_n / choose_n_1 (lib.rs:1830-1881) with our RNG; returns count, pairs in out */
+static uint64_t choose_n(uint64_t n, const uint64_t *maxes, uint64_t n_part, uint64_t exclude,
+                         rng_t *rng, uint64_t (*out)[2]) {
+  uint64_t total = 0;
+  for (uint64_t p = 0; p < n_part; p++) total += maxes[p];
+  if (total * 2 > n) { /* choose_n_1: enumerate, shuffle, truncate */
+    uint64_t(*all)[2] = (uint64_t(*)[2])malloc((total ? total : 1) * sizeof(*all));
+    uint64_t c = 0;
+    for (uint64_t p = 0; p < n_part; p++)
+      for (uint64_t i = 0; i < maxes[p]; i++) {
+        if (p == 0 && i == exclude) continue;
+        all[c][0] = p;
+        all[c][1] = i;
+        c++;
+      }
+    for (uint64_t i = c; i > 1; i--) {
+      uint64_t j = rng_below(rng, i);
+      uint64_t t0 = all[i - 1][0], t1 = all[i - 1][1];
+      all[i - 1][0] = all[j][0];
+      all[i - 1][1] = all[j][1];
+      all[j][0] = t0;
+      all[j][1] = t1;
+    }
+    if (c > n) c = n;
+    memcpy(out, all, c * sizeof(*all));
+    free(all);
+    return c;
+  }
+  /* rejection sampling, Exp(1) over partitions (lib.rs:1865-1880) */
+  uint64_t count = 0;
+  while (count != n) {
+    float e = -logf(rng_unit(rng));
+    uint64_t which = (uint64_t)floorf(e);
+    if (which >= n_part) which = 0;
+    uint64_t sel = rng_below(rng, maxes[which]);
+    if (which == 0 && sel == exclude) continue;
+    int dup = 0;
+    for (uint64_t i = 0; i < count; i++)
+      if (out[i][0] == which && out[i][1] == sel) {
+        dup = 1;
+        break;
+      }
+    if (dup) continue;
+    out[count][0] = which;
+    out[count][1] = sel;
+    count++;
+  }
+  return count;
+}
+
+/* generate_layer (lib.rs:675-823).  `vs` is sorted in place. */
+static void generate_layer(orc_hnsw *h, uint64_t *vs, uint64_t n, uint64_t M,
+                           const orc_search_params *isp, int nthreads) {
+  qsort(vs, n, sizeof(uint64_t), u64_cmp);
+  uint64_t n_above = h->layer_count;
+  uint64_t *neighbors = (uint64_t *)malloc((n * M ? n * M : 1) * sizeof(uint64_t));
+  float *ndist = (float *)malloc((n * M ? n * M : 1) * sizeof(float));
+  for (uint64_t i = 0; i < n * M; i++) {
+    neighbors[i] = ORC_EMPTY;
+    ndist[i] = FLT_MAX;
+  }
+  ipart_t *ip = (ipart_t *)calloc(n ? n : 1, sizeof(ipart_t));
+  layer_t self_layer;
+  self_layer.node_count = n;
+  self_layer.M = M;
+  self_layer.nodes = vs;
+  self_layer.neighbors = neighbors;
+  int nt = pick_threads(nthreads);
+  (void)nt;
+  /* 1. generate_initial_partitions (search.rs:32-71) */
+#pragma omp parallel num_threads(nt)
+  {
+    scratch_t s;
+    scratch_init(&s);
+    uint64_t ef = isp->number_of_candidates;
+    pq_t cand;
+    cand.cap = ef;
+    cand.data = (uint64_t *)malloc((ef ? ef : 1) * sizeof(uint64_t));
+    cand.pri = (float *)malloc((ef ? ef : 1) * sizeof(float));
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+      ipart_t *e = &ip[i];
+      e->node = (uint64_t)i;
+      e->vec = vs[i];
+      if (n_above == 0) { /* compare_all: brute force against the whole layer */
+        e->dl = (pair_t *)malloc((n ? n : 1) * sizeof(pair_t));
+        uint64_t c = 0;
+        for (uint64_t j = 0; j < n; j++) {
+          if (vs[j] == vs[i]) continue;
+          e->dl[c].id = j; /* NodeId == position in sorted vs */
+          e->dl[c].d = orc_distance(h->metric, h->dim, h->rows + vs[i] * h->dim,
+                                    h->rows + vs[j] * h->dim);
+          c++;
+        }
+        /* sorted by (d, VectorId); positions are monotone in VectorId so (d, node) is the same */
+        qsort(e->dl, c, sizeof(pair_t), pair_cmp);
+        e->n_d = c;
+      } else {
+        for (uint64_t k = 0; k < ef; k++) {
+          cand.data[k] = ORC_EMPTY;
+          cand.pri[k] = FLT_MAX;
+        }
+        query_t q;
+        q.h = h;
+        q.qvec = h->rows + vs[i] * h->dim;
+        search_layers(h, h->layers, n_above, &q, isp, ORC_EMPTY, &cand, &s, NULL, NULL, NULL);
+        uint64_t c = 0;
+        pair_t *dst = e->d;
+        if (ef > 8) {
+          e->dl = (pair_t *)malloc(ef * sizeof(pair_t));
+          dst = e->dl;
+        }
+        for (uint64_t k = 0; k < ef && cand.data[k] != ORC_EMPTY; k++) {
+          if (cand.data[k] == vs[i]) continue; /* initial_vector_distances drops self */
+          int64_t node = layer_get_node(&self_layer, cand.data[k]);
+          dst[c].id = (uint64_t)node; /* every upper-layer vector is in this layer (nesting) */
+          dst[c].d = cand.pri[k];
+          c++;
+        }
+        e->n_d = c;
+      }
+    }
+    free(cand.data);
+    free(cand.pri);
+    scratch_free(&s);
+  }
+  qsort(ip, n, sizeof(ipart_t), ipart_cmp);
+
+  /* 2. partition groups keyed by the closest super (lib.rs:711-713).  group_of[node] =
+   *    key (NodeId of closest super, or ORC_EMPTY for None); members kept in sorted order. */
+  uint64_t *key = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+  for (uint64_t i = 0; i < n; i++) {
+    const pair_t *d = ip[i].dl ? ip[i].dl : ip[i].d;
+    key[i] = ip[i].n_d ? d[0].id : ORC_EMPTY;
+  }
+  /* group sizes / offsets indexed by key NodeId (+1 slot for None) */
+  uint64_t *gcount = (uint64_t *)calloc(n + 2, sizeof(uint64_t));
+  for (uint64_t i = 0; i < n; i++) gcount[(key[i] == ORC_EMPTY ? n : key[i]) + 1]++;
+  for (uint64_t i = 0; i <= n; i++) gcount[i + 1] += gcount[i];
+  uint64_t *gfill = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+  uint64_t *gmembers = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t)); /* index into ip[] */
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t g = key[i] == ORC_EMPTY ? n : key[i];
+    gmembers[gcount[g] + gfill[g]++] = i;
+  }
+  uint64_t layer_count_seed = h->layer_count;
+
+  /* 3. score candidates inside the partitions of my nearest supers (lib.rs:719-787) */
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+  for (int64_t ii = 0; ii < (int64_t)n; ii++) {
+    const ipart_t *e = &ip[ii];
+    const pair_t *d0 = e->dl ? e->dl : e->d;
+    uint64_t nsup = e->n_d;
+    /* partitions = groups of each of my supers that exist as a key (:733-736) */
+    uint64_t *pstart = (uint64_t *)malloc((nsup + 1) * sizeof(uint64_t));
+    uint64_t *pmax = (uint64_t *)malloc((nsup + 1) * sizeof(uint64_t));
+    uint64_t np = 0;
+    for (uint64_t k = 0; k < nsup; k++) {
+      uint64_t g = d0[k].id;
+      uint64_t sz = gcount[g + 1] - gcount[g];
+      if (sz == 0) continue;
+      pstart[np] = gcount[g];
+      pmax[np] = sz;
+      np++;
+    }
+    if (np == 0) { /* "probably we're in the top layer. best add ourselves." (:737-740) */
+      uint64_t g = key[ii] == ORC_EMPTY ? n : key[ii];
+      pstart[0] = gcount[g];
+      pmax[0] = gcount[g + 1] - gcount[g];
+      np = 1;
+    }
+    uint64_t total = 0;
+    for (uint64_t p = 0; p < np; p++) total += pmax[p];
+    uint64_t choice_count = M * 5 < total ? M * 5 : total;
+    uint64_t(*choices)[2] = (uint64_t(*)[2])malloc((total + 1) * sizeof(*choices));
+    rng_t rng;
+    rng.s = layer_count_seed + e->vec + n; /* seed formula of lib.rs:729-731 */
+    uint64_t nch = choose_n(choice_count, pmax, np, e->node, &rng, choices);
+    pair_t *all = (pair_t *)malloc((nsup + nch + 1) * sizeof(pair_t));
+    uint64_t na = 0;
+    for (uint64_t k = 0; k < nsup; k++) all[na++] = d0[k];
+    for (uint64_t c = 0; c < nch; c++) {
+      const ipart_t *o = &ip[gmembers[pstart[choices[c][0]] + choices[c][1]]];
+      all[na].id = o->node;
+      all[na].d = orc_distance(h->metric, h->dim, h->rows + e->vec * h->dim,
+                               h->rows + o->vec * h->dim);
+      na++;
+    }
+    qsort(all, na, sizeof(pair_t), pair_cmp);
+    uint64_t w = 0; /* dedup consecutive equal pairs, drop self, take M (:757-763) */
+    uint64_t out = 0;
+    for (uint64_t k = 0; k < na; k++) {
+      if (w > 0 && all[k].id == all[w - 1].id && all[k].d == all[w - 1].d) continue;
+      all[w++] = all[k];
+    }
+    for (uint64_t k = 0; k < w && out < M; k++) {
+      if (all[k].id == e->node) continue;
+      neighbors[e->node * M + out] = all[k].id;
+      ndist[e->node * M + out] = all[k].d;
+      out++;
+    }
+    free(all);
+    free(choices);
+    free(pstart);
+    free(pmax);
+  }
+
+  /* 4. make neighbourhoods bidirectional (lib.rs:789-815); sequential = one legal
+   *    interleaving of the reference's lock-ordered parallel loop */
+  pair_t *copy = (pair_t *)malloc((M ? M : 1) * sizeof(pair_t));
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t c = 0;
+    for (uint64_t k = 0; k < M; k++) {
+      if (neighbors[i * M + k] == ORC_EMPTY) break; /* iter() stops at the first empty */
+      copy[c].id = neighbors[i * M + k];
+      copy[c].d = ndist[i * M + k];
+      c++;
+    }
+    for (uint64_t k = 0; k < c; k++) {
+      pq_t q = {neighbors + copy[k].id * M, ndist + copy[k].id * M, M};
+      pq_insert(&q, i, copy[k].d);
+    }
+  }
+  free(copy);
+
+  for (uint64_t i = 0; i < n; i++) free(ip[i].dl);
+  free(ip);
+  free(key);
+  free(gcount);
+  free(gfill);
+  free(gmembers);
+  free(ndist);
+  layer_t *l = push_layer_raw(h, n, M);
+  memcpy(l->nodes, vs, n * sizeof(uint64_t));
+  memcpy(l->neighbors, neighbors, n * M * sizeof(uint64_t));
+  free(neighbors);
+}
+
+/* link_nodes_in_layer_to_better_neighbors over all nodes (lib.rs:1070-1154) */
+static uint64_t link_layer(orc_hnsw *h, uint64_t layer_from_top, const orc_search_params *sp,
+                           int nthreads) {
+  uint64_t nsz = h->bp.neighborhood_size; /* self.neighborhood_size(), even on layer 0 (:1093) */
+  layer_t *cur = &h->layers[layer_from_top];
+  uint64_t n = cur->node_count, M = cur->M;
+  /* pseudo stack: layers above + a snapshot of the current layer */
+  layer_t *stack = (layer_t *)malloc((layer_from_top + 1) * sizeof(layer_t));
+  memcpy(stack, h->layers, layer_from_top * sizeof(layer_t));
+  layer_t snap = *cur;
+  snap.neighbors = (uint64_t *)malloc((n * M ? n * M : 1) * sizeof(uint64_t));
+  memcpy(snap.neighbors, cur->neighbors, n * M * sizeof(uint64_t));
+  stack[layer_from_top] = snap;
+  uint64_t ef = sp->number_of_candidates;
+  uint64_t keep = nsz < ef ? nsz : ef;
+  uint64_t *mid = (uint64_t *)malloc((n * keep ? n * keep : 1) * sizeof(uint64_t));
+  float *mdist = (float *)malloc((n * keep ? n * keep : 1) * sizeof(float));
+  uint32_t *mcnt = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel num_threads(nt)
+  {
+    scratch_t s;
+    scratch_init(&s);
+    pq_t cand;
+    cand.cap = ef;
+    cand.data = (uint64_t *)malloc((ef ? ef : 1) * sizeof(uint64_t));
+    cand.pri = (float *)malloc((ef ? ef : 1) * sizeof(float));
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+      for (uint64_t k = 0; k < ef; k++) {
+        cand.data[k] = ORC_EMPTY;
+        cand.pri[k] = FLT_MAX;
+      }
+      uint64_t vector = snap.nodes[i];
+      query_t q;
+      q.h = h;
+      q.qvec = h->rows + vector * h->dim;
+      search_layers(h, stack, layer_from_top + 1, &q, sp, vector, &cand, &s, NULL, NULL, NULL);
+      uint32_t c = 0;
+      for (uint64_t k = 0; k < ef && cand.data[k] != ORC_EMPTY && c < keep; k++) {
+        mid[(uint64_t)i * keep + c] = cand.data[k];
+        mdist[(uint64_t)i * keep + c] = cand.pri[k];
+        c++;
+      }
+      mcnt[i] = c;
+    }
+    free(cand.data);
+    free(cand.pri);
+    scratch_free(&s);
+  }
+  /* sequential linking against the LIVE rows (one legal interleaving of :1118-1148) */
+  uint64_t count = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t vector = snap.nodes[i];
+    for (uint32_t m = 0; m < mcnt[i]; m++) {
+      uint64_t nvec = mid[i * keep + m];
+      float distance = mdist[i * keep + m];
+      if (nvec == vector) break;
+      int64_t nb = layer_get_node(&snap, nvec);
+      uint64_t *row = cur->neighbors + (uint64_t)nb * M;
+      int64_t pos = -1;
+      for (uint64_t j = 0; j < M; j++) {
+        uint64_t x = row[j];
+        if (x == ORC_EMPTY || x == i) {
+          pos = (int64_t)j;
+          break;
+        }
+        float other = orc_distance(h->metric, h->dim, h->rows + snap.nodes[x] * h->dim,
+                                   h->rows + nvec * h->dim);
+        if (distance < other || (distance == other && i < x)) {
+          pos = (int64_t)j;
+          break;
+        }
+      }
+      if (pos < 0) continue;
+      if (row[pos] == i) continue; /* already linked */
+      for (int64_t j = (int64_t)M - 2; j >= pos; j--) row[j + 1] = row[j];
+      row[pos] = i;
+      count++;
+    }
+  }
+  free(mid);
+  free(mdist);
+  free(mcnt);
+  free(snap.neighbors);
+  free(stack);
+  return count;
+}
+
+/* stochastic_recall_at (lib.rs:1463-1499); note it searches the WHOLE index */
+static float stochastic_recall_at(const orc_hnsw *h, uint64_t at,
+                                  const orc_optimization_params *op, int nthreads) {
+  const layer_t *layer = &h->layers[at];
+  uint64_t total = layer->node_count;
+  uint64_t selection = (uint64_t)((float)total * op->recall_proportion);
+  if (selection < 1) selection = 1;
+  uint64_t *vecs = (uint64_t *)malloc(total * sizeof(uint64_t));
+  memcpy(vecs, layer->nodes, total * sizeof(uint64_t));
+  if (selection != total) {
+    rng_t rng;
+    rng.s = 42; /* StdRng::seed_from_u64(42) in the reference; our generator */
+    shuffle_u64(vecs, total, &rng);
+  }
+  uint64_t ef = op->search.number_of_candidates;
+  uint64_t *ids = (uint64_t *)malloc(selection * ef * sizeof(uint64_t));
+  float *ds = (float *)malloc(selection * ef * sizeof(float));
+  uint32_t *cn = (uint32_t *)malloc(selection * sizeof(uint32_t));
+  orc_search_batch(h, NULL, vecs, selection, &op->search, 0, NULL, ef, ids, ds, cn, NULL, NULL,
+                   NULL, nthreads);
+  uint64_t relevant = 0;
+  for (uint64_t i = 0; i < selection; i++)
+    for (uint32_t k = 0; k < cn[i]; k++)
+      if (ids[i * ef + k] == vecs[i]) {
+        relevant++;
+        break;
+      }
+  free(ids);
+  free(ds);
+  free(cn);
+  free(vecs);
+  return (float)relevant / (float)selection;
+}
+
+float orc_stochastic_recall(const orc_hnsw *h, const orc_optimization_params *op, int nthreads) {
+  return stochastic_recall_at(h, h->layer_count - 1, op, nthreads);
+}
+
+/* improve_neighbors_upto (lib.rs:1515-1544) */
+static float improve_neighbors_upto(orc_hnsw *h, uint64_t upto,
+                                    const orc_optimization_params *op, int has_last,
+                                    float last_recall_in, int nthreads) {
+  float last_recall = has_last ? last_recall_in : 0.0f;
+  float last_improvement = 1.0f;
+  while (last_improvement >= op->neighborhood_threshold && last_recall < 1.0f) {
+    for (uint64_t l = 0; l < upto; l++) link_layer(h, l, &op->search, nthreads);
+    float recall = stochastic_recall_at(h, upto - 1, op, nthreads);
+    last_improvement = recall - last_recall;
+    last_recall = recall;
+  }
+  return last_recall;
+}
+
+/* improve_index_at (lib.rs:1546-1603), promotion treated as "nothing to promote" */
+static float improve_index_at(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
+                              int nthreads) {
+  const orc_optimization_params *op = &bp->optimization;
+  float recall = stochastic_recall_at(h, layer_from_top, op, nthreads);
+  float improvement = 1.0f;
+  int bailout = 1;
+  while (improvement >= op->promotion_threshold && recall < 1.0f && bailout != 0) {
+    float last_recall = recall;
+    uint64_t cur = 0;
+    while (cur <= layer_from_top && bailout != 0) {
+      recall = improve_neighbors_upto(h, cur + 1, op, 0, 0.0f, nthreads);
+      cur += 1; /* recall == 1.0 -> continue; else promote_at_layer (skipped) -> +1 */
+    }
+    bailout -= 1;
+    improvement = recall - last_recall;
+  }
+  return recall;
+}
+
+float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
+  float recall = orc_stochastic_recall(h, &bp->optimization, nthreads); /* lib.rs:1671 */
+  for (uint64_t l = 0; l < h->layer_count; l++) recall = improve_index_at(h, l, bp, nthreads);
+  return recall;
+}
+
+orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float *rows,
+                       const uint64_t *vs_in, uint64_t n_vs, const orc_build_params *bp,
+                       uint64_t seed, int improve, int nthreads) {
+  if (n_vs == 0) return NULL; /* assert!(total_size > 0) lib.rs:837 */
+  orc_hnsw *h = orc_hnsw_new(metric, dim, n_vectors, rows);
+  h->bp = *bp;
+  uint64_t *vs = (uint64_t *)malloc(n_vs * sizeof(uint64_t));
+  memcpy(vs, vs_in, n_vs * sizeof(uint64_t));
+  rng_t rng;
+  rng.s = seed;
+  shuffle_u64(vs, n_vs, &rng); /* lib.rs:832-833 (thread_rng in the reference) */
+  uint64_t parts[64];
+  uint64_t np = orc_calculate_partitions(n_vs, bp->order, parts, 64);
+  for (uint64_t i = 0; i < np; i++) {
+    uint64_t level = np - i - 1;
+    uint64_t len = parts[i] < n_vs ? parts[i] : n_vs;
+    uint64_t M = level == 0 ? bp->zero_layer_neighborhood_size : bp->neighborhood_size;
+    uint64_t *slice = (uint64_t *)malloc((len ? len : 1) * sizeof(uint64_t));
+    memcpy(slice, vs, len * sizeof(uint64_t));
+    generate_layer(h, slice, len, M, &bp->initial_partition_search, nthreads);
+    free(slice);
+    if (improve) orc_improve_index(h, bp, nthreads); /* lib.rs:876 */
+  }
+  free(vs);
+  return h;
+}
+
+/* ------------------------------------------------ serialize (serialize.rs) */
+
+static int write_file(const char *path, const void *buf, size_t len) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return -1;
+  size_t w = len ? fwrite(buf, 1, len, f) : 0;
+  fclose(f);
+  return w == len ? 0 : -1;
+}
+
+static char *read_file(const char *path, size_t *len) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return NULL;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  char *buf = (char *)malloc((size_t)sz + 1);
+  size_t r = sz ? fread(buf, 1, (size_t)sz, f) : 0;
+  fclose(f);
+  if (r != (size_t)sz) {
+    free(buf);
+    return NULL;
+  }
+  buf[sz] = 0;
+  if (len) *len = (size_t)sz;
+  return buf;
+}
+
+/* serde_json prints f32 with the shortest round-trip representation; %.9g round-trips too
+ * and is accepted by serde on the way back in. */
+static void json_sp(char *o, const orc_search_params *sp) {
+  sprintf(o,
+          "{\"number_of_candidates\":%llu,\"upper_layer_candidate_count\":%llu,\"probe_depth\":%llu}",
+          (unsigned long long)sp->number_of_candidates,
+          (unsigned long long)sp->upper_layer_candidate_count,
+          (unsigned long long)sp->probe_depth);
+}
+
+int orc_serialize(const orc_hnsw *h, const char *dir) {
+  mkdir(dir, 0777);
+  char path[4096], sp1[256], sp2[256], meta[2048];
+  json_sp(sp1, &h->bp.optimization.search);
+  json_sp(sp2, &h->bp.initial_partition_search);
+  snprintf(meta, sizeof meta,
+           "{\"layer_count\":%llu,\"build_parameters\":{\"order\":%llu,"
+           "\"zero_layer_neighborhood_size\":%llu,\"neighborhood_size\":%llu,"
+           "\"optimization\":{\"promotion_threshold\":%.9g,\"neighborhood_threshold\":%.9g,"
+           "\"recall_proportion\":%.9g,\"promotion_proportion\":%.9g,\"search\":%s},"
+           "\"initial_partition_search\":%s}}",
+           (unsigned long long)h->layer_count, (unsigned long long)h->bp.order,
+           (unsigned long long)h->bp.zero_layer_neighborhood_size,
+           (unsigned long long)h->bp.neighborhood_size,
+           (double)h->bp.optimization.promotion_threshold,
+           (double)h->bp.optimization.neighborhood_threshold,
+           (double)h->bp.optimization.recall_proportion,
+           (double)h->bp.optimization.promotion_proportion, sp1, sp2);
+  snprintf(path, sizeof path, "%s/meta", dir);
+  if (write_file(path, meta, strlen(meta))) return -1;
+  if (h->layer_count > 0) { /* comparator entry: user-defined in the reference */
+    snprintf(path, sizeof path, "%s/comparator", dir);
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    uint64_t hdr[4] = {0x3142574e53485042ULL /* "BPHSNWB1" tag */, (uint64_t)h->metric, h->dim,
+                       h->n_vectors};
+    fwrite(hdr, sizeof hdr, 1, f);
+    fwrite(h->rows, sizeof(float), h->dim * h->n_vectors, f);
+    fclose(f);
+  }
+  for (uint64_t i = 0; i < h->layer_count; i++) {
+    uint64_t num = h->layer_count - i - 1; /* counted from the bottom (serialize.rs:67) */
+    const layer_t *l = &h->layers[i];
+    char lm[256];
+    snprintf(lm, sizeof lm, "{\"node_count\":%llu,\"neighborhood_size\":%llu}",
+             (unsigned long long)l->node_count, (unsigned long long)l->M);
+    snprintf(path, sizeof path, "%s/layer.meta.%llu", dir, (unsigned long long)num);
+    if (write_file(path, lm, strlen(lm))) return -1;
+    snprintf(path, sizeof path, "%s/layer.nodes.%llu", dir, (unsigned long long)num);
+    if (write_file(path, l->nodes, l->node_count * sizeof(uint64_t))) return -1;
+    snprintf(path, sizeof path, "%s/layer.neighbors.%llu", dir, (unsigned long long)num);
+    if (write_file(path, l->neighbors, l->node_count * l->M * sizeof(uint64_t))) return -1;
+  }
+  return 0;
+}
+
+/* tiny JSON field readers: enough for the flat numeric objects serde_json emits */
+static int json_u64(const char *s, const char *key, uint64_t *out) {
+  char pat[128];
+  snprintf(pat, sizeof pat, "\"%s\"", key);
+  const char *p = strstr(s, pat);
+  if (!p) return -1;
+  p = strchr(p + strlen(pat), ':');
+  if (!p) return -1;
+  *out = strtoull(p + 1, NULL, 10);
+  return 0;
+}
+static int json_f32(const char *s, const char *key, float *out) {
+  char pat[128];
+  snprintf(pat, sizeof pat, "\"%s\"", key);
+  const char *p = strstr(s, pat);
+  if (!p) return -1;
+  p = strchr(p + strlen(pat), ':');
+  if (!p) return -1;
+  *out = strtof(p + 1, NULL);
+  return 0;
+}
+static int json_sp_read(const char *s, const char *key, orc_search_params *sp) {
+  char pat[128];
+  snprintf(pat, sizeof pat, "\"%s\"", key);
+  const char *p = strstr(s, pat);
+  if (!p) return -1;
+  return json_u64(p, "number_of_candidates", &sp->number_of_candidates) |
+         json_u64(p, "upper_layer_candidate_count", &sp->upper_layer_candidate_count) |
+         json_u64(p, "probe_depth", &sp->probe_depth);
+}
+
+orc_hnsw *orc_deserialize(const char *dir, int *err) {
+  char path[4096];
+  int e = 0;
+  snprintf(path, sizeof path, "%s/meta", dir);
+  char *meta = read_file(path, NULL);
+  if (!meta) {
+    if (err) *err = -1;
+    return NULL;
+  }
+  uint64_t layer_count = 0;
+  orc_build_params bp;
+  orc_default_build_params(&bp);
+  e |= json_u64(meta, "layer_count", &layer_count);
+  e |= json_u64(meta, "order", &bp.order);
+  e |= json_u64(meta, "zero_layer_neighborhood_size", &bp.zero_layer_neighborhood_size);
+  /* "neighborhood_size" also matches inside "zero_layer_neighborhood_size": look after it */
+  {
+    const char *p = strstr(meta, "\"zero_layer_neighborhood_size\"");
+    if (p) e |= json_u64(p + 30, "neighborhood_size", &bp.neighborhood_size);
+    else e = -1;
+  }
+  e |= json_f32(meta, "promotion_threshold", &bp.optimization.promotion_threshold);
+  e |= json_f32(meta, "neighborhood_threshold", &bp.optimization.neighborhood_threshold);
+  e |= json_f32(meta, "recall_proportion", &bp.optimization.recall_proportion);
+  e |= json_f32(meta, "promotion_proportion", &bp.optimization.promotion_proportion);
+  e |= json_sp_read(meta, "search", &bp.optimization.search);
+  e |= json_sp_read(meta, "initial_partition_search", &bp.initial_partition_search);
+  free(meta);
+  if (e) {
+    if (err) *err = -2;
+    return NULL;
+  }
+  snprintf(path, sizeof path, "%s/comparator", dir);
+  FILE *f = fopen(path, "rb");
+  if (!f) { /* serialize.rs:143-145 */
+    if (err) *err = -3;
+    return NULL;
+  }
+  uint64_t hdr[4];
+  if (fread(hdr, sizeof hdr, 1, f) != 1 || hdr[0] != 0x3142574e53485042ULL) {
+    fclose(f);
+    if (err) *err = -1;
+    return NULL;
+  }
+  float *rows = (float *)malloc((hdr[2] * hdr[3] ? hdr[2] * hdr[3] : 1) * sizeof(float));
+  size_t got = fread(rows, sizeof(float), hdr[2] * hdr[3], f);
+  fclose(f);
+  if (got != hdr[2] * hdr[3]) {
+    free(rows);
+    if (err) *err = -1;
+    return NULL;
+  }
+  orc_hnsw *h = orc_hnsw_new((int)hdr[1], hdr[2], hdr[3], rows);
+  h->owned_rows = rows;
+  h->bp = bp;
+  for (uint64_t i = 0; i < layer_count; i++) {
+    uint64_t num = layer_count - i - 1;
+    snprintf(path, sizeof path, "%s/layer.meta.%llu", dir, (unsigned long long)num);
+    char *lm = read_file(path, NULL);
+    uint64_t nc = 0, M = 0;
+    if (!lm || json_u64(lm, "node_count", &nc) || json_u64(lm, "neighborhood_size", &M)) {
+      free(lm);
+      orc_hnsw_free(h);
+      if (err) *err = lm ? -2 : -1;
+      return NULL;
+    }
+    free(lm);
+    layer_t *l = push_layer_raw(h, nc, M);
+    size_t len = 0;
+    snprintf(path, sizeof path, "%s/layer.nodes.%llu", dir, (unsigned long long)num);
+    char *b = read_file(path, &len);
+    if (!b || len < nc * sizeof(uint64_t)) { /* read_exact: short file is an io error */
+      free(b);
+      orc_hnsw_free(h);
+      if (err) *err = -1;
+      return NULL;
+    }
+    memcpy(l->nodes, b, nc * sizeof(uint64_t));
+    free(b);
+    snprintf(path, sizeof path, "%s/layer.neighbors.%llu", dir, (unsigned long long)num);
+    b = read_file(path, &len);
+    if (!b || len < nc * M * sizeof(uint64_t)) {
+      free(b);
+      orc_hnsw_free(h);
+      if (err) *err = -1;
+      return NULL;
+    }
+    memcpy(l->neighbors, b, nc * M * sizeof(uint64_t));
+    free(b);
+  }
+  if (err) *err = 0;
+  return h;
+}

@@ -1,0 +1,258 @@
+"""Pins the CPU oracle to the reference's own known-answer tests (CPU only).
+
+Each test names the reference test it restates (paths relative to /root/reference/).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import EMPTY, nine_point, nine_point_layers, random_normed
+
+FMAX = np.float32(3.4028235e38)
+E = int(EMPTY)
+
+
+def _q(ids, prs):
+    return np.array(ids, dtype=np.uint64), np.array(prs, dtype=np.float32)
+
+
+# ---- src/priority_queue.rs:229-284 fixed_length_insertion ----
+def test_pq_fixed_length_insertion(oracle):
+    d, p = _q([0, 3, E], [0.1, 1.2, FMAX])
+    oracle.pq_insert(d, p, 4, 0.01)
+    assert d.tolist() == [4, 0, 3] and p.tolist() == _q([], [0.01, 0.1, 1.2])[1].tolist()
+    d, p = _q([E, E, E], [FMAX, FMAX, FMAX])
+    oracle.pq_insert(d, p, 4, 0.01)
+    assert d.tolist() == [4, E, E] and p.tolist() == [np.float32(0.01), FMAX, FMAX]
+    d, p = _q([4, E, E], [0.01, FMAX, FMAX])  # don't double count
+    oracle.pq_insert(d, p, 4, 0.01)
+    assert d.tolist() == [4, E, E] and p.tolist() == [np.float32(0.01), FMAX, FMAX]
+    d, p = _q([1, 2, 3], [0.1, 0.2, 0.4])  # push off the end
+    oracle.pq_insert(d, p, 4, 0.3)
+    assert d.tolist() == [1, 2, 4] and p.tolist() == _q([], [0.1, 0.2, 0.3])[1].tolist()
+    d, p = _q([1, 2, 3], [0.1, 0.2, 0.3])  # insert past the end
+    oracle.pq_insert(d, p, 4, 0.4)
+    assert d.tolist() == [1, 2, 3] and p.tolist() == _q([], [0.1, 0.2, 0.3])[1].tolist()
+
+
+# ---- :286-300 fixed_length_merge ----
+def test_pq_fixed_length_merge(oracle):
+    d, p = _q([0, 2, 4], [0.0, 0.2, 0.4])
+    oracle.pq_merge(d, p, *_q([1, 3, 5], [0.1, 0.3, 0.5]))
+    assert d.tolist() == [0, 1, 2] and p.tolist() == _q([], [0.0, 0.1, 0.2])[1].tolist()
+
+
+# ---- :302-309 last_element ----
+def test_pq_last_element(oracle):
+    d, p = _q([0, 3, E], [0.1, 1.2, FMAX])
+    n = oracle.pq_len(p)
+    assert (int(d[n - 1]), p[n - 1]) == (3, np.float32(1.2))
+
+
+# ---- :311-326 useless_merge ----
+def test_pq_useless_merge(oracle):
+    d, p = _q([0, 3, 5], [0.0, 0.3, 0.5])
+    assert oracle.pq_merge(d, p, *_q([6, 7, 8], [0.6, 0.7, 0.8])) is False
+    assert d.tolist() == [0, 3, 5]
+
+
+# ---- :328-341 productive_merge ----
+def test_pq_productive_merge(oracle):
+    d, p = _q([0, 3, 5], [0.0, 0.3, 0.5])
+    assert oracle.pq_merge(d, p, *_q([1, 2, 4], [0.1, 0.2, 0.4])) is True
+    assert d.tolist() == [0, 1, 2] and p.tolist() == _q([], [0.0, 0.1, 0.2])[1].tolist()
+
+
+# ---- :343-356 repeated_merge ----
+def test_pq_repeated_merge(oracle):
+    d, p = _q([0, 3, 5], [0.0, 0.0, 0.0])
+    assert oracle.pq_merge(d, p, *_q([0, 4, 3], [0.0, 0.0, 0.0])) is True
+    assert d.tolist() == [0, 3, 4] and p.tolist() == [0.0, 0.0, 0.0]
+
+
+# ---- :358-371 merge_with_empty ----
+def test_pq_merge_with_empty(oracle):
+    d, p = _q([0, 3, E], [0.0, 1.2, FMAX])
+    assert oracle.pq_merge(d, p, *_q([0, 3, 4], [0.0, 0.0, 0.0])) is True
+    assert d.tolist() == [0, 3, 4] and p.tolist() == [0.0, 0.0, 0.0]
+
+
+# ---- :373-439 lots_of_zeros ----
+def test_pq_lots_of_zeros(oracle):
+    d, p = _q([0] + [E] * 8, [0.0] + [FMAX] * 8)
+    ids, prs = _q([3, 4, 1, 2, 6, 7], [0.29289323, 0.4227, 1.0, 1.0, 1.0, 1.0])
+    assert oracle.pq_merge(d, p, ids, prs) is True
+    assert d.tolist() == [0, 3, 4, 1, 2, 6, 7, E, E]
+    assert p.tolist() == _q([], [0.0, 0.29289323, 0.4227, 1.0, 1.0, 1.0, 1.0, FMAX, FMAX])[1].tolist()
+
+
+def test_pq_merge_flag_quirk(oracle):
+    """head ties the tail run, walks off the end, one more follows."""
+    d, p = _q([1, 2, 3], [0.1, 0.5, 0.5])
+    assert oracle.pq_merge(d, p, *_q([9, 10], [0.5, 0.7])) is True   # nothing stored, flag raised
+    assert d.tolist() == [1, 2, 3]
+    d, p = _q([1, 2, 3], [0.1, 0.5, 0.5])
+    assert oracle.pq_merge(d, p, *_q([9], [0.5])) is False           # single element: no flag
+    d, p = _q([1, 2, 3], [0.1, 0.5, 0.5])
+    assert oracle.pq_merge(d, p, *_q([9, 10], [0.6, 0.7])) is False  # strictly beyond: break
+
+
+def test_pq_merge_closed_form_fuzz(oracle):
+    """The kernel's closed form of merge's flag + 'exact top-cap' contents vs the literal loop."""
+    rng = np.random.default_rng(7)
+    for trial in range(20000):
+        cap = int(rng.integers(1, 9))
+        fill = int(rng.integers(0, cap + 1))
+        levels = int(rng.integers(1, 5))
+        pool = rng.permutation(40)[: fill + 8].astype(np.uint64)
+        qi = pool[:fill]
+        qp = rng.integers(0, levels, size=fill).astype(np.float32) * np.float32(0.25)
+        order = np.lexsort((qi, qp))
+        d = np.full(cap, EMPTY, dtype=np.uint64)
+        p = np.full(cap, FMAX, dtype=np.float32)
+        d[:fill], p[:fill] = qi[order], qp[order]
+        nb = int(rng.integers(0, 8))
+        bi = pool[fill:fill + nb]
+        bp = rng.integers(0, levels + 1, size=nb).astype(np.float32) * np.float32(0.25)
+        o = np.lexsort((bi, bp))
+        bi, bp = bi[o], bp[o]
+        flag_cf = oracle.pq_merge_flag_closed_form(d, p, bi, bp)
+        # expected contents: exact top-cap of the union by (priority, id)
+        ai = np.concatenate([d[:fill], bi])
+        ap = np.concatenate([p[:fill], bp])
+        oo = np.lexsort((ai, ap))[:cap]
+        flag = oracle.pq_merge(d, p, bi, bp)
+        assert flag == flag_cf, (trial, d, p, bi, bp)
+        n = len(oo)
+        assert d[:n].tolist() == ai[oo].tolist() and p[:n].tolist() == ap[oo].tolist()
+        assert all(int(x) == E for x in d[n:])
+
+
+# ---- src/lib.rs:2476-2512 test_final_idx ----
+def test_final_idx(oracle):
+    assert oracle.final_neighbor_idx(10, [E] * 10, 0) == 0
+    assert oracle.final_neighbor_idx(10, [1] * 10, 0) == 10
+    assert oracle.final_neighbor_idx(10, [1, 2, 3, 4, 5] + [E] * 5, 0) == 5
+    # only TRAILING sentinels are trimmed
+    assert oracle.final_neighbor_idx(4, [1, E, 3, E], 0) == 3
+
+
+# ---- src/lib.rs:2300-2304, 2345-2356 and SURVEY section 8 layer sizes ----
+def test_calculate_partitions(oracle):
+    assert len(oracle.calculate_partitions(1, 24)) == 1
+    assert oracle.calculate_partitions(9, 6) == [1, 9]
+    assert oracle.calculate_partitions(10_000, 12) == [5, 69, 833, 10_000]
+    assert oracle.calculate_partitions(1_000_000, 12) == [4, 48, 578, 6944, 83333, 1_000_000]
+    sizes = oracle.calculate_partitions(1000, 2)[::-1]
+    assert oracle.calculate_partitions_for_additions(sizes[1:], 100, 2) == \
+        [100, 50, 25, 13, 6, 3, 2, 1, 1, 1]
+
+
+# ---- src/lib.rs:2057-2065 distance known answers (test_nearness_search) ----
+def test_distance_known_answers(oracle):
+    g = nine_point()
+    got = {int(i): oracle.distance(oracle.ONE_MINUS_DOT, g["query"], g["rows"][i]) for i in range(9)}
+    for vid, d in g["nearness_result"]:
+        assert got[vid] == np.float32(d), (vid, got[vid], d)
+
+
+def test_distance_metrics_sequential(oracle):
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=257).astype(np.float32)
+    b = rng.normal(size=257).astype(np.float32)
+    acc = np.float32(0.0)
+    for x, y in zip(a, b):
+        acc = np.float32(acc + np.float32(x * y))
+    assert oracle.distance(oracle.COS_HALF, a, b) == np.float32((np.float32(1.0) - acc) / np.float32(2.0))
+    assert oracle.distance(oracle.ONE_MINUS_DOT, a, b) == np.float32(np.float32(1.0) - acc)
+    cl = np.float32(np.float32(acc - np.float32(1.0)) / np.float32(-2.0))
+    assert oracle.distance(oracle.COS_CLAMP, a, b) == np.float32(min(max(cl, 0.0), 1.0))
+    acc2 = np.float32(0.0)
+    for x, y in zip(a, b):
+        t = np.float32(x - y)
+        acc2 = np.float32(acc2 + np.float32(t * t))
+    assert abs(float(oracle.distance(oracle.L2_SQRT, a, b)) - float(np.sqrt(acc2))) <= 1e-6 * float(np.sqrt(acc2))
+
+
+# ---- src/lib.rs:2358-2377 test_knn on the golden graph ----
+def test_knn_golden(oracle):
+    g, layers = nine_point_layers()
+    h = oracle.Hnsw.from_layers(oracle.ONE_MINUS_DOT, g["rows"], layers)
+    ids, ds, cnt = h.knn(1, 1)
+    for v, (nid, d) in enumerate(g["knn_1_1"]):
+        assert cnt[v] == 1 and int(ids[v, 0]) == nid and ds[v, 0] == np.float32(d), (v, ids[v], ds[v])
+
+
+# ---- src/lib.rs:2379-2420 test_threshold_nn on the golden graph ----
+def test_threshold_nn_golden(oracle):
+    g, layers = nine_point_layers()
+    h = oracle.Hnsw.from_layers(oracle.ONE_MINUS_DOT, g["rows"], layers)
+    off, ids, ds = h.threshold_nn(0.3, 1, 6)
+    for v, want in enumerate(g["threshold_nn_0.3_1_6"]):
+        got = [(int(i), float(d)) for i, d in zip(ids[off[v]:off[v + 1]], ds[off[v]:off[v + 1]])]
+        assert got == [(i, float(np.float32(d))) for i, d in want], (v, got, want)
+
+
+# ---- src/lib.rs:2046-2068 test_nearness_search: full list for entry points 0/6/7 ----
+@pytest.mark.parametrize("entry", [0, 6, 7])
+def test_nearness_search_golden(oracle, entry):
+    g, layers = nine_point_layers(entry)
+    h = oracle.Hnsw.from_layers(oracle.ONE_MINUS_DOT, g["rows"], layers)
+    ids, ds, cnt = h.search(queries=g["query"], sp=oracle.search_params(300, 300, 2))
+    got = [(int(i), float(d)) for i, d in zip(ids[0, :cnt[0]], ds[0, :cnt[0]])]
+    assert got == [(i, float(np.float32(d))) for i, d in g["nearness_result"]]
+
+
+# ---- src/lib.rs:2154-2164 test_search: every stored vector finds itself at rank 0 ----
+@pytest.mark.parametrize("entry", range(9))
+def test_search_self_at_rank0(oracle, entry):
+    g, layers = nine_point_layers(entry)
+    h = oracle.Hnsw.from_layers(oracle.ONE_MINUS_DOT, g["rows"], layers)
+    ids, ds, cnt = h.search(queries=g["rows"], sp=oracle.search_params(300, 300, 2))
+    for i in range(9):
+        # match_within_epsilon (search.rs:173-187)
+        hit = [int(v) for v, d in zip(ids[i, :cnt[i]], ds[i, :cnt[i]]) if abs(d) < 1e-5]
+        if i == 4:  # [0.5773]*3 is not unit length: 1 - dot = 1.7e-4, outside the epsilon
+            assert int(ids[i, 0]) == 4
+        else:
+            assert i in hit
+
+
+def test_search_exclude_and_upto(oracle):
+    g, layers = nine_point_layers(0)
+    h = oracle.Hnsw.from_layers(oracle.ONE_MINUS_DOT, g["rows"], layers)
+    ids, ds, cnt = h.search(stored_ids=[8], exclude=[8])
+    assert 8 not in ids[0, :cnt[0]].tolist() and int(ids[0, 0]) == 4
+    ids, ds, cnt = h.search(stored_ids=[8], upto_layers=1)  # search_upto: top layer only
+    assert ids[0, :cnt[0]].tolist() == [0]
+
+
+def test_build_and_serialize_roundtrip(oracle, tmp_path):
+    rows = random_normed(600, 16, 3)
+    bp = oracle.default_build_params()
+    h = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=bp, seed=5)
+    sizes = [l[0].size for l in h.layers()]
+    assert sizes == oracle.calculate_partitions(600, 12)
+    # layer invariants (search.rs:142-171): ascending nodes, nesting
+    ls = h.layers()
+    for up, low in zip(ls[:-1], ls[1:]):
+        assert np.all(np.diff(up[0].astype(np.int64)) > 0)
+        assert np.isin(up[0], low[0]).all()
+    # recall bar after improve (lib.rs:2224-2229 shape, smaller data)
+    ids, ds, cnt = h.search(queries=rows)
+    assert (ids[:, 0] == np.arange(600, dtype=np.uint64)).mean() >= 0.99
+    d = tmp_path / "idx"
+    h.serialize(str(d))
+    # serialize.rs layout: N counts from the bottom, raw native-endian u64
+    n_layers = len(ls)
+    raw = np.fromfile(d / "layer.nodes.0", dtype=np.uint64)
+    assert raw.tolist() == ls[-1][0].tolist()
+    rawn = np.fromfile(d / f"layer.neighbors.{n_layers - 1}", dtype=np.uint64)
+    assert rawn.tolist() == ls[0][1].reshape(-1).tolist()
+    h2 = oracle.Hnsw.deserialize(str(d))
+    for a, b in zip(ls, h2.layers()):
+        assert a[2] == b[2] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    i2, d2, c2 = h2.search(queries=rows[:50])
+    assert np.array_equal(i2, ids[:50]) and np.array_equal(d2, ds[:50])
+    (d / "comparator").unlink()
+    with pytest.raises(FileNotFoundError):   # SerializationError::IndexNotFound
+        oracle.Hnsw.deserialize(str(d))
