@@ -1,0 +1,228 @@
+/*
+ * phnsw.h -- C ABI of the B200-native HNSW search/build engine.
+ *
+ * This is the drop-in boundary for the distance-bound hot path of the Rust crate
+ * terminusdb-labs/parallel-hnsw.  The crate has no FFI of its own: its boundary is the
+ * generic trait `Comparator` (src/lib.rs:53-74), monomorphised Rust that a GPU cannot
+ * call.  The boundary therefore moves up one level: the crate's host files
+ * (src/search.rs, src/lib.rs, src/pq.rs, src/bigvec.rs) keep their public signatures
+ * and forward to the entry points below (INTEGRATION.md shows the Rust `extern "C"`
+ * block and the forwarding bodies).  Every entry point names the reference item it
+ * replaces; paths are relative to the reference crate root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; ids are u64 exactly as the crate's
+ *     `VectorId(usize)` / `NodeId(usize)` (src/types.rs:3-14); the empty id is !0.
+ *   - every call returns a phnsw_status (0 = ok); nothing unwinds across the ABI.  The
+ *     crate signals the same conditions by panic!/unwrap (e.g. src/lib.rs:181, :261,
+ *     src/types.rs:86) or by SerializationError (src/serialize.rs:11-19).
+ *   - host pointers unless the name ends in `_device`; the library owns its HBM copies.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     PHNSW_ERR_NO_DEVICE.
+ */
+#ifndef PHNSW_H
+#define PHNSW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHNSW_EMPTY_ID UINT64_MAX /* src/types.rs:9-14, EmptyValue :16-39 */
+
+typedef enum {
+  PHNSW_OK = 0,
+  PHNSW_ERR_INVALID = 1,     /* bad argument (the crate would panic / fail an assert) */
+  PHNSW_ERR_NO_DEVICE = 2,   /* no CUDA device: there is no CPU fallback */
+  PHNSW_ERR_CUDA = 3,        /* CUDA runtime error, see phnsw_last_error() */
+  PHNSW_ERR_IO = 4,          /* SerializationError::Io     (src/serialize.rs:13-14) */
+  PHNSW_ERR_FORMAT = 5,      /* SerializationError::Serde  (src/serialize.rs:15-16) */
+  PHNSW_ERR_NOT_FOUND = 6,   /* SerializationError::IndexNotFound (src/serialize.rs:17-18) */
+  PHNSW_ERR_CAPACITY = 7,    /* a per-query device scratch area overflowed (never silent) */
+  PHNSW_ERR_INTERRUPTED = 8, /* progress callback asked to stop (src/progress.rs:8-10) */
+  PHNSW_ERR_GRAPH = 9        /* malformed graph: candidate missing from a layer (lib.rs:261) */
+} phnsw_status;
+
+/* Built-in distance bodies: the Comparator impls the crate ships (compare_raw). */
+typedef enum {
+  PHNSW_METRIC_COS_HALF = 0,      /* src/bigvec.rs:41-53   (1 - sum a*b) / 2          */
+  PHNSW_METRIC_ONE_MINUS_DOT = 1, /* src/lib.rs:1985-1991, benches/bench.rs:24-30     */
+  PHNSW_METRIC_L2_SQRT = 2,       /* src/lib.rs:2431-2437  sqrt(sum (a-b)^2)          */
+  PHNSW_METRIC_COS_CLAMP = 3      /* src/pq.rs:481-497     clamp((sum a*b-1)/-2,0,1)  */
+} phnsw_metric;
+
+/* src/parameters.rs:3-18 */
+typedef struct {
+  uint64_t number_of_candidates;
+  uint64_t upper_layer_candidate_count;
+  uint64_t probe_depth;
+} phnsw_search_params;
+
+/* src/parameters.rs:20-40 */
+typedef struct {
+  float promotion_threshold;
+  float neighborhood_threshold;
+  float recall_proportion;
+  float promotion_proportion;
+  phnsw_search_params search;
+} phnsw_optimization_params;
+
+/* src/parameters.rs:42-64 */
+typedef struct {
+  uint64_t order;
+  uint64_t zero_layer_neighborhood_size;
+  uint64_t neighborhood_size;
+  phnsw_optimization_params optimization;
+  phnsw_search_params initial_partition_search;
+} phnsw_build_params;
+
+/* One layer exactly as `layer.nodes.N` / `layer.neighbors.N` hold it
+ * (src/lib.rs:85-91, src/serialize.rs:88-121): ascending VectorIds and
+ * node_count * neighborhood_size NodeIds with trailing !0 padding. */
+typedef struct {
+  uint64_t node_count;
+  uint64_t neighborhood_size;
+  const uint64_t *nodes;
+  const uint64_t *neighbors;
+} phnsw_layer_desc;
+
+typedef struct phnsw_store phnsw_store;   /* device-resident vectors = the Comparator */
+typedef struct phnsw_index phnsw_index;   /* device-resident Hnsw<C> */
+
+/* progress callback: ProgressMonitor::{alive,update} (src/progress.rs:12-16).  Called
+ * between kernel batches with a short phase name and a fraction; non-zero = Interrupt. */
+typedef int (*phnsw_progress_fn)(void *user, const char *phase, double fraction);
+
+/* ---- library ---- */
+int phnsw_abi_version(void);
+const char *phnsw_last_error(void);        /* thread-local, valid until the next call */
+int phnsw_device_count(void);
+void phnsw_default_search_params(phnsw_search_params *sp); /* parameters.rs:10-18 */
+void phnsw_default_build_params(phnsw_build_params *bp);   /* parameters.rs:30-64 */
+/* calculate_partitions (src/lib.rs:1883-1899): layer sizes top first, returns the count */
+uint64_t phnsw_calculate_partitions(uint64_t total_size, uint64_t order, uint64_t *out,
+                                    uint64_t out_cap);
+
+/* ---- vector store: Comparator::lookup + compare_raw, BigComparator (src/bigvec.rs:36-57) ---- */
+phnsw_status phnsw_store_create(phnsw_metric metric, uint64_t dim, uint64_t n,
+                                const float *rows_host, int device, phnsw_store **out);
+/* same, copying from a row-major device buffer (synthetic data generated in HBM) */
+phnsw_status phnsw_store_create_device(phnsw_metric metric, uint64_t dim, uint64_t n,
+                                       const float *rows_device, int device, phnsw_store **out);
+void phnsw_store_destroy(phnsw_store *s);
+uint64_t phnsw_store_len(const phnsw_store *s);
+uint64_t phnsw_store_dim(const phnsw_store *s);
+int phnsw_store_metric(const phnsw_store *s);
+/* the HBM copy of the rows (row i at rows + i * pitch_floats); for callers that already
+ * live on the device (bench, multi-GPU plumbing) */
+const float *phnsw_store_rows_device(const phnsw_store *s, uint64_t *pitch_floats);
+/* Comparator::compare_vec(Stored(a[i]), Stored(b[i])) (src/lib.rs:69-73), bit-exact f32 */
+phnsw_status phnsw_store_compare(const phnsw_store *s, const uint64_t *a, const uint64_t *b,
+                                 uint64_t n, float *out);
+/* read rows back (Comparator::lookup), host destination */
+phnsw_status phnsw_store_get_rows(const phnsw_store *s, const uint64_t *ids, uint64_t n,
+                                  float *out_rows);
+
+/* ---- index: Hnsw<C>{layers, build_parameters} (src/lib.rs:585-651) ---- */
+/* layers[0] is the TOP layer, as Hnsw.layers; arrays are compacted to u32 in HBM */
+phnsw_status phnsw_index_from_layers(phnsw_store *s, uint64_t layer_count,
+                                     const phnsw_layer_desc *layers,
+                                     const phnsw_build_params *bp, phnsw_index **out);
+void phnsw_index_destroy(phnsw_index *ix);
+uint64_t phnsw_index_layer_count(const phnsw_index *ix);          /* lib.rs:644-646 */
+uint64_t phnsw_index_vector_count(const phnsw_index *ix);         /* lib.rs:592-594 */
+uint64_t phnsw_index_entry_vector(const phnsw_index *ix);         /* lib.rs:639-642 */
+void phnsw_index_build_params(const phnsw_index *ix, phnsw_build_params *bp);
+phnsw_status phnsw_index_layer_info(const phnsw_index *ix, uint64_t layer_from_top,
+                                    uint64_t *node_count, uint64_t *neighborhood_size);
+/* copy one layer out as u64 (the exact content of layer.nodes.N / layer.neighbors.N) */
+phnsw_status phnsw_index_export_layer(const phnsw_index *ix, uint64_t layer_from_top,
+                                      uint64_t *nodes_out, uint64_t *neighbors_out);
+/* serialize_hnsw / deserialize_hnsw (src/serialize.rs:33-209): byte-identical `meta`,
+ * `layer.meta.N`, `layer.nodes.N`, `layer.neighbors.N`; the `comparator` entry (user
+ * defined in the crate) holds metric/dim/count + raw rows.  load creates its own store
+ * (returned through store_out, destroy it after the index). */
+/* Per-query device scratch sizes (entries; 0 keeps the current value): shared-memory visited
+ * table, its HBM spill table, and the HBM frontier spill list (the crate's unbounded
+ * visit_queue, lib.rs:182-186).  Exhaustion is never silent: PHNSW_ERR_CAPACITY. */
+phnsw_status phnsw_index_set_scratch(phnsw_index *ix, uint32_t visited_smem_entries,
+                                     uint32_t visited_spill_entries,
+                                     uint32_t frontier_spill_entries);
+phnsw_status phnsw_index_save(const phnsw_index *ix, const char *dir);
+/* the `build_parameters` JSON object exactly as serde_json writes it into `meta` */
+phnsw_status phnsw_format_build_params(const phnsw_build_params *bp, char *out, uint64_t out_cap);
+phnsw_status phnsw_index_load(const char *dir, int device, phnsw_store **store_out,
+                              phnsw_index **index_out);
+
+/*
+ * Hnsw::search / search_upto / search::search_layers(v, sp, layers, exclude)
+ * (src/lib.rs:654-665, src/search.rs:84-140) for a batch of queries -- one warp per
+ * query on the device.  Exactly one of `queries` (nq x dim, AbstractVector::Unstored)
+ * and `stored_ids` (AbstractVector::Stored) is non-NULL.  upto_layers_from_top = 0
+ * searches all layers.  exclude: NULL or nq VectorIds (PHNSW_EMPTY_ID = None).
+ * Output per query: up to min(number_of_candidates, max_out) pairs ascending by
+ * (distance, id); unused slots hold PHNSW_EMPTY_ID / FLT_MAX.
+ * out_ndist / out_nexp (optional, nq x layer_count u32): distance evaluations and
+ * expansions per layer (the algorithmic-bytes counters of SURVEY section 8d).
+ */
+phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
+                                const uint64_t *stored_ids, uint64_t nq,
+                                const phnsw_search_params *sp, uint64_t upto_layers_from_top,
+                                const uint64_t *exclude, uint64_t max_out, uint64_t *out_ids,
+                                float *out_dists, uint32_t *out_counts, uint32_t *out_ndist,
+                                uint32_t *out_nexp);
+/* same with every buffer already in HBM, asynchronous on `cuda_stream` (a cudaStream_t);
+ * errors raised by the kernel surface at phnsw_index_sync() */
+phnsw_status phnsw_search_batch_device(const phnsw_index *ix, const float *queries,
+                                       const uint64_t *stored_ids, uint64_t nq,
+                                       const phnsw_search_params *sp,
+                                       uint64_t upto_layers_from_top, const uint64_t *exclude,
+                                       uint64_t max_out, uint64_t *out_ids, float *out_dists,
+                                       uint32_t *out_counts, uint32_t *out_ndist,
+                                       uint32_t *out_nexp, void *cuda_stream);
+phnsw_status phnsw_index_sync(const phnsw_index *ix, void *cuda_stream);
+
+/* Hnsw::knn(k, probe_depth) (src/lib.rs:905-928): all-points kNN on the bottom layer;
+ * outputs are node_count x k in bottom-layer node order, self removed */
+phnsw_status phnsw_knn(const phnsw_index *ix, uint64_t k, uint64_t probe_depth,
+                       uint64_t *out_ids, float *out_dists, uint32_t *out_counts);
+/* Hnsw::threshold_nn (src/lib.rs:930-962): CSR result; free the three buffers with
+ * phnsw_free */
+phnsw_status phnsw_threshold_nn(const phnsw_index *ix, float threshold, uint64_t probe_depth,
+                                uint64_t initial_search_depth, uint64_t **out_offsets,
+                                uint64_t **out_ids, float **out_dists);
+void phnsw_free(void *p);
+
+/* Hnsw::generate (src/lib.rs:825-893) and improve_index / improve_neighbors
+ * (src/lib.rs:1515-1544, 1664-1685) on the device; exclusive access (&mut self). */
+phnsw_status phnsw_generate(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
+                            const phnsw_build_params *bp, uint64_t seed,
+                            phnsw_progress_fn progress, void *user, phnsw_index **out);
+phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
+                                 phnsw_progress_fn progress, void *user, float *recall_out);
+/* stochastic_recall (src/lib.rs:1463-1505) */
+phnsw_status phnsw_stochastic_recall(const phnsw_index *ix,
+                                     const phnsw_optimization_params *op, float *recall_out);
+
+/* exact brute-force kNN over the whole store (test-side exact recall, do_test_recall
+ * src/lib.rs:2166-2192 / compare_all src/search.rs:13-30); results ascending (d, id) */
+phnsw_status phnsw_bruteforce_knn(const phnsw_store *s, const float *queries, uint64_t nq,
+                                  uint64_t k, uint64_t *out_ids, float *out_dists);
+
+/* same with queries and outputs already in HBM */
+phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *queries_device,
+                                         uint64_t nq, uint64_t k, uint64_t *out_ids_device,
+                                         float *out_dists_device, void *cuda_stream);
+
+/* cross-shard top-k merge by (distance, id): `shards` lists of nq x k pairs laid out
+ * shard-major (the all-gather receive buffer); no reference analogue (single index) */
+phnsw_status phnsw_merge_topk_device(const uint64_t *ids, const float *dists, uint64_t shards,
+                                     uint64_t nq, uint64_t k, uint64_t *out_ids,
+                                     float *out_dists, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHNSW_H */

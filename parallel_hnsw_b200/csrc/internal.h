@@ -1,0 +1,121 @@
+// internal.h -- host-side structures behind the opaque handles of include/phnsw.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/phnsw.h"
+#include "common.cuh"
+#include "search_kernel.cuh"
+
+namespace phnsw {
+
+void set_error(const char *fmt, ...);
+phnsw_status cuda_fail(cudaError_t e, const char *what);
+
+#define PH_CUDA(expr)                                          \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return phnsw::cuda_fail(_e, #expr); \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, need);
+      want = need;
+    }
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T *as() const { return (T *)p; }
+};
+
+// per-stream scratch of the search kernel (one slot per resident warp)
+struct Workspace {
+  DevBuf ovf, spill, saved, ctrl;  // ctrl: [0] work counter, [1] status
+  DevBuf stage_q, stage_ids, stage_excl, out_ids, out_dists, out_counts, out_nd, out_ne;
+  uint32_t slots = 0, ovf_cap = 0, spill_cap = 0, cap_pad = 0;
+  void release() {
+    ovf.release(); spill.release(); saved.release(); ctrl.release();
+    stage_q.release(); stage_ids.release(); stage_excl.release();
+    out_ids.release(); out_dists.release(); out_counts.release(); out_nd.release(); out_ne.release();
+  }
+};
+
+struct LayerStore {
+  uint64_t node_count = 0, M = 0;
+  uint32_t *nodes = nullptr;      // device, node_count
+  uint32_t *neighbors = nullptr;  // device, node_count * M
+  uint32_t *vec2node = nullptr;   // device, n_vectors (null when nodes[i] == i for all i)
+  bool identity = false;
+};
+
+}  // namespace phnsw
+
+struct phnsw_store {
+  int device = 0;
+  int metric = 0;
+  uint64_t dim = 0, n = 0;
+  uint32_t pitch = 0;    // floats per row in HBM (dim rounded up to a multiple of 4, zero padded)
+  float *rows = nullptr; // device
+};
+
+struct phnsw_index {
+  phnsw_store *store = nullptr;
+  std::vector<phnsw::LayerStore> layers;  // top first
+  phnsw::LayerDev *d_layers = nullptr;    // device mirror
+  phnsw_build_params bp;
+  int sm_count = 148;
+  int max_smem = 0;
+  uint32_t hash_cap = 4096, ovf_cap = 8192, spill_cap = 16384;
+  mutable std::mutex mu;
+  mutable std::map<cudaStream_t, phnsw::Workspace> ws;
+};
+
+namespace phnsw {
+
+struct SearchCall {
+  uint32_t mode = 0;  // 0 search_layers, 1 knn, 2 threshold_nn
+  const float *queries = nullptr;  // device
+  uint32_t qpitch = 0;
+  const uint64_t *stored_ids = nullptr;  // device
+  const uint64_t *exclude = nullptr;     // device
+  uint32_t nq = 0, q_offset = 0;
+  uint32_t cap = 0, cap_max = 0, upper = 0, probe = 0, n_layers = 0, max_out = 0;
+  float threshold = 0.f;
+  uint64_t *out_ids = nullptr;
+  float *out_dists = nullptr;
+  uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr;
+};
+
+// launches the traversal kernel on `stream` (asynchronous); status word is read by sync_status
+phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStream_t stream);
+phnsw_status sync_status(const phnsw_index *ix, cudaStream_t stream);
+phnsw_status sync_status_bits(const phnsw_index *ix, cudaStream_t stream, uint32_t *bits);
+phnsw_status upload_layer_tables(phnsw_index *ix);
+phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp, phnsw_index **out);
+// takes ownership of device arrays nodes/neighbors (u32); builds vec2node as needed
+phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint64_t M,
+                                     uint32_t *nodes, uint32_t *neighbors);
+
+}  // namespace phnsw

@@ -1,0 +1,360 @@
+"""Host-side mirror of the crate's public surface for the hot path, over the C ABI.
+
+Reference items mirrored (paths relative to the crate root):
+  SearchParameters / OptimizationParameters / BuildParameters   src/parameters.rs:3-64
+  BigComparator (the vector store behind Comparator::lookup)     src/bigvec.rs:36-57
+  Hnsw::{generate, search, search_upto, knn, threshold_nn, improve_index, stochastic_recall,
+         serialize, deserialize, layer_count, vector_count, entry_vector, get_layer_from_top}
+                                                                 src/lib.rs:585-1699
+Names and argument meaning follow the crate; batches replace rayon `par_iter` over queries.
+Errors the crate raises by panic!/Result surface as PhnswError with the matching status.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _native as N
+from ._native import PhnswError  # noqa: F401  (re-export)
+
+EMPTY = np.uint64(N.EMPTY_ID)
+FLT_MAX = np.float32(3.4028235e38)
+
+COS_HALF, ONE_MINUS_DOT, L2_SQRT, COS_CLAMP = 0, 1, 2, 3
+
+
+def SearchParameters(number_of_candidates=300, upper_layer_candidate_count=300, probe_depth=2):
+    """src/parameters.rs:3-18 (Default: 300 / 300 / 2)."""
+    return N.SearchParams(number_of_candidates, upper_layer_candidate_count, probe_depth)
+
+
+def BuildParameters(**kw):
+    """src/parameters.rs:42-64 Default, fields overridable by keyword."""
+    bp = N.BuildParams()
+    N.lib().phnsw_default_build_params(C.byref(bp))
+    for k, v in kw.items():
+        if not hasattr(bp, k):
+            raise TypeError("BuildParameters has no field %r" % k)
+        setattr(bp, k, v)
+    return bp
+
+
+def calculate_partitions(total_size, order):
+    """src/lib.rs:1883-1899: layer sizes, top first."""
+    out = (C.c_uint64 * 64)()
+    n = N.lib().phnsw_calculate_partitions(total_size, order, out, 64)
+    return [int(out[i]) for i in range(n)]
+
+
+def device_count():
+    return int(N.lib().phnsw_device_count())
+
+
+def _is_device(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _host(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_device(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class BigComparator:
+    """Device-resident vectors + a built-in distance = the crate's Comparator for this path
+    (src/lib.rs:53-74; BigComparator src/bigvec.rs:36-57).  `rows` is n x dim f32, host numpy
+    or a CUDA torch tensor; the library keeps its own copy in HBM."""
+
+    def __init__(self, rows, metric=COS_HALF, device=0):
+        h = C.c_void_p()
+        if _is_device(rows):
+            assert rows.dim() == 2 and rows.is_contiguous() and rows.element_size() == 4
+            n, dim = rows.shape
+            N.check(N.lib().phnsw_store_create_device(metric, dim, n, _ptr(rows), device, C.byref(h)))
+        else:
+            rows = _host(rows, np.float32)
+            assert rows.ndim == 2
+            n, dim = rows.shape
+            N.check(N.lib().phnsw_store_create(metric, dim, n, _ptr(rows), device, C.byref(h)))
+        self._h = h
+        self.metric, self.dim, self.n, self.device = metric, int(dim), int(n), device
+
+    @classmethod
+    def _adopt(cls, handle, device):
+        self = cls.__new__(cls)
+        self._h = handle
+        L = N.lib()
+        self.metric = int(L.phnsw_store_metric(handle))
+        self.dim = int(L.phnsw_store_dim(handle))
+        self.n = int(L.phnsw_store_len(handle))
+        self.device = device
+        return self
+
+    def __len__(self):
+        return self.n
+
+    def lookup(self, ids):
+        """Comparator::lookup (src/lib.rs:60): rows for VectorIds."""
+        ids = _host(np.atleast_1d(ids), np.uint64)
+        out = np.empty((ids.size, self.dim), dtype=np.float32)
+        N.check(N.lib().phnsw_store_get_rows(self._h, _ptr(ids), ids.size, _ptr(out)))
+        return out
+
+    def compare_vec(self, a, b):
+        """Comparator::compare_vec(Stored(a), Stored(b)) (src/lib.rs:69-73), batched."""
+        a = _host(np.atleast_1d(a), np.uint64)
+        b = _host(np.atleast_1d(b), np.uint64)
+        assert a.size == b.size
+        out = np.empty(a.size, dtype=np.float32)
+        N.check(N.lib().phnsw_store_compare(self._h, _ptr(a), _ptr(b), a.size, _ptr(out)))
+        return out
+
+    def rows_device(self):
+        """(device pointer, pitch in floats) of the HBM copy."""
+        pitch = C.c_uint64()
+        p = N.lib().phnsw_store_rows_device(self._h, C.byref(pitch))
+        return p, int(pitch.value)
+
+    def bruteforce_knn(self, queries, k):
+        """Exact kNN, ascending (d, id) -- test-side ground truth (src/lib.rs:2166-2192)."""
+        if _is_device(queries):
+            import torch
+            nq = queries.shape[0]
+            ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+            ds = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+            st = torch.cuda.current_stream(queries.device).cuda_stream
+            N.check(N.lib().phnsw_bruteforce_knn_device(self._h, _ptr(queries), nq, k, _ptr(ids),
+                                                        _ptr(ds), C.c_void_p(st)))
+            return ids, ds
+        queries = _host(queries, np.float32)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint64)
+        ds = np.empty((nq, k), dtype=np.float32)
+        N.check(N.lib().phnsw_bruteforce_knn(self._h, _ptr(queries), nq, k, _ptr(ids), _ptr(ds)))
+        return ids, ds
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().phnsw_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Hnsw:
+    """Device-resident Hnsw<C> (src/lib.rs:585-651)."""
+
+    def __init__(self, handle, comparator):
+        self._h = handle
+        self.comparator = comparator  # keeps the store alive (Layer.comparator, lib.rs:86)
+
+    # ---- construction -------------------------------------------------------------------
+    @classmethod
+    def from_layers(cls, comparator, layers, build_parameters=None):
+        """layers: [(nodes u64[n], neighbors u64[n, M], M)], top first -- Hnsw{layers,..}."""
+        descs = (N.LayerDesc * len(layers))()
+        keep = []
+        for i, (nodes, neigh, M) in enumerate(layers):
+            nodes = _host(nodes, np.uint64)
+            neigh = _host(neigh, np.uint64).reshape(-1)
+            if neigh.size != nodes.size * M:
+                raise ValueError("layer %d: neighbors must hold node_count * M ids" % i)
+            keep += [nodes, neigh]
+            descs[i] = N.LayerDesc(nodes.size, M, nodes.ctypes.data_as(N.u64p),
+                                   neigh.ctypes.data_as(N.u64p))
+        bp = build_parameters or BuildParameters()
+        h = C.c_void_p()
+        N.check(N.lib().phnsw_index_from_layers(comparator._h, len(layers), descs, C.byref(bp),
+                                                C.byref(h)))
+        return cls(h, comparator)
+
+    @classmethod
+    def generate(cls, comparator, vs=None, build_parameters=None, progress=None, seed=1):
+        """Hnsw::generate(c, vs, bp, progress) (src/lib.rs:825-893) on the device."""
+        if vs is None:
+            vs = np.arange(len(comparator), dtype=np.uint64)
+        vs = _host(vs, np.uint64)
+        bp = build_parameters or BuildParameters()
+        cb = _progress_cb(progress)
+        h = C.c_void_p()
+        N.check(N.lib().phnsw_generate(comparator._h, _ptr(vs), vs.size, C.byref(bp), seed, cb,
+                                       None, C.byref(h)))
+        return cls(h, comparator)
+
+    @classmethod
+    def deserialize(cls, path, device=0):
+        """Hnsw::deserialize (src/lib.rs:1693-1699, src/serialize.rs:126-209)."""
+        s, h = C.c_void_p(), C.c_void_p()
+        N.check(N.lib().phnsw_index_load(os.fsencode(path), device, C.byref(s), C.byref(h)))
+        return cls(h, BigComparator._adopt(s, device))
+
+    def serialize(self, path):
+        """Hnsw::serialize (src/lib.rs:1688-1691, src/serialize.rs:33-124)."""
+        N.check(N.lib().phnsw_index_save(self._h, os.fsencode(path)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().phnsw_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- accessors ----------------------------------------------------------------------
+    def layer_count(self):
+        return int(N.lib().phnsw_index_layer_count(self._h))
+
+    def vector_count(self):
+        return int(N.lib().phnsw_index_vector_count(self._h))
+
+    def __len__(self):
+        return self.vector_count()
+
+    def entry_vector(self):
+        return int(N.lib().phnsw_index_entry_vector(self._h))
+
+    @property
+    def build_parameters(self):
+        bp = N.BuildParams()
+        N.lib().phnsw_index_build_params(self._h, C.byref(bp))
+        return bp
+
+    def get_layer_from_top(self, i):
+        """(nodes u64[n], neighbors u64[n, M], M) of Hnsw.layers[i]."""
+        nc, M = C.c_uint64(), C.c_uint64()
+        N.check(N.lib().phnsw_index_layer_info(self._h, i, C.byref(nc), C.byref(M)))
+        nodes = np.empty(nc.value, dtype=np.uint64)
+        neigh = np.empty((nc.value, M.value), dtype=np.uint64)
+        N.check(N.lib().phnsw_index_export_layer(self._h, i, _ptr(nodes), _ptr(neigh)))
+        return nodes, neigh, int(M.value)
+
+    def layers(self):
+        return [self.get_layer_from_top(i) for i in range(self.layer_count())]
+
+    def set_scratch(self, visited_smem=0, visited_spill=0, frontier_spill=0):
+        N.check(N.lib().phnsw_index_set_scratch(self._h, visited_smem, visited_spill,
+                                                frontier_spill))
+
+    # ---- search -------------------------------------------------------------------------
+    def search(self, queries=None, sp=None, stored_ids=None, exclude=None, upto=0, max_out=None,
+               stats=False):
+        """Hnsw::search / search_upto / search_layers(.., exclude) for a batch.
+
+        queries: nq x dim f32 (AbstractVector::Unstored) or stored_ids: nq VectorIds
+        (AbstractVector::Stored).  Returns (ids u64[nq, max_out], dists f32[nq, max_out],
+        counts u32[nq]) ascending by (dist, id); with stats=True also per-layer counters of
+        distance evaluations and expansions.  Host numpy in -> host numpy out."""
+        sp = sp or SearchParameters()
+        L = self.layer_count()
+        if (queries is None) == (stored_ids is None):
+            raise ValueError("exactly one of queries / stored_ids")
+        if queries is not None:
+            queries = _host(queries, np.float32)
+            if queries.ndim == 1:
+                queries = queries[None, :]
+            if queries.shape[1] != self.comparator.dim:
+                raise ValueError("query dimension %d != %d" % (queries.shape[1], self.comparator.dim))
+            nq = queries.shape[0]
+        else:
+            stored_ids = _host(np.atleast_1d(stored_ids), np.uint64)
+            nq = stored_ids.size
+        if exclude is not None:
+            exclude = _host(exclude, np.uint64)
+            assert exclude.size == nq
+        max_out = int(max_out or sp.number_of_candidates)
+        ids = np.empty((nq, max_out), dtype=np.uint64)
+        ds = np.empty((nq, max_out), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        nd = np.zeros((nq, L), dtype=np.uint32) if stats else None
+        ne = np.zeros((nq, L), dtype=np.uint32) if stats else None
+        N.check(N.lib().phnsw_search_batch(self._h, _ptr(queries), _ptr(stored_ids), nq,
+                                           C.byref(sp), upto, _ptr(exclude), max_out, _ptr(ids),
+                                           _ptr(ds), _ptr(cnt), _ptr(nd), _ptr(ne)))
+        if stats:
+            return ids, ds, cnt, nd, ne
+        return ids, ds, cnt
+
+    def search_device(self, queries, sp, out_ids, out_dists, out_counts=None, max_out=None,
+                      stream=None, out_ndist=None, out_nexp=None, upto=0):
+        """Asynchronous variant: every buffer is a CUDA tensor; call sync() before reading."""
+        max_out = int(max_out or out_ids.shape[1])
+        st = C.c_void_p(stream or 0)
+        N.check(N.lib().phnsw_search_batch_device(
+            self._h, _ptr(queries), None, queries.shape[0], C.byref(sp), upto, None, max_out,
+            _ptr(out_ids), _ptr(out_dists), _ptr(out_counts), _ptr(out_ndist), _ptr(out_nexp), st))
+
+    def sync(self, stream=None):
+        N.check(N.lib().phnsw_index_sync(self._h, C.c_void_p(stream or 0)))
+
+    def knn(self, k, probe_depth):
+        """Hnsw::knn (src/lib.rs:905-928): rows follow bottom-layer node order."""
+        n = self.vector_count()
+        ids = np.full((n, k), EMPTY, dtype=np.uint64)
+        ds = np.full((n, k), FLT_MAX, dtype=np.float32)
+        cnt = np.zeros(n, dtype=np.uint32)
+        N.check(N.lib().phnsw_knn(self._h, k, probe_depth, _ptr(ids), _ptr(ds), _ptr(cnt)))
+        return ids, ds, cnt
+
+    def threshold_nn(self, threshold, probe_depth, initial_search_depth):
+        """Hnsw::threshold_nn (src/lib.rs:930-962): CSR (offsets, ids, dists)."""
+        n = self.vector_count()
+        off, ids, ds = N.u64p(), N.u64p(), N.f32p()
+        N.check(N.lib().phnsw_threshold_nn(self._h, threshold, probe_depth, initial_search_depth,
+                                           C.byref(off), C.byref(ids), C.byref(ds)))
+        offsets = np.ctypeslib.as_array(off, shape=(n + 1,)).copy()
+        total = int(offsets[-1])
+        ids_a = np.ctypeslib.as_array(ids, shape=(max(total, 1),)).copy()[:total]
+        ds_a = np.ctypeslib.as_array(ds, shape=(max(total, 1),)).copy()[:total]
+        for p in (off, ids, ds):
+            N.lib().phnsw_free(C.cast(p, C.c_void_p))
+        return offsets, ids_a, ds_a
+
+    # ---- build refinement ---------------------------------------------------------------
+    def improve_index(self, build_parameters=None, progress=None):
+        """Hnsw::improve_index (src/lib.rs:1664-1685); returns the final stochastic recall."""
+        bp = build_parameters or self.build_parameters
+        r = C.c_float()
+        N.check(N.lib().phnsw_improve_index(self._h, C.byref(bp), _progress_cb(progress), None,
+                                            C.byref(r)))
+        return float(r.value)
+
+    def stochastic_recall(self, optimization_parameters=None):
+        """Hnsw::stochastic_recall (src/lib.rs:1501-1505)."""
+        op = optimization_parameters or self.build_parameters.optimization
+        r = C.c_float()
+        N.check(N.lib().phnsw_stochastic_recall(self._h, C.byref(op), C.byref(r)))
+        return float(r.value)
+
+
+def _progress_cb(progress):
+    """ProgressMonitor (src/progress.rs:12-29): callable(phase, fraction) -> truthy = Interrupt."""
+    if progress is None:
+        return C.cast(None, N.PROGRESS_FN)
+
+    def cb(_user, phase, frac):
+        try:
+            return 1 if progress(phase.decode(), frac) else 0
+        except Exception:
+            return 1
+    fn = N.PROGRESS_FN(cb)
+    _progress_cb._keep = fn
+    return fn
+
+
+def merge_topk_device(ids, dists, shards, nq, k, out_ids, out_dists, stream=None):
+    """Cross-shard top-k merge over the all-gather receive buffer (no crate analogue)."""
+    N.check(N.lib().phnsw_merge_topk_device(_ptr(ids), _ptr(dists), shards, nq, k, _ptr(out_ids),
+                                            _ptr(out_dists), C.c_void_p(stream or 0)))

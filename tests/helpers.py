@@ -41,10 +41,13 @@ def random_normed(n, dim, seed):
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
-def clustered(n, dim, seed, n_clusters=64, spread=0.15, normalise=False, integer=False):
-    """Gaussian-mixture data (SIFT/Deep-shaped configs of SURVEY section 8d)."""
+def clustered(n, dim, seed, n_clusters=64, spread=0.15, normalise=False, integer=False,
+              centers_seed=977):
+    """Gaussian-mixture data (SIFT/Deep-shaped configs of SURVEY section 8d).  The mixture
+    (centres) is keyed by centers_seed so that rows and queries drawn with different `seed`
+    come from the same distribution."""
+    centers = np.random.default_rng(centers_seed).normal(size=(n_clusters, dim)).astype(np.float32)
     rng = np.random.default_rng(seed)
-    centers = rng.normal(size=(n_clusters, dim)).astype(np.float32)
     which = rng.integers(0, n_clusters, size=n)
     x = centers[which] + spread * rng.normal(size=(n, dim)).astype(np.float32)
     if integer:

@@ -1,0 +1,311 @@
+"""GPU parity: the CUDA traversal path (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): ids equal for >= 99.9 % of queries, distances within 1e-5
+relative.  The kernels accumulate in the crate's own order (sequential, unfused f32), so these
+tests demand more: bit-identical ids, distances, counts and per-layer work counters.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import EMPTY, clustered, nine_point, nine_point_layers, random_normed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ph():
+    import parallel_hnsw_b200 as p
+    if p.device_count() == 0:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return p
+
+
+def _assert_same(res_gpu, res_orc, what=""):
+    gi, gd, gc = res_gpu[:3]
+    oi, od, oc = res_orc[:3]
+    assert np.array_equal(gc, oc), what + " counts differ"
+    assert np.array_equal(gi, oi), what + " ids differ in %d rows" % int((gi != oi).any(1).sum())
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32)), what + " distances not bit-equal"
+
+
+def _pair(ph, oracle, metric, rows, layers, bp=None):
+    comp = ph.BigComparator(rows, metric)
+    g = ph.Hnsw.from_layers(comp, layers, bp)
+    o = oracle.Hnsw.from_layers(metric, rows, layers)
+    return g, o
+
+
+# ------------------------------------------------------------------ reference known answers
+def test_nine_point_knn_golden(ph, oracle):
+    """src/lib.rs:2358-2377 test_knn on the golden graph of src/lib.rs:2093-2148."""
+    g, layers = nine_point_layers(0)
+    gh, oh = _pair(ph, oracle, ph.ONE_MINUS_DOT, g["rows"], layers)
+    ids, ds, cnt = gh.knn(1, 1)
+    exp = g["knn_1_1"]
+    assert [int(x) for x in ids[:, 0]] == [e[0] for e in exp]
+    assert np.allclose(ds[:, 0], np.array([e[1] for e in exp], np.float32), rtol=0, atol=0)
+    _assert_same((ids, ds, cnt), oh.knn(1, 1))
+
+
+def test_nine_point_threshold_nn_golden(ph, oracle):
+    """src/lib.rs:2379-2420 test_threshold_nn."""
+    g, layers = nine_point_layers(0)
+    gh, oh = _pair(ph, oracle, ph.ONE_MINUS_DOT, g["rows"], layers)
+    off, ids, ds = gh.threshold_nn(0.3, 1, 6)
+    ooff, oids, ods = oh.threshold_nn(0.3, 1, 6)
+    assert np.array_equal(off, ooff) and np.array_equal(ids, oids)
+    assert np.array_equal(ds.view(np.uint32), ods.view(np.uint32))
+    exp = g["threshold_nn_0.3_1_6"]
+    for i, row in enumerate(exp):
+        got = [(int(a), float(b)) for a, b in zip(ids[off[i]:off[i + 1]], ds[off[i]:off[i + 1]])]
+        assert [a for a, _ in got] == [r[0] for r in row]
+        assert np.array_equal(np.array([b for _, b in got], np.float32),
+                              np.array([r[1] for r in row], np.float32))
+
+
+@pytest.mark.parametrize("entry", [0, 3, 6, 7])
+def test_nine_point_search_all_entries(ph, oracle, entry):
+    """src/lib.rs:2046-2068 test_nearness_search distances; every entry point vs oracle."""
+    g, layers = nine_point_layers(entry)
+    gh, oh = _pair(ph, oracle, ph.ONE_MINUS_DOT, g["rows"], layers)
+    sp = ph.SearchParameters(300, 300, 2)
+    res = gh.search(g["query"][None, :], sp)
+    _assert_same(res, oh.search(queries=g["query"][None, :], sp=oracle.search_params(300, 300, 2)))
+    golden = {int(i): np.float32(d) for i, d in g["nearness_result"]}
+    for i, d in zip(res[0][0, :res[2][0]], res[1][0, :res[2][0]]):
+        assert golden[int(i)] == d
+
+
+def test_store_compare_and_lookup(ph, oracle):
+    rows = random_normed(300, 100, 5)
+    for metric in (ph.COS_HALF, ph.ONE_MINUS_DOT, ph.L2_SQRT, ph.COS_CLAMP):
+        comp = ph.BigComparator(rows, metric)
+        a = np.arange(0, 300, dtype=np.uint64)
+        b = (a * 7 + 3) % 300
+        got = comp.compare_vec(a, b)
+        exp = np.array([oracle.distance(metric, rows[i], rows[j]) for i, j in zip(a, b)], np.float32)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+        assert np.array_equal(comp.lookup([3, 299, 0]), rows[[3, 299, 0]])
+    with pytest.raises(ph.PhnswError):
+        comp.compare_vec([300], [0])
+
+
+# ------------------------------------------------------------------ config 1: 10k x 128 cosine
+@pytest.fixture(scope="module")
+def cfg1(ph, oracle):
+    rows = random_normed(10000, 128, 42)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, seed=1, improve=False)
+    layers = oh.layers()
+    comp = ph.BigComparator(rows, ph.COS_HALF)
+    gh = ph.Hnsw.from_layers(comp, layers)
+    queries = random_normed(1000, 128, 1000000007)
+    return rows, oh, gh, queries
+
+
+def test_cfg1_search_bit_exact(ph, oracle, cfg1):
+    rows, oh, gh, queries = cfg1
+    sp = ph.SearchParameters()
+    g = gh.search(queries, sp, stats=True)
+    o = oh.search(queries=queries, stats=True)
+    _assert_same(g, o, "ef=300")
+    assert np.array_equal(g[3].astype(np.uint64), o[3]), "n_dist differs"
+    assert np.array_equal(g[4].astype(np.uint64), o[4]), "n_exp differs"
+    # recall@10 against exact ground truth, both sides
+    gt, gtd = gh.comparator.bruteforce_knn(queries, 10)
+    rec = np.mean([len(set(a[:10]) & set(b)) / 10.0 for a, b in zip(g[0], gt)])
+    assert rec >= 0.9, rec
+
+
+@pytest.mark.parametrize("ef,upper,probe,max_out", [(6, 6, 2, 6), (1, 1, 1, 1), (300, 10, 1, 10),
+                                                     (64, 300, 5, 64), (1000, 300, 2, 100)])
+def test_cfg1_search_parameter_sweep(ph, oracle, cfg1, ef, upper, probe, max_out):
+    rows, oh, gh, queries = cfg1
+    q = queries[:200]
+    g = gh.search(q, ph.SearchParameters(ef, upper, probe), max_out=max_out, stats=True)
+    o = oh.search(queries=q, sp=oracle.search_params(ef, upper, probe), max_out=max_out, stats=True)
+    _assert_same(g, o)
+    assert np.array_equal(g[3].astype(np.uint64), o[3])
+    assert np.array_equal(g[4].astype(np.uint64), o[4])
+
+
+def test_cfg1_stored_exclude_upto(ph, oracle, cfg1):
+    rows, oh, gh, queries = cfg1
+    ids = np.arange(0, 10000, 37, dtype=np.uint64)
+    sp, osp = ph.SearchParameters(300, 300, 2), oracle.search_params(300, 300, 2)
+    _assert_same(gh.search(stored_ids=ids, sp=sp), oh.search(stored_ids=ids, sp=osp), "stored")
+    g = gh.search(stored_ids=ids, sp=sp, exclude=ids)
+    _assert_same(g, oh.search(stored_ids=ids, sp=osp, exclude=ids), "exclude")
+    assert not (g[0] == ids[:, None]).any()
+    # every stored vector finds itself at rank 0 (src/lib.rs:2154-2164)
+    g = gh.search(stored_ids=ids, sp=sp)
+    assert (g[0][:, 0] == ids).mean() >= 0.99
+    for upto in (1, 2, 3):
+        _assert_same(gh.search(queries[:100], sp, upto=upto),
+                     oh.search(queries=queries[:100], sp=osp, upto_layers=upto), "upto %d" % upto)
+
+
+def test_cfg1_knn_and_threshold(ph, oracle, cfg1):
+    rows, oh, gh, queries = cfg1
+    _assert_same(gh.knn(10, 2), oh.knn(10, 2), "knn(10,2)")
+    _assert_same(gh.knn(1, 1), oh.knn(1, 1), "knn(1,1)")
+    off, ids, ds = gh.threshold_nn(0.42, 2, 4)
+    ooff, oids, ods = oh.threshold_nn(0.42, 2, 4)
+    assert np.array_equal(off, ooff) and np.array_equal(ids, oids)
+    assert np.array_equal(ds.view(np.uint32), ods.view(np.uint32))
+    assert off[-1] > 0
+
+
+def test_cfg1_small_scratch_spills_and_overflow_is_loud(ph, oracle, cfg1):
+    rows, oh, gh, queries = cfg1
+    q = queries[:64]
+    o = oh.search(queries=q)
+    gh.set_scratch(visited_smem=256, visited_spill=8192, frontier_spill=4096)
+    _assert_same(gh.search(q), o, "spilling visited set")
+    gh.set_scratch(visited_smem=256, visited_spill=64, frontier_spill=16)
+    with pytest.raises(ph.PhnswError) as e:
+        gh.search(q)
+    assert e.value.status == 7  # PHNSW_ERR_CAPACITY
+    gh.set_scratch(visited_smem=4096, visited_spill=16384, frontier_spill=8192)
+    _assert_same(gh.search(q), o, "restored")
+
+
+# ------------------------------------------------------------------ other metrics / shapes
+@pytest.mark.parametrize("metric_name,dim,n", [("L2_SQRT", 96, 6000), ("L2_SQRT", 30, 3000),
+                                               ("ONE_MINUS_DOT", 100, 5000),
+                                               ("COS_CLAMP", 200, 3000), ("COS_HALF", 1536, 2000)])
+def test_other_shapes(ph, oracle, metric_name, dim, n):
+    metric = getattr(ph, metric_name)
+    if metric_name == "L2_SQRT":
+        rows = clustered(n, dim, 11, integer=(dim == 96))
+    else:
+        rows = random_normed(n, dim, 13)
+    oh = oracle.Hnsw.generate(metric, rows, seed=3, improve=False)
+    comp = ph.BigComparator(rows, metric)
+    gh = ph.Hnsw.from_layers(comp, oh.layers())
+    queries = rows[::17] + np.float32(0.01)
+    g = gh.search(queries, stats=True)
+    o = oh.search(queries=queries, stats=True)
+    _assert_same(g, o, metric_name)
+    assert np.array_equal(g[3].astype(np.uint64), o[3])
+    _assert_same(gh.knn(5, 2), oh.knn(5, 2), "knn")
+
+
+def test_duplicate_vectors_and_ties(ph, oracle):
+    """Integer-valued L2 data with many exact duplicates: ties ordered by id, merge quirk Q1."""
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 3, size=(200, 16)).astype(np.float32)
+    rows = np.ascontiguousarray(base[rng.integers(0, 200, size=4000)])
+    oh = oracle.Hnsw.generate(oracle.L2_SQRT, rows, seed=5, improve=False)
+    comp = ph.BigComparator(rows, ph.L2_SQRT)
+    gh = ph.Hnsw.from_layers(comp, oh.layers())
+    for ef in (300, 24, 5):
+        g = gh.search(rows[:500], ph.SearchParameters(ef, ef, 2), stats=True)
+        o = oh.search(queries=rows[:500], sp=oracle.search_params(ef, ef, 2), stats=True)
+        _assert_same(g, o, "ties ef=%d" % ef)
+        assert np.array_equal(g[4].astype(np.uint64), o[4])
+    _assert_same(gh.knn(8, 2), oh.knn(8, 2), "knn ties")
+
+
+def test_single_layer_and_tiny(ph, oracle):
+    rows = random_normed(7, 8, 1)
+    nodes = np.arange(7, dtype=np.uint64)
+    neigh = np.full((7, 4), EMPTY, dtype=np.uint64)
+    for i in range(7):
+        neigh[i, 0] = (i + 1) % 7
+        neigh[i, 1] = (i + 3) % 7
+    layers = [(nodes, neigh, 4)]
+    gh, oh = _pair(ph, oracle, ph.COS_HALF, rows, layers)
+    _assert_same(gh.search(rows), oh.search(queries=rows))
+    _assert_same(gh.knn(3, 2), oh.knn(3, 2))
+
+
+def test_bad_inputs_are_loud(ph, oracle):
+    rows = random_normed(50, 8, 1)
+    comp = ph.BigComparator(rows, ph.COS_HALF)
+    nodes = np.arange(50, dtype=np.uint64)
+    neigh = np.full((50, 4), EMPTY, dtype=np.uint64)
+    neigh[:, 0] = (nodes + 1) % 50
+    bad = neigh.copy()
+    bad[3, 0] = 50  # out of range
+    with pytest.raises(ph.PhnswError):
+        ph.Hnsw.from_layers(comp, [(nodes, bad, 4)])
+    with pytest.raises(ph.PhnswError):
+        ph.Hnsw.from_layers(comp, [(nodes[::-1].copy(), neigh, 4)])  # not ascending
+    # candidate missing from the lower layer (src/lib.rs:261 unwrap)
+    top = (np.array([49], np.uint64), np.full((1, 4), EMPTY, np.uint64), 4)
+    low = (np.arange(40, dtype=np.uint64), neigh[:40] % 40, 4)
+    gh = ph.Hnsw.from_layers(comp, [top, low])
+    with pytest.raises(ph.PhnswError) as e:
+        gh.search(rows[:4])
+    assert e.value.status == 9
+    gh = ph.Hnsw.from_layers(comp, [(nodes, neigh, 4)])
+    with pytest.raises(ph.PhnswError):
+        gh.search(rows[:4], ph.SearchParameters(0, 0, 2))
+    q = rows[:4].copy()
+    q[1, 2] = np.nan
+    with pytest.raises(ph.PhnswError):
+        gh.search(q)
+
+
+# ------------------------------------------------------------------ brute force / merge / io
+def test_bruteforce_exact(ph, oracle):
+    for metric, dim in ((ph.L2_SQRT, 96), (ph.COS_HALF, 130)):
+        rows = clustered(5000, dim, 2) if metric == ph.L2_SQRT else random_normed(5000, dim, 2)
+        comp = ph.BigComparator(rows, metric)
+        q = rows[:70] + np.float32(0.5)
+        ids, ds = comp.bruteforce_knn(q, 17)
+        for i in range(70):
+            d = np.array([oracle.distance(metric, q[i], r) for r in rows], np.float32)
+            order = np.lexsort((np.arange(5000), d))[:17]
+            assert np.array_equal(ids[i], order.astype(np.uint64))
+            assert np.array_equal(ds[i].view(np.uint32), d[order].view(np.uint32))
+
+
+def test_merge_topk_device(ph):
+    import torch
+    rng = np.random.default_rng(0)
+    shards, nq, k = 4, 300, 10
+    d = np.sort(rng.integers(0, 50, size=(shards, nq, k)).astype(np.float32), axis=2)
+    ids = rng.integers(0, 1000, size=(shards, nq, k)).astype(np.int64)
+    # make (d, id) ascending inside each list
+    for s in range(shards):
+        for q in range(nq):
+            o = np.lexsort((ids[s, q], d[s, q]))
+            ids[s, q], d[s, q] = ids[s, q][o], d[s, q][o]
+    ids[0, 5, 7:] = -1
+    d[0, 5, 7:] = np.float32(3.4028235e38)
+    dev = torch.device("cuda:0")
+    ti, td = torch.from_numpy(ids).to(dev), torch.from_numpy(d).to(dev)
+    oi = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ph.merge_topk_device(ti, td, shards, nq, k, oi, od, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    oi, od = oi.cpu().numpy(), od.cpu().numpy()
+    for q in range(nq):
+        pairs = sorted({(float(d[s, q, j]), int(ids[s, q, j])) for s in range(shards)
+                        for j in range(k) if ids[s, q, j] != -1})[:k]
+        assert [p[1] for p in pairs] == [int(x) for x in oi[q]]
+        assert [p[0] for p in pairs] == [float(x) for x in od[q]]
+
+
+def test_serialize_round_trip_with_oracle(ph, oracle, cfg1, tmp_path):
+    rows, oh, gh, queries = cfg1
+    d1, d2 = str(tmp_path / "gpu"), str(tmp_path / "orc")
+    gh.serialize(d1)
+    oh.serialize(d2)
+    import filecmp
+    import os
+    names = sorted(os.listdir(d2))
+    assert sorted(os.listdir(d1)) == names
+    for n in names:
+        if n == "meta":
+            continue  # build parameters differ (oracle handle carries its own)
+        assert filecmp.cmp(os.path.join(d1, n), os.path.join(d2, n), shallow=False), n
+    g2 = ph.Hnsw.deserialize(d2)     # oracle-written index served by the GPU
+    o2 = oracle.Hnsw.deserialize(d1)  # GPU-written index read by the oracle
+    q = queries[:50]
+    _assert_same(g2.search(q), o2.search(queries=q))
+    with pytest.raises(ph.PhnswError) as e:
+        os.remove(os.path.join(d1, "comparator"))
+        ph.Hnsw.deserialize(d1)
+    assert e.value.status == 6  # IndexNotFound
