@@ -200,6 +200,10 @@ void phnsw_free(void *p);
 phnsw_status phnsw_generate(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
                             const phnsw_build_params *bp, uint64_t seed,
                             phnsw_progress_fn progress, void *user, phnsw_index **out);
+/* same; improve = 0 skips the improve_index call after every layer (src/lib.rs:876) */
+phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
+                                 const phnsw_build_params *bp, uint64_t seed, int improve,
+                                 phnsw_progress_fn progress, void *user, phnsw_index **out);
 phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out);
 /* stochastic_recall (src/lib.rs:1463-1505) */

@@ -244,8 +244,11 @@ class Hnsw:
             raise OSError("serialize failed: %d" % rc)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_hnsw_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            try:
+                _lib.orc_hnsw_free(self._h)
+            except Exception:
+                pass
             self._h = None
 
     @property

@@ -933,54 +933,38 @@ static int ipart_cmp(const void *a, const void *b) {
   return x->node < y->node ? -1 : (x->node > y->node); /* unstable in the reference; fixed here */
 }
 
-/* choose_n / choose_n_1 (lib.rs:1830-1881) with our RNG; returns count, pairs in out */
+/* choose_n (lib.rs:1830-1881).  In the reference `n` is min(5*M, sum(maxes)) (lib.rs:742-743),
+ * so `sum * 2 > n` always holds and choose_n always delegates to choose_n_1: enumerate every
+ * (partition, index) pair except (0, exclude), shuffle, truncate to n; the rejection-sampling
+ * branch (lib.rs:1861-1880) is dead code.  shuffle + truncate(n) is restated as the first n
+ * steps of a forward Fisher-Yates draw with our own generator (parity unpinned: the crate uses
+ * rand 0.8.5 StdRng, whose stream no reference test pins); when everything fits (c <= n) no
+ * random numbers are consumed and the result is the full enumeration. */
 static uint64_t choose_n(uint64_t n, const uint64_t *maxes, uint64_t n_part, uint64_t exclude,
                          rng_t *rng, uint64_t (*out)[2]) {
   uint64_t total = 0;
   for (uint64_t p = 0; p < n_part; p++) total += maxes[p];
-  if (total * 2 > n) { /* choose_n_1: enumerate, shuffle, truncate */
-    uint64_t(*all)[2] = (uint64_t(*)[2])malloc((total ? total : 1) * sizeof(*all));
-    uint64_t c = 0;
-    for (uint64_t p = 0; p < n_part; p++)
-      for (uint64_t i = 0; i < maxes[p]; i++) {
-        if (p == 0 && i == exclude) continue;
-        all[c][0] = p;
-        all[c][1] = i;
-        c++;
-      }
-    for (uint64_t i = c; i > 1; i--) {
-      uint64_t j = rng_below(rng, i);
-      uint64_t t0 = all[i - 1][0], t1 = all[i - 1][1];
-      all[i - 1][0] = all[j][0];
-      all[i - 1][1] = all[j][1];
-      all[j][0] = t0;
-      all[j][1] = t1;
+  int has_ex = n_part > 0 && exclude < maxes[0];
+  uint64_t c = total - (has_ex ? 1 : 0);
+  if (n > c) n = c;
+  uint64_t *perm = (uint64_t *)malloc((c ? c : 1) * sizeof(uint64_t));
+  for (uint64_t f = 0; f < c; f++) perm[f] = f;
+  if (c > n)
+    for (uint64_t i = 0; i < n; i++) {
+      uint64_t j = i + rng_below(rng, c - i);
+      uint64_t t = perm[i];
+      perm[i] = perm[j];
+      perm[j] = t;
     }
-    if (c > n) c = n;
-    memcpy(out, all, c * sizeof(*all));
-    free(all);
-    return c;
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t e = perm[i] + ((has_ex && perm[i] >= exclude) ? 1 : 0); /* enumeration index */
+    uint64_t p = 0;
+    while (e >= maxes[p]) e -= maxes[p++];
+    out[i][0] = p;
+    out[i][1] = e;
   }
-  /* rejection sampling, Exp(1) over partitions (lib.rs:1865-1880) */
-  uint64_t count = 0;
-  while (count != n) {
-    float e = -logf(rng_unit(rng));
-    uint64_t which = (uint64_t)floorf(e);
-    if (which >= n_part) which = 0;
-    uint64_t sel = rng_below(rng, maxes[which]);
-    if (which == 0 && sel == exclude) continue;
-    int dup = 0;
-    for (uint64_t i = 0; i < count; i++)
-      if (out[i][0] == which && out[i][1] == sel) {
-        dup = 1;
-        break;
-      }
-    if (dup) continue;
-    out[count][0] = which;
-    out[count][1] = sel;
-    count++;
-  }
-  return count;
+  free(perm);
+  return n;
 }
 
 /* generate_layer (lib.rs:675-823).  `vs` is sorted in place. */

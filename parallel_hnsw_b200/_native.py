@@ -92,6 +92,8 @@ SIGNATURES = {
     "phnsw_free": (None, [vp]),
     "phnsw_generate": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(BuildParams), C.c_uint64,
                                  PROGRESS_FN, vp, C.POINTER(vp)]),
+    "phnsw_generate_with": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(BuildParams), C.c_uint64,
+                                      C.c_int, PROGRESS_FN, vp, C.POINTER(vp)]),
     "phnsw_improve_index": (C.c_int, [vp, C.POINTER(BuildParams), PROGRESS_FN, vp, f32p]),
     "phnsw_stochastic_recall": (C.c_int, [vp, C.POINTER(OptimizationParams), f32p]),
     "phnsw_bruteforce_knn": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),

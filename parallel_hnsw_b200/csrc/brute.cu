@@ -211,6 +211,7 @@ phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *quer
   if (nq == 0) return PHNSW_OK;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   PH_CUDA(cudaSetDevice(s->device));
+  cudaGetLastError();  // do not attribute a stale error of an earlier call to this one
   // chunk of rows whose distance matrix stays around 1 GiB
   uint64_t chunk = (1ull << 28) / nq;
   chunk = std::max<uint64_t>(chunk, 4096);

@@ -1,0 +1,109 @@
+// distance.cuh -- warp-level "score a list of stored vectors against one vector" primitive
+// shared by the build kernels (K3).  Same data path as the traversal kernel: rows are pulled
+// into a per-warp shared-memory landing zone by 1-D bulk (TMA) copies, one per row and up to 32
+// in flight, then each lane reduces its own row in the crate's order (strictly sequential f32,
+// multiply and add unfused; src/bigvec.rs:47-53, src/lib.rs:2431-2437).
+#pragma once
+#include "common.cuh"
+
+namespace phnsw {
+
+constexpr int kScoreRows = 32;
+constexpr int kScoreChunk = 128;
+constexpr int kScoreStride = kScoreChunk + 4;
+
+template <int METRIC>
+struct RowScorer {
+  const float *rows;
+  uint32_t pitch, dim_pad;
+  float *qvec;     // shared, dim_pad floats
+  float *stage;    // shared, kScoreRows * kScoreStride floats
+  uint64_t *mbar;  // shared, 2 barriers (initialised by the caller, count 1)
+  uint32_t ph = 0;
+  uint32_t nan_seen = 0;
+  int lane;
+
+  static __host__ __device__ constexpr uint32_t stage_bytes() {
+    return kScoreRows * kScoreStride * 4;
+  }
+
+  __device__ __forceinline__ float accum4(float acc, const float4 &x, const float4 &q) const {
+    if (METRIC == kL2Sqrt) {
+      float t;
+      t = __fsub_rn(q.x, x.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+      t = __fsub_rn(q.y, x.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+      t = __fsub_rn(q.z, x.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+      t = __fsub_rn(q.w, x.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+    } else {
+      acc = __fadd_rn(acc, __fmul_rn(q.x, x.x));
+      acc = __fadd_rn(acc, __fmul_rn(q.y, x.y));
+      acc = __fadd_rn(acc, __fmul_rn(q.z, x.z));
+      acc = __fadd_rn(acc, __fmul_rn(q.w, x.w));
+    }
+    return acc;
+  }
+  __device__ __forceinline__ float finalize(float acc) const {
+    if (METRIC == kCosHalf) return __fdiv_rn(__fsub_rn(1.0f, acc), 2.0f);
+    if (METRIC == kOneMinusDot) return __fsub_rn(1.0f, acc);
+    if (METRIC == kL2Sqrt) return __fsqrt_rn(acc);
+    float x = __fdiv_rn(__fsub_rn(acc, 1.0f), -2.0f);
+    x = x < 0.0f ? 0.0f : x;
+    x = x > 1.0f ? 1.0f : x;
+    return x;
+  }
+
+  __device__ void load_query(uint32_t vid) {
+    const float *src = rows + (size_t)vid * pitch;
+    for (uint32_t i = lane; i < dim_pad; i += 32) qvec[i] = src[i];
+    __syncwarp();
+  }
+
+  // out[j] = distance(qvec, vector vids[j]) for j in [0, nn); vids/out live in shared memory
+  __device__ void score(const uint32_t *vids, uint32_t nn, float *out) {
+    const uint32_t nchunks = (dim_pad + kScoreChunk - 1) / kScoreChunk;
+    const uint32_t S = nchunks > 1 ? 2u : 1u;
+    const uint32_t R = kScoreRows / S;
+    const uint32_t npass = (nn + R - 1) / R;
+    const uint32_t ntiles = npass * nchunks;
+    uint32_t vec_issue = 0;
+    float acc = 0.0f;
+    for (uint32_t t = 0; t < ntiles + S - 1; t++) {
+      if (t < ntiles) {
+        uint32_t p = t / nchunks, c = t - p * nchunks, s = t % S;
+        uint32_t j = p * R + lane;
+        bool active = (uint32_t)lane < R && j < nn;
+        if (c == 0 && active) vec_issue = vids[j];
+        uint32_t rows_p = min(R, nn - p * R);
+        uint32_t fl = min((uint32_t)kScoreChunk, dim_pad - c * kScoreChunk);
+        if (lane == 0) mbar_arrive_expect_tx(&mbar[s], rows_p * fl * 4);
+        __syncwarp();
+        if (active)
+          bulk_g2s(stage + (s * R + lane) * kScoreStride,
+                   rows + (size_t)vec_issue * pitch + c * kScoreChunk, fl * 4, &mbar[s]);
+      }
+      if (t + 1 >= S) {
+        uint32_t tc = t + 1 - S;
+        uint32_t p = tc / nchunks, c = tc - p * nchunks, s = tc % S;
+        mbar_wait(&mbar[s], (ph >> s) & 1u);
+        ph ^= (1u << s);
+        uint32_t j = p * R + lane;
+        if ((uint32_t)lane < R && j < nn) {
+          if (c == 0) acc = 0.0f;
+          uint32_t fl4 = min((uint32_t)kScoreChunk, dim_pad - c * kScoreChunk) / 4;
+          const float4 *rp = (const float4 *)(stage + (s * R + lane) * kScoreStride);
+          const float4 *qp = (const float4 *)(qvec + c * kScoreChunk);
+#pragma unroll 4
+          for (uint32_t k = 0; k < fl4; k++) acc = accum4(acc, rp[k], qp[k]);
+          if (c == nchunks - 1) {
+            float d = finalize(acc);
+            if (d != d) nan_seen = 1;
+            out[j] = d;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+};
+
+}  // namespace phnsw

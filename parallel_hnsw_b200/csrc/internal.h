@@ -68,6 +68,7 @@ struct LayerStore {
   uint32_t *neighbors = nullptr;  // device, node_count * M
   uint32_t *vec2node = nullptr;   // device, n_vectors (null when nodes[i] == i for all i)
   bool identity = false;
+  std::vector<uint32_t> h_nodes;  // host copy of `nodes` (recall sampling, lib.rs:1468-1481)
 };
 
 }  // namespace phnsw
@@ -105,7 +106,7 @@ struct SearchCall {
   float threshold = 0.f;
   uint64_t *out_ids = nullptr;
   float *out_dists = nullptr;
-  uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr;
+  uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr, *out_selfhit = nullptr;
 };
 
 // launches the traversal kernel on `stream` (asynchronous); status word is read by sync_status

@@ -237,6 +237,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.out_counts = c.out_counts;
   a.out_ndist = c.out_nd;
   a.out_nexp = c.out_ne;
+  a.out_selfhit = c.out_selfhit;
   a.stats_stride = (uint32_t)ix->layers.size();
   a.work_counter = ws.ctrl.as<unsigned int>();
   a.status = ws.ctrl.as<uint32_t>() + 1;
@@ -347,6 +348,9 @@ phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint6
     return PHNSW_ERR_GRAPH;
   }
   l.identity = !hf[0] && node_count == ix->store->n;
+  l.h_nodes.resize(node_count);
+  if (node_count)
+    PH_CUDA(cudaMemcpy(l.h_nodes.data(), nodes, node_count * 4, cudaMemcpyDeviceToHost));
   if (!l.identity) {
     PH_CUDA(cudaMalloc(&l.vec2node, std::max<uint64_t>(ix->store->n, 1) * 4));
     PH_CUDA(cudaMemset(l.vec2node, 0xFF, std::max<uint64_t>(ix->store->n, 1) * 4));

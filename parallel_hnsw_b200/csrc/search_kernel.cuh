@@ -70,6 +70,8 @@ struct SearchArgs {
   uint32_t *out_counts;
   uint32_t *out_ndist;     // optional, nq x stats_stride
   uint32_t *out_nexp;
+  uint32_t *out_selfhit;   // optional, nq: 1 when stored_ids[q] is among the results
+                           // (stochastic_recall_at, lib.rs:1486-1494)
   uint32_t stats_stride;
   unsigned int *work_counter;
   uint32_t *status;
@@ -658,13 +660,21 @@ struct WarpSearch {
       }
       __syncwarp();
     }
+    if (a.out_selfhit && a.stored_ids) {
+      const uint32_t self = (uint32_t)a.stored_ids[q];
+      bool hit = false;
+      for (uint32_t i = lane; i < len; i += 32) hit |= ((uint32_t)cand[i] == self);
+      hit = __any_sync(0xffffffffu, hit);
+      if (lane == 0) a.out_selfhit[q] = hit ? 1u : 0u;
+    }
     // candidates.iter().collect() (search.rs:139)
     uint32_t n_out = min(len, a.max_out);
-    for (uint32_t i = lane; i < a.max_out; i += 32) {
-      uint64_t k = i < n_out ? cand[i] : 0;
-      a.out_ids[(size_t)q * a.max_out + i] = i < n_out ? (uint64_t)(uint32_t)k : ~0ull;
-      a.out_dists[(size_t)q * a.max_out + i] = i < n_out ? key_dist(k) : 3.4028234663852886e38f;
-    }
+    if (a.out_ids)
+      for (uint32_t i = lane; i < a.max_out; i += 32) {
+        uint64_t k = i < n_out ? cand[i] : 0;
+        a.out_ids[(size_t)q * a.max_out + i] = i < n_out ? (uint64_t)(uint32_t)k : ~0ull;
+        a.out_dists[(size_t)q * a.max_out + i] = i < n_out ? key_dist(k) : 3.4028234663852886e38f;
+      }
     if (a.out_counts && lane == 0) a.out_counts[q] = n_out;
   }
 

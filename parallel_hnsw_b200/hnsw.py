@@ -179,16 +179,18 @@ class Hnsw:
         return cls(h, comparator)
 
     @classmethod
-    def generate(cls, comparator, vs=None, build_parameters=None, progress=None, seed=1):
-        """Hnsw::generate(c, vs, bp, progress) (src/lib.rs:825-893) on the device."""
+    def generate(cls, comparator, vs=None, build_parameters=None, progress=None, seed=1,
+                 improve=True):
+        """Hnsw::generate(c, vs, bp, progress) (src/lib.rs:825-893) on the device.
+        improve=False skips the improve_index call the crate makes after every layer."""
         if vs is None:
             vs = np.arange(len(comparator), dtype=np.uint64)
         vs = _host(vs, np.uint64)
         bp = build_parameters or BuildParameters()
         cb = _progress_cb(progress)
         h = C.c_void_p()
-        N.check(N.lib().phnsw_generate(comparator._h, _ptr(vs), vs.size, C.byref(bp), seed, cb,
-                                       None, C.byref(h)))
+        N.check(N.lib().phnsw_generate_with(comparator._h, _ptr(vs), vs.size, C.byref(bp), seed,
+                                            1 if improve else 0, cb, None, C.byref(h)))
         return cls(h, comparator)
 
     @classmethod
