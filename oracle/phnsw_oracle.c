@@ -1124,23 +1124,26 @@ static void generate_layer(orc_hnsw *h, uint64_t *vs, uint64_t n, uint64_t M,
     free(pmax);
   }
 
-  /* 4. make neighbourhoods bidirectional (lib.rs:789-815); sequential = one legal
-   *    interleaving of the reference's lock-ordered parallel loop */
-  pair_t *copy = (pair_t *)malloc((M ? M : 1) * sizeof(pair_t));
-  for (uint64_t i = 0; i < n; i++) {
-    uint64_t c = 0;
-    for (uint64_t k = 0; k < M; k++) {
-      if (neighbors[i * M + k] == ORC_EMPTY) break; /* iter() stops at the first empty */
-      copy[c].id = neighbors[i * M + k];
-      copy[c].d = ndist[i * M + k];
-      c++;
-    }
-    for (uint64_t k = 0; k < c; k++) {
-      pq_t q = {neighbors + copy[k].id * M, ndist + copy[k].id * M, M};
-      pq_insert(&q, i, copy[k].d);
-    }
+  /* 4. make neighbourhoods bidirectional (lib.rs:789-815).  The reference runs this loop on
+   *    rayon workers: each takes a copy of its own row under a read lock, then inserts itself
+   *    into every listed neighbour's queue under that neighbour's write lock, so the outcome
+   *    depends on the schedule.  Restated here as the schedule-independent interleaving: every
+   *    worker reads its own row before any insert lands (all copies first, then all inserts).
+   *    Each insert is a top-M filter on (d, id), so the insert order itself is immaterial. */
+  {
+    uint64_t *cid = (uint64_t *)malloc((n * M ? n * M : 1) * sizeof(uint64_t));
+    float *cd = (float *)malloc((n * M ? n * M : 1) * sizeof(float));
+    memcpy(cid, neighbors, n * M * sizeof(uint64_t));
+    memcpy(cd, ndist, n * M * sizeof(float));
+    for (uint64_t i = 0; i < n; i++)
+      for (uint64_t k = 0; k < M; k++) {
+        if (cid[i * M + k] == ORC_EMPTY) break; /* iter() stops at the first empty */
+        pq_t q = {neighbors + cid[i * M + k] * M, ndist + cid[i * M + k] * M, M};
+        pq_insert(&q, i, cd[i * M + k]);
+      }
+    free(cid);
+    free(cd);
   }
-  free(copy);
 
   for (uint64_t i = 0; i < n; i++) free(ip[i].dl);
   free(ip);
