@@ -203,6 +203,7 @@ extern "C" {
 phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *queries_device,
                                          uint64_t nq, uint64_t k, uint64_t *out_ids_device,
                                          float *out_dists_device, void *cuda_stream) {
+  PH_ENTRY();
   if (!s || !queries_device || !out_ids_device || !out_dists_device || k == 0 || k > 2048 ||
       nq > 0x7FFFFFFFull) {
     set_error("bruteforce_knn: bad arguments (1 <= k <= 2048)");
@@ -253,6 +254,7 @@ phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *quer
 
 phnsw_status phnsw_bruteforce_knn(const phnsw_store *s, const float *queries, uint64_t nq,
                                   uint64_t k, uint64_t *out_ids, float *out_dists) {
+  PH_ENTRY();
   if (!s || !queries || !out_ids || !out_dists) return PHNSW_ERR_INVALID;
   if (nq == 0) return PHNSW_OK;
   if (phnsw_device_count() == 0) {
@@ -283,6 +285,7 @@ phnsw_status phnsw_bruteforce_knn(const phnsw_store *s, const float *queries, ui
 phnsw_status phnsw_merge_topk_device(const uint64_t *ids, const float *dists, uint64_t shards,
                                      uint64_t nq, uint64_t k, uint64_t *out_ids, float *out_dists,
                                      void *cuda_stream) {
+  PH_ENTRY();
   if (!ids || !dists || !out_ids || !out_dists || shards == 0 || shards > 16 || k == 0) {
     set_error("merge_topk: bad arguments (1 <= shards <= 16)");
     return PHNSW_ERR_INVALID;

@@ -412,13 +412,22 @@ __global__ void u32_to_u64_kernel(const uint32_t *in, uint64_t *out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
 }
-// search hits (VectorIds, first `keep` per query) -> NodeIds of the layer
-__global__ void map_hits_kernel(const uint64_t *ids, size_t total, const uint32_t *vec2node,
-                                uint32_t *dst) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  uint64_t v = ids[t];
-  dst[t] = v == ~0ull ? kEmpty32 : (vec2node ? vec2node[(uint32_t)v] : (uint32_t)v);
+// search hits (VectorIds, first `keep` per query) -> NodeIds of the layer.  The crate stops at
+// the first hit that is the searching vector itself (`break`, lib.rs:1119-1121; only the entry
+// vector can survive `exclude`, search.rs:110-111, 133): that hit and everything after it is
+// dropped.
+__global__ void map_hits_kernel(const uint64_t *ids, const uint64_t *self_ids, uint32_t n,
+                                uint32_t keep, const uint32_t *vec2node, uint32_t *dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t self = self_ids[i];
+  bool stop = false;
+  for (uint32_t m = 0; m < keep; m++) {
+    uint64_t v = ids[(size_t)i * keep + m];
+    if (v == ~0ull || v == self) stop = true;
+    dst[(size_t)i * keep + m] =
+        stop ? kEmpty32 : (vec2node ? vec2node[(uint32_t)v] : (uint32_t)v);
+  }
 }
 
 // ------------------------------------------------------------------ host helpers
@@ -694,8 +703,8 @@ static phnsw_status link_layer(phnsw_index *ix, uint32_t l, const phnsw_search_p
   if (rc != PHNSW_OK) return rc;
   rc = sync_status(ix, st);
   if (rc != PHNSW_OK) return rc;
-  map_hits_kernel<<<blocks_for((size_t)n * keep), 256, 0, st>>>(o_ids, (size_t)n * keep,
-                                                               L.identity ? nullptr : L.vec2node, dst);
+  map_hits_kernel<<<blocks_for(n), 256, 0, st>>>(o_ids, q_ids, n, keep,
+                                                 L.identity ? nullptr : L.vec2node, dst);
   cudaError_t e = PH_METRIC_DISPATCH(s->metric, launch_row_dist)(
       s, L.nodes, L.neighbors, n, M, row_d, ctrl, ix->sm_count, ix->max_smem, st);
   if (e != cudaSuccess) return cuda_fail(e, "row_dist_kernel");
@@ -818,6 +827,7 @@ extern "C" {
 phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
                                  const phnsw_build_params *bp_in, uint64_t seed, int improve,
                                  phnsw_progress_fn progress, void *user, phnsw_index **out) {
+  PH_ENTRY();
   if (!s || !out || (n && !vector_ids)) return PHNSW_ERR_INVALID;
   *out = nullptr;
   if (n == 0) {  // assert!(total_size > 0) lib.rs:837
@@ -886,6 +896,7 @@ phnsw_status phnsw_generate(phnsw_store *s, const uint64_t *vector_ids, uint64_t
 
 phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out) {
+  PH_ENTRY();
   if (!ix) return PHNSW_ERR_INVALID;
   phnsw_build_params b = bp ? *bp : ix->bp;
   Progress pg{progress, user};
@@ -897,6 +908,7 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
 
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix, const phnsw_optimization_params *op,
                                      float *recall_out) {
+  PH_ENTRY();
   if (!ix || !recall_out || ix->layers.empty()) return PHNSW_ERR_INVALID;
   phnsw_optimization_params o = op ? *op : ix->bp.optimization;
   return stochastic_recall_at(ix, (uint32_t)ix->layers.size() - 1, o, recall_out);

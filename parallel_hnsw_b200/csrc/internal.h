@@ -2,7 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -22,6 +25,27 @@ phnsw_status cuda_fail(cudaError_t e, const char *what);
     cudaError_t _e = (expr);                                   \
     if (_e != cudaSuccess) return phnsw::cuda_fail(_e, #expr); \
   } while (0)
+
+// Every compute entry point starts with PH_ENTRY(): a stale (non-sticky) CUDA error left by an
+// earlier call must not be attributed to this one.  PHNSW_TRACE=1 reports who left it.
+struct ApiEntry {
+  const char *name;
+  explicit ApiEntry(const char *n) : name(n) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && getenv("PHNSW_TRACE"))
+      fprintf(stderr, "[phnsw] stale CUDA error %d (%s) on entry to %s\n", (int)e,
+              cudaGetErrorString(e), name);
+  }
+  ~ApiEntry() {
+    if (getenv("PHNSW_TRACE")) {
+      cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess)
+        fprintf(stderr, "[phnsw] CUDA error %d (%s) pending on exit from %s\n", (int)e,
+                cudaGetErrorString(e), name);
+    }
+  }
+};
+#define PH_ENTRY() phnsw::ApiEntry _ph_entry(__func__)
 
 // grow-only device buffer
 struct DevBuf {
@@ -74,6 +98,9 @@ struct LayerStore {
 }  // namespace phnsw
 
 struct phnsw_store {
+  // the caller's handle holds one reference, every index built over the store another: the
+  // rows stay alive until the last of them is destroyed, in whatever order that happens
+  std::atomic<int> refs{1};
   int device = 0;
   int metric = 0;
   uint64_t dim = 0, n = 0;
@@ -113,6 +140,7 @@ struct SearchCall {
 phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStream_t stream);
 phnsw_status sync_status(const phnsw_index *ix, cudaStream_t stream);
 phnsw_status sync_status_bits(const phnsw_index *ix, cudaStream_t stream, uint32_t *bits);
+void store_release(phnsw_store *s);
 phnsw_status upload_layer_tables(phnsw_index *ix);
 phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp, phnsw_index **out);
 // takes ownership of device arrays nodes/neighbors (u32); builds vec2node as needed

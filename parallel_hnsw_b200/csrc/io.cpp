@@ -259,6 +259,7 @@ phnsw_status phnsw_format_build_params(const phnsw_build_params *bp, char *out, 
 }
 
 phnsw_status phnsw_index_save(const phnsw_index *ix, const char *dir) {
+  PH_ENTRY();
   if (!ix || !dir) return PHNSW_ERR_INVALID;
   std::string d(dir);
   if (mkdir_p(d) != 0) {
@@ -315,6 +316,7 @@ phnsw_status phnsw_index_save(const phnsw_index *ix, const char *dir) {
 
 phnsw_status phnsw_index_load(const char *dir, int device, phnsw_store **store_out,
                               phnsw_index **index_out) {
+  PH_ENTRY();
   if (!dir || !store_out || !index_out) return PHNSW_ERR_INVALID;
   *store_out = nullptr;
   *index_out = nullptr;

@@ -363,6 +363,14 @@ phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint6
   return PHNSW_OK;
 }
 
+void store_release(phnsw_store *s) {
+  if (!s) return;
+  if (s->refs.fetch_sub(1) != 1) return;
+  cudaSetDevice(s->device);
+  if (s->rows) cudaFree(s->rows);
+  delete s;
+}
+
 static void free_layer(LayerStore &l) {
   if (l.nodes) cudaFree(l.nodes);
   if (l.neighbors) cudaFree(l.neighbors);
@@ -376,6 +384,7 @@ phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp,
   PH_CUDA(cudaSetDevice(s->device));
   phnsw_index *ix = new phnsw_index();
   ix->store = s;
+  s->refs.fetch_add(1);
   if (bp) ix->bp = *bp;
   else phnsw_default_build_params(&ix->bp);
   cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, s->device);
@@ -477,6 +486,7 @@ static phnsw_status store_alloc(phnsw_metric metric, uint64_t dim, uint64_t n, i
 
 phnsw_status phnsw_store_create(phnsw_metric metric, uint64_t dim, uint64_t n,
                                 const float *rows_host, int device, phnsw_store **out) {
+  PH_ENTRY();
   if (n && !rows_host) return PHNSW_ERR_INVALID;
   phnsw_status rc = store_alloc(metric, dim, n, device, out);
   if (rc != PHNSW_OK) return rc;
@@ -499,6 +509,7 @@ phnsw_status phnsw_store_create(phnsw_metric metric, uint64_t dim, uint64_t n,
 
 phnsw_status phnsw_store_create_device(phnsw_metric metric, uint64_t dim, uint64_t n,
                                        const float *rows_device, int device, phnsw_store **out) {
+  PH_ENTRY();
   if (n && !rows_device) return PHNSW_ERR_INVALID;
   phnsw_status rc = store_alloc(metric, dim, n, device, out);
   if (rc != PHNSW_OK) return rc;
@@ -517,10 +528,8 @@ phnsw_status phnsw_store_create_device(phnsw_metric metric, uint64_t dim, uint64
 }
 
 void phnsw_store_destroy(phnsw_store *s) {
-  if (!s) return;
-  cudaSetDevice(s->device);
-  if (s->rows) cudaFree(s->rows);
-  delete s;
+  PH_ENTRY();
+  store_release(s);
 }
 uint64_t phnsw_store_len(const phnsw_store *s) { return s ? s->n : 0; }
 uint64_t phnsw_store_dim(const phnsw_store *s) { return s ? s->dim : 0; }
@@ -533,6 +542,7 @@ const float *phnsw_store_rows_device(const phnsw_store *s, uint64_t *pitch_float
 
 phnsw_status phnsw_store_compare(const phnsw_store *s, const uint64_t *a, const uint64_t *b,
                                  uint64_t n, float *out) {
+  PH_ENTRY();
   if (!s || (n && (!a || !b || !out))) return PHNSW_ERR_INVALID;
   if (!n) return PHNSW_OK;
   PH_CUDA(cudaSetDevice(s->device));
@@ -563,6 +573,7 @@ phnsw_status phnsw_store_compare(const phnsw_store *s, const uint64_t *a, const 
 
 phnsw_status phnsw_store_get_rows(const phnsw_store *s, const uint64_t *ids, uint64_t n,
                                   float *out_rows) {
+  PH_ENTRY();
   if (!s || (n && (!ids || !out_rows))) return PHNSW_ERR_INVALID;
   if (!n) return PHNSW_OK;
   PH_CUDA(cudaSetDevice(s->device));
@@ -592,6 +603,7 @@ phnsw_status phnsw_store_get_rows(const phnsw_store *s, const uint64_t *ids, uin
 phnsw_status phnsw_index_from_layers(phnsw_store *s, uint64_t layer_count,
                                      const phnsw_layer_desc *layers, const phnsw_build_params *bp,
                                      phnsw_index **out) {
+  PH_ENTRY();
   if (!s || !out || (layer_count && !layers)) return PHNSW_ERR_INVALID;
   *out = nullptr;
   phnsw_index *ix = nullptr;
@@ -656,12 +668,14 @@ phnsw_status phnsw_index_from_layers(phnsw_store *s, uint64_t layer_count,
 }
 
 void phnsw_index_destroy(phnsw_index *ix) {
+  PH_ENTRY();
   if (!ix) return;
   cudaSetDevice(ix->store->device);
   cudaDeviceSynchronize();
   for (auto &l : ix->layers) free_layer(l);
   if (ix->d_layers) cudaFree(ix->d_layers);
   for (auto &kv : ix->ws) kv.second.release();
+  store_release(ix->store);
   delete ix;
 }
 
@@ -680,6 +694,7 @@ phnsw_status phnsw_index_layer_info(const phnsw_index *ix, uint64_t layer_from_t
 }
 
 uint64_t phnsw_index_entry_vector(const phnsw_index *ix) {  // search.rs:9-11
+  PH_ENTRY();
   if (!ix || ix->layers.empty()) return PHNSW_EMPTY_ID;
   uint32_t v = 0;
   cudaSetDevice(ix->store->device);
@@ -690,6 +705,7 @@ uint64_t phnsw_index_entry_vector(const phnsw_index *ix) {  // search.rs:9-11
 
 phnsw_status phnsw_index_export_layer(const phnsw_index *ix, uint64_t layer_from_top,
                                       uint64_t *nodes_out, uint64_t *neighbors_out) {
+  PH_ENTRY();
   if (!ix || layer_from_top >= ix->layers.size()) return PHNSW_ERR_INVALID;
   const LayerStore &l = ix->layers[layer_from_top];
   PH_CUDA(cudaSetDevice(ix->store->device));
@@ -729,6 +745,7 @@ phnsw_status phnsw_search_batch_device(const phnsw_index *ix, const float *queri
                                        uint64_t max_out, uint64_t *out_ids, float *out_dists,
                                        uint32_t *out_counts, uint32_t *out_ndist,
                                        uint32_t *out_nexp, void *cuda_stream) {
+  PH_ENTRY();
   if (!ix || !sp || (!!queries == !!stored_ids) || !out_ids || !out_dists) {
     set_error("search_batch: exactly one of queries / stored_ids, and output buffers, required");
     return PHNSW_ERR_INVALID;
@@ -766,6 +783,7 @@ phnsw_status phnsw_search_batch_device(const phnsw_index *ix, const float *queri
 }
 
 phnsw_status phnsw_index_sync(const phnsw_index *ix, void *cuda_stream) {
+  PH_ENTRY();
   if (!ix) return PHNSW_ERR_INVALID;
   return sync_status(ix, (cudaStream_t)cuda_stream);
 }
@@ -776,6 +794,7 @@ phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
                                 const uint64_t *exclude, uint64_t max_out, uint64_t *out_ids,
                                 float *out_dists, uint32_t *out_counts, uint32_t *out_ndist,
                                 uint32_t *out_nexp) {
+  PH_ENTRY();
   if (!ix || !sp || (!!queries == !!stored_ids) || !out_ids || !out_dists) {
     set_error("search_batch: exactly one of queries / stored_ids, and output buffers, required");
     return PHNSW_ERR_INVALID;
@@ -837,6 +856,7 @@ phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
 // Hnsw::knn, src/lib.rs:905-928
 phnsw_status phnsw_knn(const phnsw_index *ix, uint64_t k, uint64_t probe_depth, uint64_t *out_ids,
                        float *out_dists, uint32_t *out_counts) {
+  PH_ENTRY();
   if (!ix || ix->layers.empty() || !out_ids || !out_dists || probe_depth == 0) {
     set_error("knn: bad arguments");
     return PHNSW_ERR_INVALID;
@@ -892,6 +912,7 @@ phnsw_status phnsw_knn(const phnsw_index *ix, uint64_t k, uint64_t probe_depth, 
 phnsw_status phnsw_threshold_nn(const phnsw_index *ix, float threshold, uint64_t probe_depth,
                                 uint64_t initial_search_depth, uint64_t **out_offsets,
                                 uint64_t **out_ids, float **out_dists) {
+  PH_ENTRY();
   if (!ix || ix->layers.empty() || !out_offsets || !out_ids || !out_dists || probe_depth == 0 ||
       initial_search_depth > 32768) {
     set_error("threshold_nn: bad arguments");

