@@ -255,11 +255,13 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.nvtx.range_push("timed")
     e0.record()
     for _ in range(args.steps):
         gh.search_device(dq, sp, oi, od, oc, stream=stream)
     e1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     gh.sync(stream)
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libphnsw.so")
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "-cudart", "static",
+] + (["-DPHNSW_LANDING_ROWS=" + os.environ["PHNSW_LANDING_ROWS"]] if os.environ.get("PHNSW_LANDING_ROWS") else []) + [
 ]
 
 

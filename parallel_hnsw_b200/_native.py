@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphnsw.so")
+LIB_PATH = os.environ.get("PHNSW_LIB") or os.path.join(_HERE, "libphnsw.so")  # PHNSW_LIB: dev override
 
 EMPTY_ID = 0xFFFFFFFFFFFFFFFF
 

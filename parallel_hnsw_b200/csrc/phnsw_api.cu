@@ -389,6 +389,11 @@ phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp,
   else phnsw_default_build_params(&ix->bp);
   cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, s->device);
   cudaDeviceGetAttribute(&ix->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+  if (const char *e = getenv("PHNSW_HASH_CAP")) {  // tuning knob for experiments
+    uint32_t v = (uint32_t)atoi(e), p2 = 64;
+    while (p2 < v) p2 <<= 1;
+    ix->hash_cap = p2;
+  }
   *out = ix;
   return PHNSW_OK;
 }

@@ -30,7 +30,10 @@
 
 namespace phnsw {
 
-constexpr int kLandingRows = 32;          // landing-zone rows per warp: 1 stage x 32 rows when a
+#ifndef PHNSW_LANDING_ROWS
+#define PHNSW_LANDING_ROWS 32
+#endif
+constexpr int kLandingRows = PHNSW_LANDING_ROWS;          // landing-zone rows per warp: 1 stage x 32 rows when a
                                           // row is one chunk, else 2 stages x 16 rows (pipelined)
 constexpr int kChunk = 128;               // floats of a row staged per bulk copy (512 B)
 constexpr int kRowStride = kChunk + 4;    // +16 B pad: conflict-free LDS.128 across rows
