@@ -144,12 +144,12 @@ phnsw_status phnsw_index_export_layer(const phnsw_index *ix, uint64_t layer_from
  * `layer.meta.N`, `layer.nodes.N`, `layer.neighbors.N`; the `comparator` entry (user
  * defined in the crate) holds metric/dim/count + raw rows.  load creates its own store
  * (returned through store_out, destroy it after the index). */
-/* Per-query device scratch sizes (entries; 0 keeps the current value): shared-memory visited
- * table, its HBM spill table, and the HBM frontier spill list (the crate's unbounded
- * visit_queue, lib.rs:182-186).  Exhaustion is never silent: PHNSW_ERR_CAPACITY. */
-phnsw_status phnsw_index_set_scratch(phnsw_index *ix, uint32_t visited_smem_entries,
-                                     uint32_t visited_spill_entries,
-                                     uint32_t frontier_spill_entries);
+/* Per-query device scratch sizes (entries; 0 keeps the current value): the log of visited
+ * nodes that makes clearing the HBM visited bitmap O(visited) (overflow is harmless: the whole
+ * bitmap is cleared instead), and the HBM frontier spill list (the crate's unbounded
+ * visit_queue, lib.rs:182-186), whose exhaustion is never silent: PHNSW_ERR_CAPACITY. */
+phnsw_status phnsw_index_set_scratch(phnsw_index *ix, uint32_t visited_log_entries,
+                                     uint32_t reserved, uint32_t frontier_spill_entries);
 phnsw_status phnsw_index_save(const phnsw_index *ix, const char *dir);
 /* the `build_parameters` JSON object exactly as serde_json writes it into `meta` */
 phnsw_status phnsw_format_build_params(const phnsw_build_params *bp, char *out, uint64_t out_cap);

@@ -76,11 +76,11 @@ struct DevBuf {
 
 // per-stream scratch of the search kernel (one slot per resident warp)
 struct Workspace {
-  DevBuf ovf, spill, saved, ctrl;  // ctrl: [0] work counter, [1] status
+  DevBuf ovf, bitmap, vlog, saved, ctrl;  // ctrl: [0] work counter, [1] status
   DevBuf stage_q, stage_ids, stage_excl, out_ids, out_dists, out_counts, out_nd, out_ne;
-  uint32_t slots = 0, ovf_cap = 0, spill_cap = 0, cap_pad = 0;
+  uint32_t slots = 0, ovf_cap = 0, vlog_cap = 0, bitmap_words = 0, cap_pad = 0;
   void release() {
-    ovf.release(); spill.release(); saved.release(); ctrl.release();
+    ovf.release(); bitmap.release(); vlog.release(); saved.release(); ctrl.release();
     stage_q.release(); stage_ids.release(); stage_excl.release();
     out_ids.release(); out_dists.release(); out_counts.release(); out_nd.release(); out_ne.release();
   }
@@ -115,7 +115,7 @@ struct phnsw_index {
   phnsw_build_params bp;
   int sm_count = 148;
   int max_smem = 0;
-  uint32_t hash_cap = 4096, ovf_cap = 8192, spill_cap = 16384;
+  uint32_t vlog_cap = 8192, ovf_cap = 8192;  // per-query device scratch (entries)
   mutable std::mutex mu;
   mutable std::map<cudaStream_t, phnsw::Workspace> ws;
 };

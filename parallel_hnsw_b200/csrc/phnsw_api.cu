@@ -171,7 +171,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   PH_CUDA(cudaSetDevice(s->device));
   const uint32_t cap_max = std::max(c.cap, c.cap_max);
   const uint32_t cap_pad = round_up(std::max(cap_max, 1u), 32);
-  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, ix->hash_cap);
+  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
     set_error("search: per-query shared memory %u B exceeds %zu B (dim %llu, capacity %u)",
@@ -184,6 +184,13 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   if (w < 1) w = 1;
   uint32_t grid = std::min<uint32_t>((uint32_t)ix->sm_count, (c.nq + w - 1) / w);
   const uint32_t slots = grid * w;
+  uint64_t max_nodes = 0;
+  for (uint32_t i = 0; i < c.n_layers; i++) max_nodes = std::max(max_nodes, ix->layers[i].node_count);
+  if (max_nodes >= 0x7FFFFFFFull) {
+    set_error("search: layers of 2^31 nodes or more are not supported");
+    return PHNSW_ERR_INVALID;
+  }
+  const uint32_t need_words = (uint32_t)((max_nodes + 31) / 32);
 
   Workspace *wsp;
   {
@@ -196,18 +203,26 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64, stream));
   }
   const uint32_t max_slots = (uint32_t)ix->sm_count * 16;
-  if (ws.slots < slots || ws.ovf_cap != ix->ovf_cap || ws.spill_cap != ix->spill_cap ||
-      ws.cap_pad < cap_pad) {
+  if (ws.slots < slots || ws.ovf_cap != ix->ovf_cap || ws.vlog_cap != ix->vlog_cap ||
+      ws.bitmap_words < need_words || ws.cap_pad < cap_pad) {
     PH_CUDA(cudaStreamSynchronize(stream));
-    uint32_t ns = std::max(ws.slots, std::min(max_slots, std::max(slots, max_slots)));
+    uint32_t ns = std::max(ws.slots, std::max(slots, max_slots));
     uint32_t ncp = std::max(ws.cap_pad, cap_pad);
+    // the bitmap grows in steps so that a build (layers of increasing size) reallocates rarely
+    uint32_t nbw = std::max(ws.bitmap_words, need_words);
+    if (nbw > ws.bitmap_words) nbw = std::max<uint32_t>(nbw, 1024);
     PH_CUDA(ws.ovf.reserve((size_t)ns * ix->ovf_cap * 8));
-    PH_CUDA(ws.spill.reserve((size_t)ns * ix->spill_cap * 4));
+    PH_CUDA(ws.vlog.reserve((size_t)ns * ix->vlog_cap * 4));
     PH_CUDA(ws.saved.reserve((size_t)ns * ncp * 8));
-    PH_CUDA(cudaMemsetAsync(ws.spill.p, 0xFF, (size_t)ns * ix->spill_cap * 4, stream));
+    if (nbw != ws.bitmap_words || ns != ws.slots) {
+      PH_CUDA(ws.bitmap.reserve((size_t)ns * nbw * 4));
+      // the kernels leave their slots clean; a fresh or regrown area starts zeroed
+      PH_CUDA(cudaMemsetAsync(ws.bitmap.p, 0, (size_t)ns * nbw * 4, stream));
+    }
     ws.slots = ns;
     ws.ovf_cap = ix->ovf_cap;
-    ws.spill_cap = ix->spill_cap;
+    ws.vlog_cap = ix->vlog_cap;
+    ws.bitmap_words = nbw;
     ws.cap_pad = ncp;
   }
   PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 4, stream));  // work counter; status is sticky until sync
@@ -243,10 +258,11 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.status = ws.ctrl.as<uint32_t>() + 1;
   a.ovf = ws.ovf.as<uint64_t>();
   a.ovf_cap = ix->ovf_cap;
-  a.spill = ws.spill.as<uint32_t>();
-  a.spill_cap = ix->spill_cap;
+  a.bitmap = ws.bitmap.as<uint32_t>();
+  a.bitmap_words = ws.bitmap_words;
+  a.vlog = ws.vlog.as<uint32_t>();
+  a.vlog_cap = ix->vlog_cap;
   a.saved = ws.saved.as<uint64_t>();
-  a.hash_cap = ix->hash_cap;
   a.cap_pad = cap_pad;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
 
   const size_t smem = (size_t)lay.total * w;
@@ -389,11 +405,7 @@ phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp,
   else phnsw_default_build_params(&ix->bp);
   cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, s->device);
   cudaDeviceGetAttribute(&ix->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
-  if (const char *e = getenv("PHNSW_HASH_CAP")) {  // tuning knob for experiments
-    uint32_t v = (uint32_t)atoi(e), p2 = 64;
-    while (p2 < v) p2 <<= 1;
-    ix->hash_cap = p2;
-  }
+
   *out = ix;
   return PHNSW_OK;
 }
@@ -731,13 +743,12 @@ phnsw_status phnsw_index_export_layer(const phnsw_index *ix, uint64_t layer_from
   return PHNSW_OK;
 }
 
-phnsw_status phnsw_index_set_scratch(phnsw_index *ix, uint32_t visited_smem_entries,
-                                     uint32_t visited_spill_entries, uint32_t frontier_spill_entries) {
+phnsw_status phnsw_index_set_scratch(phnsw_index *ix, uint32_t visited_log_entries,
+                                     uint32_t reserved, uint32_t frontier_spill_entries) {
+  (void)reserved;
   if (!ix) return PHNSW_ERR_INVALID;
-  auto pow2 = [](uint32_t x) { uint32_t p = 64; while (p < x) p <<= 1; return p; };
   std::lock_guard<std::mutex> g(ix->mu);
-  if (visited_smem_entries) ix->hash_cap = pow2(visited_smem_entries);
-  if (visited_spill_entries) ix->spill_cap = pow2(visited_spill_entries);
+  if (visited_log_entries) ix->vlog_cap = std::max(visited_log_entries, 32u);
   if (frontier_spill_entries) ix->ovf_cap = frontier_spill_entries;
   return PHNSW_OK;
 }

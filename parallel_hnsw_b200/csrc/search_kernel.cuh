@@ -4,25 +4,28 @@
 //   Layer::closest_nodes            src/lib.rs:175-248   (the hot loop)
 //   Layer::closest_vectors          src/lib.rs:250-277
 //   search_layers_instrumented      src/search.rs:93-140 (top -> bottom descent)
-//   Hnsw::knn                       src/lib.rs:905-928   (mode 1)
+//   Hnsw::knn / threshold_nn        src/lib.rs:905-962   (modes 1, 2)
 //   PriorityQueue::{merge, insert}  src/priority_queue.rs:70-144 (in-kernel candidate set)
 //
 // Design (B200-first, not a transliteration):
 //   * persistent grid, one warp = one query at a time, work handed out by an atomic counter;
-//   * per-warp shared memory holds the query vector, the candidate set as sorted 64-bit
-//     (distance,id) keys, the visited hash set, the neighbour batch and a 2-stage landing
-//     zone for vector rows;
-//   * neighbour rows are fetched with 1-D bulk (TMA) copies -- one per row, issued by up to
-//     32 lanes at once, completion counted on an mbarrier -- so a warp keeps up to 32 rows
-//     (16 KB) in flight without holding them in registers;
+//     per-warp shared memory is kept to ~13 KB (d = 128) so that 16 warps stay resident per SM:
+//     the walk is a chain of dependent latencies and only occupancy hides them;
+//   * the candidate set (PriorityQueue of capacity ef) is an UNSORTED pool of 64-bit
+//     (distance,id) keys in shared memory plus its running maximum: "merge" becomes append /
+//     replace-the-maximum, "pop the best unexpanded node" a warp-wide min scan (REDUX), and the
+//     pool is only sorted when an ordered result is actually needed.  The contents are the
+//     exact top-ef of everything merged, which is all the crate's sorted array guarantees;
+//   * the visited set is a per-warp bitmap in HBM (1 bit per node, read through L2, set with
+//     fire-and-forget REDs) with a log of the set bits so that clearing costs O(visited);
+//   * neighbour rows are fetched with 1-D bulk (TMA) copies -- one per row, issued by up to 16
+//     lanes at once, completion counted on an mbarrier -- into a padded landing zone;
 //   * distances are accumulated lane-per-row in strict left-to-right f32 order with separate
 //     multiply and add (no FMA), i.e. bit-identical to the crate's scalar loops
-//     (src/bigvec.rs:47-53); the padded row stride makes the 128-bit shared loads
-//     conflict-free;
+//     (src/bigvec.rs:47-53);
 //   * the reference's unbounded frontier (every discovered node stays poppable,
-//     lib.rs:211-220, 243-244) is kept exactly: nodes inside the candidate set carry an
-//     "expanded" bit, everything else spills to a per-warp list in HBM that is only scanned
-//     when the candidate set has no unexpanded entry left;
+//     lib.rs:211-220, 243-244) is kept exactly: nodes inside the pool carry an "expanded" bit,
+//     everything else spills to a per-warp list in HBM that is only scanned when it can matter;
 //   * merge()'s return flag (including its walk-off-the-end quirk) is evaluated in closed
 //     form (oracle: orc_pq_merge_flag_closed_form, fuzzed against the literal loop).
 #pragma once
@@ -31,10 +34,10 @@
 namespace phnsw {
 
 #ifndef PHNSW_LANDING_ROWS
-#define PHNSW_LANDING_ROWS 32
+#define PHNSW_LANDING_ROWS 16
 #endif
-constexpr int kLandingRows = PHNSW_LANDING_ROWS;          // landing-zone rows per warp: 1 stage x 32 rows when a
-                                          // row is one chunk, else 2 stages x 16 rows (pipelined)
+constexpr int kLandingRows = PHNSW_LANDING_ROWS;  // landing-zone rows per warp (1 stage x R rows
+                                                  // when a row is one chunk, else 2 x R/2)
 constexpr int kChunk = 128;               // floats of a row staged per bulk copy (512 B)
 constexpr int kRowStride = kChunk + 4;    // +16 B pad: conflict-free LDS.128 across rows
 constexpr int kMaxStages = 2;
@@ -80,167 +83,139 @@ struct SearchArgs {
   uint32_t *status;
   uint64_t *ovf;           // per-warp frontier spill, ovf_cap keys each
   uint32_t ovf_cap;
-  uint32_t *spill;         // per-warp visited spill table, spill_cap (pow2) each, kEmpty32 filled
-  uint32_t spill_cap;
+  uint32_t *bitmap;        // per-warp visited bitmap, bitmap_words each, all zero between uses
+  uint32_t bitmap_words;
+  uint32_t *vlog;          // per-warp log of visited node ids, vlog_cap each
+  uint32_t vlog_cap;
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
-  uint32_t hash_cap;       // pow2 shared-memory visited table entries per warp
-  uint32_t cap_pad;        // cap rounded up to a multiple of 32
+  uint32_t cap_pad;        // pool entries per warp in shared memory (>= cap_max, multiple of 32)
 };
 
 // per-warp shared memory carve-up (bytes); shared by host (launch size) and device
 struct WarpSmemLayout {
-  uint32_t off_q, off_stage, off_cand, off_bkeys, off_bsorted, off_bpos, off_bid, off_hash,
-      off_mbar, total;
+  uint32_t off_q, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, total;
 };
-__host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uint32_t cap_pad,
-                                                           uint32_t hash_cap) {
+__host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uint32_t cap_pad) {
   WarpSmemLayout l;
   uint32_t o = 0;
   l.off_q = o;       o += ((dim_pad * 4 + 15) / 16) * 16;
   l.off_stage = o;   o += kLandingRows * kRowStride * 4;
-  l.off_cand = o;    o += cap_pad * 8;
+  l.off_pool = o;    o += cap_pad * 8;
   l.off_bkeys = o;   o += kMaxBatch * 8;
   l.off_bsorted = o; o += kMaxBatch * 8;
-  l.off_bpos = o;    o += kMaxBatch * 4;
   l.off_bid = o;     o += kMaxBatch * 4;
-  l.off_hash = o;    o += hash_cap * 4;
   l.off_mbar = o;    o += kMaxStages * 8;
   l.total = ((o + 127) / 128) * 128;
   return l;
 }
+// u64 keys the landing zone can hold when it doubles as sort scratch
+constexpr uint32_t kSortScratch = kLandingRows * kRowStride * 4 / 8;
 
 #ifdef __CUDACC__
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint64_t kHiMask = 0xFFFFFFFF00000000ull;
+
+// warp-wide min / max of 64-bit keys on the REDUX unit (two 32-bit reductions)
+__device__ __forceinline__ uint64_t warp_min_key(uint64_t v) {
+  uint32_t hi = (uint32_t)(v >> 32);
+  uint32_t mh = __reduce_min_sync(kFull, hi);
+  uint32_t lo = hi == mh ? (uint32_t)v : 0xffffffffu;
+  uint32_t ml = __reduce_min_sync(kFull, lo);
+  return ((uint64_t)mh << 32) | ml;
+}
+__device__ __forceinline__ uint64_t warp_max_key(uint64_t v) {
+  uint32_t hi = (uint32_t)(v >> 32);
+  uint32_t mh = __reduce_max_sync(kFull, hi);
+  uint32_t lo = hi == mh ? (uint32_t)v : 0u;
+  uint32_t ml = __reduce_max_sync(kFull, lo);
+  return ((uint64_t)mh << 32) | ml;
+}
 
 template <int METRIC>
 struct WarpSearch {
   const SearchArgs &a;
   float *qvec;
   float *stage;
-  uint64_t *cand;
+  uint64_t *pool;
   uint64_t *bkeys;
   uint64_t *bsorted;
-  uint32_t *bpos;
   uint32_t *bid;
-  uint32_t *hash;
   uint64_t *mbar;
   uint64_t *ovf;
-  uint32_t *spill;
+  uint32_t *bm;
+  uint32_t *vlog;
   uint64_t *saved;
   const int lane;
   // warp-uniform state
-  uint32_t cap, len, lb;
+  uint32_t cap, len;
+  uint64_t pmax;       // largest key of the pool (flag masked); valid whenever len == cap
+  uint32_t pmax_slot;
   uint32_t ovf_n;
   uint64_t ovf_min;
-  uint32_t vis_n, spill_n;
-  bool spill_on, spill_dirty;
+  uint32_t vlog_n;
+  bool vlog_over;
   uint32_t ph;    // mbarrier phase bits, one per stage
   uint32_t stat;  // status bits raised by this warp
-  uint32_t hash_shift;
 
   __device__ WarpSearch(const SearchArgs &args, unsigned char *smem, uint32_t slot, int lane_)
       : a(args), lane(lane_) {
-    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, a.hash_cap);
+    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad);
     qvec = (float *)(smem + l.off_q);
     stage = (float *)(smem + l.off_stage);
-    cand = (uint64_t *)(smem + l.off_cand);
+    pool = (uint64_t *)(smem + l.off_pool);
     bkeys = (uint64_t *)(smem + l.off_bkeys);
     bsorted = (uint64_t *)(smem + l.off_bsorted);
-    bpos = (uint32_t *)(smem + l.off_bpos);
     bid = (uint32_t *)(smem + l.off_bid);
-    hash = (uint32_t *)(smem + l.off_hash);
     mbar = (uint64_t *)(smem + l.off_mbar);
     ovf = a.ovf + (size_t)slot * a.ovf_cap;
-    spill = a.spill + (size_t)slot * a.spill_cap;
+    bm = a.bitmap + (size_t)slot * a.bitmap_words;
+    vlog = a.vlog + (size_t)slot * a.vlog_cap;
     saved = a.saved + (size_t)slot * a.cap_pad;
     ph = 0;
     stat = 0;
-    spill_dirty = false;
-    hash_shift = 32 - (31 - __clz(a.hash_cap));
     cap = a.cap;
-    len = lb = ovf_n = vis_n = spill_n = 0;
+    len = ovf_n = vlog_n = 0;
+    vlog_over = false;
+    pmax = kEmptyKey;
+    pmax_slot = 0;
     ovf_min = kEmptyKey;
-    spill_on = false;
   }
 
-  // ------------------------------------------------------------------ visited set
-  __device__ __forceinline__ uint32_t hslot(uint32_t id, uint32_t shift) const {
-    return (id * 0x9E3779B1u) >> shift;
-  }
+  // ------------------------------------------------------------------ visited bitmap
+  // clear every bit set since the last reset (by replaying the log, or the whole bitmap if the
+  // log overflowed)
   __device__ void visited_reset() {
-    for (uint32_t i = lane; i < a.hash_cap; i += 32) hash[i] = kEmpty32;
-    if (spill_dirty) {
-      for (uint32_t i = lane; i < a.spill_cap; i += 32) spill[i] = kEmpty32;
-      spill_dirty = false;
-    }
-    vis_n = spill_n = 0;
-    spill_on = false;
     __syncwarp();
-  }
-  __device__ bool visited_contains(uint32_t id) const {
-    uint32_t mask = a.hash_cap - 1;
-    uint32_t h = hslot(id, hash_shift);
-    while (true) {
-      uint32_t v = hash[h];
-      if (v == id) return true;
-      if (v == kEmpty32) break;
-      h = (h + 1) & mask;
-    }
-    if (spill_n) {
-      uint32_t smask = a.spill_cap - 1;
-      uint32_t sshift = 32 - (31 - __clz(a.spill_cap));
-      uint32_t s = hslot(id, sshift);
-      while (true) {
-        uint32_t v = ld_cg_u32(&spill[s]);
-        if (v == id) return true;
-        if (v == kEmpty32) break;
-        s = (s + 1) & smask;
-      }
-    }
-    return false;
-  }
-  // all lanes call; lanes with active==true insert their id.  n_new = upper bound on inserts.
-  __device__ void visited_insert(bool active, uint32_t id, uint32_t n_new) {
-    if (!spill_on && (vis_n + n_new) * 4 > a.hash_cap * 3) spill_on = true;  // keep load <= 3/4
-    bool fresh = false;
-    if (!spill_on) {
-      if (active) {
-        uint32_t mask = a.hash_cap - 1;
-        uint32_t h = hslot(id, hash_shift);
-        while (true) {
-          uint32_t old = atomicCAS(&hash[h], kEmpty32, id);
-          if (old == kEmpty32) { fresh = true; break; }
-          if (old == id) break;
-          h = (h + 1) & mask;
-        }
-      }
-      vis_n += __popc(__ballot_sync(0xffffffffu, fresh));
+    if (vlog_over) {
+      for (uint32_t w = lane; w < a.bitmap_words; w += 32) bm[w] = 0u;
     } else {
-      if ((spill_n + n_new) * 4 > a.spill_cap * 3) {
-        stat |= kStatOverflowVisited;  // loud: surfaces as PHNSW_ERR_CAPACITY
-      } else {
-        if (active) {
-          uint32_t smask = a.spill_cap - 1;
-          uint32_t sshift = 32 - (31 - __clz(a.spill_cap));
-          uint32_t s = hslot(id, sshift);
-          while (true) {
-            uint32_t old = atomicCAS(&spill[s], kEmpty32, id);
-            if (old == kEmpty32) { fresh = true; break; }
-            if (old == id) break;
-            s = (s + 1) & smask;
-          }
-        }
-        spill_n += __popc(__ballot_sync(0xffffffffu, fresh));
-        spill_dirty = true;
-        __threadfence_block();
-      }
+      for (uint32_t i = lane; i < vlog_n; i += 32) bm[ld_cg_u32(&vlog[i]) >> 5] = 0u;
     }
+    vlog_n = 0;
+    vlog_over = false;
     __syncwarp();
+  }
+  __device__ __forceinline__ bool visited_test(uint32_t id) const {
+    return (ld_cg_u32(&bm[id >> 5]) >> (id & 31)) & 1u;
+  }
+  // all lanes call; lanes with active==true mark their id
+  __device__ void visited_set(bool active, uint32_t id) {
+    if (active) atomicOr(&bm[id >> 5], 1u << (id & 31));
+    uint32_t m = __ballot_sync(kFull, active);
+    uint32_t cnt = __popc(m);
+    if (vlog_n + cnt > a.vlog_cap) {
+      vlog_over = true;  // not an error: the next reset clears the whole bitmap instead
+    } else {
+      if (active) vlog[vlog_n + __popc(m & ((1u << lane) - 1))] = id;
+      vlog_n += cnt;
+    }
   }
 
   // ------------------------------------------------------------------ frontier spill list
   // append keys of lanes with pred==true (all lanes call)
   __device__ void ovf_append(bool pred, uint64_t key) {
-    uint32_t m = __ballot_sync(0xffffffffu, pred);
+    uint32_t m = __ballot_sync(kFull, pred);
     if (!m) return;
     uint32_t cnt = __popc(m);
     if (ovf_n + cnt > a.ovf_cap) {
@@ -248,22 +223,22 @@ struct WarpSearch {
       return;
     }
     if (pred) ovf[ovf_n + __popc(m & ((1u << lane) - 1))] = key;
-    uint64_t mn = warp_min_u64(pred ? key : kEmptyKey);
+    uint64_t mn = warp_min_key(pred ? key : kEmptyKey);
     ovf_min = mn < ovf_min ? mn : ovf_min;
     ovf_n += cnt;
-    __syncwarp();
   }
   // remove and return the smallest spilled key (ovf_n > 0)
   __device__ uint64_t ovf_pop_min() {
+    __syncwarp();
     uint64_t best = kEmptyKey;
     uint32_t bi = 0;
     for (uint32_t i = lane; i < ovf_n; i += 32) {
       uint64_t k = ld_cg_u64(&ovf[i]);
       if (k < best) { best = k; bi = i; }
     }
-    uint64_t mn = warp_min_u64(best);
-    uint32_t who = __ffs(__ballot_sync(0xffffffffu, best == mn)) - 1;
-    uint32_t idx = __shfl_sync(0xffffffffu, bi, who);
+    uint64_t mn = warp_min_key(best);
+    uint32_t who = __ffs(__ballot_sync(kFull, best == mn)) - 1;
+    uint32_t idx = __shfl_sync(kFull, bi, who);
     uint64_t lastk = ld_cg_u64(&ovf[ovf_n - 1]);
     __syncwarp();
     if (lane == 0) ovf[idx] = lastk;
@@ -274,8 +249,116 @@ struct WarpSearch {
       uint64_t k = ld_cg_u64(&ovf[i]);
       nb = k < nb ? k : nb;
     }
-    ovf_min = warp_min_u64(nb);
+    ovf_min = warp_min_key(nb);
     return mn;
+  }
+
+  // ------------------------------------------------------------------ candidate pool
+  __device__ void rescan_max() {
+    uint64_t best = 0;
+    uint32_t bs = 0;
+    for (uint32_t s = lane; s < len; s += 32) {
+      uint64_t k = pool[s] & kFlagMask64;
+      if (k >= best) { best = k; bs = s; }
+    }
+    uint64_t mx = warp_max_key(best);
+    uint32_t who = (__ffs(__ballot_sync(kFull, best == mx && (uint32_t)lane < len)) - 1) & 31;
+    pmax = mx;
+    pmax_slot = __shfl_sync(kFull, bs, who);
+  }
+  // smallest (d,id) among unexpanded pool entries; its slot is returned through *slot
+  __device__ uint64_t scan_min_unexpanded(uint32_t *slot) {
+    uint64_t best = kEmptyKey;
+    uint32_t bs = 0;
+    for (uint32_t s = lane; s < len; s += 32) {
+      uint64_t k = pool[s];
+      if (!((uint32_t)k & kFlagExpanded) && k < best) { best = k; bs = s; }
+    }
+    uint64_t mn = warp_min_key(best);
+    uint32_t who = __ffs(__ballot_sync(kFull, best == mn)) - 1;
+    *slot = __shfl_sync(kFull, bs, who);
+    return mn;
+  }
+  // Merge bsorted[0..nb) (ascending, unique, disjoint from the pool) into the pool: the result
+  // is the exact top-cap of the union (priority_queue.rs:109-144 contents).  With
+  // spill==true, unexpanded entries that fall out and batch entries that do not fit go to the
+  // frontier spill list (the reference keeps them in visit_queue, lib.rs:211-220).
+  __device__ void insert_batch(uint32_t nb, bool spill) {
+    if (nb == 0) return;
+    const uint32_t take = min(cap - len, nb);
+    for (uint32_t t = lane; t < take; t += 32) pool[len + t] = bsorted[t];
+    len += take;
+    __syncwarp();
+    if (take == nb) {
+      if (len == cap) rescan_max();
+      return;
+    }
+    if (take > 0) rescan_max();  // just became full; otherwise pmax is already valid
+    uint32_t j = take;
+    while (j < nb) {
+      const uint64_t key = bsorted[j];
+      if (key >= pmax) break;
+      const uint64_t ev = pool[pmax_slot];
+      if (spill && !((uint32_t)ev & kFlagExpanded)) {
+        if (ovf_n < a.ovf_cap) {
+          if (lane == 0) ovf[ovf_n] = ev;
+          ovf_n++;
+          ovf_min = ev < ovf_min ? ev : ovf_min;
+        } else {
+          stat |= kStatOverflowFrontier;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) pool[pmax_slot] = key;
+      __syncwarp();
+      j++;
+      rescan_max();
+    }
+    if (spill)
+      for (uint32_t t0 = j; t0 < nb; t0 += 32) {
+        uint32_t t = t0 + lane;
+        ovf_append(t < nb, t < nb ? bsorted[t] : 0);
+      }
+  }
+  // pool[0..len) -> ascending order (flags cleared); bitonic network in the landing zone
+  __device__ void sort_pool() {
+    uint64_t *scr = (uint64_t *)stage;
+    uint32_t P = 32;
+    while (P < len) P <<= 1;
+    __syncwarp();
+    if (P > kSortScratch) {  // too large for the scratch area: selection sort in place
+      for (uint32_t s = lane; s < len; s += 32) pool[s] &= kFlagMask64;
+      __syncwarp();
+      for (uint32_t i = 0; i + 1 < len; i++) {
+        uint64_t best = kEmptyKey;
+        uint32_t bs = i;
+        for (uint32_t s = i + lane; s < len; s += 32) {
+          uint64_t k = pool[s];
+          if (k < best) { best = k; bs = s; }
+        }
+        uint64_t mn = warp_min_key(best);
+        uint32_t who = __ffs(__ballot_sync(kFull, best == mn)) - 1;
+        uint32_t ms = __shfl_sync(kFull, bs, who);
+        if (lane == 0) { uint64_t t = pool[i]; pool[i] = mn; pool[ms] = t; }
+        __syncwarp();
+      }
+      return;
+    }
+    for (uint32_t s = lane; s < P; s += 32) scr[s] = s < len ? (pool[s] & kFlagMask64) : kEmptyKey;
+    __syncwarp();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = lane; t < (P >> 1); t += 32) {
+          uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+          uint32_t p = i | j;
+          uint64_t x = scr[i], y = scr[p];
+          bool up = (i & k) == 0;
+          if ((x > y) == up) { scr[i] = y; scr[p] = x; }
+        }
+        __syncwarp();
+      }
+    for (uint32_t s = lane; s < len; s += 32) pool[s] = scr[s];
+    __syncwarp();
   }
 
   // ------------------------------------------------------------------ distances
@@ -381,98 +464,24 @@ struct WarpSearch {
     __syncwarp();
   }
 
-  // ------------------------------------------------------------------ candidate-set merge
-  // Merge bsorted[0..nb) (ascending, unique, disjoint from cand) into cand: the result is the
-  // exact top-cap of the union (priority_queue.rs:109-144 contents).  With spill==true,
-  // unexpanded entries that fall off and batch entries that do not fit go to the frontier
-  // spill list (the reference keeps them in visit_queue, lib.rs:211-220).
-  __device__ void merge_batch(uint32_t nb, bool spill_rejects) {
-    if (nb == 0) return;
-    for (uint32_t j = lane; j < nb; j += 32) {
-      uint64_t key = bsorted[j];
-      uint32_t lo = 0, hi = len;
-      while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if ((cand[mid] & kFlagMask64) < key) lo = mid + 1;
-        else hi = mid;
-      }
-      bpos[j] = lo;
-    }
-    __syncwarp();
-    const uint32_t first = bpos[0];
-    if (first >= cap) {  // full and nothing fits
-      if (spill_rejects)
-        for (uint32_t j0 = 0; j0 < nb; j0 += 32) {
-          uint32_t j = j0 + lane;
-          ovf_append(j < nb, j < nb ? bsorted[j] : 0);
-        }
-      return;
-    }
-    // shift the tail [first, len) upwards, highest chunk first (in place, no aliasing)
-    uint32_t hi_end = len;
-    while (hi_end > first) {
-      uint32_t lo_start = hi_end - first > 32 ? hi_end - 32 : first;
-      uint32_t i = lo_start + lane;
-      bool act = i < hi_end;
-      uint64_t key = 0;
-      uint32_t np = 0;
-      if (act) {
-        key = cand[i];
-        uint32_t lo = 0, hi = nb;  // #batch elements inserted at or before i
-        while (lo < hi) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (bpos[mid] <= i) lo = mid + 1;
-          else hi = mid;
-        }
-        np = i + lo;
-      }
-      __syncwarp();
-      if (act && np < cap) cand[np] = key;
-      if (spill_rejects) {
-        bool fell = act && np >= cap && !((uint32_t)key & kFlagExpanded);
-        ovf_append(fell, key);
-      }
-      __syncwarp();
-      hi_end = lo_start;
-    }
-    for (uint32_t j0 = 0; j0 < nb; j0 += 32) {
-      uint32_t j = j0 + lane;
-      bool act = j < nb;
-      uint32_t np = act ? j + bpos[j] : 0;
-      uint64_t key = act ? bsorted[j] : 0;
-      if (act && np < cap) cand[np] = key;
-      if (spill_rejects) ovf_append(act && np >= cap, key);
-    }
-    len = min(cap, len + nb);
-    lb = min(lb, first);
-    __syncwarp();
-  }
-
   // ------------------------------------------------------------------ closest_nodes
-  // lib.rs:175-248 on `layer`; cand[0..len) holds NodeId keys, all unexpanded, all in visited.
+  // lib.rs:175-248 on `layer`; pool[0..len) holds NodeId keys, all unexpanded, all marked in
+  // the visited bitmap.
   __device__ void closest_nodes(const LayerDev &layer, uint32_t probe, uint32_t *n_dist,
                                 uint32_t *n_exp) {
-    lb = 0;
     ovf_n = 0;
     ovf_min = kEmptyKey;
+    if (len == cap) rescan_max();
     const uint32_t M = layer.M;
     while (true) {
       // ---- pop the smallest (d,id) among all discovered, unexpanded nodes
-      int ci = -1;
-      for (uint32_t base = lb & ~31u; base < len; base += 32) {
-        uint32_t i = base + lane;
-        bool un = i < len && i >= lb && !((uint32_t)cand[i] & kFlagExpanded);
-        uint32_t m = __ballot_sync(0xffffffffu, un);
-        if (m) { ci = (int)(base + __ffs(m) - 1); break; }
-      }
-      uint64_t ckey = ci >= 0 ? (cand[ci] & kFlagMask64) : kEmptyKey;
+      uint32_t slot;
+      const uint64_t ckey = scan_min_unexpanded(&slot);
       uint32_t next;
       if (ovf_n > 0 && ovf_min < ckey) {
         next = key_id(ovf_pop_min());
-      } else if (ci >= 0) {
-        __syncwarp();
-        if (lane == 0) cand[ci] = cand[ci] | (uint64_t)kFlagExpanded;
-        lb = (uint32_t)ci + 1;
+      } else if (ckey != kEmptyKey) {
+        if (lane == 0) pool[slot] = ckey | (uint64_t)kFlagExpanded;
         next = key_id(ckey);
         __syncwarp();
       } else {
@@ -483,8 +492,8 @@ struct WarpSearch {
       const uint32_t *row = layer.neighbors + (size_t)next * M;
       uint32_t n0 = lane < M ? __ldg(&row[lane]) : kEmpty32;
       uint32_t n1 = lane + 32 < M ? __ldg(&row[lane + 32]) : kEmpty32;
-      uint32_t v0 = __ballot_sync(0xffffffffu, n0 != kEmpty32);
-      uint32_t v1 = __ballot_sync(0xffffffffu, n1 != kEmpty32);
+      uint32_t v0 = __ballot_sync(kFull, n0 != kEmpty32);
+      uint32_t v1 = __ballot_sync(kFull, n1 != kEmpty32);
       uint32_t valid = v1 ? 64 - __clz(v1) : 32 - __clz(v0);  // __clz(0) == 32
       bool in0 = (uint32_t)lane < valid, in1 = (uint32_t)lane + 32 < valid;
       if ((in0 && n0 >= layer.node_count) || (in1 && n1 >= layer.node_count)) {
@@ -493,10 +502,10 @@ struct WarpSearch {
         in1 = in1 && n1 < layer.node_count;
       }
       // ---- drop already visited ones (lib.rs:198); duplicates inside the row both pass
-      bool u0 = in0 && !visited_contains(n0);
-      bool u1 = in1 && !visited_contains(n1);
-      uint32_t m0 = __ballot_sync(0xffffffffu, u0);
-      uint32_t m1 = __ballot_sync(0xffffffffu, u1);
+      bool u0 = in0 && !visited_test(n0);
+      bool u1 = in1 && !visited_test(n1);
+      uint32_t m0 = __ballot_sync(kFull, u0);
+      uint32_t m1 = __ballot_sync(kFull, u1);
       uint32_t nn = __popc(m0) + __popc(m1);
       uint32_t lt = (1u << lane) - 1;
       if (u0) bid[__popc(m0 & lt)] = n0;
@@ -505,14 +514,14 @@ struct WarpSearch {
       *n_dist += nn;
       bool did = false;
       if (nn > 0) {
+        visited_set(u0, n0);                     // lib.rs:209 (order is immaterial)
+        if (m1) visited_set(u1, n1);
         compute_distances(layer, nn);            // lib.rs:199-204
         sort_batch(nn);                          // lib.rs:206
-        visited_insert(u0, n0, nn);              // lib.rs:209
-        if (m1) visited_insert(u1, n1, nn);
         // merge()'s flag, closed form (see oracle orc_pq_merge_flag_closed_form)
         uint64_t b0 = bsorted[0];
         bool full = len == cap;
-        uint64_t tail = full ? (cand[cap - 1] & kFlagMask64) : kEmptyKey;
+        uint64_t tail = full ? pmax : kEmptyKey;
         did = !full || b0 < tail || (nn >= 2 && (uint32_t)(b0 >> 32) == (uint32_t)(tail >> 32));
         // duplicates inside one neighbour row stay poppable once more (visit_queue is a
         // multiset): park the extra copies in the spill list, merge the unique ones
@@ -522,7 +531,7 @@ struct WarpSearch {
           uint32_t j = j0 + lane;
           dup |= (j > 0 && j < nn && bsorted[j] == bsorted[j - 1]);
         }
-        if (__any_sync(0xffffffffu, dup)) {
+        if (__any_sync(kFull, dup)) {
           __syncwarp();
           if (lane == 0) {
             uint32_t w = 1;
@@ -537,13 +546,13 @@ struct WarpSearch {
             }
             nbu = w;
           }
-          nbu = __shfl_sync(0xffffffffu, nbu, 0);
-          ovf_n = __shfl_sync(0xffffffffu, ovf_n, 0);
-          ovf_min = __shfl_sync(0xffffffffu, ovf_min, 0);
-          stat |= __shfl_sync(0xffffffffu, stat, 0);
+          nbu = __shfl_sync(kFull, nbu, 0);
+          ovf_n = __shfl_sync(kFull, ovf_n, 0);
+          ovf_min = __shfl_sync(kFull, ovf_min, 0);
+          stat |= __shfl_sync(kFull, stat, 0);
           __syncwarp();
         }
-        merge_batch(nbu, true);                  // lib.rs:211-226
+        insert_batch(nbu, true);                 // lib.rs:211-226
       }
       if (!did) {                                // lib.rs:233-238: cumulative, never reset
         if (--probe == 0) break;
@@ -570,6 +579,119 @@ struct WarpSearch {
     __syncwarp();
   }
 
+  // emit the `want` smallest pool entries in ascending order through f(rank, key); entries are
+  // consumed (flagged / reordered).  Flags must be clear on entry.  Returns the number emitted.
+  template <class F>
+  __device__ uint32_t emit_smallest(uint32_t want, F f) {
+    uint32_t n = min(want, len);
+    if (n > 24) {
+      sort_pool();
+      for (uint32_t i = lane; i < n; i += 32) f(i, pool[i]);
+      __syncwarp();
+      return n;
+    }
+    for (uint32_t r = 0; r < n; r++) {
+      uint32_t slot;
+      uint64_t k = scan_min_unexpanded(&slot);
+      if (lane == 0) {
+        pool[slot] = k | (uint64_t)kFlagExpanded;
+        f(r, k);
+      }
+      __syncwarp();
+    }
+    return n;
+  }
+
+  // the end of one layer of search_layers_instrumented (search.rs:127-136): the layer returns
+  // its first `count` entries that pass `include` (lib.rs:268-276) and those are merged into
+  // the incoming candidates saved[0..old_len).  Pool keys are VectorId keys on entry and exit.
+  __device__ void finish_layer(uint32_t count, uint32_t excl, bool hit, uint32_t old_len,
+                               uint64_t pmax_v) {
+    if (!hit && len <= count) {
+      // Everything the layer found is returned.  Incoming candidates that are no longer in the
+      // pool were evicted by smaller keys from a full pool, so the merged set IS the pool.
+      return;
+    }
+    if (len <= count) {
+      // The excluded vector is in the pool: the layer returns the pool minus that entry.  What
+      // the merge can add back is the smallest incoming candidate that is not in the returned
+      // set: the excluded vector itself if it came in as a candidate (search.rs:110-111), or --
+      // when the pool was full, so one slot is free now -- a candidate that was evicted (its
+      // key is above the pool's maximum).
+      const bool was_full = len == cap;
+      bool mine = false;
+      uint32_t myslot = 0;
+      for (uint32_t i = lane; i < len; i += 32)
+        if ((uint32_t)pool[i] == excl) { mine = true; myslot = i; }
+      uint32_t mm = __ballot_sync(kFull, mine);
+      uint32_t s = __shfl_sync(kFull, myslot, (__ffs(mm) - 1) & 31);
+      __syncwarp();
+      if (lane == 0) pool[s] = pool[len - 1];
+      len--;
+      uint64_t add = kEmptyKey;
+      for (uint32_t i = lane; i < old_len; i += 32) {
+        uint64_t k = ld_cg_u64(&saved[i]);
+        if ((uint32_t)k == excl || (was_full && k > pmax_v)) add = k < add ? k : add;
+      }
+      add = warp_min_key(add);
+      __syncwarp();
+      if (add != kEmptyKey) {
+        if (lane == 0) pool[len] = add;
+        len++;
+      }
+      __syncwarp();
+      return;
+    }
+    // general path (upper_layer_candidate_count below the capacity): sort, filter, truncate,
+    // then merge the incoming candidates that are not already there
+    sort_pool();
+    uint32_t w = 0;
+    for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+      uint32_t i = i0 + lane;
+      bool act = i < len;
+      uint64_t k = act ? pool[i] : 0;
+      act = act && (uint32_t)k != excl;
+      uint32_t m = __ballot_sync(kFull, act);
+      uint32_t pos = w + __popc(m & ((1u << lane) - 1));
+      __syncwarp();
+      if (act && pos < count) pool[pos] = k;
+      w += __popc(m);
+      __syncwarp();
+    }
+    len = min(w, count);  // pool[0..len) ascending
+    const uint32_t sorted_len = len;
+    // pass 1: compact the incoming candidates that are absent from the returned set
+    uint32_t n_abs = 0;
+    for (uint32_t i0 = 0; i0 < old_len; i0 += 32) {
+      uint32_t i = i0 + lane;
+      bool act = i < old_len;
+      uint64_t k = act ? ld_cg_u64(&saved[i]) : kEmptyKey;
+      if (act) {
+        uint32_t lo = 0, hi = sorted_len;
+        while (lo < hi) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (pool[mid] < k) lo = mid + 1;
+          else hi = mid;
+        }
+        if (lo < sorted_len && pool[lo] == k) act = false;
+      }
+      uint32_t m = __ballot_sync(kFull, act);
+      __syncwarp();
+      if (act) saved[n_abs + __popc(m & ((1u << lane) - 1))] = k;
+      n_abs += __popc(m);
+      __syncwarp();
+    }
+    // pass 2: merge them (ascending order is kept by the compaction)
+    if (len == cap && n_abs) rescan_max();
+    for (uint32_t i = 0; i < n_abs; i++) {
+      uint64_t k = ld_cg_u64(&saved[i]);
+      if (lane == 0) bsorted[0] = k;
+      __syncwarp();
+      insert_batch(1, false);
+    }
+    __syncwarp();
+  }
+
   // search_layers_instrumented, src/search.rs:93-140
   __device__ void run_search(uint32_t q) {
     const uint32_t excl =
@@ -584,7 +706,7 @@ struct WarpSearch {
       nd_l = 1;
       uint32_t ev = top.nodes ? top.nodes[0] : 0;
       uint64_t k = bkeys[0];
-      if (lane == 0) cand[0] = (k & 0xFFFFFFFF00000000ull) | ev;  // VectorId key
+      if (lane == 0) pool[0] = (k & kHiMask) | ev;  // VectorId key
       len = 1;
       __syncwarp();
     }
@@ -600,7 +722,7 @@ struct WarpSearch {
         bool act = i < old_len;
         uint32_t node = 0;
         if (act) {
-          uint64_t k = cand[i];
+          uint64_t k = pool[i];
           saved[i] = k;
           uint32_t v = (uint32_t)k;
           node = layer.vec2node ? __ldg(&layer.vec2node[v]) : v;
@@ -608,76 +730,54 @@ struct WarpSearch {
             stat |= kStatMissingNode;
             node = 0;
           }
-          cand[i] = (k & 0xFFFFFFFF00000000ull) | node;
+          pool[i] = (k & kHiMask) | node;
         }
-        visited_insert(act, node, min(32u, old_len - i0));
+        visited_set(act, node);
       }
       __syncwarp();
       closest_nodes(layer, a.probe_depth, &nd_l, &ne_l);
       if (a.out_ndist && lane == 0) a.out_ndist[(size_t)q * a.stats_stride + li] = nd_l;
       if (a.out_nexp && lane == 0) a.out_nexp[(size_t)q * a.stats_stride + li] = ne_l;
       nd_l = ne_l = 0;
-      // NodeId -> VectorId, drop `exclude`, keep the first `count` (lib.rs:268-276)
-      uint32_t w = 0;
-      for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-        uint32_t i = i0 + lane;
-        bool act = i < len;
-        uint64_t k = 0;
-        if (act) {
-          k = cand[i];
-          uint32_t node = key_id(k);
-          uint32_t v = layer.nodes ? __ldg(&layer.nodes[node]) : node;
-          k = (k & 0xFFFFFFFF00000000ull) | v;
-          act = v != excl;
-        }
-        uint32_t m = __ballot_sync(0xffffffffu, act);
-        uint32_t pos = w + __popc(m & ((1u << lane) - 1));
-        __syncwarp();
-        if (act && pos < count) cand[pos] = k;
-        w += __popc(m);
-        __syncwarp();
+      // NodeId -> VectorId (lib.rs:268-276); look for the excluded vector on the way
+      uint64_t pmax_v = kEmptyKey;
+      if (len == cap) {
+        uint32_t pn = key_id(pmax);
+        pmax_v = (pmax & kHiMask) | (layer.nodes ? __ldg(&layer.nodes[pn]) : pn);
       }
-      len = min(w, count);
-      // candidates.merge_pairs(&closest) (search.rs:136): union with the incoming
-      // candidates, exact duplicates dropped, best `cap` kept
-      for (uint32_t i0 = 0; i0 < old_len; i0 += 32) {
-        uint32_t i = i0 + lane;
-        bool act = i < old_len;
-        uint64_t k = act ? ld_cg_u64(&saved[i]) : kEmptyKey;
-        if (act) {  // already present?
-          uint32_t lo = 0, hi = len;
-          while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (cand[mid] < k) lo = mid + 1;
-            else hi = mid;
-          }
-          if (lo < len && cand[lo] == k) act = false;
-          if (lo >= cap) act = false;  // beyond a full set: cannot enter
-        }
-        uint32_t m = __ballot_sync(0xffffffffu, act);
-        if (m) {
-          if (act) bsorted[__popc(m & ((1u << lane) - 1))] = k;
-          __syncwarp();
-          merge_batch(__popc(m), false);
-        }
+      bool hit = false;
+      for (uint32_t i = lane; i < len; i += 32) {
+        uint64_t k = pool[i];
+        uint32_t node = key_id(k);
+        uint32_t v = layer.nodes ? __ldg(&layer.nodes[node]) : node;
+        hit |= v == excl;
+        pool[i] = (k & kHiMask) | v;
       }
+      hit = __any_sync(kFull, hit);
       __syncwarp();
+      finish_layer(count, excl, hit, old_len, pmax_v);
     }
     if (a.out_selfhit && a.stored_ids) {
       const uint32_t self = (uint32_t)a.stored_ids[q];
       bool hit = false;
-      for (uint32_t i = lane; i < len; i += 32) hit |= ((uint32_t)cand[i] == self);
-      hit = __any_sync(0xffffffffu, hit);
+      for (uint32_t i = lane; i < len; i += 32) hit |= ((uint32_t)pool[i] == self);
+      hit = __any_sync(kFull, hit);
       if (lane == 0) a.out_selfhit[q] = hit ? 1u : 0u;
     }
     // candidates.iter().collect() (search.rs:139)
     uint32_t n_out = min(len, a.max_out);
-    if (a.out_ids)
-      for (uint32_t i = lane; i < a.max_out; i += 32) {
-        uint64_t k = i < n_out ? cand[i] : 0;
-        a.out_ids[(size_t)q * a.max_out + i] = i < n_out ? (uint64_t)(uint32_t)k : ~0ull;
-        a.out_dists[(size_t)q * a.max_out + i] = i < n_out ? key_dist(k) : 3.4028234663852886e38f;
+    if (a.out_ids) {
+      uint64_t *oi = a.out_ids + (size_t)q * a.max_out;
+      float *od = a.out_dists + (size_t)q * a.max_out;
+      n_out = emit_smallest(a.max_out, [&](uint32_t r, uint64_t k) {
+        oi[r] = (uint64_t)(uint32_t)k;
+        od[r] = key_dist(k);
+      });
+      for (uint32_t i = n_out + lane; i < a.max_out; i += 32) {
+        oi[i] = ~0ull;
+        od[i] = 3.4028234663852886e38f;
       }
+    }
     if (a.out_counts && lane == 0) a.out_counts[q] = n_out;
   }
 
@@ -687,32 +787,39 @@ struct WarpSearch {
     uint32_t nd_l = 0, ne_l = 0;
     const uint32_t node = a.q_offset + q;
     visited_reset();
-    if (lane == 0) cand[0] = make_key(0.0f, node);
+    if (lane == 0) pool[0] = make_key(0.0f, node);
     len = 1;
-    visited_insert(lane == 0, node, 1);
+    visited_set(lane == 0, node);
     __syncwarp();
     closest_nodes(layer, a.probe_depth, &nd_l, &ne_l);
     if (a.out_ndist && lane == 0) a.out_ndist[(size_t)q * a.stats_stride] = nd_l;
     if (a.out_nexp && lane == 0) a.out_nexp[(size_t)q * a.stats_stride] = ne_l;
-    uint32_t w = 0;
-    for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-      uint32_t i = i0 + lane;
-      bool act = i < len;
-      uint64_t k = act ? cand[i] : 0;
-      act = act && key_id(k) != node;  // .filter(|(n,_)| *n != node)
-      uint32_t m = __ballot_sync(0xffffffffu, act);
-      uint32_t pos = w + __popc(m & ((1u << lane) - 1));
-      if (act && pos < a.max_out) {
-        uint32_t nid = key_id(k);
-        a.out_ids[(size_t)q * a.max_out + pos] = layer.nodes ? layer.nodes[nid] : nid;
-        a.out_dists[(size_t)q * a.max_out + pos] = key_dist(k);
-      }
-      w += __popc(m);
+    // .filter(|(n,_)| *n != node).take(k): drop self from the pool, then emit the k smallest
+    bool mine = false;
+    uint32_t myslot = 0;
+    for (uint32_t i = lane; i < len; i += 32) {
+      uint64_t k = pool[i] & kFlagMask64;
+      pool[i] = k;
+      if ((uint32_t)k == node) { mine = true; myslot = i; }
     }
-    uint32_t n_out = min(w, a.max_out);
+    uint32_t mm = __ballot_sync(kFull, mine);
+    __syncwarp();
+    if (mm) {
+      uint32_t s = __shfl_sync(kFull, myslot, __ffs(mm) - 1);
+      if (lane == 0) pool[s] = pool[len - 1];
+      len--;
+      __syncwarp();
+    }
+    uint64_t *oi = a.out_ids + (size_t)q * a.max_out;
+    float *od = a.out_dists + (size_t)q * a.max_out;
+    uint32_t n_out = emit_smallest(a.max_out, [&](uint32_t r, uint64_t k) {
+      uint32_t nid = key_id(k);
+      oi[r] = layer.nodes ? layer.nodes[nid] : nid;
+      od[r] = key_dist(k);
+    });
     for (uint32_t i = n_out + lane; i < a.max_out; i += 32) {
-      a.out_ids[(size_t)q * a.max_out + i] = ~0ull;
-      a.out_dists[(size_t)q * a.max_out + i] = 3.4028234663852886e38f;
+      oi[i] = ~0ull;
+      od[i] = 3.4028234663852886e38f;
     }
     if (a.out_counts && lane == 0) a.out_counts[q] = n_out;
   }
@@ -724,7 +831,7 @@ struct WarpSearch {
     const LayerDev &layer = a.layers[a.n_layers - 1];
     uint32_t nd_l = 0, ne_l = 0;
     const uint32_t node = a.q_offset + q;
-    if (lane == 0) cand[0] = make_key(0.0f, node);
+    if (lane == 0) pool[0] = make_key(0.0f, node);
     len = 1;
     __syncwarp();
     float last = 0.0f;
@@ -737,15 +844,16 @@ struct WarpSearch {
         bool act = i < len;
         uint32_t id = 0;
         if (act) {
-          uint64_t k = cand[i] & kFlagMask64;
-          cand[i] = k;
+          uint64_t k = pool[i] & kFlagMask64;
+          pool[i] = k;
           id = (uint32_t)k;
         }
-        visited_insert(act, id, min(32u, len - i0));
+        visited_set(act, id);
       }
       __syncwarp();
       closest_nodes(layer, a.probe_depth, &nd_l, &ne_l);
-      last = key_dist(cand[len - 1]);
+      if (len < cap) rescan_max();  // pq.last(): the largest entry
+      last = key_dist(pmax);
       if (last < a.threshold && len == cap) {  // resize_capacity(capacity * 2)
         if (cap * 2 > a.cap_max) {
           stat |= kStatOverflowFrontier;
@@ -757,21 +865,22 @@ struct WarpSearch {
     if (a.out_ndist && lane == 0) a.out_ndist[(size_t)q * a.stats_stride] = nd_l;
     if (a.out_nexp && lane == 0) a.out_nexp[(size_t)q * a.stats_stride] = ne_l;
     // .filter(n != node).take_while(d < threshold)
+    sort_pool();
     uint32_t w = 0;
     bool stop = false;
     for (uint32_t i0 = 0; i0 < len && !stop; i0 += 32) {
       uint32_t i = i0 + lane;
       bool act = i < len;
-      uint64_t k = act ? cand[i] : 0;
+      uint64_t k = act ? pool[i] : 0;
       bool self = act && key_id(k) == node;
       bool over = act && !self && !(key_dist(k) < a.threshold);
-      uint32_t mo = __ballot_sync(0xffffffffu, over);
+      uint32_t mo = __ballot_sync(kFull, over);
       if (mo) {
         act = act && (uint32_t)lane < (uint32_t)(__ffs(mo) - 1);
         stop = true;
       }
       act = act && !self;
-      uint32_t m = __ballot_sync(0xffffffffu, act);
+      uint32_t m = __ballot_sync(kFull, act);
       uint32_t pos = w + __popc(m & ((1u << lane) - 1));
       if (act && pos < a.max_out) {
         uint32_t nid = key_id(k);
@@ -791,7 +900,7 @@ __global__ void __launch_bounds__(512) search_kernel(const SearchArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t warps_per_cta = blockDim.x >> 5;
-  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, a.hash_cap);
+  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad);
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
   WarpSearch<METRIC> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);
   if (lane == 0) {
@@ -811,9 +920,8 @@ __global__ void __launch_bounds__(512) search_kernel(const SearchArgs a) {
     else if (a.mode == 1) ws.run_knn(q);
     else ws.run_threshold(q);
   }
-  // leave the HBM visited spill table clean for the next launch that uses this slot
-  if (ws.spill_dirty)
-    for (uint32_t i = lane; i < a.spill_cap; i += 32) ws.spill[i] = kEmpty32;
+  // hand a clean bitmap to the next launch that uses this slot
+  ws.visited_reset();
   uint32_t st = ws.stat;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);

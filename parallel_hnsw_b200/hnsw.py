@@ -246,9 +246,8 @@ class Hnsw:
     def layers(self):
         return [self.get_layer_from_top(i) for i in range(self.layer_count())]
 
-    def set_scratch(self, visited_smem=0, visited_spill=0, frontier_spill=0):
-        N.check(N.lib().phnsw_index_set_scratch(self._h, visited_smem, visited_spill,
-                                                frontier_spill))
+    def set_scratch(self, visited_log=0, frontier_spill=0):
+        N.check(N.lib().phnsw_index_set_scratch(self._h, visited_log, 0, frontier_spill))
 
     # ---- search -------------------------------------------------------------------------
     def search(self, queries=None, sp=None, stored_ids=None, exclude=None, upto=0, max_out=None,

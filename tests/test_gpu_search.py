@@ -178,17 +178,18 @@ def test_cfg1_knn_and_threshold(ph, oracle, cfg1):
     assert off[-1] > 0
 
 
-def test_cfg1_small_scratch_spills_and_overflow_is_loud(ph, oracle, cfg1):
+def test_cfg1_small_scratch_is_exact_and_overflow_is_loud(ph, oracle, cfg1):
     rows, oh, gh, queries = cfg1
     q = queries[:64]
     o = oh.search(queries=q)
-    gh.set_scratch(visited_smem=256, visited_spill=8192, frontier_spill=4096)
-    _assert_same(gh.search(q), o, "spilling visited set")
-    gh.set_scratch(visited_smem=256, visited_spill=64, frontier_spill=16)
+    gh.set_scratch(visited_log=64, frontier_spill=8192)  # log overflows: whole-bitmap clears
+    _assert_same(gh.search(q), o, "overflowing visited log")
+    _assert_same(gh.search(q), o, "and again (clean bitmap handed over)")
+    gh.set_scratch(visited_log=8192, frontier_spill=16)
     with pytest.raises(ph.PhnswError) as e:
         gh.search(q)
     assert e.value.status == 7  # PHNSW_ERR_CAPACITY
-    gh.set_scratch(visited_smem=4096, visited_spill=16384, frontier_spill=8192)
+    gh.set_scratch(visited_log=8192, frontier_spill=8192)
     _assert_same(gh.search(q), o, "restored")
 
 
@@ -352,9 +353,12 @@ def test_store_outlives_its_handle_while_an_index_uses_it(ph, oracle):
     gh.close()
 
 
-def test_visited_spill_leaves_no_state_between_launches(ph, oracle, cfg1):
-    """A launch whose visited sets spill to HBM must hand clean tables to the next launch."""
+def test_no_state_leaks_between_launches(ph, oracle, cfg1):
+    """Every launch must hand clean per-slot scratch (visited bitmap) to the next one."""
     rows, oh, gh, queries = cfg1
     q = queries[:300]
-    gh.search(q, ph.SearchParameters(2000, 300, 2), max_out=10)  # > 3072 visited per query
-    _assert_same(gh.search(q), oh.search(queries=q), "after a spilling launch")
+    gh.search(q, ph.SearchParameters(2000, 300, 2), max_out=10)
+    _assert_same(gh.search(q), oh.search(queries=q), "after a large-ef launch")
+    gh.knn(5, 2)
+    _assert_same(gh.search(q, ph.SearchParameters(40, 7, 3)),
+                 oh.search(queries=q, sp=oracle.search_params(40, 7, 3)), "upper count < ef")
