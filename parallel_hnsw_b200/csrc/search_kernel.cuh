@@ -149,7 +149,7 @@ struct WarpSearch {
   const int lane;
   // warp-uniform state
   uint32_t cap, len;
-  uint64_t pmax;       // largest key of the pool (flag masked); valid whenever len == cap
+  uint64_t pmax;       // largest key of the pool (flag masked) as of the last rescan_max()
   uint32_t pmax_slot;
   uint32_t ovf_n;
   uint64_t ovf_min;
@@ -279,26 +279,47 @@ struct WarpSearch {
     *slot = __shfl_sync(kFull, bs, who);
     return mn;
   }
+  // every lane's two largest pool entries (flag-masked keys, 0 = none) among its own slots
+  // lane, lane + 32, ...: one pass that serves both as "what is the tail" and as the source of
+  // the successive maxima a batch insert evicts
+  uint64_t h1, h2;
+  uint32_t s1, s2, used;
+  __device__ void heads_scan() {
+    h1 = h2 = 0;
+    s1 = s2 = 0;
+    for (uint32_t s = lane; s < len; s += 32) {
+      uint64_t k = pool[s] & kFlagMask64;
+      if (k > h1) { h2 = h1; s2 = s1; h1 = k; s1 = s; }
+      else if (k > h2) { h2 = k; s2 = s; }
+    }
+    used = 0;
+  }
   // Merge bsorted[0..nb) (ascending, unique, disjoint from the pool) into the pool: the result
   // is the exact top-cap of the union (priority_queue.rs:109-144 contents).  With
   // spill==true, unexpanded entries that fall out and batch entries that do not fit go to the
   // frontier spill list (the reference keeps them in visit_queue, lib.rs:211-220).
-  __device__ void insert_batch(uint32_t nb, bool spill) {
+  // heads_valid: heads_scan() already ran on the current (full) pool.
+  __device__ void insert_batch(uint32_t nb, bool spill, bool heads_valid) {
     if (nb == 0) return;
     const uint32_t take = min(cap - len, nb);
     for (uint32_t t = lane; t < take; t += 32) pool[len + t] = bsorted[t];
     len += take;
     __syncwarp();
-    if (take == nb) {
-      if (len == cap) rescan_max();
-      return;
-    }
-    if (take > 0) rescan_max();  // just became full; otherwise pmax is already valid
+    if (take == nb) return;
+    if (take > 0 || !heads_valid) heads_scan();
+    // The pool is full.  Batch keys ascend, old maxima descend: b_j enters iff it is below the
+    // (j+1)-th largest old entry, which it then replaces.  Keys inserted on the way are
+    // smaller than every later batch key, so they never become eviction targets here.
     uint32_t j = take;
     while (j < nb) {
       const uint64_t key = bsorted[j];
-      if (key >= pmax) break;
-      const uint64_t ev = pool[pmax_slot];
+      if (__any_sync(kFull, used >= 2)) heads_scan();  // a lane ran out of known maxima
+      const uint64_t head = used == 0 ? h1 : h2;
+      const uint64_t mx = warp_max_key(head);
+      if (key >= mx) break;
+      const uint32_t who = __ffs(__ballot_sync(kFull, head == mx)) - 1;
+      const uint32_t slot = __shfl_sync(kFull, used == 0 ? s1 : s2, who);
+      const uint64_t ev = pool[slot];
       if (spill && !((uint32_t)ev & kFlagExpanded)) {
         if (ovf_n < a.ovf_cap) {
           if (lane == 0) ovf[ovf_n] = ev;
@@ -308,11 +329,11 @@ struct WarpSearch {
           stat |= kStatOverflowFrontier;
         }
       }
+      if ((uint32_t)lane == who) used++;
       __syncwarp();
-      if (lane == 0) pool[pmax_slot] = key;
+      if (lane == 0) pool[slot] = key;
       __syncwarp();
       j++;
-      rescan_max();
     }
     if (spill)
       for (uint32_t t0 = j; t0 < nb; t0 += 32) {
@@ -391,6 +412,37 @@ struct WarpSearch {
   // result bkeys[j] = key(distance, bid[j]).  Tiles of R rows x one 512 B chunk are copied
   // by the bulk-copy engine into stage t % S and consumed lane-per-row.
   __device__ void compute_distances(const LayerDev &layer, uint32_t nn) {
+    if (a.dim_pad <= (uint32_t)kChunk) {  // one bulk copy per row: no chunk pipeline needed
+      const uint32_t fl4 = a.dim_pad / 4;
+      for (uint32_t p0 = 0; p0 < nn; p0 += kLandingRows) {
+        const uint32_t j = p0 + lane;
+        const bool active = (uint32_t)lane < (uint32_t)kLandingRows && j < nn;
+        const uint32_t rows_p = min((uint32_t)kLandingRows, nn - p0);
+        uint32_t node = 0;
+        if (lane == 0) mbar_arrive_expect_tx(&mbar[0], rows_p * a.dim_pad * 4);
+        __syncwarp();  // also orders the previous readers of the landing zone before the refill
+        if (active) {
+          node = bid[j];
+          uint32_t vec = layer.nodes ? __ldg(&layer.nodes[node]) : node;
+          bulk_g2s(stage + lane * kRowStride, a.rows + (size_t)vec * a.pitch, a.dim_pad * 4,
+                   &mbar[0]);
+        }
+        mbar_wait(&mbar[0], ph & 1u);
+        ph ^= 1u;
+        if (active) {
+          float acc = 0.0f;
+          const float4 *rp = (const float4 *)(stage + lane * kRowStride);
+          const float4 *qp = (const float4 *)qvec;
+#pragma unroll 8
+          for (uint32_t k = 0; k < fl4; k++) acc = accum4(acc, rp[k], qp[k]);
+          float d = finalize(acc);
+          if (d != d) stat |= kStatNaN;
+          bkeys[j] = make_key(d, node);
+        }
+      }
+      __syncwarp();
+      return;
+    }
     const uint32_t nchunks = (a.dim_pad + kChunk - 1) / kChunk;
     const uint32_t S = nchunks > 1 ? 2u : 1u;
     const uint32_t R = kLandingRows / S;
@@ -471,7 +523,6 @@ struct WarpSearch {
                                 uint32_t *n_exp) {
     ovf_n = 0;
     ovf_min = kEmptyKey;
-    if (len == cap) rescan_max();
     const uint32_t M = layer.M;
     while (true) {
       // ---- pop the smallest (d,id) among all discovered, unexpanded nodes
@@ -521,7 +572,11 @@ struct WarpSearch {
         // merge()'s flag, closed form (see oracle orc_pq_merge_flag_closed_form)
         uint64_t b0 = bsorted[0];
         bool full = len == cap;
-        uint64_t tail = full ? pmax : kEmptyKey;
+        uint64_t tail = kEmptyKey;
+        if (full) {
+          heads_scan();
+          tail = warp_max_key(h1);
+        }
         did = !full || b0 < tail || (nn >= 2 && (uint32_t)(b0 >> 32) == (uint32_t)(tail >> 32));
         // duplicates inside one neighbour row stay poppable once more (visit_queue is a
         // multiset): park the extra copies in the spill list, merge the unique ones
@@ -552,7 +607,7 @@ struct WarpSearch {
           stat |= __shfl_sync(kFull, stat, 0);
           __syncwarp();
         }
-        insert_batch(nbu, true);                 // lib.rs:211-226
+        insert_batch(nbu, true, full);           // lib.rs:211-226
       }
       if (!did) {                                // lib.rs:233-238: cumulative, never reset
         if (--probe == 0) break;
@@ -682,12 +737,11 @@ struct WarpSearch {
       __syncwarp();
     }
     // pass 2: merge them (ascending order is kept by the compaction)
-    if (len == cap && n_abs) rescan_max();
     for (uint32_t i = 0; i < n_abs; i++) {
       uint64_t k = ld_cg_u64(&saved[i]);
       if (lane == 0) bsorted[0] = k;
       __syncwarp();
-      insert_batch(1, false);
+      insert_batch(1, false, false);
     }
     __syncwarp();
   }
@@ -741,7 +795,8 @@ struct WarpSearch {
       nd_l = ne_l = 0;
       // NodeId -> VectorId (lib.rs:268-276); look for the excluded vector on the way
       uint64_t pmax_v = kEmptyKey;
-      if (len == cap) {
+      if (len == cap && a.exclude) {
+        rescan_max();
         uint32_t pn = key_id(pmax);
         pmax_v = (pmax & kHiMask) | (layer.nodes ? __ldg(&layer.nodes[pn]) : pn);
       }
@@ -852,7 +907,7 @@ struct WarpSearch {
       }
       __syncwarp();
       closest_nodes(layer, a.probe_depth, &nd_l, &ne_l);
-      if (len < cap) rescan_max();  // pq.last(): the largest entry
+      rescan_max();  // pq.last(): the largest entry
       last = key_dist(pmax);
       if (last < a.threshold && len == cap) {  // resize_capacity(capacity * 2)
         if (cap * 2 > a.cap_max) {
@@ -895,7 +950,7 @@ struct WarpSearch {
 };
 
 template <int METRIC>
-__global__ void __launch_bounds__(512) search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
