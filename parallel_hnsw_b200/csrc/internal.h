@@ -92,6 +92,7 @@ struct LayerStore {
   uint32_t *neighbors = nullptr;  // device, node_count * M
   uint32_t *vec2node = nullptr;   // device, n_vectors (null when nodes[i] == i for all i)
   bool identity = false;
+  bool row_dups = false;  // some neighbourhood lists an id twice
   std::vector<uint32_t> h_nodes;  // host copy of `nodes` (recall sampling, lib.rs:1468-1481)
 };
 

@@ -62,6 +62,20 @@ __global__ void nodes_check_kernel(const uint32_t *__restrict__ nodes, uint32_t 
   if (v != i) atomicOr(&flags[0], 1u);
   if (i > 0 && nodes[i - 1] >= v) atomicOr(&flags[1], 1u);
 }
+// flags[2]: some neighbourhood lists the same id twice (legal in the crate; the traversal
+// kernel then takes its duplicate-aware path for this layer)
+__global__ void row_dups_kernel(const uint32_t *__restrict__ nb, uint32_t n, uint32_t M,
+                                uint32_t *flags) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t *row = nb + (size_t)i * M;
+  for (uint32_t x = 1; x < M; x++) {
+    uint32_t v = row[x];
+    if (v == kEmpty32) continue;
+    for (uint32_t y = 0; y < x; y++)
+      if (row[y] == v) { atomicOr(&flags[2], 1u); return; }
+  }
+}
 __global__ void vec2node_kernel(const uint32_t *__restrict__ nodes, uint32_t n,
                                 uint32_t *__restrict__ vec2node) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +166,6 @@ static cudaError_t launch_typed(const SearchArgs &a, int grid, int block, size_t
   return cudaGetLastError();
 }
 
-static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
 phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStream_t stream) {
   const phnsw_store *s = ix->store;
@@ -170,7 +183,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     }
   PH_CUDA(cudaSetDevice(s->device));
   const uint32_t cap_max = std::max(c.cap, c.cap_max);
-  const uint32_t cap_pad = round_up(std::max(cap_max, 1u), 32);
+  const uint32_t cap_pad = pool_entries(std::max(cap_max, 1u));
   WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
@@ -334,6 +347,7 @@ phnsw_status upload_layer_tables(phnsw_index *ix) {
     h[i].vec2node = l.identity ? nullptr : l.vec2node;
     h[i].node_count = (uint32_t)l.node_count;
     h[i].M = (uint32_t)l.M;
+    h[i].row_dups = l.row_dups ? 1u : 0u;
   }
   if (ix->d_layers) cudaFree(ix->d_layers);
   ix->d_layers = nullptr;
@@ -351,13 +365,17 @@ phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint6
   l.nodes = nodes;
   l.neighbors = neighbors;
   uint32_t *flags = nullptr;
-  PH_CUDA(cudaMalloc(&flags, 8));
-  PH_CUDA(cudaMemset(flags, 0, 8));
-  if (node_count)
+  PH_CUDA(cudaMalloc(&flags, 16));
+  PH_CUDA(cudaMemset(flags, 0, 16));
+  if (node_count) {
     nodes_check_kernel<<<(unsigned)((node_count + 255) / 256), 256>>>(nodes, (uint32_t)node_count,
                                                                      flags);
-  uint32_t hf[2];
-  PH_CUDA(cudaMemcpy(hf, flags, 8, cudaMemcpyDeviceToHost));
+    if (M) row_dups_kernel<<<(unsigned)((node_count + 127) / 128), 128>>>(
+        neighbors, (uint32_t)node_count, (uint32_t)M, flags);
+  }
+  uint32_t hf[3];
+  PH_CUDA(cudaMemcpy(hf, flags, 12, cudaMemcpyDeviceToHost));
+  l.row_dups = hf[2] != 0;
   cudaFree(flags);
   if (hf[1]) {
     set_error("layer nodes are not strictly ascending VectorIds (Layer.nodes, lib.rs:85-91)");

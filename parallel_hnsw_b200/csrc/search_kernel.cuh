@@ -49,6 +49,7 @@ struct LayerDev {
   const uint32_t *vec2node;   // VectorId -> NodeId or kEmpty32 (get_node); null = identity
   uint32_t node_count;
   uint32_t M;
+  uint32_t row_dups;          // 1 when some neighbourhood lists the same id twice
 };
 
 struct SearchArgs {
@@ -88,7 +89,7 @@ struct SearchArgs {
   uint32_t *vlog;          // per-warp log of visited node ids, vlog_cap each
   uint32_t vlog_cap;
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
-  uint32_t cap_pad;        // pool entries per warp in shared memory (>= cap_max, multiple of 32)
+  uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
 };
 
 // per-warp shared memory carve-up (bytes); shared by host (launch size) and device
@@ -107,6 +108,11 @@ __host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uin
   l.off_mbar = o;    o += kMaxStages * 8;
   l.total = ((o + 127) / 128) * 128;
   return l;
+}
+// physical pool size for a candidate capacity: room for appends between two compactions
+__host__ __device__ inline uint32_t pool_entries(uint32_t cap) {
+  uint32_t slack = cap / 4 > 64 ? cap / 4 : 64;
+  return (cap + slack + 31) / 32 * 32;
 }
 // u64 keys the landing zone can hold when it doubles as sort scratch
 constexpr uint32_t kSortScratch = kLandingRows * kRowStride * 4 / 8;
@@ -149,6 +155,7 @@ struct WarpSearch {
   const int lane;
   // warp-uniform state
   uint32_t cap, len;
+  uint64_t U;          // upper bound of the candidate set's tail (exact after a compaction)
   uint64_t pmax;       // largest key of the pool (flag masked) as of the last rescan_max()
   uint32_t pmax_slot;
   uint32_t ovf_n;
@@ -279,67 +286,105 @@ struct WarpSearch {
     *slot = __shfl_sync(kFull, bs, who);
     return mn;
   }
-  // every lane's two largest pool entries (flag-masked keys, 0 = none) among its own slots
-  // lane, lane + 32, ...: one pass that serves both as "what is the tail" and as the source of
-  // the successive maxima a batch insert evicts
-  uint64_t h1, h2;
-  uint32_t s1, s2, used;
-  __device__ void heads_scan() {
-    h1 = h2 = 0;
-    s1 = s2 = 0;
-    for (uint32_t s = lane; s < len; s += 32) {
-      uint64_t k = pool[s] & kFlagMask64;
-      if (k > h1) { h2 = h1; s2 = s1; h1 = k; s1 = s; }
-      else if (k > h2) { h2 = k; s2 = s; }
-    }
-    used = 0;
-  }
-  // Merge bsorted[0..nb) (ascending, unique, disjoint from the pool) into the pool: the result
-  // is the exact top-cap of the union (priority_queue.rs:109-144 contents).  With
-  // spill==true, unexpanded entries that fall out and batch entries that do not fit go to the
-  // frontier spill list (the reference keeps them in visit_queue, lib.rs:211-220).
-  // heads_valid: heads_scan() already ran on the current (full) pool.
-  __device__ void insert_batch(uint32_t nb, bool spill, bool heads_valid) {
-    if (nb == 0) return;
-    const uint32_t take = min(cap - len, nb);
-    for (uint32_t t = lane; t < take; t += 32) pool[len + t] = bsorted[t];
-    len += take;
+  // The pool is physical storage for up to a.cap_pad keys: the candidate set proper is the
+  // `cap` smallest of pool[0..len).  New keys under the bound U are simply appended; when the
+  // storage runs out, compact() selects the exact `cap` smallest (radix select on the 64-bit
+  // keys, 8 bits per pass, histogram in the landing zone), moves the rest to the frontier
+  // spill list if they are still unexpanded, and tightens U to the new tail.
+  __device__ void compact(bool spill) {
+    if (len <= cap) return;
     __syncwarp();
-    if (take == nb) return;
-    if (take > 0 || !heads_valid) heads_scan();
-    // The pool is full.  Batch keys ascend, old maxima descend: b_j enters iff it is below the
-    // (j+1)-th largest old entry, which it then replaces.  Keys inserted on the way are
-    // smaller than every later batch key, so they never become eviction targets here.
-    uint32_t j = take;
-    while (j < nb) {
-      const uint64_t key = bsorted[j];
-      if (__any_sync(kFull, used >= 2)) heads_scan();  // a lane ran out of known maxima
-      const uint64_t head = used == 0 ? h1 : h2;
-      const uint64_t mx = warp_max_key(head);
-      if (key >= mx) break;
-      const uint32_t who = __ffs(__ballot_sync(kFull, head == mx)) - 1;
-      const uint32_t slot = __shfl_sync(kFull, used == 0 ? s1 : s2, who);
-      const uint64_t ev = pool[slot];
-      if (spill && !((uint32_t)ev & kFlagExpanded)) {
-        if (ovf_n < a.ovf_cap) {
-          if (lane == 0) ovf[ovf_n] = ev;
-          ovf_n++;
-          ovf_min = ev < ovf_min ? ev : ovf_min;
-        } else {
-          stat |= kStatOverflowFrontier;
+    uint32_t *hist = (uint32_t *)stage;
+    const uint64_t first = pool[0] & kFlagMask64;
+    uint64_t diff = 0;
+    for (uint32_t s = lane; s < len; s += 32) diff |= (pool[s] & kFlagMask64) ^ first;
+    diff = ((uint64_t)__reduce_or_sync(kFull, (uint32_t)(diff >> 32)) << 32) |
+           __reduce_or_sync(kFull, (uint32_t)diff);
+    int d = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;  // highest digit that differs
+    uint64_t pmask = d == 7 ? 0ull : ~((1ull << (8 * (d + 1))) - 1);
+    uint64_t prefix = first & pmask;
+    uint32_t k = cap;  // wanted: the k-th smallest among the keys matching the prefix
+    uint64_t T = 0;
+    bool found = false;
+    for (; d >= 0 && !found; d--) {
+      for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+      __syncwarp();
+      const uint32_t sh = 8 * d;
+      for (uint32_t s = lane; s < len; s += 32) {
+        uint64_t km = pool[s] & kFlagMask64;
+        if ((km & pmask) == prefix) atomicAdd(&hist[(uint32_t)(km >> sh) & 255u], 1u);
+      }
+      __syncwarp();
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { c[i] = hist[lane * 8 + i]; sum += c[i]; }
+      uint32_t cum = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(kFull, cum, o);
+        if (lane >= o) cum += v;
+      }
+      const uint32_t L = __ffs(__ballot_sync(kFull, cum >= k)) - 1;
+      uint32_t bin = 0, kk = 0, cnt = 0;
+      if ((uint32_t)lane == L) {
+        uint32_t acc = cum - sum;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (cnt == 0 && acc + c[i] >= k) { bin = lane * 8 + i; kk = k - acc; cnt = c[i]; }
+          acc += c[i];
         }
       }
-      if ((uint32_t)lane == who) used++;
-      __syncwarp();
-      if (lane == 0) pool[slot] = key;
-      __syncwarp();
-      j++;
-    }
-    if (spill)
-      for (uint32_t t0 = j; t0 < nb; t0 += 32) {
-        uint32_t t = t0 + lane;
-        ovf_append(t < nb, t < nb ? bsorted[t] : 0);
+      bin = __shfl_sync(kFull, bin, L);
+      k = __shfl_sync(kFull, kk, L);
+      cnt = __shfl_sync(kFull, cnt, L);
+      prefix |= (uint64_t)bin << sh;
+      pmask |= 0xFFull << sh;
+      if (cnt == 1) {  // a single key carries this prefix: that is the tail
+        uint64_t mine = 0;
+        for (uint32_t s = lane; s < len; s += 32) {
+          uint64_t km = pool[s] & kFlagMask64;
+          if ((km & pmask) == prefix) mine = km;
+        }
+        T = ((uint64_t)__reduce_max_sync(kFull, (uint32_t)(mine >> 32)) << 32) |
+            __reduce_max_sync(kFull, (uint32_t)mine);
+        found = true;
       }
+      __syncwarp();
+    }
+    if (!found) T = prefix;  // all 64 bits decided
+    // partition in place: keys <= T stay (exactly `cap` of them: keys are unique)
+    const uint32_t old_len = len;
+    uint32_t w = 0;
+    for (uint32_t r0 = 0; r0 < old_len; r0 += 32) {
+      uint32_t i = r0 + lane;
+      bool act = i < old_len;
+      uint64_t key = act ? pool[i] : 0;
+      uint64_t km = key & kFlagMask64;
+      bool keep = act && km <= T;
+      bool ev = act && !keep && !((uint32_t)key & kFlagExpanded);
+      uint32_t mk = __ballot_sync(kFull, keep);
+      __syncwarp();
+      if (keep) pool[w + __popc(mk & ((1u << lane) - 1))] = key;
+      w += __popc(mk);
+      if (spill) ovf_append(ev, km);
+      __syncwarp();
+    }
+    len = w;
+    U = T;
+  }
+  // insert one key into an exact pool (len <= cap) without spilling: the slow, general path
+  __device__ void insert_one(uint64_t key) {
+    if (len < cap) {
+      if (lane == 0) pool[len] = key;
+      len++;
+      __syncwarp();
+      return;
+    }
+    rescan_max();
+    if (key < pmax) {
+      if (lane == 0) pool[pmax_slot] = key;
+      __syncwarp();
+    }
   }
   // pool[0..len) -> ascending order (flags cleared); bitonic network in the landing zone
   __device__ void sort_pool() {
@@ -517,23 +562,30 @@ struct WarpSearch {
   }
 
   // ------------------------------------------------------------------ closest_nodes
-  // lib.rs:175-248 on `layer`; pool[0..len) holds NodeId keys, all unexpanded, all marked in
-  // the visited bitmap.
+  // lib.rs:175-248 on `layer`; pool[0..len) holds NodeId keys (len <= cap), all unexpanded,
+  // all marked in the visited bitmap.  On return the pool is exact again (len <= cap).
   __device__ void closest_nodes(const LayerDev &layer, uint32_t probe, uint32_t *n_dist,
                                 uint32_t *n_exp) {
     ovf_n = 0;
     ovf_min = kEmptyKey;
+    U = kEmptyKey;
     const uint32_t M = layer.M;
+    const uint32_t lt = (1u << lane) - 1;
+    // the smallest unexpanded pool entry, carried from one expansion to the next
+    uint64_t nx_key = kEmptyKey;
+    uint32_t nx_slot = 0;
+    bool nx_valid = false;
     while (true) {
       // ---- pop the smallest (d,id) among all discovered, unexpanded nodes
-      uint32_t slot;
-      const uint64_t ckey = scan_min_unexpanded(&slot);
+      if (!nx_valid) nx_key = scan_min_unexpanded(&nx_slot);
       uint32_t next;
-      if (ovf_n > 0 && ovf_min < ckey) {
+      if (ovf_n > 0 && ovf_min < nx_key) {
         next = key_id(ovf_pop_min());
-      } else if (ckey != kEmptyKey) {
-        if (lane == 0) pool[slot] = ckey | (uint64_t)kFlagExpanded;
-        next = key_id(ckey);
+        nx_valid = true;  // the pool did not change
+      } else if (nx_key != kEmptyKey) {
+        if (lane == 0) pool[nx_slot] = nx_key | (uint64_t)kFlagExpanded;
+        next = key_id(nx_key);
+        nx_valid = false;
         __syncwarp();
       } else {
         break;  // frontier exhausted
@@ -558,7 +610,6 @@ struct WarpSearch {
       uint32_t m0 = __ballot_sync(kFull, u0);
       uint32_t m1 = __ballot_sync(kFull, u1);
       uint32_t nn = __popc(m0) + __popc(m1);
-      uint32_t lt = (1u << lane) - 1;
       if (u0) bid[__popc(m0 & lt)] = n0;
       if (u1) bid[__popc(m0) + __popc(m1 & lt)] = n1;
       __syncwarp();
@@ -567,52 +618,101 @@ struct WarpSearch {
       if (nn > 0) {
         visited_set(u0, n0);                     // lib.rs:209 (order is immaterial)
         if (m1) visited_set(u1, n1);
-        compute_distances(layer, nn);            // lib.rs:199-204
-        sort_batch(nn);                          // lib.rs:206
-        // merge()'s flag, closed form (see oracle orc_pq_merge_flag_closed_form)
-        uint64_t b0 = bsorted[0];
-        bool full = len == cap;
-        uint64_t tail = kEmptyKey;
-        if (full) {
-          heads_scan();
-          tail = warp_max_key(h1);
-        }
-        did = !full || b0 < tail || (nn >= 2 && (uint32_t)(b0 >> 32) == (uint32_t)(tail >> 32));
-        // duplicates inside one neighbour row stay poppable once more (visit_queue is a
-        // multiset): park the extra copies in the spill list, merge the unique ones
+        compute_distances(layer, nn);            // lib.rs:199-204 -> bkeys[0..nn)
+        const uint64_t *bk = bkeys;
         uint32_t nbu = nn;
-        bool dup = false;
-        for (uint32_t j0 = 0; j0 < nn; j0 += 32) {
-          uint32_t j = j0 + lane;
-          dup |= (j > 0 && j < nn && bsorted[j] == bsorted[j - 1]);
-        }
-        if (__any_sync(kFull, dup)) {
-          __syncwarp();
-          if (lane == 0) {
-            uint32_t w = 1;
-            for (uint32_t j = 1; j < nn; j++) {
-              uint64_t k = bsorted[j];
-              if (k == bsorted[w - 1]) {
-                if (ovf_n < a.ovf_cap) ovf[ovf_n++] = k; else stat |= kStatOverflowFrontier;
-                ovf_min = k < ovf_min ? k : ovf_min;
-              } else {
-                bsorted[w++] = k;
-              }
-            }
-            nbu = w;
+        if (layer.row_dups) {
+          // a row that lists an id twice yields equal keys: visit_queue is a multiset, so the
+          // extra copies stay poppable once more (spill list) while the set takes one
+          sort_batch(nn);                        // lib.rs:206
+          bk = bsorted;
+          bool dup = false;
+          for (uint32_t j0 = 0; j0 < nn; j0 += 32) {
+            uint32_t j = j0 + lane;
+            dup |= (j > 0 && j < nn && bsorted[j] == bsorted[j - 1]);
           }
-          nbu = __shfl_sync(kFull, nbu, 0);
-          ovf_n = __shfl_sync(kFull, ovf_n, 0);
-          ovf_min = __shfl_sync(kFull, ovf_min, 0);
-          stat |= __shfl_sync(kFull, stat, 0);
+          if (__any_sync(kFull, dup)) {
+            __syncwarp();
+            if (lane == 0) {
+              uint32_t w = 1;
+              for (uint32_t j = 1; j < nn; j++) {
+                uint64_t k = bsorted[j];
+                if (k == bsorted[w - 1]) {
+                  if (ovf_n < a.ovf_cap) ovf[ovf_n++] = k; else stat |= kStatOverflowFrontier;
+                  ovf_min = k < ovf_min ? k : ovf_min;
+                } else {
+                  bsorted[w++] = k;
+                }
+              }
+              nbu = w;
+            }
+            nbu = __shfl_sync(kFull, nbu, 0);
+            ovf_n = __shfl_sync(kFull, ovf_n, 0);
+            ovf_min = __shfl_sync(kFull, ovf_min, 0);
+            stat |= __shfl_sync(kFull, stat, 0);
+            __syncwarp();
+          }
+        }
+        // smallest new key (lib.rs:206 sorts; only the head of that order matters here)
+        uint64_t mine0 = (uint32_t)lane < nbu ? bk[lane] : kEmptyKey;
+        uint64_t mine1 = (uint32_t)lane + 32 < nbu ? bk[lane + 32] : kEmptyKey;
+        const uint64_t b0 = warp_min_key(mine0 < mine1 ? mine0 : mine1);
+        // ---- one pass over the pool: rank of b0 (merge()'s return flag in closed form, see
+        // oracle orc_pq_merge_flag_closed_form) and the next node to pop
+        const uint32_t b0hi = (uint32_t)(b0 >> 32);
+        uint32_t A = 0, B = 0;
+        uint64_t best = kEmptyKey;
+        uint32_t bs = 0;
+        for (uint32_t s = lane; s < len; s += 32) {
+          uint64_t k = pool[s];
+          uint64_t km = k & kFlagMask64;
+          A += km < b0;
+          B += (uint32_t)(km >> 32) < b0hi;
+          if (!((uint32_t)k & kFlagExpanded) && km < best) { best = km; bs = s; }
+        }
+        A = __reduce_add_sync(kFull, A);
+        B = __reduce_add_sync(kFull, B);
+        nx_key = warp_min_key(best);
+        nx_slot = __shfl_sync(kFull, bs, __ffs(__ballot_sync(kFull, best == nx_key)) - 1);
+        nx_valid = true;
+        // full: the candidate set holds `cap` entries; its tail is the cap-th smallest key.
+        // b0 < tail  <=>  fewer than cap keys are below b0; tail and b0 tie on the distance
+        // <=>  b0 is not below the tail but fewer than cap keys have a smaller distance.
+        const bool full = len >= cap;
+        did = !full || A < cap || (nn >= 2 && B < cap);
+        // ---- merge (lib.rs:211-226): keys under the bound join the pool, the rest can never
+        // enter the candidate set and go straight to the frontier spill list
+        for (uint32_t t0 = 0; t0 < nbu; t0 += 32) {
+          uint32_t t = t0 + lane;
+          bool act = t < nbu;
+          uint64_t key = act ? bk[t] : kEmptyKey;
+          bool in = act && key < U;
+          uint32_t m = __ballot_sync(kFull, in);
+          if (len + __popc(m) > a.cap_pad) {
+            compact(true);
+            nx_valid = false;  // slots moved
+            in = act && key < U;
+            m = __ballot_sync(kFull, in);
+          }
+          uint32_t pos = len + __popc(m & lt);
+          if (in) pool[pos] = key;
+          len += __popc(m);
+          if (nx_valid) {  // the next pop may be one of the keys just added
+            uint64_t mk = warp_min_key(in ? key : kEmptyKey);
+            if (mk < nx_key) {
+              nx_slot = __shfl_sync(kFull, pos, __ffs(__ballot_sync(kFull, in && key == mk)) - 1);
+              nx_key = mk;
+            }
+          }
+          ovf_append(act && !in, key);
           __syncwarp();
         }
-        insert_batch(nbu, true, full);           // lib.rs:211-226
       }
       if (!did) {                                // lib.rs:233-238: cumulative, never reset
         if (--probe == 0) break;
       }
     }
+    compact(false);
   }
 
   // ------------------------------------------------------------------ whole-query drivers
@@ -737,12 +837,7 @@ struct WarpSearch {
       __syncwarp();
     }
     // pass 2: merge them (ascending order is kept by the compaction)
-    for (uint32_t i = 0; i < n_abs; i++) {
-      uint64_t k = ld_cg_u64(&saved[i]);
-      if (lane == 0) bsorted[0] = k;
-      __syncwarp();
-      insert_batch(1, false, false);
-    }
+    for (uint32_t i = 0; i < n_abs; i++) insert_one(ld_cg_u64(&saved[i]));
     __syncwarp();
   }
 
