@@ -575,6 +575,9 @@ struct WarpSearch {
     uint64_t nx_key = kEmptyKey;
     uint32_t nx_slot = 0;
     bool nx_valid = false;
+    // neighbour row of the node that will most likely be popped next, requested while the
+    // current expansion is still being merged (hides one dependent HBM round trip)
+    uint32_t pf_id = kEmpty32, pf_n0 = kEmpty32, pf_n1 = kEmpty32;
     while (true) {
       // ---- pop the smallest (d,id) among all discovered, unexpanded nodes
       if (!nx_valid) nx_key = scan_min_unexpanded(&nx_slot);
@@ -592,9 +595,16 @@ struct WarpSearch {
       }
       (*n_exp)++;
       // ---- neighbours of `next`, trailing sentinels trimmed (lib.rs:114-125, 144-148)
-      const uint32_t *row = layer.neighbors + (size_t)next * M;
-      uint32_t n0 = lane < M ? __ldg(&row[lane]) : kEmpty32;
-      uint32_t n1 = lane + 32 < M ? __ldg(&row[lane + 32]) : kEmpty32;
+      uint32_t n0, n1;
+      if (next == pf_id) {
+        n0 = pf_n0;
+        n1 = pf_n1;
+      } else {
+        const uint32_t *row = layer.neighbors + (size_t)next * M;
+        n0 = lane < M ? __ldg(&row[lane]) : kEmpty32;
+        n1 = lane + 32 < M ? __ldg(&row[lane + 32]) : kEmpty32;
+      }
+      pf_id = kEmpty32;
       uint32_t v0 = __ballot_sync(kFull, n0 != kEmpty32);
       uint32_t v1 = __ballot_sync(kFull, n1 != kEmpty32);
       uint32_t valid = v1 ? 64 - __clz(v1) : 32 - __clz(v0);  // __clz(0) == 32
@@ -680,6 +690,18 @@ struct WarpSearch {
         // <=>  b0 is not below the tail but fewer than cap keys have a smaller distance.
         const bool full = len >= cap;
         did = !full || A < cap || (nn >= 2 && B < cap);
+        if (did || probe > 1) {  // the walk continues: request the next row now
+          uint64_t i0 = mine0 < U ? mine0 : kEmptyKey, i1 = mine1 < U ? mine1 : kEmptyKey;
+          uint64_t pk = warp_min_key(i0 < i1 ? i0 : i1);
+          pk = pk < nx_key ? pk : nx_key;
+          pk = ovf_min < pk ? ovf_min : pk;
+          if (pk != kEmptyKey) {
+            pf_id = key_id(pk);
+            const uint32_t *prow = layer.neighbors + (size_t)pf_id * M;
+            pf_n0 = lane < M ? __ldg(&prow[lane]) : kEmpty32;
+            pf_n1 = lane + 32 < M ? __ldg(&prow[lane + 32]) : kEmpty32;
+          }
+        }
         // ---- merge (lib.rs:211-226): keys under the bound join the pool, the rest can never
         // enter the candidate set and go straight to the frontier spill list
         for (uint32_t t0 = 0; t0 < nbu; t0 += 32) {
