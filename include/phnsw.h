@@ -220,6 +220,48 @@ phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *quer
                                          uint64_t nq, uint64_t k, uint64_t *out_ids_device,
                                          float *out_dists_device, void *cuda_stream);
 
+/* ---- product quantisation: QuantizedHnsw (src/pq.rs:120-477) ----
+ * One codebook shared by all sub-spaces, sampled from the data's own sub-vectors
+ * (random_centroids, pq.rs:261-285); codes are u16 (pq.rs:20); a vector is quantised by searching
+ * the centroid HNSW once per sub-vector (HnswQuantizer::quantize, pq.rs:61-71); the main graph is
+ * built on code-to-code distances = `quantized_metric` applied to the two reconstructions (the
+ * crate's test comparators, pq.rs:585-599); a query is answered by quantise -> walk the code
+ * graph -> re-rank every hit with the full comparator -> sort by (d, id) (pq.rs:346-364). */
+typedef struct phnsw_pq phnsw_pq;
+typedef struct {
+  phnsw_build_params centroids;
+  phnsw_build_params hnsw;
+  phnsw_search_params quantized_search;
+} phnsw_pq_build_params; /* src/parameters.rs:66-71 */
+void phnsw_default_pq_build_params(phnsw_pq_build_params *bp);
+/* QuantizedHnsw::new (pq.rs:287-344); `full` = the FullComparator (SIZE = its dim), SIZE must be a
+ * multiple of centroid_size (CENTROID_SIZE), number_of_centroids <= 65535 */
+phnsw_status phnsw_pq_build(phnsw_store *full, uint64_t number_of_centroids, uint64_t centroid_size,
+                            phnsw_metric centroid_metric, phnsw_metric quantized_metric,
+                            const phnsw_pq_build_params *bp, uint64_t seed,
+                            phnsw_progress_fn progress, void *user, phnsw_pq **out);
+void phnsw_pq_destroy(phnsw_pq *pq);
+uint64_t phnsw_pq_centroid_count(const phnsw_pq *pq);
+uint64_t phnsw_pq_quantized_size(const phnsw_pq *pq);   /* QUANTIZED_SIZE */
+uint64_t phnsw_pq_centroid_size(const phnsw_pq *pq);    /* CENTROID_SIZE */
+/* borrowed handles (owned by the pq object): quantizer().hnsw, centroid_comparator(), the code
+ * graph (improve_index / stochastic_recall / threshold_nn forward to it, pq.rs:366-413) */
+phnsw_index *phnsw_pq_centroid_index(const phnsw_pq *pq);
+phnsw_store *phnsw_pq_centroid_store(const phnsw_pq *pq);
+phnsw_index *phnsw_pq_index(const phnsw_pq *pq);
+/* all stored codes, n x QUANTIZED_SIZE u16 (quantized_comparator().lookup) */
+phnsw_status phnsw_pq_codes(const phnsw_pq *pq, uint16_t *codes_out);
+/* Quantizer::quantize / reconstruct (pq.rs:19-22, 61-82) for n vectors */
+phnsw_status phnsw_pq_quantize(const phnsw_pq *pq, const float *vecs, uint64_t n, uint16_t *codes_out);
+phnsw_status phnsw_pq_reconstruct(const phnsw_pq *pq, const uint16_t *codes, uint64_t n,
+                                  float *vecs_out);
+/* QuantizedHnsw::search (pq.rs:346-364) for a batch: up to min(number_of_candidates, max_out)
+ * re-ranked pairs per query, ascending (d, id) */
+phnsw_status phnsw_pq_search_batch(const phnsw_pq *pq, const float *queries,
+                                   const uint64_t *stored_ids, uint64_t nq,
+                                   const phnsw_search_params *sp, uint64_t max_out,
+                                   uint64_t *out_ids, float *out_dists, uint32_t *out_counts);
+
 /* cross-shard top-k merge by (distance, id): `shards` lists of nq x k pairs laid out
  * shard-major (the all-gather receive buffer); no reference analogue (single index) */
 phnsw_status phnsw_merge_topk_device(const uint64_t *ids, const float *dists, uint64_t shards,

@@ -51,6 +51,11 @@ class BuildParams(C.Structure):
                 ("initial_partition_search", SearchParams)]
 
 
+class PqBuildParams(C.Structure):
+    _fields_ = [("centroids", BuildParams), ("hnsw", BuildParams),
+                ("quantized_search", SearchParams)]
+
+
 _lib = None
 
 
@@ -114,6 +119,29 @@ def lib():
     L.orc_num_threads.restype = C.c_int
     L.orc_default_search_params.argtypes = [C.POINTER(SearchParams)]
     L.orc_default_build_params.argtypes = [C.POINTER(BuildParams)]
+    u16p = C.POINTER(C.c_uint16)
+    L.orc_default_pq_build_params.argtypes = [C.POINTER(PqBuildParams)]
+    L.orc_pq_build.restype = C.c_void_p
+    L.orc_pq_build.argtypes = [C.c_int, C.c_uint64, C.c_uint64, f32p, C.c_uint64, C.c_uint64,
+                               C.c_int, C.c_int, C.POINTER(PqBuildParams), C.c_uint64, C.c_int]
+    L.orc_pq_free.argtypes = [C.c_void_p]
+    L.orc_pq_centroid_count.restype = C.c_uint64
+    L.orc_pq_centroid_count.argtypes = [C.c_void_p]
+    L.orc_pq_centroids.restype = f32p
+    L.orc_pq_centroids.argtypes = [C.c_void_p]
+    L.orc_pq_codes.restype = u16p
+    L.orc_pq_codes.argtypes = [C.c_void_p]
+    L.orc_pq_centroid_hnsw.restype = C.c_void_p
+    L.orc_pq_centroid_hnsw.argtypes = [C.c_void_p]
+    L.orc_pq_hnsw.restype = C.c_void_p
+    L.orc_pq_hnsw.argtypes = [C.c_void_p]
+    L.orc_pq_quantize.restype = C.c_int
+    L.orc_pq_quantize.argtypes = [C.c_void_p, f32p, C.c_uint64, u16p, C.c_int]
+    L.orc_pq_reconstruct.restype = C.c_int
+    L.orc_pq_reconstruct.argtypes = [C.c_void_p, u16p, C.c_uint64, f32p]
+    L.orc_pq_search.restype = C.c_int
+    L.orc_pq_search.argtypes = [C.c_void_p, f32p, u64p, C.c_uint64, C.POINTER(SearchParams),
+                                C.c_uint64, u64p, f32p, u32p, C.c_int]
     _lib = L
     return L
 
@@ -353,3 +381,83 @@ class Hnsw:
     def stochastic_recall(self, op=None, nthreads=0):
         op = op or self.build_parameters.optimization
         return float(lib().orc_stochastic_recall(self._h, C.byref(op), nthreads))
+
+
+def default_pq_build_params():
+    bp = PqBuildParams()
+    lib().orc_default_pq_build_params(C.byref(bp))
+    return bp
+
+
+class _BorrowedHnsw(Hnsw):
+    def __del__(self):
+        self._h = None
+
+
+class QuantizedHnsw:
+    """Oracle QuantizedHnsw (src/pq.rs:120-477)."""
+
+    def __init__(self, rows, number_of_centroids, centroid_size, full_metric, centroid_metric,
+                 quantized_metric, bp=None, seed=1, nthreads=0):
+        self.rows = np.ascontiguousarray(rows, dtype=np.float32)
+        bp = bp or default_pq_build_params()
+        n, size = self.rows.shape
+        self.size, self.cs, self.Q, self.n = size, centroid_size, size // centroid_size, n
+        self._h = lib().orc_pq_build(full_metric, size, n, _p(self.rows, C.c_float),
+                                     number_of_centroids, centroid_size, centroid_metric,
+                                     quantized_metric, C.byref(bp), seed, nthreads)
+        if not self._h:
+            raise ValueError("orc_pq_build failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_pq_free(self._h)
+            self._h = None
+
+    def centroids(self):
+        k = int(lib().orc_pq_centroid_count(self._h))
+        return np.ctypeslib.as_array(lib().orc_pq_centroids(self._h), shape=(k, self.cs)).copy()
+
+    def codes(self):
+        return np.ctypeslib.as_array(lib().orc_pq_codes(self._h), shape=(self.n, self.Q)).copy()
+
+    def hnsw(self):
+        return _BorrowedHnsw(lib().orc_pq_hnsw(self._h))
+
+    def centroid_hnsw(self):
+        return _BorrowedHnsw(lib().orc_pq_centroid_hnsw(self._h))
+
+    def quantize(self, vecs, nthreads=0):
+        vecs = np.ascontiguousarray(np.atleast_2d(vecs), dtype=np.float32)
+        out = np.empty((vecs.shape[0], self.Q), dtype=np.uint16)
+        rc = lib().orc_pq_quantize(self._h, _p(vecs, C.c_float), vecs.shape[0],
+                                   _p(out, C.c_uint16), nthreads)
+        if rc:
+            raise RuntimeError("quantize failed")
+        return out
+
+    def reconstruct(self, codes):
+        codes = np.ascontiguousarray(np.atleast_2d(codes), dtype=np.uint16)
+        out = np.empty((codes.shape[0], self.size), dtype=np.float32)
+        if lib().orc_pq_reconstruct(self._h, _p(codes, C.c_uint16), codes.shape[0],
+                                    _p(out, C.c_float)):
+            raise RuntimeError("reconstruct failed")
+        return out
+
+    def search(self, queries=None, stored_ids=None, sp=None, max_out=None, nthreads=0):
+        sp = sp or default_search_params()
+        if queries is not None:
+            queries = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+            nq, qp, sp_ = queries.shape[0], _p(queries, C.c_float), None
+        else:
+            stored_ids = np.ascontiguousarray(stored_ids, dtype=np.uint64)
+            nq, qp, sp_ = stored_ids.size, None, _p(stored_ids, C.c_uint64)
+        max_out = max_out or int(sp.number_of_candidates)
+        ids = np.empty((nq, max_out), dtype=np.uint64)
+        ds = np.empty((nq, max_out), dtype=np.float32)
+        cnt = np.empty(nq, dtype=np.uint32)
+        rc = lib().orc_pq_search(self._h, qp, sp_, nq, C.byref(sp), max_out, _p(ids, C.c_uint64),
+                                 _p(ds, C.c_float), _p(cnt, C.c_uint32), nthreads)
+        if rc:
+            raise RuntimeError("pq search failed")
+        return ids, ds, cnt

@@ -1562,3 +1562,219 @@ orc_hnsw *orc_deserialize(const char *dir, int *err) {
   if (err) *err = 0;
   return h;
 }
+
+/* ------------------------------------------------ PQ (src/pq.rs) */
+
+struct orc_pq {
+  uint64_t size, centroid_size, quantized_size; /* SIZE, CENTROID_SIZE, QUANTIZED_SIZE */
+  uint64_t n;
+  int full_metric, centroid_metric, quantized_metric;
+  const float *full_rows; /* borrowed */
+  uint64_t n_centroids;
+  float *centroids;       /* n_centroids x centroid_size */
+  orc_hnsw *centroid_hnsw;
+  uint16_t *codes;        /* n x quantized_size */
+  float *recon;           /* n x size: what QuantizedComparator::compare_raw reconstructs */
+  orc_hnsw *hnsw;         /* graph over the codes */
+  orc_pq_build_params bp;
+};
+
+void orc_default_pq_build_params(orc_pq_build_params *bp) { /* parameters.rs:66-71 (Default) */
+  orc_default_build_params(&bp->centroids);
+  orc_default_build_params(&bp->hnsw);
+  orc_default_search_params(&bp->quantized_search);
+}
+
+static uint64_t g_sub_dim; /* comparator context for qsort */
+static int subvec_cmp(const void *a, const void *b) { /* Vec<OrderedFloat> lexicographic */
+  const float *x = (const float *)a, *y = (const float *)b;
+  for (uint64_t i = 0; i < g_sub_dim; i++) {
+    if (x[i] < y[i]) return -1;
+    if (x[i] > y[i]) return 1;
+  }
+  return 0;
+}
+
+/* random_centroids (pq.rs:261-285): selection(K) = the first K vectors (the crate's test
+ * VectorSelector, pq.rs:651-660) -> every sub-vector -> sort, dedup, shuffle, truncate(K).
+ * shuffle: our generator (thread_rng in the crate, parity unpinned). */
+static uint64_t pq_random_centroids(const float *rows, uint64_t n, uint64_t size, uint64_t cs,
+                                    uint64_t K, uint64_t seed, float **out) {
+  uint64_t Q = size / cs;
+  uint64_t sel = K < n ? K : n;
+  uint64_t cnt = sel * Q;
+  float *c = (float *)malloc((cnt ? cnt : 1) * cs * sizeof(float));
+  for (uint64_t i = 0; i < sel; i++)
+    for (uint64_t q = 0; q < Q; q++)
+      memcpy(c + (i * Q + q) * cs, rows + i * size + q * cs, cs * sizeof(float));
+  g_sub_dim = cs;
+  qsort(c, cnt, cs * sizeof(float), subvec_cmp);
+  uint64_t w = 0;
+  for (uint64_t i = 0; i < cnt; i++) { /* dedup(): consecutive equal arrays (PartialEq on f32) */
+    int same = w > 0;
+    if (same)
+      for (uint64_t t = 0; t < cs; t++)
+        if (!(c[(w - 1) * cs + t] == c[i * cs + t])) {
+          same = 0;
+          break;
+        }
+    if (same) continue;
+    if (w != i) memcpy(c + w * cs, c + i * cs, cs * sizeof(float));
+    w++;
+  }
+  rng_t rng;
+  rng.s = seed;
+  float *tmp = (float *)malloc(cs * sizeof(float));
+  for (uint64_t i = w; i > 1; i--) {
+    uint64_t j = rng_below(&rng, i);
+    memcpy(tmp, c + (i - 1) * cs, cs * sizeof(float));
+    memcpy(c + (i - 1) * cs, c + j * cs, cs * sizeof(float));
+    memcpy(c + j * cs, tmp, cs * sizeof(float));
+  }
+  free(tmp);
+  if (w > K) w = K;
+  *out = c;
+  return w;
+}
+
+/* HnswQuantizer::quantize (pq.rs:61-71) for n vectors: one centroid-index search per sub-vector,
+ * code = id of the first result */
+int orc_pq_quantize(const orc_pq *pq, const float *vecs, uint64_t n, uint16_t *codes, int nthreads) {
+  uint64_t Q = pq->quantized_size, nq = n * Q;
+  uint64_t *ids = (uint64_t *)malloc((nq ? nq : 1) * sizeof(uint64_t));
+  float *ds = (float *)malloc((nq ? nq : 1) * sizeof(float));
+  uint32_t *cnt = (uint32_t *)malloc((nq ? nq : 1) * sizeof(uint32_t));
+  /* the sub-vectors of consecutive rows are consecutive centroid_size-float queries */
+  int rc = orc_search_batch(pq->centroid_hnsw, vecs, NULL, nq, &pq->bp.quantized_search, 0, NULL,
+                            1, ids, ds, cnt, NULL, NULL, NULL, nthreads);
+  for (uint64_t i = 0; i < nq && rc == 0; i++) {
+    if (cnt[i] == 0) rc = -1; /* distances[0] would panic */
+    else codes[i] = (uint16_t)ids[i];
+  }
+  free(ids);
+  free(ds);
+  free(cnt);
+  return rc;
+}
+
+/* Quantizer::reconstruct (pq.rs:73-82) */
+int orc_pq_reconstruct(const orc_pq *pq, const uint16_t *codes, uint64_t n, float *out) {
+  uint64_t Q = pq->quantized_size, cs = pq->centroid_size;
+  for (uint64_t i = 0; i < n; i++)
+    for (uint64_t q = 0; q < Q; q++) {
+      uint64_t c = codes[i * Q + q];
+      if (c >= pq->n_centroids) return -1;
+      memcpy(out + i * pq->size + q * cs, pq->centroids + c * cs, cs * sizeof(float));
+    }
+  return 0;
+}
+
+/* QuantizedHnsw::new (pq.rs:287-344) */
+orc_pq *orc_pq_build(int full_metric, uint64_t size, uint64_t n, const float *rows,
+                     uint64_t number_of_centroids, uint64_t centroid_size, int centroid_metric,
+                     int quantized_metric, const orc_pq_build_params *bp, uint64_t seed,
+                     int nthreads) {
+  if (centroid_size == 0 || size % centroid_size || n == 0 || number_of_centroids == 0 ||
+      number_of_centroids > 65535)
+    return NULL;
+  orc_pq *pq = (orc_pq *)calloc(1, sizeof(orc_pq));
+  pq->size = size;
+  pq->centroid_size = centroid_size;
+  pq->quantized_size = size / centroid_size;
+  pq->n = n;
+  pq->full_metric = full_metric;
+  pq->centroid_metric = centroid_metric;
+  pq->quantized_metric = quantized_metric;
+  pq->full_rows = rows;
+  pq->bp = *bp;
+  pq->n_centroids = pq_random_centroids(rows, n, size, centroid_size, number_of_centroids, seed,
+                                        &pq->centroids);
+  uint64_t *vids = (uint64_t *)malloc(pq->n_centroids * sizeof(uint64_t));
+  for (uint64_t i = 0; i < pq->n_centroids; i++) vids[i] = i;
+  /* Hnsw::generate (improves after every layer) + one more improve_index (pq.rs:307-312) */
+  pq->centroid_hnsw = orc_generate(centroid_metric, centroid_size, pq->n_centroids, pq->centroids,
+                                   vids, pq->n_centroids, &bp->centroids, seed + 1, 1, nthreads);
+  orc_improve_index(pq->centroid_hnsw, &bp->centroids, nthreads);
+  free(vids);
+  pq->codes = (uint16_t *)malloc(n * pq->quantized_size * sizeof(uint16_t));
+  if (orc_pq_quantize(pq, rows, n, pq->codes, nthreads)) {
+    orc_pq_free(pq);
+    return NULL;
+  }
+  pq->recon = (float *)malloc(n * size * sizeof(float));
+  orc_pq_reconstruct(pq, pq->codes, n, pq->recon);
+  vids = (uint64_t *)malloc(n * sizeof(uint64_t));
+  for (uint64_t i = 0; i < n; i++) vids[i] = i;
+  /* graph over the codes; compare_raw of the quantized comparator = metric of the
+   * reconstructions (the crate's test comparators, pq.rs:585-599) */
+  pq->hnsw = orc_generate(quantized_metric, size, n, pq->recon, vids, n, &bp->hnsw, seed + 2, 1,
+                          nthreads);
+  free(vids);
+  return pq;
+}
+
+void orc_pq_free(orc_pq *pq) {
+  if (!pq) return;
+  if (pq->centroid_hnsw) orc_hnsw_free(pq->centroid_hnsw);
+  if (pq->hnsw) orc_hnsw_free(pq->hnsw);
+  free(pq->centroids);
+  free(pq->codes);
+  free(pq->recon);
+  free(pq);
+}
+
+uint64_t orc_pq_centroid_count(const orc_pq *pq) { return pq->n_centroids; }
+const float *orc_pq_centroids(const orc_pq *pq) { return pq->centroids; }
+const uint16_t *orc_pq_codes(const orc_pq *pq) { return pq->codes; }
+orc_hnsw *orc_pq_centroid_hnsw(const orc_pq *pq) { return pq->centroid_hnsw; }
+orc_hnsw *orc_pq_hnsw(const orc_pq *pq) { return pq->hnsw; }
+
+/* QuantizedHnsw::search (pq.rs:346-364): quantize the query, search the code graph with the
+ * reconstruction as an Unstored vector, re-rank every hit with the full comparator, sort (d, id) */
+int orc_pq_search(const orc_pq *pq, const float *queries, const uint64_t *stored_ids, uint64_t nq,
+                  const orc_search_params *sp, uint64_t max_out, uint64_t *out_ids,
+                  float *out_dists, uint32_t *out_counts, int nthreads) {
+  uint64_t ef = sp->number_of_candidates;
+  float *raw = (float *)malloc((nq ? nq : 1) * pq->size * sizeof(float));
+  for (uint64_t i = 0; i < nq; i++)
+    memcpy(raw + i * pq->size,
+           queries ? queries + i * pq->size : pq->full_rows + stored_ids[i] * pq->size,
+           pq->size * sizeof(float));
+  uint16_t *codes = (uint16_t *)malloc((nq ? nq : 1) * pq->quantized_size * sizeof(uint16_t));
+  float *recon = (float *)malloc((nq ? nq : 1) * pq->size * sizeof(float));
+  uint64_t *ids = (uint64_t *)malloc((nq * ef ? nq * ef : 1) * sizeof(uint64_t));
+  float *ds = (float *)malloc((nq * ef ? nq * ef : 1) * sizeof(float));
+  uint32_t *cnt = (uint32_t *)malloc((nq ? nq : 1) * sizeof(uint32_t));
+  int rc = orc_pq_quantize(pq, raw, nq, codes, nthreads);
+  if (!rc) rc = orc_pq_reconstruct(pq, codes, nq, recon);
+  if (!rc)
+    rc = orc_search_batch(pq->hnsw, recon, NULL, nq, sp, 0, NULL, ef, ids, ds, cnt, NULL, NULL,
+                          NULL, nthreads);
+  if (!rc) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < (int64_t)nq; i++) {
+      pair_t *r = (pair_t *)malloc((cnt[i] ? cnt[i] : 1) * sizeof(pair_t));
+      for (uint32_t k = 0; k < cnt[i]; k++) {
+        r[k].id = ids[(uint64_t)i * ef + k];
+        /* full_comparator.compare_vec(Stored(id), v) (pq.rs:356-358) */
+        r[k].d = orc_distance(pq->full_metric, pq->size, pq->full_rows + r[k].id * pq->size,
+                              raw + (uint64_t)i * pq->size);
+      }
+      qsort(r, cnt[i], sizeof(pair_t), pair_cmp);
+      uint64_t c = cnt[i] < max_out ? cnt[i] : max_out;
+      for (uint64_t k = 0; k < max_out; k++) {
+        out_ids[(uint64_t)i * max_out + k] = k < c ? r[k].id : ORC_EMPTY;
+        out_dists[(uint64_t)i * max_out + k] = k < c ? r[k].d : FLT_MAX;
+      }
+      if (out_counts) out_counts[i] = (uint32_t)c;
+      free(r);
+    }
+  }
+  free(raw);
+  free(codes);
+  free(recon);
+  free(ids);
+  free(ds);
+  free(cnt);
+  return rc;
+}

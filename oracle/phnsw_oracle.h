@@ -163,6 +163,33 @@ float orc_stochastic_recall(const orc_hnsw *h, const orc_optimization_params *op
 int orc_serialize(const orc_hnsw *h, const char *dir);
 orc_hnsw *orc_deserialize(const char *dir, int *err);
 
+/* ---- PQ (src/pq.rs): QuantizedHnsw::{new, search}, Quantizer::{quantize, reconstruct} ---- */
+typedef struct {
+  orc_build_params centroids;
+  orc_build_params hnsw;
+  orc_search_params quantized_search;
+} orc_pq_build_params; /* parameters.rs:66-71 */
+typedef struct orc_pq orc_pq;
+void orc_default_pq_build_params(orc_pq_build_params *bp);
+/* rows borrowed; quantized_metric = what the quantized comparator applies to two reconstructions
+ * (the crate's test comparators: pq.rs:585-599); centroid assignment is the crate's own
+ * approximate one: a search on the centroid HNSW (pq.rs:61-71) */
+orc_pq *orc_pq_build(int full_metric, uint64_t size, uint64_t n, const float *rows,
+                     uint64_t number_of_centroids, uint64_t centroid_size, int centroid_metric,
+                     int quantized_metric, const orc_pq_build_params *bp, uint64_t seed,
+                     int nthreads);
+void orc_pq_free(orc_pq *pq);
+uint64_t orc_pq_centroid_count(const orc_pq *pq);
+const float *orc_pq_centroids(const orc_pq *pq);
+const uint16_t *orc_pq_codes(const orc_pq *pq);
+orc_hnsw *orc_pq_centroid_hnsw(const orc_pq *pq);
+orc_hnsw *orc_pq_hnsw(const orc_pq *pq);
+int orc_pq_quantize(const orc_pq *pq, const float *vecs, uint64_t n, uint16_t *codes, int nthreads);
+int orc_pq_reconstruct(const orc_pq *pq, const uint16_t *codes, uint64_t n, float *out);
+int orc_pq_search(const orc_pq *pq, const float *queries, const uint64_t *stored_ids, uint64_t nq,
+                  const orc_search_params *sp, uint64_t max_out, uint64_t *out_ids,
+                  float *out_dists, uint32_t *out_counts, int nthreads);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -46,6 +46,11 @@ class LayerDesc(C.Structure):
                 ("neighbors", C.POINTER(C.c_uint64))]
 
 
+class PqBuildParams(C.Structure):  # src/parameters.rs:66-71
+    _fields_ = [("centroids", BuildParams), ("hnsw", BuildParams),
+                ("quantized_search", SearchParams)]
+
+
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_double)
 
 u64p, f32p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p
@@ -98,6 +103,22 @@ SIGNATURES = {
     "phnsw_stochastic_recall": (C.c_int, [vp, C.POINTER(OptimizationParams), f32p]),
     "phnsw_bruteforce_knn": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
     "phnsw_bruteforce_knn_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
+    "phnsw_default_pq_build_params": (None, [C.POINTER(PqBuildParams)]),
+    "phnsw_pq_build": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                 C.POINTER(PqBuildParams), C.c_uint64, PROGRESS_FN, vp,
+                                 C.POINTER(vp)]),
+    "phnsw_pq_destroy": (None, [vp]),
+    "phnsw_pq_centroid_count": (C.c_uint64, [vp]),
+    "phnsw_pq_quantized_size": (C.c_uint64, [vp]),
+    "phnsw_pq_centroid_size": (C.c_uint64, [vp]),
+    "phnsw_pq_centroid_index": (vp, [vp]),
+    "phnsw_pq_centroid_store": (vp, [vp]),
+    "phnsw_pq_index": (vp, [vp]),
+    "phnsw_pq_codes": (C.c_int, [vp, vp]),
+    "phnsw_pq_quantize": (C.c_int, [vp, vp, C.c_uint64, vp]),
+    "phnsw_pq_reconstruct": (C.c_int, [vp, vp, C.c_uint64, vp]),
+    "phnsw_pq_search_batch": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams), C.c_uint64,
+                                        vp, vp, vp]),
     "phnsw_merge_topk_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
 }
 

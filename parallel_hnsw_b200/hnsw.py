@@ -340,6 +340,113 @@ class Hnsw:
         return float(r.value)
 
 
+def PqBuildParameters():
+    """src/parameters.rs:66-71 Default."""
+    bp = N.PqBuildParams()
+    N.lib().phnsw_default_pq_build_params(C.byref(bp))
+    return bp
+
+
+class _Borrowed(Hnsw):
+    """An index owned by another object (never destroyed from here)."""
+
+    def close(self):
+        self._h = None
+
+
+class QuantizedHnsw:
+    """QuantizedHnsw<SIZE, CENTROID_SIZE, QUANTIZED_SIZE, ..> (src/pq.rs:120-477) on the device."""
+
+    def __init__(self, handle, full_comparator):
+        self._h = handle
+        self.comparator = full_comparator
+
+    @classmethod
+    def new(cls, number_of_centroids, full_comparator, centroid_size, bp=None, progress=None,
+            centroid_metric=L2_SQRT, quantized_metric=COS_CLAMP, seed=1):
+        """QuantizedHnsw::new(number_of_centroids, comparator, bp, progress) (pq.rs:287-344)."""
+        bp = bp or PqBuildParameters()
+        h = C.c_void_p()
+        N.check(N.lib().phnsw_pq_build(full_comparator._h, number_of_centroids, centroid_size,
+                                       centroid_metric, quantized_metric, C.byref(bp), seed,
+                                       _progress_cb(progress), None, C.byref(h)))
+        return cls(h, full_comparator)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().phnsw_pq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def vector_count(self):
+        return len(self.comparator)
+
+    @property
+    def quantized_size(self):
+        return int(N.lib().phnsw_pq_quantized_size(self._h))
+
+    @property
+    def centroid_size(self):
+        return int(N.lib().phnsw_pq_centroid_size(self._h))
+
+    def centroids(self):
+        """centroid_comparator() rows (K x CENTROID_SIZE)."""
+        L = N.lib()
+        k = int(L.phnsw_pq_centroid_count(self._h))
+        out = np.empty((k, self.centroid_size), dtype=np.float32)
+        ids = np.arange(k, dtype=np.uint64)
+        N.check(L.phnsw_store_get_rows(L.phnsw_pq_centroid_store(self._h), _ptr(ids), k, _ptr(out)))
+        return out
+
+    def codes(self):
+        out = np.empty((self.vector_count(), self.quantized_size), dtype=np.uint16)
+        N.check(N.lib().phnsw_pq_codes(self._h, _ptr(out)))
+        return out
+
+    def hnsw(self):
+        """The graph over the codes (borrowed): improve_index / stochastic_recall / layers."""
+        return _Borrowed(C.c_void_p(N.lib().phnsw_pq_index(self._h)), self)
+
+    def centroid_hnsw(self):
+        return _Borrowed(C.c_void_p(N.lib().phnsw_pq_centroid_index(self._h)), self)
+
+    def quantize(self, vecs):
+        """Quantizer::quantize (pq.rs:61-71), batched."""
+        vecs = _host(np.atleast_2d(vecs), np.float32)
+        out = np.empty((vecs.shape[0], self.quantized_size), dtype=np.uint16)
+        N.check(N.lib().phnsw_pq_quantize(self._h, _ptr(vecs), vecs.shape[0], _ptr(out)))
+        return out
+
+    def reconstruct(self, codes):
+        """Quantizer::reconstruct (pq.rs:73-82), batched."""
+        codes = _host(np.atleast_2d(codes), np.uint16)
+        out = np.empty((codes.shape[0], self.quantized_size * self.centroid_size), dtype=np.float32)
+        N.check(N.lib().phnsw_pq_reconstruct(self._h, _ptr(codes), codes.shape[0], _ptr(out)))
+        return out
+
+    def search(self, queries=None, sp=None, stored_ids=None, max_out=None):
+        """QuantizedHnsw::search (pq.rs:346-364), batched."""
+        sp = sp or SearchParameters()
+        if queries is not None:
+            queries = _host(np.atleast_2d(queries), np.float32)
+            nq = queries.shape[0]
+        else:
+            stored_ids = _host(np.atleast_1d(stored_ids), np.uint64)
+            nq = stored_ids.size
+        max_out = int(max_out or sp.number_of_candidates)
+        ids = np.empty((nq, max_out), dtype=np.uint64)
+        ds = np.empty((nq, max_out), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        N.check(N.lib().phnsw_pq_search_batch(self._h, _ptr(queries), _ptr(stored_ids), nq,
+                                              C.byref(sp), max_out, _ptr(ids), _ptr(ds), _ptr(cnt)))
+        return ids, ds, cnt
+
+
 def _progress_cb(progress):
     """ProgressMonitor (src/progress.rs:12-29): callable(phase, fraction) -> truthy = Interrupt."""
     if progress is None:

@@ -1,0 +1,114 @@
+"""GPU parity for the product-quantised index (src/pq.rs): QuantizedHnsw::{new, search},
+Quantizer::{quantize, reconstruct} against the CPU oracle's restatement.
+
+Every stage of the crate's pipeline is deterministic given the seed (our generator replaces
+thread_rng, parity unpinned), so centroids, codes, both graphs and the re-ranked results are
+expected to be identical.  Distances are compared by value: the crate's clamp keeps -0.0
+(pq.rs:481-487) where the device returns +0.0 (equal under OrderedFloat).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import random_normed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ph():
+    import parallel_hnsw_b200 as p
+    if p.device_count() == 0:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return p
+
+
+def _same_graph(g, o):
+    gl, ol = g.layers(), o.layers()
+    assert len(gl) == len(ol)
+    for (gn, gnb, gm), (on, onb, om) in zip(gl, ol):
+        assert gm == om and np.array_equal(gn, on) and np.array_equal(gnb, onb)
+
+
+@pytest.fixture(scope="module")
+def small(ph, oracle):
+    """The shape of the crate's test_small_pq (pq.rs:864-918): 16-d vectors, 4 x 4-d codes,
+    100 centroids; centroid metric without a square root so that every stage is exact."""
+    rows = random_normed(4000, 16, 5)
+    comp = ph.BigComparator(rows, ph.COS_CLAMP)
+    g = ph.QuantizedHnsw.new(100, comp, 4, centroid_metric=ph.ONE_MINUS_DOT,
+                             quantized_metric=ph.COS_CLAMP, seed=3)
+    o = oracle.QuantizedHnsw(rows, 100, 4, oracle.COS_CLAMP, oracle.ONE_MINUS_DOT,
+                             oracle.COS_CLAMP, seed=3)
+    return rows, g, o
+
+
+def test_pq_build_matches_oracle(ph, oracle, small):
+    rows, g, o = small
+    assert g.quantized_size == 4 and g.centroid_size == 4
+    assert np.array_equal(g.centroids(), o.centroids())          # random_centroids
+    _same_graph(g.centroid_hnsw(), o.centroid_hnsw())            # centroid HNSW + improve_index
+    assert np.array_equal(g.codes(), o.codes())                  # HnswQuantizer::quantize
+    _same_graph(g.hnsw(), o.hnsw())                              # graph over the codes
+    assert g.hnsw().stochastic_recall() == o.hnsw().stochastic_recall()
+
+
+def test_pq_quantize_reconstruct(ph, oracle, small):
+    rows, g, o = small
+    v = random_normed(500, 16, 99)
+    cg, co = g.quantize(v), o.quantize(v)
+    assert np.array_equal(cg, co)
+    rg, ro = g.reconstruct(cg), o.reconstruct(co)
+    assert np.array_equal(rg, ro)
+    # a reconstruction is a concatenation of centroids (pq.rs:73-82)
+    cents = g.centroids()
+    assert np.array_equal(rg[7], cents[cg[7]].reshape(-1))
+    with pytest.raises(ph.PhnswError):
+        g.reconstruct(np.full((1, 4), 60000, np.uint16))
+
+
+def test_pq_search_matches_oracle(ph, oracle, small):
+    rows, g, o = small
+    q = random_normed(300, 16, 123)
+    for ef, max_out in ((300, 300), (50, 10)):
+        gi, gd, gc = g.search(q, ph.SearchParameters(ef, ef, 2), max_out=max_out)
+        oi, od, oc = o.search(queries=q, sp=oracle.search_params(ef, ef, 2), max_out=max_out)
+        assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+        assert np.array_equal(gd, od)  # by value (-0.0 == +0.0)
+        assert np.all(np.diff(gd[:, :gc.min()], axis=1) >= 0)  # re-ranked order
+    ids = np.arange(0, 4000, 13, dtype=np.uint64)
+    gi, gd, gc = g.search(stored_ids=ids, max_out=5)
+    oi, od, oc = o.search(stored_ids=ids, max_out=5)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    # the crate's own check (pq.rs:897-913): a stored vector's first match is itself
+    assert (gi[:, 0] == ids).mean() >= 0.9
+
+
+def test_pq_reference_shape_1536(ph, oracle):
+    """SIZE 1536, CENTROID_SIZE 16, QUANTIZED_SIZE 96, euclidean centroids, cosine over the
+    reconstructions (pq.rs:538-599, 840-862), scaled down in count."""
+    rows = random_normed(700, 1536, 42)
+    comp = ph.BigComparator(rows, ph.COS_CLAMP)
+    g = ph.QuantizedHnsw.new(400, comp, 16, centroid_metric=ph.L2_SQRT,
+                             quantized_metric=ph.COS_CLAMP, seed=9)
+    o = oracle.QuantizedHnsw(rows, 400, 16, oracle.COS_CLAMP, oracle.L2_SQRT, oracle.COS_CLAMP,
+                             seed=9)
+    assert g.quantized_size == 96
+    assert np.array_equal(g.centroids(), o.centroids())
+    same = (g.codes() == o.codes()).mean()
+    assert same >= 0.999  # sqrt vs powf(0.5) on the euclidean centroid distance (near ties)
+    q = rows[:50]
+    gi, gd, gc = g.search(q, max_out=10)
+    assert (gi[:, 0] == np.arange(50)).mean() >= 0.9
+    if same == 1.0:
+        _same_graph(g.hnsw(), o.hnsw())
+        oi, od, oc = o.search(queries=q, max_out=10)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+def test_pq_bad_arguments(ph):
+    rows = random_normed(100, 16, 1)
+    comp = ph.BigComparator(rows, ph.COS_CLAMP)
+    with pytest.raises(ph.PhnswError):
+        ph.QuantizedHnsw.new(70000, comp, 4)   # codes are u16
+    with pytest.raises(ph.PhnswError):
+        ph.QuantizedHnsw.new(10, comp, 5)      # SIZE not a multiple of CENTROID_SIZE
