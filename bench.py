@@ -107,6 +107,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask the OS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def recall_at_k(ids, gt, k):
     hit = 0
     for a, b in zip(ids, gt):
@@ -129,7 +137,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    cores = orc.num_threads()
+    cores = host_cores()
     k = 10
     sample_q = min(args.nq, args.ref_queries)
     rows = sift_like(args.n, args.dim, 1234).numpy()
@@ -156,10 +164,10 @@ def run_reference(args):
         oh = orc.Hnsw.from_layers(orc.L2_SQRT, rows, layers)
     sp = orc.search_params(args.ef, args.ef, 2)
     for _ in range(args.warmup):
-        oh.search(queries=queries[:max(64, sample_q // 8)], sp=sp, max_out=k)
+        oh.search(queries=queries[:max(64, sample_q // 8)], sp=sp, max_out=k, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oh.search(queries=queries, sp=sp, max_out=k)
+        oh.search(queries=queries, sp=sp, max_out=k, nthreads=cores)
     dt = time.perf_counter() - t0
     qps = sample_q * args.steps / dt
     sample = "%d of %d queries per step, %s, %d OpenMP threads" % (sample_q, args.nq, graph, cores)
@@ -208,6 +216,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     k = 10
     stream = torch.cuda.current_stream().cuda_stream
@@ -310,10 +320,11 @@ def main():
     cq = min(args.nq, args.cpu_queries)
     oh = orc.Hnsw.from_layers(orc.L2_SQRT, rows_h.numpy(), gh.layers())
     osp = orc.search_params(args.ef, args.ef, 2)
-    oh.search(queries=queries_h.numpy()[:64], sp=osp, max_out=k)
+    cores = host_cores()
+    oh.search(queries=queries_h.numpy()[:64], sp=osp, max_out=k, nthreads=cores)
     t0 = time.perf_counter()
     o_ids, o_ds, o_cnt, o_nd, o_ne = oh.search(queries=queries_h.numpy()[:cq], sp=osp, max_out=k,
-                                               stats=True)
+                                               stats=True, nthreads=cores)
     cpu_dt = time.perf_counter() - t0
     g_ids = oi.cpu().numpy().astype(np.uint64)[:cq]
     ids_equal = float((g_ids == o_ids).all(1).mean())
@@ -363,7 +374,7 @@ def main():
                      "algorithmic_bytes_per_launch": abytes,
                      "n_dist_per_query": float(ndist.sum() / args.nq),
                      "n_exp_per_query": float(nexp.sum() / args.nq)},
-        "cpu_baseline": {"value": cq / cpu_dt, "unit": "queries/s", "cores": orc.num_threads(),
+        "cpu_baseline": {"value": cq / cpu_dt, "unit": "queries/s", "cores": cores,
                          "kind": "port",
                          "sample": "%d of %d queries on the same device-built graph" % (cq, args.nq)},
         "clocks": clocks,
@@ -401,13 +412,13 @@ def run_sharded(args, ph, dist, dev, rank, world, k, stream):
     mi = torch.empty((args.nq, k), dtype=torch.int64, device=dev)
     md = torch.empty((args.nq, k), dtype=torch.float32, device=dev)
 
+    from parallel_hnsw_b200.sharded import ShardedHnsw
+    sh = ShardedHnsw(gh, rank * args.n, rank, world)
+
     def step():
-        dist.broadcast(dq, src=0)
-        gh.search_device(dq, sp, oi, od, oc, stream=stream)
-        gid = torch.where(oi >= 0, oi + rank * args.n, oi)
-        dist.all_gather_into_tensor(gi, gid)
-        dist.all_gather_into_tensor(gd, od)
-        ph.merge_topk_device(gi, gd, world, args.nq, k, mi, md, stream)
+        r = sh.search(dq, sp, k, src=0, stream=stream)
+        mi.copy_(r[0])
+        md.copy_(r[1])
 
     for _ in range(args.warmup):
         step()

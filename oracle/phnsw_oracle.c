@@ -52,9 +52,9 @@ int orc_num_threads(void) {
 }
 
 static int pick_threads(int nthreads) {
-  int m = orc_num_threads();
-  if (nthreads <= 0 || nthreads > m) return m;
-  return nthreads;
+  /* an explicit request wins over OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */
+  if (nthreads > 0) return nthreads > 1024 ? 1024 : nthreads;
+  return orc_num_threads();
 }
 
 /* ------------------------------------------------- queue: priority_queue.rs */

@@ -256,3 +256,24 @@ def test_build_and_serialize_roundtrip(oracle, tmp_path):
     (d / "comparator").unlink()
     with pytest.raises(FileNotFoundError):   # SerializationError::IndexNotFound
         oracle.Hnsw.deserialize(str(d))
+
+
+# ---- src/pq.rs: the crate's PQ tests are print harnesses (pq.rs:840-918 end in panic!()); what
+# they print -- a stored vector's first match is itself -- is asserted here on the oracle ----
+def test_pq_small_shape(oracle):
+    rows = random_normed(1500, 16, 5)
+    pq = oracle.QuantizedHnsw(rows, 100, 4, oracle.COS_CLAMP, oracle.L2_SQRT, oracle.COS_CLAMP,
+                              seed=3)
+    cents = pq.centroids()
+    assert cents.shape == (100, 4)
+    # every centroid is a sub-vector of one of the first 100 rows (random_centroids, pq.rs:261-285)
+    subs = {tuple(x) for x in rows[:100].reshape(-1, 4)}
+    assert all(tuple(c) in subs for c in cents)
+    codes = pq.codes()
+    assert codes.shape == (1500, 4) and codes.max() < 100
+    rec = pq.reconstruct(codes[:5])
+    assert np.array_equal(rec[2], cents[codes[2]].reshape(-1))
+    assert np.array_equal(pq.quantize(rows[:5]), codes[:5])
+    ids, ds, cnt = pq.search(stored_ids=np.arange(0, 1500, 7, dtype=np.uint64), max_out=3)
+    assert (ids[:, 0] == np.arange(0, 1500, 7)).mean() >= 0.9
+    assert np.all(np.diff(ds[:, :cnt.min()], axis=1) >= 0)
