@@ -262,6 +262,26 @@ phnsw_status phnsw_pq_search_batch(const phnsw_pq *pq, const float *queries,
                                    const phnsw_search_params *sp, uint64_t max_out,
                                    uint64_t *out_ids, float *out_dists, uint32_t *out_counts);
 
+/* ---- ADC: asymmetric-distance search over u8 codes (BASELINE.json north_star kernel 2) ----
+ * No crate analogue on its live path (its search is symmetric + re-rank, pq.rs:346-364; its
+ * k-means, pq.rs:215-259, is dead code): definitions are the oracle's and reproduced bit for bit.
+ * A PQ8 store holds QUANTIZED_SIZE u8 codes per vector and ONE codebook shared by all sub-spaces
+ * (as the crate's quantizer does); an index over it (phnsw_index_from_layers with any graph over
+ * the same vector ids) is searched with per-query tables of partial distances in shared memory:
+ * distance(q, v) = finalize_metric(sum_s table[s][code_v[s]]).  Search-only. */
+/* codebook = random_centroids initialisation (pq.rs:261-285) + kmeans_iters Lloyd steps
+ * (exact nearest-centroid assignment, means summed in index order); K <= 256.  codebook_out:
+ * host, K x centroid_size floats; *k_out = centroids actually produced (<= K). */
+phnsw_status phnsw_pq8_train(const phnsw_store *full, uint64_t K, uint64_t centroid_size,
+                             uint64_t kmeans_iters, uint64_t seed, float *codebook_out,
+                             uint64_t *k_out);
+/* encode every vector of `full` (exact nearest centroid per sub-vector, L2) into a PQ8 store
+ * that keeps `full`'s metric and dimension */
+phnsw_status phnsw_pq8_store_create(const phnsw_store *full, const float *codebook, uint64_t K,
+                                    uint64_t centroid_size, phnsw_store **out);
+/* the codes, n x QUANTIZED_SIZE u8 */
+phnsw_status phnsw_pq8_store_codes(const phnsw_store *s, uint8_t *codes_out);
+
 /* cross-shard top-k merge by (distance, id): `shards` lists of nq x k pairs laid out
  * shard-major (the all-gather receive buffer); no reference analogue (single index) */
 phnsw_status phnsw_merge_topk_device(const uint64_t *ids, const float *dists, uint64_t shards,

@@ -139,6 +139,13 @@ def lib():
     L.orc_pq_quantize.argtypes = [C.c_void_p, f32p, C.c_uint64, u16p, C.c_int]
     L.orc_pq_reconstruct.restype = C.c_int
     L.orc_pq_reconstruct.argtypes = [C.c_void_p, u16p, C.c_uint64, f32p]
+    u8p = C.POINTER(C.c_uint8)
+    L.orc_pq8_encode.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint64, f32p, C.c_uint64, u8p,
+                                 C.c_int]
+    L.orc_pq8_train.restype = C.c_uint64
+    L.orc_pq8_train.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                C.c_uint64, f32p, C.c_int]
+    L.orc_hnsw_set_pq8.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint64, f32p]
     L.orc_pq_search.restype = C.c_int
     L.orc_pq_search.argtypes = [C.c_void_p, f32p, u64p, C.c_uint64, C.POINTER(SearchParams),
                                 C.c_uint64, u64p, f32p, u32p, C.c_int]
@@ -461,3 +468,31 @@ class QuantizedHnsw:
         if rc:
             raise RuntimeError("pq search failed")
         return ids, ds, cnt
+
+
+def pq8_train(rows, K, cs, iters=5, seed=1, nthreads=0):
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    out = np.zeros((K, cs), dtype=np.float32)
+    k = lib().orc_pq8_train(_p(rows, C.c_float), rows.shape[0], rows.shape[1], cs, K, iters, seed,
+                            _p(out, C.c_float), nthreads)
+    return out[:k].copy()
+
+
+def pq8_encode(rows, codebook, cs, nthreads=0):
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    codebook = np.ascontiguousarray(codebook, dtype=np.float32)
+    codes = np.empty((rows.shape[0], rows.shape[1] // cs), dtype=np.uint8)
+    lib().orc_pq8_encode(_p(rows, C.c_float), rows.shape[0], rows.shape[1], cs,
+                         _p(codebook, C.c_float), codebook.shape[0], _p(codes, C.c_uint8), nthreads)
+    return codes
+
+
+def attach_pq8(hnsw, codes, codebook, cs):
+    """ADC view: `hnsw` (built over any rows with the same ids) scores stored vectors through
+    the u8 codes from now on.  Keeps the arrays alive on the handle."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    codebook = np.ascontiguousarray(codebook, dtype=np.float32)
+    hnsw._pq8 = (codes, codebook)
+    lib().orc_hnsw_set_pq8(hnsw._h, _p(codes, C.c_uint8), codes.shape[1], codebook.shape[0], cs,
+                           _p(codebook, C.c_float))
+    return hnsw

@@ -271,6 +271,10 @@ struct orc_hnsw {
   uint64_t layer_count, layer_cap;
   layer_t *layers; /* top first */
   orc_build_params bp;
+  /* optional ADC view (no crate analogue, see orc_hnsw_set_pq8): u8 codes + shared codebook */
+  const uint8_t *pq_codes;
+  const float *pq_codebook;
+  uint64_t pq_Q, pq_K, pq_cs;
 };
 
 orc_hnsw *orc_hnsw_new(int metric, uint64_t dim, uint64_t n, const float *rows) {
@@ -346,10 +350,52 @@ static int64_t layer_get_node(const layer_t *l, uint64_t v) {
 typedef struct {
   const orc_hnsw *h;
   const float *qvec;
+  const float *lut; /* ADC: Q x K partial distances of this query, or NULL */
 } query_t;
 
+/* finish a distance from the accumulated sum; the ADC path is our own definition and uses the
+ * correctly rounded sqrtf (the crate's powf(0.5) only applies to its own comparators) */
+static inline float adc_finalize(int metric, float r) {
+  switch (metric) {
+    case ORC_L2_SQRT: return sqrtf(r);
+    case ORC_COS_HALF: return (1.0f - r) / 2.0f;
+    case ORC_ONE_MINUS_DOT: return 1.0f - r;
+    default: {
+      float x = (r - 1.0f) / -2.0f;
+      if (x < 0.0f) x = 0.0f;
+      if (x > 1.0f) x = 1.0f;
+      return x;
+    }
+  }
+}
+
 static inline float dist_to_stored(const query_t *q, uint64_t vid) {
+  if (q->lut) { /* asymmetric distance: sum the query's table entries selected by the codes */
+    const orc_hnsw *h = q->h;
+    const uint8_t *code = h->pq_codes + vid * h->pq_Q;
+    float r = 0.0f;
+    for (uint64_t s = 0; s < h->pq_Q; s++) r += q->lut[s * h->pq_K + code[s]];
+    return adc_finalize(h->metric, r);
+  }
   return orc_distance(q->h->metric, q->h->dim, q->qvec, q->h->rows + vid * q->h->dim);
+}
+
+/* per-query ADC table: lut[s*K + k] = partial distance between sub-vector s of the query and
+ * centroid k (sequential, unfused f32) */
+static void adc_build_lut(const orc_hnsw *h, const float *qvec, float *lut) {
+  for (uint64_t s = 0; s < h->pq_Q; s++)
+    for (uint64_t k = 0; k < h->pq_K; k++) {
+      const float *a = qvec + s * h->pq_cs, *c = h->pq_codebook + k * h->pq_cs;
+      float r = 0.0f;
+      if (h->metric == ORC_L2_SQRT)
+        for (uint64_t t = 0; t < h->pq_cs; t++) {
+          float d = a[t] - c[t];
+          r += d * d;
+        }
+      else
+        for (uint64_t t = 0; t < h->pq_cs; t++) r += a[t] * c[t];
+      lut[s * h->pq_K + k] = r;
+    }
 }
 
 /* ---------------------------------------------------- visited set (HashSet) */
@@ -686,6 +732,7 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
     cand.pri = (float *)malloc((ef ? ef : 1) * sizeof(float));
     uint64_t *nd = (uint64_t *)calloc(h->layer_count + 1, sizeof(uint64_t));
     uint64_t *ne = (uint64_t *)calloc(h->layer_count + 1, sizeof(uint64_t));
+    float *lut = NULL, *recon = NULL;
 #pragma omp for schedule(dynamic, 8)
     for (int64_t qi = 0; qi < (int64_t)nq; qi++) {
       for (uint64_t i = 0; i < ef; i++) {
@@ -696,7 +743,26 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
       memset(ne, 0, (h->layer_count + 1) * sizeof(uint64_t));
       query_t q;
       q.h = h;
-      q.qvec = queries ? queries + (uint64_t)qi * h->dim : h->rows + stored_ids[qi] * h->dim;
+      q.lut = NULL;
+      if (h->pq_codes) {
+        if (!lut) {
+          lut = (float *)malloc(h->pq_Q * h->pq_K * sizeof(float));
+          recon = (float *)malloc(h->dim * sizeof(float));
+        }
+        if (queries) {
+          q.qvec = queries + (uint64_t)qi * h->dim;
+        } else { /* Stored: the query is the reconstruction of its own codes */
+          const uint8_t *code = h->pq_codes + stored_ids[qi] * h->pq_Q;
+          for (uint64_t sq = 0; sq < h->pq_Q; sq++)
+            memcpy(recon + sq * h->pq_cs, h->pq_codebook + code[sq] * h->pq_cs,
+                   h->pq_cs * sizeof(float));
+          q.qvec = recon;
+        }
+        adc_build_lut(h, q.qvec, lut);
+        q.lut = lut;
+      } else {
+        q.qvec = queries ? queries + (uint64_t)qi * h->dim : h->rows + stored_ids[qi] * h->dim;
+      }
       uint64_t idx_dist = UINT64_MAX;
       int64_t rc = search_layers(h, h->layers, L, &q, sp, exclude ? exclude[qi] : ORC_EMPTY,
                                  &cand, &s, &idx_dist, nd, ne);
@@ -723,6 +789,8 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
     }
     free(nd);
     free(ne);
+    free(lut);
+    free(recon);
     free(cand.data);
     free(cand.pri);
     scratch_free(&s);
@@ -758,6 +826,7 @@ int orc_knn(const orc_hnsw *h, uint64_t k, uint64_t probe_depth, uint64_t *out_i
       pq_merge(&pq, &node, &zero, 1); /* seeded with (self, 0.0) lib.rs:918 */
       query_t q;
       q.h = h;
+      q.lut = NULL;
       q.qvec = h->rows + layer->nodes[i] * h->dim;
       closest_nodes(layer, &q, &pq, probe_depth, &s, NULL, NULL);
       uint64_t cnt = 0;
@@ -809,6 +878,7 @@ int orc_threshold_nn(const orc_hnsw *h, float threshold, uint64_t probe_depth,
       pq_merge(&pq, &node, &zero, 1);
       query_t q;
       q.h = h;
+      q.lut = NULL;
       q.qvec = h->rows + layer->nodes[i] * h->dim;
       float last = 0.0f;
       uint64_t last_size = 0;
@@ -1021,6 +1091,7 @@ static void generate_layer(orc_hnsw *h, uint64_t *vs, uint64_t n, uint64_t M,
         }
         query_t q;
         q.h = h;
+        q.lut = NULL;
         q.qvec = h->rows + vs[i] * h->dim;
         search_layers(h, h->layers, n_above, &q, isp, ORC_EMPTY, &cand, &s, NULL, NULL, NULL);
         uint64_t c = 0;
@@ -1195,6 +1266,7 @@ static uint64_t link_layer(orc_hnsw *h, uint64_t layer_from_top, const orc_searc
       uint64_t vector = snap.nodes[i];
       query_t q;
       q.h = h;
+      q.lut = NULL;
       q.qvec = h->rows + vector * h->dim;
       search_layers(h, stack, layer_from_top + 1, &q, sp, vector, &cand, &s, NULL, NULL, NULL);
       uint32_t c = 0;
@@ -1777,4 +1849,84 @@ int orc_pq_search(const orc_pq *pq, const float *queries, const uint64_t *stored
   free(ds);
   free(cnt);
   return rc;
+}
+
+
+/* ------------------------------------------------ ADC over u8 codes + k-means codebook
+ * (BASELINE.json north_star kernels 2 and 4a; the crate itself has neither: its k-means is dead
+ * code (pq.rs:215-259, linfa, parity unpinned) and its search is symmetric + re-rank).  The
+ * definitions below are ours; the CUDA path must reproduce them bit for bit. */
+
+static inline float l2_sqrtf(uint64_t dim, const float *a, const float *b) {
+  float r = 0.0f;
+  for (uint64_t i = 0; i < dim; i++) {
+    float d = a[i] - b[i];
+    r += d * d;
+  }
+  return sqrtf(r);
+}
+
+/* exact nearest centroid of every sub-vector: argmin by (sqrtf L2, centroid id) */
+void orc_pq8_encode(const float *rows, uint64_t n, uint64_t size, uint64_t cs,
+                    const float *codebook, uint64_t K, uint8_t *codes, int nthreads) {
+  uint64_t Q = size / cs;
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int64_t i = 0; i < (int64_t)(n * Q); i++) {
+    const float *x = rows + (uint64_t)i * cs; /* rows are size = Q*cs floats: sub-vectors consecutive */
+    float best = FLT_MAX;
+    uint64_t bi = 0;
+    for (uint64_t k = 0; k < K; k++) {
+      float d = l2_sqrtf(cs, x, codebook + k * cs);
+      if (d < best) {
+        best = d;
+        bi = k;
+      }
+    }
+    codes[i] = (uint8_t)bi;
+  }
+}
+
+/* codebook training: random_centroids initialisation (pq.rs:261-285) + `iters` Lloyd steps
+ * (assign = orc_pq8_encode, update = mean of the members summed in index order; an empty
+ * cluster keeps its centroid).  Returns the number of centroids (<= K). */
+uint64_t orc_pq8_train(const float *rows, uint64_t n, uint64_t size, uint64_t cs, uint64_t K,
+                       uint64_t iters, uint64_t seed, float *codebook_out, int nthreads) {
+  float *c = NULL;
+  uint64_t Kc = pq_random_centroids(rows, n, size, cs, K, seed, &c);
+  uint64_t Q = size / cs, m = n * Q;
+  uint8_t *codes = (uint8_t *)malloc(m ? m : 1);
+  float *sum = (float *)malloc(Kc * cs * sizeof(float));
+  uint64_t *cnt = (uint64_t *)malloc(Kc * sizeof(uint64_t));
+  for (uint64_t it = 0; it < iters; it++) {
+    orc_pq8_encode(rows, n, size, cs, c, Kc, codes, nthreads);
+    memset(sum, 0, Kc * cs * sizeof(float));
+    memset(cnt, 0, Kc * sizeof(uint64_t));
+    for (uint64_t i = 0; i < m; i++) {
+      uint64_t k = codes[i];
+      for (uint64_t t = 0; t < cs; t++) sum[k * cs + t] += rows[i * cs + t];
+      cnt[k]++;
+    }
+    for (uint64_t k = 0; k < Kc; k++)
+      if (cnt[k])
+        for (uint64_t t = 0; t < cs; t++) c[k * cs + t] = sum[k * cs + t] / (float)cnt[k];
+  }
+  memcpy(codebook_out, c, Kc * cs * sizeof(float));
+  free(c);
+  free(codes);
+  free(sum);
+  free(cnt);
+  return Kc;
+}
+
+/* attach an ADC view to an index: searches then score stored vectors through the codes
+ * (arrays borrowed) */
+void orc_hnsw_set_pq8(orc_hnsw *h, const uint8_t *codes, uint64_t Q, uint64_t K, uint64_t cs,
+                      const float *codebook) {
+  h->pq_codes = codes;
+  h->pq_Q = Q;
+  h->pq_K = K;
+  h->pq_cs = cs;
+  h->pq_codebook = codebook;
 }

@@ -190,6 +190,14 @@ int orc_pq_search(const orc_pq *pq, const float *queries, const uint64_t *stored
                   const orc_search_params *sp, uint64_t max_out, uint64_t *out_ids,
                   float *out_dists, uint32_t *out_counts, int nthreads);
 
+/* ---- ADC over u8 codes + k-means codebook (north_star kernels 2 / 4a; our own definitions) ---- */
+void orc_pq8_encode(const float *rows, uint64_t n, uint64_t size, uint64_t cs,
+                    const float *codebook, uint64_t K, uint8_t *codes, int nthreads);
+uint64_t orc_pq8_train(const float *rows, uint64_t n, uint64_t size, uint64_t cs, uint64_t K,
+                       uint64_t iters, uint64_t seed, float *codebook_out, int nthreads);
+void orc_hnsw_set_pq8(orc_hnsw *h, const uint8_t *codes, uint64_t Q, uint64_t K, uint64_t cs,
+                      const float *codebook);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

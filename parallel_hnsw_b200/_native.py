@@ -119,6 +119,9 @@ SIGNATURES = {
     "phnsw_pq_reconstruct": (C.c_int, [vp, vp, C.c_uint64, vp]),
     "phnsw_pq_search_batch": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams), C.c_uint64,
                                         vp, vp, vp]),
+    "phnsw_pq8_train": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, u64p]),
+    "phnsw_pq8_store_create": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
+    "phnsw_pq8_store_codes": (C.c_int, [vp, vp]),
     "phnsw_merge_topk_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
 }
 

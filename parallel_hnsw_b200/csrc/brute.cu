@@ -210,6 +210,10 @@ phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *quer
     return PHNSW_ERR_INVALID;
   }
   if (nq == 0) return PHNSW_OK;
+  if (!s->rows) {
+    set_error("bruteforce_knn: not available on a PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
   cudaStream_t st = (cudaStream_t)cuda_stream;
   PH_CUDA(cudaSetDevice(s->device));
   cudaGetLastError();  // do not attribute a stale error of an earlier call to this one

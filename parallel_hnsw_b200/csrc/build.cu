@@ -830,6 +830,10 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
   PH_ENTRY();
   if (!s || !out || (n && !vector_ids)) return PHNSW_ERR_INVALID;
   *out = nullptr;
+  if (!s->rows) {
+    set_error("generate: build the graph over an f32 store; a PQ8 store is search-only");
+    return PHNSW_ERR_INVALID;
+  }
   if (n == 0) {  // assert!(total_size > 0) lib.rs:837
     set_error("generate: empty vector list");
     return PHNSW_ERR_INVALID;
@@ -898,6 +902,10 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out) {
   PH_ENTRY();
   if (!ix) return PHNSW_ERR_INVALID;
+  if (!ix->store->rows) {
+    set_error("improve_index: not available on a PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
   phnsw_build_params b = bp ? *bp : ix->bp;
   Progress pg{progress, user};
   float recall = 0.0f;

@@ -106,7 +106,13 @@ struct phnsw_store {
   int metric = 0;
   uint64_t dim = 0, n = 0;
   uint32_t pitch = 0;    // floats per row in HBM (dim rounded up to a multiple of 4, zero padded)
-  float *rows = nullptr; // device
+  float *rows = nullptr; // device (null for a PQ8 store)
+  // PQ8 store (ADC): u8 codes + one codebook shared by all sub-spaces; dim = SIZE of a query
+  uint8_t *codes8 = nullptr;   // device, n x cpitch bytes
+  uint32_t cpitch = 0;         // bytes per code row (QUANTIZED_SIZE rounded up to 16)
+  float *codebook = nullptr;   // device, pq_K x pq_cs
+  uint32_t pq_Q = 0, pq_K = 0, pq_cs = 0;
+  bool is_pq8() const { return codes8 != nullptr; }
 };
 
 struct phnsw_index {

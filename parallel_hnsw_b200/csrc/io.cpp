@@ -261,6 +261,10 @@ phnsw_status phnsw_format_build_params(const phnsw_build_params *bp, char *out, 
 phnsw_status phnsw_index_save(const phnsw_index *ix, const char *dir) {
   PH_ENTRY();
   if (!ix || !dir) return PHNSW_ERR_INVALID;
+  if (!ix->store->rows) {
+    set_error("save: not available on a PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
   std::string d(dir);
   if (mkdir_p(d) != 0) {
     set_error("save: cannot create %s: %s", dir, strerror(errno));

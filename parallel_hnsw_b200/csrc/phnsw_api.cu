@@ -146,24 +146,34 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }
 
 // ------------------------------------------------------------------ search launch
-template <int METRIC>
+template <int METRIC, int PQ>
 static cudaError_t launch_typed(const SearchArgs &a, int grid, int block, size_t smem,
                                 cudaStream_t stream) {
   static thread_local size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 8 && configured[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC>,
+    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[dev] = smem;
   } else if (dev >= 8) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC>,
+    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  search_kernel<METRIC><<<grid, block, smem, stream>>>(a);
+  search_kernel<METRIC, PQ><<<grid, block, smem, stream>>>(a);
   return cudaGetLastError();
+}
+template <int PQ>
+static cudaError_t launch_metric(int metric, const SearchArgs &a, int grid, int block, size_t smem,
+                                 cudaStream_t stream) {
+  switch (metric) {
+    case kCosHalf: return launch_typed<kCosHalf, PQ>(a, grid, block, smem, stream);
+    case kOneMinusDot: return launch_typed<kOneMinusDot, PQ>(a, grid, block, smem, stream);
+    case kL2Sqrt: return launch_typed<kL2Sqrt, PQ>(a, grid, block, smem, stream);
+    default: return launch_typed<kCosClamp, PQ>(a, grid, block, smem, stream);
+  }
 }
 
 
@@ -184,7 +194,12 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   PH_CUDA(cudaSetDevice(s->device));
   const uint32_t cap_max = std::max(c.cap, c.cap_max);
   const uint32_t cap_pad = pool_entries(std::max(cap_max, 1u));
-  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad);
+  const bool pq8 = s->is_pq8();
+  if (pq8 && (c.mode != 0 || (s->cpitch + 16) * 32 > kLandingRows * kRowStride * 4)) {
+    set_error("search: a PQ8 (ADC) store supports search_layers only, with at most 248 codes per vector");
+    return PHNSW_ERR_INVALID;
+  }
+  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, pq8 ? s->pq_Q * s->pq_K : 0);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
     set_error("search: per-query shared memory %u B exceeds %zu B (dim %llu, capacity %u)",
@@ -245,6 +260,12 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.rows = s->rows;
   a.dim_pad = s->pitch;
   a.pitch = s->pitch;
+  a.codes = s->codes8;
+  a.cpitch = s->cpitch;
+  a.codebook = s->codebook;
+  a.pq_Q = s->pq_Q;
+  a.pq_K = s->pq_K;
+  a.pq_cs = s->pq_cs;
   a.layers = ix->d_layers;
   a.n_layers = c.n_layers;
   a.mode = c.mode;
@@ -279,13 +300,8 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.cap_pad = cap_pad;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
 
   const size_t smem = (size_t)lay.total * w;
-  cudaError_t e;
-  switch (s->metric) {
-    case kCosHalf: e = launch_typed<kCosHalf>(a, grid, w * 32, smem, stream); break;
-    case kOneMinusDot: e = launch_typed<kOneMinusDot>(a, grid, w * 32, smem, stream); break;
-    case kL2Sqrt: e = launch_typed<kL2Sqrt>(a, grid, w * 32, smem, stream); break;
-    default: e = launch_typed<kCosClamp>(a, grid, w * 32, smem, stream); break;
-  }
+  cudaError_t e = pq8 ? launch_metric<1>(s->metric, a, grid, w * 32, smem, stream)
+                      : launch_metric<0>(s->metric, a, grid, w * 32, smem, stream);
   if (e != cudaSuccess) return cuda_fail(e, "search_kernel launch");
   return PHNSW_OK;
 }
@@ -402,6 +418,8 @@ void store_release(phnsw_store *s) {
   if (s->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(s->device);
   if (s->rows) cudaFree(s->rows);
+  if (s->codes8) cudaFree(s->codes8);
+  if (s->codebook) cudaFree(s->codebook);
   delete s;
 }
 
@@ -580,6 +598,10 @@ phnsw_status phnsw_store_compare(const phnsw_store *s, const uint64_t *a, const 
   PH_ENTRY();
   if (!s || (n && (!a || !b || !out))) return PHNSW_ERR_INVALID;
   if (!n) return PHNSW_OK;
+  if (!s->rows) {
+    set_error("store_compare: not available on a PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
   PH_CUDA(cudaSetDevice(s->device));
   uint64_t *d_ab = nullptr;
   float *d_out = nullptr;
@@ -611,6 +633,10 @@ phnsw_status phnsw_store_get_rows(const phnsw_store *s, const uint64_t *ids, uin
   PH_ENTRY();
   if (!s || (n && (!ids || !out_rows))) return PHNSW_ERR_INVALID;
   if (!n) return PHNSW_OK;
+  if (!s->rows) {
+    set_error("store_get_rows: not available on a PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
   PH_CUDA(cudaSetDevice(s->device));
   uint64_t *d_ids = nullptr;
   float *d_out = nullptr;

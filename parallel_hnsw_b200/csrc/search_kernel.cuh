@@ -88,18 +88,26 @@ struct SearchArgs {
   uint32_t bitmap_words;
   uint32_t *vlog;          // per-warp log of visited node ids, vlog_cap each
   uint32_t vlog_cap;
+  // ADC over u8 codes (PQ stores): rows == nullptr, vectors are code rows scored through a
+  // per-query table of partial distances held in shared memory
+  const uint8_t *codes;    // n_vectors x cpitch bytes (cpitch % 16 == 0, tail zero padded)
+  uint32_t cpitch;
+  const float *codebook;   // pq_K x pq_cs f32 (one codebook shared by all sub-spaces)
+  uint32_t pq_Q, pq_K, pq_cs;
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
   uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
 };
 
 // per-warp shared memory carve-up (bytes); shared by host (launch size) and device
 struct WarpSmemLayout {
-  uint32_t off_q, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, total;
+  uint32_t off_q, off_lut, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, total;
 };
-__host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uint32_t cap_pad) {
+__host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uint32_t cap_pad,
+                                                           uint32_t lut_floats = 0) {
   WarpSmemLayout l;
   uint32_t o = 0;
   l.off_q = o;       o += ((dim_pad * 4 + 15) / 16) * 16;
+  l.off_lut = o;     o += ((lut_floats * 4 + 15) / 16) * 16;
   l.off_stage = o;   o += kLandingRows * kRowStride * 4;
   l.off_pool = o;    o += cap_pad * 8;
   l.off_bkeys = o;   o += kMaxBatch * 8;
@@ -138,10 +146,11 @@ __device__ __forceinline__ uint64_t warp_max_key(uint64_t v) {
   return ((uint64_t)mh << 32) | ml;
 }
 
-template <int METRIC>
+template <int METRIC, int PQ>
 struct WarpSearch {
   const SearchArgs &a;
   float *qvec;
+  float *lut;
   float *stage;
   uint64_t *pool;
   uint64_t *bkeys;
@@ -167,8 +176,9 @@ struct WarpSearch {
 
   __device__ WarpSearch(const SearchArgs &args, unsigned char *smem, uint32_t slot, int lane_)
       : a(args), lane(lane_) {
-    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad);
+    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0);
     qvec = (float *)(smem + l.off_q);
+    lut = (float *)(smem + l.off_lut);
     stage = (float *)(smem + l.off_stage);
     pool = (uint64_t *)(smem + l.off_pool);
     bkeys = (uint64_t *)(smem + l.off_bkeys);
@@ -457,6 +467,43 @@ struct WarpSearch {
   // result bkeys[j] = key(distance, bid[j]).  Tiles of R rows x one 512 B chunk are copied
   // by the bulk-copy engine into stage t % S and consumed lane-per-row.
   __device__ void compute_distances(const LayerDev &layer, uint32_t nn) {
+    if (PQ) {
+      // ADC: code rows (cpitch bytes each) land 32 at a time; each lane sums its row's table
+      // entries in sub-space order, which is the order the oracle defines
+      const uint32_t rstride = a.cpitch + 16;  // bytes; the pad spreads rows over the banks
+      unsigned char *land = (unsigned char *)stage;
+      for (uint32_t p0 = 0; p0 < nn; p0 += 32) {
+        const uint32_t j = p0 + lane;
+        const bool active = j < nn;
+        const uint32_t rows_p = min(32u, nn - p0);
+        uint32_t node = 0;
+        if (lane == 0) mbar_arrive_expect_tx(&mbar[0], rows_p * a.cpitch);
+        __syncwarp();
+        if (active) {
+          node = bid[j];
+          uint32_t vec = layer.nodes ? __ldg(&layer.nodes[node]) : node;
+          bulk_g2s(land + lane * rstride, a.codes + (size_t)vec * a.cpitch, a.cpitch, &mbar[0]);
+        }
+        mbar_wait(&mbar[0], ph & 1u);
+        ph ^= 1u;
+        if (active) {
+          const uint32_t *cw = (const uint32_t *)(land + lane * rstride);
+          float acc = 0.0f;
+          for (uint32_t s = 0; s < a.pq_Q; s += 4) {
+            uint32_t w = cw[s >> 2];
+            acc = __fadd_rn(acc, lut[s * a.pq_K + (w & 255u)]);
+            if (s + 1 < a.pq_Q) acc = __fadd_rn(acc, lut[(s + 1) * a.pq_K + ((w >> 8) & 255u)]);
+            if (s + 2 < a.pq_Q) acc = __fadd_rn(acc, lut[(s + 2) * a.pq_K + ((w >> 16) & 255u)]);
+            if (s + 3 < a.pq_Q) acc = __fadd_rn(acc, lut[(s + 3) * a.pq_K + (w >> 24)]);
+          }
+          float d = finalize(acc);
+          if (d != d) stat |= kStatNaN;
+          bkeys[j] = make_key(d, node);
+        }
+      }
+      __syncwarp();
+      return;
+    }
     if (a.dim_pad <= (uint32_t)kChunk) {  // one bulk copy per row: no chunk pipeline needed
       const uint32_t fl4 = a.dim_pad / 4;
       for (uint32_t p0 = 0; p0 < nn; p0 += kLandingRows) {
@@ -739,6 +786,45 @@ struct WarpSearch {
 
   // ------------------------------------------------------------------ whole-query drivers
   __device__ void load_query(uint32_t q) {
+    if (PQ) {
+      if (a.queries) {
+        const float *src = a.queries + (size_t)q * a.qpitch;
+        for (uint32_t i = lane; i < a.dim_pad; i += 32) qvec[i] = i < a.qpitch ? src[i] : 0.0f;
+      } else {  // Stored: the query is the reconstruction of its own codes
+        uint32_t vid;
+        if (a.stored_ids) vid = (uint32_t)a.stored_ids[q];
+        else {
+          const LayerDev &l = a.layers[a.n_layers - 1];
+          vid = l.nodes ? l.nodes[a.q_offset + q] : a.q_offset + q;
+        }
+        const uint8_t *code = a.codes + (size_t)vid * a.cpitch;
+        for (uint32_t i = lane; i < a.dim_pad; i += 32) {
+          uint32_t s = i / a.pq_cs, t = i - s * a.pq_cs;
+          qvec[i] = s < a.pq_Q ? __ldg(&a.codebook[(size_t)code[s] * a.pq_cs + t]) : 0.0f;
+        }
+      }
+      __syncwarp();
+      // table of partial distances: lut[s * K + k] = partial(q_s, centroid k), sequential f32
+      const uint32_t entries = a.pq_Q * a.pq_K;
+      for (uint32_t e = lane; e < entries; e += 32) {
+        const uint32_t s = e / a.pq_K, k = e - s * a.pq_K;
+        const float *qs = qvec + s * a.pq_cs;
+        const float *c = a.codebook + (size_t)k * a.pq_cs;
+        float r = 0.0f;
+        for (uint32_t t = 0; t < a.pq_cs; t++) {
+          float cv = __ldg(&c[t]);
+          if (METRIC == kL2Sqrt) {
+            float dlt = __fsub_rn(qs[t], cv);
+            r = __fadd_rn(r, __fmul_rn(dlt, dlt));
+          } else {
+            r = __fadd_rn(r, __fmul_rn(qs[t], cv));
+          }
+        }
+        lut[e] = r;
+      }
+      __syncwarp();
+      return;
+    }
     const float *src;
     if (a.queries) {
       src = a.queries + (size_t)q * a.qpitch;
@@ -1066,15 +1152,15 @@ struct WarpSearch {
   }
 };
 
-template <int METRIC>
+template <int METRIC, int PQ>
 __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t warps_per_cta = blockDim.x >> 5;
-  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad);
+  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0);
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
-  WarpSearch<METRIC> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);
+  WarpSearch<METRIC, PQ> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);
   if (lane == 0) {
     for (int s = 0; s < kMaxStages; s++) mbar_init(&ws.mbar[s], 1);
     mbar_fence_init();

@@ -340,6 +340,36 @@ class Hnsw:
         return float(r.value)
 
 
+def pq8_train(full_comparator, K, centroid_size, kmeans_iters=5, seed=1):
+    """k-means codebook (K <= 256 centroids of centroid_size floats, shared by all sub-spaces):
+    random_centroids initialisation (pq.rs:261-285) + Lloyd steps on the device."""
+    out = np.zeros((K, centroid_size), dtype=np.float32)
+    k = C.c_uint64()
+    N.check(N.lib().phnsw_pq8_train(full_comparator._h, K, centroid_size, kmeans_iters, seed,
+                                    _ptr(out), C.byref(k)))
+    return out[:k.value].copy()
+
+
+class Pq8Comparator(BigComparator):
+    """u8-coded view of a BigComparator, searched with asymmetric distances (ADC): per-query
+    tables of partial distances in shared memory.  Search-only."""
+
+    def __init__(self, full_comparator, codebook, centroid_size):
+        codebook = _host(codebook, np.float32)
+        h = C.c_void_p()
+        N.check(N.lib().phnsw_pq8_store_create(full_comparator._h, _ptr(codebook),
+                                               codebook.shape[0], centroid_size, C.byref(h)))
+        self._h = h
+        self.metric, self.dim, self.n = full_comparator.metric, full_comparator.dim, full_comparator.n
+        self.device = full_comparator.device
+        self.quantized_size = self.dim // centroid_size
+
+    def codes(self):
+        out = np.empty((self.n, self.quantized_size), dtype=np.uint8)
+        N.check(N.lib().phnsw_pq8_store_codes(self._h, _ptr(out)))
+        return out
+
+
 def PqBuildParameters():
     """src/parameters.rs:66-71 Default."""
     bp = N.PqBuildParams()
