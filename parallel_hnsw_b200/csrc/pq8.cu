@@ -4,8 +4,9 @@
 //
 // The crate has no counterpart on its live path: its k-means (src/pq.rs:215-259, linfa) is dead
 // code with no pinned output and its search is symmetric + re-rank (src/pq.rs:346-364).  The
-// definitions are therefore the oracle's (oracle/phnsw_oracle.c: orc_pq8_train, orc_pq8_encode,
-// adc_build_lut / dist_to_stored) and the device reproduces them bit for bit:
+// definitions are therefore the ones DESIGN.md section 4 states (the CPU checker under oracle/
+// restates them as orc_pq8_train, orc_pq8_encode, adc_build_lut / dist_to_stored; nothing here
+// calls it) and the device reproduces them bit for bit:
 //   assignment  argmin over centroids of (sqrt of the sequential sum of squares, centroid id)
 //   update      mean of the members, summed in index order, one division at the end
 //   distance    finalize(sum over sub-spaces, in order, of table[s][code_s])
