@@ -135,6 +135,18 @@ uint64_t phnsw_index_layer_count(const phnsw_index *ix);          /* lib.rs:644-
 uint64_t phnsw_index_vector_count(const phnsw_index *ix);         /* lib.rs:592-594 */
 uint64_t phnsw_index_entry_vector(const phnsw_index *ix);         /* lib.rs:639-642 */
 void phnsw_index_build_params(const phnsw_index *ix, phnsw_build_params *bp);
+/* Summation order of the traversal kernel's distances (the body of Comparator::compare_raw,
+ * src/bigvec.rs:47-53, src/lib.rs:2431-2437).
+ *   PHNSW_SUM_SEQUENTIAL (default): strictly left to right, multiply and add unfused -- the
+ *     crate's scalar loop bit for bit; results are identical to the crate's on the same graph.
+ *   PHNSW_SUM_TREE: lane-strided fused partial sums + warp-shuffle butterfly (fixed order,
+ *     DESIGN.md section 4); distances agree with the sequential order to a few ulp (the
+ *     parity bar for this mode is BASELINE.json's: >= 99.9 % of queries with identical ids,
+ *     distances within 1e-5 relative).  Applies to search / knn / threshold_nn on f32 stores;
+ *     construction always uses the sequential order. */
+typedef enum { PHNSW_SUM_SEQUENTIAL = 0, PHNSW_SUM_TREE = 1 } phnsw_sum_order;
+phnsw_status phnsw_index_set_sum_order(phnsw_index *ix, int order);
+int phnsw_index_sum_order(const phnsw_index *ix);
 phnsw_status phnsw_index_layer_info(const phnsw_index *ix, uint64_t layer_from_top,
                                     uint64_t *node_count, uint64_t *neighborhood_size);
 /* copy one layer out as u64 (the exact content of layer.nodes.N / layer.neighbors.N) */

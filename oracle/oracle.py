@@ -83,6 +83,9 @@ def lib():
                                                          u64p, C.c_uint64]
     L.orc_distance.restype = C.c_float
     L.orc_distance.argtypes = [C.c_int, C.c_uint64, f32p, f32p]
+    L.orc_distance_tree.restype = C.c_float
+    L.orc_distance_tree.argtypes = [C.c_int, C.c_uint64, f32p, f32p]
+    L.orc_hnsw_set_sum_order.argtypes = [C.c_void_p, C.c_int]
     L.orc_hnsw_new.restype = C.c_void_p
     L.orc_hnsw_new.argtypes = [C.c_int, C.c_uint64, C.c_uint64, f32p]
     L.orc_hnsw_free.argtypes = [C.c_void_p]
@@ -227,6 +230,13 @@ def distance(metric, a, b):
     return np.float32(lib().orc_distance(metric, len(a), _p(a, C.c_float), _p(b, C.c_float)))
 
 
+def distance_tree(metric, a, b):
+    """The device's PHNSW_SUM_TREE summation order restated (not a crate function)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return np.float32(lib().orc_distance_tree(metric, len(a), _p(a, C.c_float), _p(b, C.c_float)))
+
+
 class Hnsw:
     """Handle on an oracle index; mirrors the reference's Hnsw surface (lib.rs:585-1699)."""
 
@@ -285,6 +295,11 @@ class Hnsw:
             except Exception:
                 pass
             self._h = None
+
+    def set_sum_order(self, order):
+        """0 = the crate's sequential sums, 1 = the device's tree order (search paths)."""
+        lib().orc_hnsw_set_sum_order(self._h, int(order))
+        return self
 
     @property
     def layer_count(self):

@@ -255,6 +255,45 @@ float orc_distance(int metric, uint64_t dim, const float *a, const float *b) {
   return NAN;
 }
 
+/* The device's alternative summation order (include/phnsw.h PHNSW_SUM_TREE; no crate
+ * analogue -- the crate only has the sequential loop above).  TEST INFRASTRUCTURE: restates the
+ * fixed order of the traversal kernel so that the tree mode can be checked bit for bit:
+ * element i belongs to lane (i / 4) % 32; each lane accumulates its elements in index order
+ * with fused multiply-adds; the 32 partials are added pairwise 16, 8, 4, 2, 1 lanes apart.
+ * Elements beyond `dim` (the device pads rows to a multiple of 4 floats) are zeros. */
+float orc_distance_tree(int metric, uint64_t dim, const float *a, const float *b) {
+  float p[32];
+  for (int l = 0; l < 32; l++) p[l] = 0.0f;
+  const uint64_t dim_pad = (dim + 3) / 4 * 4;
+  for (uint64_t i = 0; i < dim_pad; i++) {
+    const int l = (int)((i / 4) % 32);
+    const float x = i < dim ? a[i] : 0.0f, y = i < dim ? b[i] : 0.0f;
+    if (metric == ORC_L2_SQRT) {
+      float t = x - y;
+      p[l] = fmaf(t, t, p[l]);
+    } else {
+      p[l] = fmaf(x, y, p[l]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    float n[32];
+    for (int l = 0; l < 32; l++) n[l] = p[l] + p[l ^ o];
+    for (int l = 0; l < 32; l++) p[l] = n[l];
+  }
+  const float r = p[0];
+  switch (metric) {
+    case ORC_L2_SQRT: return sqrtf(r); /* the device's correctly rounded sqrt */
+    case ORC_COS_HALF: return (1.0f - r) / 2.0f;
+    case ORC_ONE_MINUS_DOT: return 1.0f - r;
+    default: {
+      float x = (r - 1.0f) / -2.0f;
+      if (x < 0.0f) x = 0.0f;
+      if (x > 1.0f) x = 1.0f;
+      return x;
+    }
+  }
+}
+
 /* -------------------------------------------------------------------- index */
 
 typedef struct {
@@ -275,6 +314,7 @@ struct orc_hnsw {
   const uint8_t *pq_codes;
   const float *pq_codebook;
   uint64_t pq_Q, pq_K, pq_cs;
+  int sum_order; /* 0 = the crate's sequential loop, 1 = orc_distance_tree (search paths only) */
 };
 
 orc_hnsw *orc_hnsw_new(int metric, uint64_t dim, uint64_t n, const float *rows) {
@@ -332,6 +372,7 @@ int orc_hnsw_layer_info(const orc_hnsw *h, uint64_t i, uint64_t *node_count, uin
 }
 
 void orc_hnsw_set_build_params(orc_hnsw *h, const orc_build_params *bp) { h->bp = *bp; }
+void orc_hnsw_set_sum_order(orc_hnsw *h, int order) { h->sum_order = order; }
 void orc_hnsw_get_build_params(const orc_hnsw *h, orc_build_params *bp) { *bp = h->bp; }
 
 /* lib.rs:129-131 get_node: binary search of a VectorId in the ascending nodes array */
@@ -377,6 +418,8 @@ static inline float dist_to_stored(const query_t *q, uint64_t vid) {
     for (uint64_t s = 0; s < h->pq_Q; s++) r += q->lut[s * h->pq_K + code[s]];
     return adc_finalize(h->metric, r);
   }
+  if (q->h->sum_order)
+    return orc_distance_tree(q->h->metric, q->h->dim, q->qvec, q->h->rows + vid * q->h->dim);
   return orc_distance(q->h->metric, q->h->dim, q->qvec, q->h->rows + vid * q->h->dim);
 }
 

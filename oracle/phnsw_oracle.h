@@ -91,6 +91,8 @@ uint64_t orc_calculate_partitions_for_additions(const uint64_t *sizes_from_botto
 
 /* distance between two raw vectors, strict left-to-right f32 accumulation */
 float orc_distance(int metric, uint64_t dim, const float *a, const float *b);
+/* the device's PHNSW_SUM_TREE order (include/phnsw.h) restated; not a crate function */
+float orc_distance_tree(int metric, uint64_t dim, const float *a, const float *b);
 
 /* ---- index ---- */
 typedef struct orc_hnsw orc_hnsw;
@@ -107,6 +109,8 @@ int orc_hnsw_layer_info(const orc_hnsw *h, uint64_t layer_from_top, uint64_t *no
                         uint64_t *neighborhood_size, const uint64_t **nodes,
                         const uint64_t **neighbors);
 void orc_hnsw_set_build_params(orc_hnsw *h, const orc_build_params *bp);
+/* 0 = the crate's sequential sums (default), 1 = orc_distance_tree on the search paths */
+void orc_hnsw_set_sum_order(orc_hnsw *h, int order);
 void orc_hnsw_get_build_params(const orc_hnsw *h, orc_build_params *bp);
 
 /*

@@ -9,13 +9,14 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libphnsw.so")
+# developer knobs: PHNSW_LIB_OUT = path of a variant library (selected at run time with
+# PHNSW_LIB), PHNSW_EXTRA_FLAGS = extra nvcc flags (e.g. -DPHNSW_TREE_WARPS=24) for it
+LIB_PATH = os.environ.get("PHNSW_LIB_OUT") or os.path.join(_HERE, "libphnsw.so")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "-cudart", "static",
-] + (["-DPHNSW_LANDING_ROWS=" + os.environ["PHNSW_LANDING_ROWS"]] if os.environ.get("PHNSW_LANDING_ROWS") else []) + [
-]
+] + os.environ.get("PHNSW_EXTRA_FLAGS", "").split()
 
 
 def _sources():
@@ -41,7 +42,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(_HERE, "build")
+    objdir = os.path.join(_HERE, "build", os.path.basename(LIB_PATH).replace(".so", "")
+                          if os.environ.get("PHNSW_LIB_OUT") else "")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []

@@ -15,6 +15,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_IO, ERR_FORMAT, ERR_NOT_FOUND, ERR
     ERR_INTERRUPTED, ERR_GRAPH = range(10)
 
 METRIC_COS_HALF, METRIC_ONE_MINUS_DOT, METRIC_L2_SQRT, METRIC_COS_CLAMP = 0, 1, 2, 3
+SUM_SEQUENTIAL, SUM_TREE = 0, 1
 
 
 class SearchParams(C.Structure):  # src/parameters.rs:3-18
@@ -77,6 +78,8 @@ SIGNATURES = {
                                           C.POINTER(BuildParams), C.POINTER(vp)]),
     "phnsw_index_destroy": (None, [vp]),
     "phnsw_index_layer_count": (C.c_uint64, [vp]),
+    "phnsw_index_set_sum_order": (C.c_int, [vp, C.c_int]),
+    "phnsw_index_sum_order": (C.c_int, [vp]),
     "phnsw_index_vector_count": (C.c_uint64, [vp]),
     "phnsw_index_entry_vector": (C.c_uint64, [vp]),
     "phnsw_index_build_params": (None, [vp, C.POINTER(BuildParams)]),

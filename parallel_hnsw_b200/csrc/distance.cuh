@@ -42,6 +42,27 @@ struct RowScorer {
     }
     return acc;
   }
+  // per-element terms and their strictly sequential sum: the same roundings as accum4
+  __device__ __forceinline__ float4 terms4(const float4 &x, const float4 &q) const {
+    float4 r;
+    if (METRIC == kL2Sqrt) {
+      float t;
+      t = __fsub_rn(q.x, x.x); r.x = __fmul_rn(t, t);
+      t = __fsub_rn(q.y, x.y); r.y = __fmul_rn(t, t);
+      t = __fsub_rn(q.z, x.z); r.z = __fmul_rn(t, t);
+      t = __fsub_rn(q.w, x.w); r.w = __fmul_rn(t, t);
+    } else {
+      r.x = __fmul_rn(q.x, x.x); r.y = __fmul_rn(q.y, x.y);
+      r.z = __fmul_rn(q.z, x.z); r.w = __fmul_rn(q.w, x.w);
+    }
+    return r;
+  }
+  __device__ __forceinline__ float sum4(float acc, const float4 &t) const {
+    acc = __fadd_rn(acc, t.x);
+    acc = __fadd_rn(acc, t.y);
+    acc = __fadd_rn(acc, t.z);
+    return __fadd_rn(acc, t.w);
+  }
   __device__ __forceinline__ float finalize(float acc) const {
     if (METRIC == kCosHalf) return __fdiv_rn(__fsub_rn(1.0f, acc), 2.0f);
     if (METRIC == kOneMinusDot) return __fsub_rn(1.0f, acc);
@@ -87,13 +108,28 @@ struct RowScorer {
         mbar_wait(&mbar[s], (ph >> s) & 1u);
         ph ^= (1u << s);
         uint32_t j = p * R + lane;
-        if ((uint32_t)lane < R && j < nn) {
+        const uint32_t fl4 = min((uint32_t)kScoreChunk, dim_pad - c * kScoreChunk) / 4;
+        if ((uint32_t)lane < fl4) {  // phase 1, all lanes: per-element terms in place
+          const float4 q4 = ((const float4 *)(qvec + c * kScoreChunk))[lane];
+          float4 *col = (float4 *)(stage + s * R * kScoreStride) + lane;
+          const uint32_t rows_c = min(R, nn - p * R);
+          uint32_t r = 0;
+          for (; r + 4 <= rows_c; r += 4) {
+            float4 x0 = col[(r + 0) * (kScoreStride / 4)], x1 = col[(r + 1) * (kScoreStride / 4)];
+            float4 x2 = col[(r + 2) * (kScoreStride / 4)], x3 = col[(r + 3) * (kScoreStride / 4)];
+            col[(r + 0) * (kScoreStride / 4)] = terms4(x0, q4);
+            col[(r + 1) * (kScoreStride / 4)] = terms4(x1, q4);
+            col[(r + 2) * (kScoreStride / 4)] = terms4(x2, q4);
+            col[(r + 3) * (kScoreStride / 4)] = terms4(x3, q4);
+          }
+          for (; r < rows_c; r++) col[r * (kScoreStride / 4)] = terms4(col[r * (kScoreStride / 4)], q4);
+        }
+        __syncwarp();
+        if ((uint32_t)lane < R && j < nn) {  // phase 2, lane per row: strictly sequential sum
           if (c == 0) acc = 0.0f;
-          uint32_t fl4 = min((uint32_t)kScoreChunk, dim_pad - c * kScoreChunk) / 4;
           const float4 *rp = (const float4 *)(stage + (s * R + lane) * kScoreStride);
-          const float4 *qp = (const float4 *)(qvec + c * kScoreChunk);
-#pragma unroll 4
-          for (uint32_t k = 0; k < fl4; k++) acc = accum4(acc, rp[k], qp[k]);
+#pragma unroll 8
+          for (uint32_t k = 0; k < fl4; k++) acc = sum4(acc, rp[k]);
           if (c == nchunks - 1) {
             float d = finalize(acc);
             if (d != d) nan_seen = 1;

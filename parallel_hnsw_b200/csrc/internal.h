@@ -123,6 +123,7 @@ struct phnsw_index {
   int sm_count = 148;
   int max_smem = 0;
   uint32_t vlog_cap = 8192, ovf_cap = 8192;  // per-query device scratch (entries)
+  int sum_order = 0;  // PHNSW_SUM_SEQUENTIAL / PHNSW_SUM_TREE: traversal distance summation
   mutable std::mutex mu;
   mutable std::map<cudaStream_t, phnsw::Workspace> ws;
 };
@@ -143,6 +144,13 @@ struct SearchCall {
   uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr, *out_selfhit = nullptr;
 };
 
+// the three kernel variants (search_seq.cu, search_tree.cu, search_pq.cu)
+cudaError_t launch_search_seq(int metric, const SearchArgs &a, int grid, int block, size_t smem,
+                              cudaStream_t stream);
+cudaError_t launch_search_tree(int metric, const SearchArgs &a, int grid, int block, size_t smem,
+                               cudaStream_t stream);
+cudaError_t launch_search_pq(int metric, const SearchArgs &a, int grid, int block, size_t smem,
+                             cudaStream_t stream);
 // launches the traversal kernel on `stream` (asynchronous); status word is read by sync_status
 phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStream_t stream);
 phnsw_status sync_status(const phnsw_index *ix, cudaStream_t stream);

@@ -146,36 +146,8 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }
 
 // ------------------------------------------------------------------ search launch
-template <int METRIC, int PQ>
-static cudaError_t launch_typed(const SearchArgs &a, int grid, int block, size_t smem,
-                                cudaStream_t stream) {
-  static thread_local size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 8 && configured[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured[dev] = smem;
-  } else if (dev >= 8) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  search_kernel<METRIC, PQ><<<grid, block, smem, stream>>>(a);
-  return cudaGetLastError();
-}
-template <int PQ>
-static cudaError_t launch_metric(int metric, const SearchArgs &a, int grid, int block, size_t smem,
-                                 cudaStream_t stream) {
-  switch (metric) {
-    case kCosHalf: return launch_typed<kCosHalf, PQ>(a, grid, block, smem, stream);
-    case kOneMinusDot: return launch_typed<kOneMinusDot, PQ>(a, grid, block, smem, stream);
-    case kL2Sqrt: return launch_typed<kL2Sqrt, PQ>(a, grid, block, smem, stream);
-    default: return launch_typed<kCosClamp, PQ>(a, grid, block, smem, stream);
-  }
-}
-
+// the kernel variants are instantiated in search_seq.cu / search_tree.cu / search_pq.cu (one
+// translation unit each, so that they compile in parallel)
 
 phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStream_t stream) {
   const phnsw_store *s = ix->store;
@@ -199,14 +171,16 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     set_error("search: a PQ8 (ADC) store supports search_layers only, with at most 248 codes per vector");
     return PHNSW_ERR_INVALID;
   }
-  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, pq8 ? s->pq_Q * s->pq_K : 0);
+  const bool tree = !pq8 && ix->sum_order == PHNSW_SUM_TREE;
+  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, pq8 ? s->pq_Q * s->pq_K : 0,
+                                        tree ? kScratchBytesTree : kLandingBytes);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
     set_error("search: per-query shared memory %u B exceeds %zu B (dim %llu, capacity %u)",
               lay.total, avail, (unsigned long long)s->dim, cap_max);
     return PHNSW_ERR_INVALID;
   }
-  uint32_t wmax = (uint32_t)std::min<size_t>(16, avail / lay.total);
+  uint32_t wmax = (uint32_t)std::min<size_t>(tree ? kTreeWarps : kSeqWarps, avail / lay.total);
   // spread small batches over all SMs before stacking warps on one SM
   uint32_t w = std::min<uint32_t>(wmax, (c.nq + ix->sm_count - 1) / ix->sm_count);
   if (w < 1) w = 1;
@@ -230,7 +204,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     PH_CUDA(ws.ctrl.reserve(64));
     PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64, stream));
   }
-  const uint32_t max_slots = (uint32_t)ix->sm_count * 16;
+  const uint32_t max_slots = (uint32_t)ix->sm_count * kMaxWarps;
   if (ws.slots < slots || ws.ovf_cap != ix->ovf_cap || ws.vlog_cap != ix->vlog_cap ||
       ws.bitmap_words < need_words || ws.cap_pad < cap_pad) {
     PH_CUDA(cudaStreamSynchronize(stream));
@@ -300,8 +274,9 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.cap_pad = cap_pad;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
 
   const size_t smem = (size_t)lay.total * w;
-  cudaError_t e = pq8 ? launch_metric<1>(s->metric, a, grid, w * 32, smem, stream)
-                      : launch_metric<0>(s->metric, a, grid, w * 32, smem, stream);
+  cudaError_t e = pq8    ? launch_search_pq(s->metric, a, grid, w * 32, smem, stream)
+                  : tree ? launch_search_tree(s->metric, a, grid, w * 32, smem, stream)
+                         : launch_search_seq(s->metric, a, grid, w * 32, smem, stream);
   if (e != cudaSuccess) return cuda_fail(e, "search_kernel launch");
   return PHNSW_OK;
 }
@@ -741,6 +716,16 @@ void phnsw_index_destroy(phnsw_index *ix) {
 }
 
 uint64_t phnsw_index_layer_count(const phnsw_index *ix) { return ix ? ix->layers.size() : 0; }
+phnsw_status phnsw_index_set_sum_order(phnsw_index *ix, int order) {
+  PH_ENTRY();
+  if (!ix || (order != PHNSW_SUM_SEQUENTIAL && order != PHNSW_SUM_TREE)) {
+    set_error("index_set_sum_order: order must be PHNSW_SUM_SEQUENTIAL or PHNSW_SUM_TREE");
+    return PHNSW_ERR_INVALID;
+  }
+  ix->sum_order = order;
+  return PHNSW_OK;
+}
+int phnsw_index_sum_order(const phnsw_index *ix) { return ix ? ix->sum_order : 0; }
 uint64_t phnsw_index_vector_count(const phnsw_index *ix) {  // lib.rs:592-594 (bottom layer)
   return ix && !ix->layers.empty() ? ix->layers.back().node_count : 0;
 }

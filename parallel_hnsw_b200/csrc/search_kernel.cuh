@@ -42,6 +42,12 @@ constexpr int kChunk = 128;               // floats of a row staged per bulk cop
 constexpr int kRowStride = kChunk + 4;    // +16 B pad: conflict-free LDS.128 across rows
 constexpr int kMaxStages = 2;
 constexpr int kMaxBatch = 64;             // max neighbourhood size handled by one expansion
+#ifndef PHNSW_TREE_WARPS
+#define PHNSW_TREE_WARPS 24
+#endif
+constexpr int kSeqWarps = 16;                 // resident warps per SM, sequential / ADC variants
+constexpr int kTreeWarps = PHNSW_TREE_WARPS;  // ... tree variant (no landing zone)
+constexpr int kMaxWarps = kTreeWarps > kSeqWarps ? kTreeWarps : kSeqWarps;
 
 struct LayerDev {
   const uint32_t *nodes;      // node -> VectorId, ascending (Layer.nodes); null = identity
@@ -102,13 +108,19 @@ struct SearchArgs {
 struct WarpSmemLayout {
   uint32_t off_q, off_lut, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, total;
 };
+// bytes of the landing zone / scratch area: the sequential-order and ADC variants land rows
+// in it; the tree-order variant reads rows straight into registers and only needs scratch for
+// the radix-select histogram and the pool sort
+constexpr uint32_t kLandingBytes = kLandingRows * kRowStride * 4;
+constexpr uint32_t kScratchBytesTree = 4096;
 __host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uint32_t cap_pad,
-                                                           uint32_t lut_floats = 0) {
+                                                           uint32_t lut_floats = 0,
+                                                           uint32_t stage_bytes = kLandingBytes) {
   WarpSmemLayout l;
   uint32_t o = 0;
   l.off_q = o;       o += ((dim_pad * 4 + 15) / 16) * 16;
   l.off_lut = o;     o += ((lut_floats * 4 + 15) / 16) * 16;
-  l.off_stage = o;   o += kLandingRows * kRowStride * 4;
+  l.off_stage = o;   o += stage_bytes;
   l.off_pool = o;    o += cap_pad * 8;
   l.off_bkeys = o;   o += kMaxBatch * 8;
   l.off_bsorted = o; o += kMaxBatch * 8;
@@ -122,8 +134,6 @@ __host__ __device__ inline uint32_t pool_entries(uint32_t cap) {
   uint32_t slack = cap / 4 > 64 ? cap / 4 : 64;
   return (cap + slack + 31) / 32 * 32;
 }
-// u64 keys the landing zone can hold when it doubles as sort scratch
-constexpr uint32_t kSortScratch = kLandingRows * kRowStride * 4 / 8;
 
 #ifdef __CUDACC__
 
@@ -146,8 +156,16 @@ __device__ __forceinline__ uint64_t warp_max_key(uint64_t v) {
   return ((uint64_t)mh << 32) | ml;
 }
 
-template <int METRIC, int PQ>
+// TREE = 0: distances summed strictly left to right, unfused (bit-identical to the crate's
+//           scalar loops); rows staged in shared memory by bulk copies.
+// TREE = 1: the sum order BASELINE.json's north_star prescribes for the kernel -- coalesced
+//           128-bit row loads, per-lane fused partial sums, warp-shuffle reduction; the order
+//           is fixed and restated by the oracle, results agree with the
+//           sequential order to a few ulp.
+template <int METRIC, int PQ, int TREE>
 struct WarpSearch {
+  static constexpr uint32_t kStageBytes = (TREE && !PQ) ? kScratchBytesTree : kLandingBytes;
+  static constexpr uint32_t kSortScratch = kStageBytes / 8;  // u64 keys the scratch can hold
   const SearchArgs &a;
   float *qvec;
   float *lut;
@@ -168,7 +186,7 @@ struct WarpSearch {
   uint64_t pmax;       // largest key of the pool (flag masked) as of the last rescan_max()
   uint32_t pmax_slot;
   uint32_t ovf_n;
-  uint64_t ovf_min;
+  uint64_t ovf_min;    // lower bound of the spilled keys that may precede a pool entry
   uint32_t vlog_n;
   bool vlog_over;
   uint32_t ph;    // mbarrier phase bits, one per stage
@@ -176,7 +194,7 @@ struct WarpSearch {
 
   __device__ WarpSearch(const SearchArgs &args, unsigned char *smem, uint32_t slot, int lane_)
       : a(args), lane(lane_) {
-    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0);
+    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0, kStageBytes);
     qvec = (float *)(smem + l.off_q);
     lut = (float *)(smem + l.off_lut);
     stage = (float *)(smem + l.off_stage);
@@ -207,7 +225,17 @@ struct WarpSearch {
     if (vlog_over) {
       for (uint32_t w = lane; w < a.bitmap_words; w += 32) bm[w] = 0u;
     } else {
-      for (uint32_t i = lane; i < vlog_n; i += 32) bm[ld_cg_u32(&vlog[i]) >> 5] = 0u;
+      for (uint32_t i0 = 0; i0 < vlog_n; i0 += 256) {  // 8 independent loads in flight per lane
+        uint32_t id[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          uint32_t i = i0 + u * 32 + lane;
+          id[u] = i < vlog_n ? ld_cg_u32(&vlog[i]) : kEmpty32;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (id[u] != kEmpty32) bm[id[u] >> 5] = 0u;
+      }
     }
     vlog_n = 0;
     vlog_over = false;
@@ -240,8 +268,9 @@ struct WarpSearch {
       return;
     }
     if (pred) ovf[ovf_n + __popc(m & ((1u << lane) - 1))] = key;
-    uint64_t mn = warp_min_key(pred ? key : kEmptyKey);
-    ovf_min = mn < ovf_min ? mn : ovf_min;
+    // no minimum is tracked here: every key spilled through this function is above the bound
+    // U, i.e. above every pool entry, so it can only be the next pop once the pool has no
+    // unexpanded entry left -- and that pop scans the whole list (ovf_pop_min)
     ovf_n += cnt;
   }
   // remove and return the smallest spilled key (ovf_n > 0)
@@ -453,6 +482,28 @@ struct WarpSearch {
     }
     return acc;
   }
+  // per-element terms of the sum, and the strictly sequential sum over them: together the
+  // same roundings as accum4 (every term is rounded to f32 before it is added)
+  __device__ __forceinline__ float4 terms4(const float4 &x, const float4 &q) const {
+    float4 r;
+    if (METRIC == kL2Sqrt) {
+      float t;
+      t = __fsub_rn(q.x, x.x); r.x = __fmul_rn(t, t);
+      t = __fsub_rn(q.y, x.y); r.y = __fmul_rn(t, t);
+      t = __fsub_rn(q.z, x.z); r.z = __fmul_rn(t, t);
+      t = __fsub_rn(q.w, x.w); r.w = __fmul_rn(t, t);
+    } else {
+      r.x = __fmul_rn(q.x, x.x); r.y = __fmul_rn(q.y, x.y);
+      r.z = __fmul_rn(q.z, x.z); r.w = __fmul_rn(q.w, x.w);
+    }
+    return r;
+  }
+  __device__ __forceinline__ float sum4(float acc, const float4 &t) const {
+    acc = __fadd_rn(acc, t.x);
+    acc = __fadd_rn(acc, t.y);
+    acc = __fadd_rn(acc, t.z);
+    return __fadd_rn(acc, t.w);
+  }
   __device__ __forceinline__ float finalize(float acc) const {
     if (METRIC == kCosHalf) return __fdiv_rn(__fsub_rn(1.0f, acc), 2.0f);
     if (METRIC == kOneMinusDot) return __fsub_rn(1.0f, acc);
@@ -461,6 +512,126 @@ struct WarpSearch {
     x = x < 0.0f ? 0.0f : x;
     x = x > 1.0f ? 1.0f : x;
     return x;
+  }
+
+  // Tree order.  Lane l owns the floats [128c + 4l, 128c + 4l + 4) of every 128-float chunk c:
+  // it accumulates them in index order with fused multiply-adds into one partial sum, and the
+  // 32 partials are added pairwise across lanes 16, 8, 4, 2, 1 apart (a butterfly; a + b is
+  // commutative, so every lane would hold the same value).  Rows are handled eight at a time:
+  // eight coalesced 512 B loads in flight per chunk, and the first three butterfly levels are
+  // done as a transposing reduction (half the values are handed to the partner lane at each
+  // level), which performs exactly the same additions with a third of the shuffles.
+  __device__ __forceinline__ float tree_accum(float acc, const float4 &x, const float4 &q) const {
+    if (METRIC == kL2Sqrt) {
+      float t;
+      t = __fsub_rn(q.x, x.x); acc = __fmaf_rn(t, t, acc);
+      t = __fsub_rn(q.y, x.y); acc = __fmaf_rn(t, t, acc);
+      t = __fsub_rn(q.z, x.z); acc = __fmaf_rn(t, t, acc);
+      t = __fsub_rn(q.w, x.w); acc = __fmaf_rn(t, t, acc);
+    } else {
+      acc = __fmaf_rn(q.x, x.x, acc);
+      acc = __fmaf_rn(q.y, x.y, acc);
+      acc = __fmaf_rn(q.z, x.z, acc);
+      acc = __fmaf_rn(q.w, x.w, acc);
+    }
+    return acc;
+  }
+  // the transposing butterfly: acc[0..8) per lane -> lane l holds the sum of row (l >> 2)
+  __device__ __forceinline__ float reduce8(const float (&acc)[8]) const {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float w4[4], w2[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float keep = b4 ? acc[i + 4] : acc[i], send = b4 ? acc[i] : acc[i + 4];
+      w4[i] = __fadd_rn(keep, __shfl_xor_sync(kFull, send, 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      float keep = b3 ? w4[i + 2] : w4[i], send = b3 ? w4[i] : w4[i + 2];
+      w2[i] = __fadd_rn(keep, __shfl_xor_sync(kFull, send, 8));
+    }
+    float keep = b2 ? w2[1] : w2[0], send = b2 ? w2[0] : w2[1];
+    float v = __fadd_rn(keep, __shfl_xor_sync(kFull, send, 4));
+    v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 2));
+    return __fadd_rn(v, __shfl_xor_sync(kFull, v, 1));
+  }
+  // rows of at most 128 floats: one 128-bit load per lane per row, no chunk loop
+  __device__ void compute_distances_tree1(const LayerDev &layer, uint32_t nn) {
+    const uint32_t fl4 = a.dim_pad / 4;
+    const bool in = (uint32_t)lane < fl4;
+    const float4 q4 = in ? ((const float4 *)qvec)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 *base = (const float4 *)a.rows + (in ? lane : 0);
+    const uint32_t pitch4 = a.pitch / 4;
+    const uint32_t *nodes = layer.nodes;
+    for (uint32_t j0 = 0; j0 < nn; j0 += 8) {
+      const uint4 ia = *(const uint4 *)&bid[j0], ib = *(const uint4 *)&bid[j0 + 4];
+      uint32_t id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+#pragma unroll
+      for (int r = 1; r < 8; r++) id[r] = j0 + r < nn ? id[r] : id[0];  // stale slots: reuse row 0
+      uint32_t vec[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) vec[r] = nodes ? __ldg(&nodes[id[r]]) : id[r];
+      float4 x[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) x[r] = __ldg(base + (size_t)vec[r] * pitch4);
+      float acc[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        float t = tree_accum(0.0f, x[r], q4);
+        acc[r] = in ? t : 0.0f;
+      }
+      const float v = reduce8(acc);
+      const uint32_t r = (uint32_t)lane >> 2, j = j0 + r;
+      if ((lane & 3) == 0 && j < nn) {
+        float d = finalize(v);
+        if (d != d) stat |= kStatNaN;
+        bkeys[j] = make_key(d, bid[j]);
+      }
+    }
+    __syncwarp();
+  }
+  __device__ void compute_distances_tree(const LayerDev &layer, uint32_t nn) {
+    constexpr int RB = 8;
+    const uint32_t fl4 = a.dim_pad / 4;
+    if (fl4 <= 32) {
+      compute_distances_tree1(layer, nn);
+      return;
+    }
+    const uint32_t nchunks = (fl4 + 31) / 32;
+    const float4 *q4p = (const float4 *)qvec;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t j0 = 0; j0 < nn; j0 += RB) {
+      const float4 *rp[RB];
+      bool valid[RB];
+#pragma unroll
+      for (int r = 0; r < RB; r++) {
+        valid[r] = j0 + r < nn;
+        uint32_t node = bid[valid[r] ? j0 + r : j0];
+        uint32_t vec = layer.nodes ? __ldg(&layer.nodes[node]) : node;
+        rp[r] = (const float4 *)(a.rows + (size_t)vec * a.pitch) + lane;
+      }
+      float acc[RB];
+#pragma unroll
+      for (int r = 0; r < RB; r++) acc[r] = 0.0f;
+      for (uint32_t c = 0; c < nchunks; c++) {
+        const bool in = c * 32 + lane < fl4;
+        const float4 q4 = in ? q4p[c * 32 + lane] : zero;
+        float4 x[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) x[r] = (in && valid[r]) ? __ldg(rp[r] + c * 32) : zero;
+#pragma unroll
+        for (int r = 0; r < RB; r++) acc[r] = tree_accum(acc[r], x[r], q4);
+      }
+      const float v = reduce8(acc);
+      // lane l now holds the sum of row j0 + (l >> 2)
+      const uint32_t j = j0 + ((uint32_t)lane >> 2);
+      if ((lane & 3) == 0 && j < nn) {
+        float d = finalize(v);
+        if (d != d) stat |= kStatNaN;
+        bkeys[j] = make_key(d, bid[j]);
+      }
+    }
+    __syncwarp();
   }
 
   // distances from the query to the vectors of nodes bid[0..nn) of `layer`;
@@ -504,8 +675,13 @@ struct WarpSearch {
       __syncwarp();
       return;
     }
+    if (TREE) {
+      compute_distances_tree(layer, nn);
+      return;
+    }
     if (a.dim_pad <= (uint32_t)kChunk) {  // one bulk copy per row: no chunk pipeline needed
       const uint32_t fl4 = a.dim_pad / 4;
+      const float4 q4 = (uint32_t)lane < fl4 ? ((const float4 *)qvec)[lane] : make_float4(0, 0, 0, 0);
       for (uint32_t p0 = 0; p0 < nn; p0 += kLandingRows) {
         const uint32_t j = p0 + lane;
         const bool active = (uint32_t)lane < (uint32_t)kLandingRows && j < nn;
@@ -521,12 +697,31 @@ struct WarpSearch {
         }
         mbar_wait(&mbar[0], ph & 1u);
         ph ^= 1u;
+        // phase 1, all 32 lanes: every landed row is replaced in place by its per-element
+        // terms ((q-x)^2 or q*x), one float4 per lane per row.  (No proxy fence before the next
+        // refill: phase 2 reads every term back, so the stores have landed long before the
+        // next bulk copy is issued; fence.proxy.async costs a MEMBAR.ALL that would also wait
+        // for the visited-bitmap REDs in flight.)
+        if ((uint32_t)lane < fl4) {
+          float4 *col = (float4 *)stage + lane;
+          uint32_t r = 0;
+          for (; r + 4 <= rows_p; r += 4) {
+            float4 x0 = col[(r + 0) * (kRowStride / 4)], x1 = col[(r + 1) * (kRowStride / 4)];
+            float4 x2 = col[(r + 2) * (kRowStride / 4)], x3 = col[(r + 3) * (kRowStride / 4)];
+            col[(r + 0) * (kRowStride / 4)] = terms4(x0, q4);
+            col[(r + 1) * (kRowStride / 4)] = terms4(x1, q4);
+            col[(r + 2) * (kRowStride / 4)] = terms4(x2, q4);
+            col[(r + 3) * (kRowStride / 4)] = terms4(x3, q4);
+          }
+          for (; r < rows_p; r++) col[r * (kRowStride / 4)] = terms4(col[r * (kRowStride / 4)], q4);
+        }
+        __syncwarp();
+        // phase 2, lane per row: the crate's strictly sequential sum over the terms
         if (active) {
           float acc = 0.0f;
           const float4 *rp = (const float4 *)(stage + lane * kRowStride);
-          const float4 *qp = (const float4 *)qvec;
 #pragma unroll 8
-          for (uint32_t k = 0; k < fl4; k++) acc = accum4(acc, rp[k], qp[k]);
+          for (uint32_t k = 0; k < fl4; k++) acc = sum4(acc, rp[k]);
           float d = finalize(acc);
           if (d != d) stat |= kStatNaN;
           bkeys[j] = make_key(d, node);
@@ -565,13 +760,28 @@ struct WarpSearch {
         mbar_wait(&mbar[s], (ph >> s) & 1u);
         ph ^= (1u << s);
         uint32_t j = p * R + lane;
-        if ((uint32_t)lane < R && j < nn) {
+        const uint32_t fl4 = min((uint32_t)kChunk, a.dim_pad - c * kChunk) / 4;
+        if ((uint32_t)lane < fl4) {  // phase 1: terms in place, one float4 per lane per row
+          const float4 q4 = ((const float4 *)(qvec + c * kChunk))[lane];
+          float4 *col = (float4 *)(stage + s * R * kRowStride) + lane;
+          const uint32_t rows_c = min(R, nn - p * R);
+          uint32_t r = 0;
+          for (; r + 4 <= rows_c; r += 4) {
+            float4 x0 = col[(r + 0) * (kRowStride / 4)], x1 = col[(r + 1) * (kRowStride / 4)];
+            float4 x2 = col[(r + 2) * (kRowStride / 4)], x3 = col[(r + 3) * (kRowStride / 4)];
+            col[(r + 0) * (kRowStride / 4)] = terms4(x0, q4);
+            col[(r + 1) * (kRowStride / 4)] = terms4(x1, q4);
+            col[(r + 2) * (kRowStride / 4)] = terms4(x2, q4);
+            col[(r + 3) * (kRowStride / 4)] = terms4(x3, q4);
+          }
+          for (; r < rows_c; r++) col[r * (kRowStride / 4)] = terms4(col[r * (kRowStride / 4)], q4);
+        }
+        __syncwarp();
+        if ((uint32_t)lane < R && j < nn) {  // phase 2: sequential sum, lane per row
           if (c == 0) acc = 0.0f;
-          uint32_t fl4 = min((uint32_t)kChunk, a.dim_pad - c * kChunk) / 4;
           const float4 *rp = (const float4 *)(stage + (s * R + lane) * kRowStride);
-          const float4 *qp = (const float4 *)(qvec + c * kChunk);
-#pragma unroll 4
-          for (uint32_t k = 0; k < fl4; k++) acc = accum4(acc, rp[k], qp[k]);
+#pragma unroll 8
+          for (uint32_t k = 0; k < fl4; k++) acc = sum4(acc, rp[k]);
           if (c == nchunks - 1) {
             float d = finalize(acc);
             if (d != d) stat |= kStatNaN;
@@ -629,7 +839,9 @@ struct WarpSearch {
       // ---- pop the smallest (d,id) among all discovered, unexpanded nodes
       if (!nx_valid) nx_key = scan_min_unexpanded(&nx_slot);
       uint32_t next;
-      if (ovf_n > 0 && ovf_min < nx_key) {
+      // ovf_min only tracks the duplicate-row keys (the one kind of spilled key that can be
+      // below a pool entry); the rest of the list matters once the pool is exhausted
+      if (ovf_n > 0 && (nx_key == kEmptyKey || ovf_min < nx_key)) {
         next = key_id(ovf_pop_min());
         nx_valid = true;  // the pool did not change
       } else if (nx_key != kEmptyKey) {
@@ -1152,15 +1364,17 @@ struct WarpSearch {
   }
 };
 
-template <int METRIC, int PQ>
-__global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
+template <int METRIC, int PQ, int TREE>
+__global__ void __launch_bounds__((TREE && !PQ ? kTreeWarps : kSeqWarps) * 32, 1)
+    search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t warps_per_cta = blockDim.x >> 5;
-  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0);
+  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0,
+                                        WarpSearch<METRIC, PQ, TREE>::kStageBytes);
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
-  WarpSearch<METRIC, PQ> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);
+  WarpSearch<METRIC, PQ, TREE> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);
   if (lane == 0) {
     for (int s = 0; s < kMaxStages; s++) mbar_init(&ws.mbar[s], 1);
     mbar_fence_init();

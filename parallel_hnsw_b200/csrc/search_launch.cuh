@@ -1,0 +1,34 @@
+// search_launch.cuh -- instantiates one variant (PQ, TREE) of the traversal kernel for the four
+// metrics; included by search_seq.cu / search_tree.cu / search_pq.cu.
+#pragma once
+#include "internal.h"
+
+namespace phnsw {
+
+template <int METRIC, int PQ, int TREE>
+static cudaError_t launch_typed(const SearchArgs &a, int grid, int block, size_t smem,
+                                cudaStream_t stream) {
+  static thread_local size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 8 || configured[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ, TREE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev < 8) configured[dev] = smem;
+  }
+  search_kernel<METRIC, PQ, TREE><<<grid, block, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template <int PQ, int TREE>
+static cudaError_t launch_metric(int metric, const SearchArgs &a, int grid, int block, size_t smem,
+                                 cudaStream_t stream) {
+  switch (metric) {
+    case kCosHalf: return launch_typed<kCosHalf, PQ, TREE>(a, grid, block, smem, stream);
+    case kOneMinusDot: return launch_typed<kOneMinusDot, PQ, TREE>(a, grid, block, smem, stream);
+    case kL2Sqrt: return launch_typed<kL2Sqrt, PQ, TREE>(a, grid, block, smem, stream);
+    default: return launch_typed<kCosClamp, PQ, TREE>(a, grid, block, smem, stream);
+  }
+}
+
+}  // namespace phnsw

@@ -21,6 +21,7 @@ EMPTY = np.uint64(N.EMPTY_ID)
 FLT_MAX = np.float32(3.4028235e38)
 
 COS_HALF, ONE_MINUS_DOT, L2_SQRT, COS_CLAMP = 0, 1, 2, 3
+SUM_SEQUENTIAL, SUM_TREE = N.SUM_SEQUENTIAL, N.SUM_TREE
 
 
 def SearchParameters(number_of_candidates=300, upper_layer_candidate_count=300, probe_depth=2):
@@ -221,6 +222,16 @@ class Hnsw:
 
     def vector_count(self):
         return int(N.lib().phnsw_index_vector_count(self._h))
+
+    def set_sum_order(self, order):
+        """Summation order of the traversal kernel's distances: SUM_SEQUENTIAL (the crate's
+        scalar loop bit for bit, default) or SUM_TREE (warp-shuffle reduction, a few ulp away;
+        see include/phnsw.h)."""
+        N.check(N.lib().phnsw_index_set_sum_order(self._h, int(order)))
+        return self
+
+    def sum_order(self):
+        return int(N.lib().phnsw_index_sum_order(self._h))
 
     def __len__(self):
         return self.vector_count()

@@ -362,3 +362,65 @@ def test_no_state_leaks_between_launches(ph, oracle, cfg1):
     gh.knn(5, 2)
     _assert_same(gh.search(q, ph.SearchParameters(40, 7, 3)),
                  oh.search(queries=q, sp=oracle.search_params(40, 7, 3)), "upper count < ef")
+
+
+# ------------------------------------------------------------------ PHNSW_SUM_TREE
+# The warp-shuffle summation order (include/phnsw.h) is restated by the oracle
+# (orc_distance_tree), so the tree mode is held to the same bit-exact bar against the oracle in
+# tree mode -- and to BASELINE.json's bar (ids equal for >= 99.9 % of queries, distances within
+# 1e-5 relative) against the crate's sequential order.
+def _tree_same(g, o, what, sqrt_metric):
+    # the tree oracle finishes L2 with the correctly rounded sqrtf, like the device
+    _assert_same(g, o, what, sqrt_metric=False)
+    assert np.array_equal(g[3].astype(np.uint64), o[3]), what + " n_dist differs"
+    assert np.array_equal(g[4].astype(np.uint64), o[4]), what + " n_exp differs"
+
+
+def test_cfg1_tree_order(ph, oracle, cfg1):
+    rows, oh, gh, queries = cfg1
+    o_seq = oh.search(queries=queries, max_out=10)
+    try:
+        gh.set_sum_order(ph.SUM_TREE)
+        oh.set_sum_order(1)
+        assert gh.sum_order() == ph.SUM_TREE
+        g = gh.search(queries, ph.SearchParameters(), stats=True)
+        _tree_same(g, oh.search(queries=queries, stats=True), "tree ef=300", False)
+        for ef, upper, probe, max_out in [(6, 6, 2, 6), (64, 300, 5, 64), (1000, 300, 2, 100)]:
+            q = queries[:200]
+            _tree_same(gh.search(q, ph.SearchParameters(ef, upper, probe), max_out=max_out, stats=True),
+                       oh.search(queries=q, sp=oracle.search_params(ef, upper, probe),
+                                 max_out=max_out, stats=True), "tree sweep", False)
+        _assert_same(gh.knn(10, 2), oh.knn(10, 2), "tree knn")
+        ids = np.arange(0, 10000, 37, dtype=np.uint64)
+        _assert_same(gh.search(stored_ids=ids, exclude=ids), oh.search(stored_ids=ids, exclude=ids),
+                     "tree stored+exclude")
+        # against the crate's order: the north-star bar
+        g10 = gh.search(queries, ph.SearchParameters(), max_out=10)
+        same = (g10[0] == o_seq[0]).all(1)
+        assert same.mean() >= 0.999, same.mean()
+        a, b = g10[1][same].astype(np.float64), o_seq[1][same].astype(np.float64)
+        assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-7)
+    finally:
+        gh.set_sum_order(ph.SUM_SEQUENTIAL)
+        oh.set_sum_order(0)
+    with pytest.raises(ph.PhnswError):
+        gh.set_sum_order(7)
+
+
+@pytest.mark.parametrize("metric_name,dim,n", [("L2_SQRT", 96, 6000), ("L2_SQRT", 30, 3000),
+                                               ("ONE_MINUS_DOT", 100, 5000),
+                                               ("COS_CLAMP", 200, 3000), ("COS_HALF", 1536, 2000)])
+def test_other_shapes_tree_order(ph, oracle, metric_name, dim, n):
+    metric = getattr(ph, metric_name)
+    if metric_name == "L2_SQRT":
+        rows = clustered(n, dim, 11, integer=(dim == 96))
+    else:
+        rows = random_normed(n, dim, 13)
+    oh = oracle.Hnsw.generate(metric, rows, seed=3, improve=False)
+    comp = ph.BigComparator(rows, metric)
+    gh = ph.Hnsw.from_layers(comp, oh.layers()).set_sum_order(ph.SUM_TREE)
+    oh.set_sum_order(1)
+    queries = rows[::17] + np.float32(0.01)
+    _tree_same(gh.search(queries, stats=True), oh.search(queries=queries, stats=True),
+               metric_name + " tree", metric == ph.L2_SQRT)
+    _assert_same(gh.knn(5, 2), oh.knn(5, 2), "tree knn")

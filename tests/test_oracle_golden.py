@@ -277,3 +277,35 @@ def test_pq_small_shape(oracle):
     ids, ds, cnt = pq.search(stored_ids=np.arange(0, 1500, 7, dtype=np.uint64), max_out=3)
     assert (ids[:, 0] == np.arange(0, 1500, 7)).mean() >= 0.9
     assert np.all(np.diff(ds[:, :cnt.min()], axis=1) >= 0)
+
+
+def test_tree_sum_order_is_within_the_north_star_tolerance(oracle):
+    """The device's PHNSW_SUM_TREE order restated (orc_distance_tree) against the crate's
+    sequential order: distances within 1e-5 relative, and on a searched index the top-10 id
+    lists equal for >= 99.9 % of the queries (BASELINE.json's parity bar)."""
+    from tests.helpers import clustered, random_normed
+    rng = np.random.default_rng(5)
+    for dim in (3, 30, 128, 130, 1536):
+        a = rng.normal(size=(50, dim)).astype(np.float32)
+        b = rng.normal(size=(50, dim)).astype(np.float32)
+        a /= np.linalg.norm(a, axis=1)[:, None]  # the dot metrics are defined on unit vectors
+        b /= np.linalg.norm(b, axis=1)[:, None]
+        for m in (oracle.L2_SQRT, oracle.COS_HALF, oracle.ONE_MINUS_DOT):
+            for x, y in zip(a, b):
+                s, t = float(oracle.distance(m, x, y)), float(oracle.distance_tree(m, x, y))
+                assert abs(s - t) <= 1e-5 * max(abs(s), 1.0), (dim, m, s, t)
+    # integer-valued data: every partial sum is an exact integer below 2^24, any order agrees
+    a = np.rint(rng.uniform(0, 218, size=(20, 128))).astype(np.float32)
+    for x in a[1:]:
+        s, t = oracle.distance(oracle.L2_SQRT, a[0], x), oracle.distance_tree(oracle.L2_SQRT, a[0], x)
+        assert abs(float(s) - float(t)) <= 2e-7 * float(s)
+    rows = random_normed(4000, 64, 9)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, seed=2, improve=False)
+    q = random_normed(1000, 64, 10)
+    seq = oh.search(queries=q, max_out=10)
+    tree = oh.set_sum_order(1).search(queries=q, max_out=10)
+    oh.set_sum_order(0)
+    same = (seq[0] == tree[0]).all(1)
+    assert same.mean() >= 0.999, same.mean()
+    rel = np.abs(seq[1][same].astype(np.float64) - tree[1][same]) / np.maximum(np.abs(seq[1][same]), 1e-30)
+    assert rel.max() <= 1e-5
