@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=2000)
     ap.add_argument("--cpu-queries", type=int, default=2000)
     ap.add_argument("--no-improve", action="store_true")
+    ap.add_argument("--sum-order", default="tree", choices=["tree", "sequential"],
+                    help="summation order of the traversal kernel's distances (include/phnsw.h)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -237,6 +239,7 @@ def main():
     layer_M = [gh.get_layer_from_top(i)[2] for i in range(L)] if rank == 0 else None
 
     sp = ph.SearchParameters(args.ef, args.ef, 2)
+    tree = args.sum_order == "tree"
     dq = queries_h.to(dev)
     oi = torch.empty((args.nq, k), dtype=torch.int64, device=dev)
     od = torch.empty((args.nq, k), dtype=torch.float32, device=dev)
@@ -246,6 +249,21 @@ def main():
 
     # ---- correctness at full size: exact ground truth + oracle cross-check on a sample ----
     gt, _ = comp.bruteforce_knn(dq, k)
+    # secondary number: the sequential summation order (bit-identical to the crate's loops)
+    gh.set_sum_order(ph.SUM_SEQUENTIAL)
+    for _ in range(args.warmup):
+        gh.search_device(dq, sp, oi, od, oc, stream=stream)
+    gh.sync(stream)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seq_steps = max(3, args.steps // 4)
+    s0.record()
+    for _ in range(seq_steps):
+        gh.search_device(dq, sp, oi, od, oc, stream=stream)
+    s1.record()
+    gh.sync(stream)
+    ms_seq = s0.elapsed_time(s1) / seq_steps
+    seq_ids, seq_ds = oi.cpu().numpy().astype(np.uint64), od.cpu().numpy().copy()
+    gh.set_sum_order(ph.SUM_TREE if tree else ph.SUM_SEQUENTIAL)
     gh.search_device(dq, sp, oi, od, oc, stream=stream, out_ndist=nd, out_nexp=ne)
     gh.sync(stream)
     recall = recall_at_k(oi.cpu().numpy(), gt.cpu().numpy(), k)
@@ -323,10 +341,23 @@ def main():
     cores = host_cores()
     oh.search(queries=queries_h.numpy()[:64], sp=osp, max_out=k, nthreads=cores)
     t0 = time.perf_counter()
-    o_ids, o_ds, o_cnt, o_nd, o_ne = oh.search(queries=queries_h.numpy()[:cq], sp=osp, max_out=k,
-                                               stats=True, nthreads=cores)
-    cpu_dt = time.perf_counter() - t0
+    q_ids, q_ds, _, q_nd, q_ne = oh.search(queries=queries_h.numpy()[:cq], sp=osp, max_out=k,
+                                           stats=True, nthreads=cores)
+    cpu_dt = time.perf_counter() - t0  # the crate's algorithm (sequential sums) is the baseline
     g_ids = oi.cpu().numpy().astype(np.uint64)[:cq]
+    # the timed order against the crate's order: BASELINE.json's bar (>= 99.9 % / 1e-5)
+    ids_equal_seq = float((g_ids == q_ids).all(1).mean())
+    m = (g_ids == q_ids)
+    rel_seq = np.abs(od.cpu().numpy()[:cq].astype(np.float64) - q_ds) / np.maximum(np.abs(q_ds), 1e-30)
+    max_rel_seq = float(rel_seq[m].max()) if m.any() else None
+    seq_dev_equal = float((seq_ids[:cq] == q_ids).all(1).mean())
+    if tree:  # and bit for bit against the oracle restating the same tree order
+        oh.set_sum_order(1)
+        o_ids, o_ds, o_cnt, o_nd, o_ne = oh.search(queries=queries_h.numpy()[:cq], sp=osp, max_out=k,
+                                                   stats=True, nthreads=cores)
+        oh.set_sum_order(0)
+    else:
+        o_ids, o_ds, o_nd, o_ne = q_ids, q_ds, q_nd, q_ne
     ids_equal = float((g_ids == o_ids).all(1).mean())
     counters_equal = float(((ndist[:cq] == o_nd.astype(np.int64)).all(1)
                             & (nexp[:cq] == o_ne.astype(np.int64)).all(1)).mean())
@@ -355,6 +386,7 @@ def main():
                    "n_vectors": args.n, "dim": args.dim, "queries_per_step_per_gpu": args.nq, "k": k,
                    "search": {"number_of_candidates": args.ef, "upper_layer_candidate_count": args.ef,
                               "probe_depth": 2},
+                   "sum_order": args.sum_order,
                    "layers_top_first": [int(x) for x in ph.calculate_partitions(args.n, 12)],
                    "cache": "inputs larger than L2 (rows %.0f MB + graph %.0f MB vs 126 MB L2)" % (
                        args.n * args.dim * 4 / 1e6, args.n * 48 * 4 / 1e6),
@@ -362,15 +394,24 @@ def main():
         "recall_at_10": recall,
         "build": {"vectors_per_s": args.n / t_build, "seconds": t_build,
                   "improve_index": not args.no_improve, "data_gen_seconds": t_gen},
-        "parity": {"sample_queries": cq, "ids_equal_frac": ids_equal,
-                   "work_counters_equal_frac": counters_equal, "max_rel_dist_err": max_rel},
+        "parity": {"sample_queries": cq, "sum_order": args.sum_order,
+                   "oracle_same_order": {"ids_equal_frac": ids_equal,
+                                         "work_counters_equal_frac": counters_equal,
+                                         "max_rel_dist_err": max_rel},
+                   "oracle_crate_order": {"ids_equal_frac": ids_equal_seq,
+                                          "max_rel_dist_err": max_rel_seq},
+                   "sequential_kernel_vs_oracle_ids_equal_frac": seq_dev_equal,
+                   "ids_equal_frac": ids_equal_seq, "max_rel_dist_err": max_rel_seq},
+        "sequential_order": {"value": world * args.nq / (ms_seq * 1e-3), "unit": "queries/s",
+                             "ms_per_step": ms_seq,
+                             "note": "same kernel with PHNSW_SUM_SEQUENTIAL (the crate's loop bit for bit)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s",
                 "h2d_bytes_per_step": int(args.nq * args.dim * 4),
                 "d2h_bytes_per_step": int(args.nq * (k * 12 + 4))},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "search_kernel<L2_SQRT>",
+                     "kernel": "search_kernel<L2_SQRT, %s>" % ("tree" if tree else "sequential"),
                      "algorithmic_bytes_per_launch": abytes,
                      "n_dist_per_query": float(ndist.sum() / args.nq),
                      "n_exp_per_query": float(nexp.sum() / args.nq)},
@@ -401,6 +442,7 @@ def run_sharded(args, ph, dist, dev, rank, world, k, stream):
     rows_h = sift_like(args.n, args.dim, 1234 + 7919 * (rank + 1))
     comp = ph.BigComparator(rows_h.numpy(), ph.L2_SQRT, device=dev.index)
     gh = ph.Hnsw.generate(comp, seed=1 + rank, improve=not args.no_improve)
+    gh.set_sum_order(ph.SUM_TREE if args.sum_order == "tree" else ph.SUM_SEQUENTIAL)
     sp = ph.SearchParameters(args.ef, args.ef, 2)
     dq = sift_like(args.nq, args.dim, 4321).to(dev) if rank == 0 else torch.empty(
         (args.nq, args.dim), dtype=torch.float32, device=dev)
