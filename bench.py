@@ -248,7 +248,13 @@ def main():
     ne = torch.zeros((args.nq, L), dtype=torch.int32, device=dev)
 
     # ---- correctness at full size: exact ground truth + oracle cross-check on a sample ----
+    comp.bruteforce_knn(dq[:256], k)  # warm-up (allocator, kernel attributes)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     gt, _ = comp.bruteforce_knn(dq, k)
+    torch.cuda.synchronize()
+    t_gt = time.perf_counter() - t0
+    gt_stats = comp.bruteforce_last_stats()
     # secondary number: the sequential summation order (bit-identical to the crate's loops)
     gh.set_sum_order(ph.SUM_SEQUENTIAL)
     for _ in range(args.warmup):
@@ -402,6 +408,18 @@ def main():
                                           "max_rel_dist_err": max_rel_seq},
                    "sequential_kernel_vs_oracle_ids_equal_frac": seq_dev_equal,
                    "ids_equal_frac": ids_equal_seq, "max_rel_dist_err": max_rel_seq},
+        "ground_truth": {
+            "what": "exact brute-force kNN of the query batch (recall denominator)",
+            "seconds": t_gt, "path": gt_stats["path"],
+            "filter_kernel": "tc_filter_kernel (tcgen05 bf16 hi/lo split GEMM, M128 N128 K16)",
+            "filter_ms": gt_stats["filter_ms"],
+            "filter_tflops": (gt_stats["filter_flops"] / gt_stats["filter_ms"] / 1e9
+                              if gt_stats["filter_ms"] > 0 else None),
+            "tensor_peak_tflops": peaks.get("bf16_tflops"),
+            "frac_of_tensor_peak": (gt_stats["filter_flops"] / gt_stats["filter_ms"] / 1e9
+                                    / peaks["bf16_tflops"]
+                                    if gt_stats["filter_ms"] > 0 and peaks.get("bf16_tflops") else None),
+            "max_candidates_per_query": gt_stats["max_candidates"]},
         "sequential_order": {"value": world * args.nq / (ms_seq * 1e-3), "unit": "queries/s",
                              "ms_per_step": ms_seq,
                              "note": "same kernel with PHNSW_SUM_SEQUENTIAL (the crate's loop bit for bit)"},

@@ -231,6 +231,17 @@ phnsw_status phnsw_bruteforce_knn(const phnsw_store *s, const float *queries, ui
 phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *queries_device,
                                          uint64_t nq, uint64_t k, uint64_t *out_ids_device,
                                          float *out_dists_device, void *cuda_stream);
+/* How the last phnsw_bruteforce_knn[_device] call of this thread ran: path 1 = tcgen05 GEMM
+ * filter + exact re-rank (same output bits), path 0 = CUDA-core exact scan.  filter_ms /
+ * filter_flops are the tensor-core kernel's duration (CUDA events) and the flops it issued. */
+typedef struct {
+  int path;
+  float filter_ms;
+  double filter_flops;
+  uint32_t max_candidates, candidate_cap;
+  uint64_t prefix_rows;
+} phnsw_bruteforce_stats;
+void phnsw_bruteforce_last_stats(phnsw_bruteforce_stats *out);
 
 /* ---- product quantisation: QuantizedHnsw (src/pq.rs:120-477) ----
  * One codebook shared by all sub-spaces, sampled from the data's own sub-vectors

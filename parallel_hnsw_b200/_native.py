@@ -52,6 +52,12 @@ class PqBuildParams(C.Structure):  # src/parameters.rs:66-71
                 ("quantized_search", SearchParams)]
 
 
+class BruteforceStats(C.Structure):
+    _fields_ = [("path", C.c_int), ("filter_ms", C.c_float), ("filter_flops", C.c_double),
+                ("max_candidates", C.c_uint32), ("candidate_cap", C.c_uint32),
+                ("prefix_rows", C.c_uint64)]
+
+
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_double)
 
 u64p, f32p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p
@@ -106,6 +112,7 @@ SIGNATURES = {
     "phnsw_stochastic_recall": (C.c_int, [vp, C.POINTER(OptimizationParams), f32p]),
     "phnsw_bruteforce_knn": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
     "phnsw_bruteforce_knn_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
+    "phnsw_bruteforce_last_stats": (None, [vp]),
     "phnsw_default_pq_build_params": (None, [C.POINTER(PqBuildParams)]),
     "phnsw_pq_build": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                  C.POINTER(PqBuildParams), C.c_uint64, PROGRESS_FN, vp,

@@ -198,6 +198,49 @@ static void launch_tile(const phnsw_store *s, const float *dq, uint32_t nq, uint
 
 using namespace phnsw;
 
+namespace phnsw {
+
+// exact top-k of rows [0, n_rows) folded into topk (nq x k keys, caller-initialised); asynchronous
+// on `st` except for the scratch allocation
+phnsw_status bf_exact_prefix(const phnsw_store *s, const float *dq, uint32_t nq, uint64_t n_rows,
+                             uint32_t k, uint64_t *topk, cudaStream_t st) {
+  // chunk of rows whose distance matrix stays around 1 GiB
+  uint64_t chunk = (1ull << 28) / nq;
+  chunk = std::max<uint64_t>(chunk, 4096);
+  chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(n_rows, 1));
+  chunk = (chunk + 63) / 64 * 64;
+  float *dmat = nullptr;
+  PH_CUDA(cudaMalloc(&dmat, (size_t)nq * chunk * 4));
+  cudaMemsetAsync(topk, 0xFF, (size_t)nq * k * 8, st);
+  const int wpb = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (96 * 1024) / ((uint64_t)k * 8)));
+  for (uint64_t row0 = 0; row0 < n_rows; row0 += chunk) {
+    uint32_t nr = (uint32_t)std::min<uint64_t>(chunk, n_rows - row0);
+    switch (s->metric) {
+      case kCosHalf: launch_tile<kCosHalf>(s, dq, nq, row0, nr, dmat, (uint32_t)chunk, st); break;
+      case kOneMinusDot: launch_tile<kOneMinusDot>(s, dq, nq, row0, nr, dmat, (uint32_t)chunk, st); break;
+      case kL2Sqrt: launch_tile<kL2Sqrt>(s, dq, nq, row0, nr, dmat, (uint32_t)chunk, st); break;
+      default: launch_tile<kCosClamp>(s, dq, nq, row0, nr, dmat, (uint32_t)chunk, st); break;
+    }
+    size_t smem = (size_t)wpb * k * 8;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bf_select_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, smem, st>>>(
+        dmat, (uint32_t)chunk, nq, row0, nr, k, topk);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(dmat);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "bruteforce_knn (exact scan)");
+  return PHNSW_OK;
+}
+
+// brute_tc.cu: the tcgen05 filter + exact re-rank; *done = 0 -> use the scan above
+phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t nq, uint64_t k,
+                               uint64_t *out_ids, float *out_dists, cudaStream_t st, int *done);
+void bruteforce_stats_reset();
+
+}  // namespace phnsw
+
 extern "C" {
 
 phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *queries_device,
@@ -217,43 +260,24 @@ phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const float *quer
   cudaStream_t st = (cudaStream_t)cuda_stream;
   PH_CUDA(cudaSetDevice(s->device));
   cudaGetLastError();  // do not attribute a stale error of an earlier call to this one
-  // chunk of rows whose distance matrix stays around 1 GiB
-  uint64_t chunk = (1ull << 28) / nq;
-  chunk = std::max<uint64_t>(chunk, 4096);
-  chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(s->n, 1));
-  chunk = (chunk + 63) / 64 * 64;
-  float *dmat = nullptr;
+  bruteforce_stats_reset();
+  // tensor-core filter + exact re-rank where the shape allows it (same bits out)
+  int done = 0;
+  phnsw_status rc = bruteforce_knn_tc(s, queries_device, nq, k, out_ids_device, out_dists_device,
+                                      st, &done);
+  if (rc != PHNSW_OK || done) return rc;
   uint64_t *topk = nullptr;
-  PH_CUDA(cudaMalloc(&dmat, nq * chunk * 4));
-  cudaError_t e = cudaMalloc(&topk, nq * k * 8);
-  if (e != cudaSuccess) {
-    cudaFree(dmat);
-    return cuda_fail(e, "cudaMalloc(topk)");
+  PH_CUDA(cudaMalloc(&topk, nq * k * 8));
+  rc = bf_exact_prefix(s, queries_device, (uint32_t)nq, s->n, (uint32_t)k, topk, st);
+  if (rc == PHNSW_OK) {
+    bf_emit_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, st>>>(topk, nq * k, out_ids_device,
+                                                                    out_dists_device);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "bruteforce_knn");
   }
-  cudaMemsetAsync(topk, 0xFF, nq * k * 8, st);
-  const int wpb = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (96 * 1024) / (k * 8)));
-  for (uint64_t row0 = 0; row0 < s->n; row0 += chunk) {
-    uint32_t nr = (uint32_t)std::min<uint64_t>(chunk, s->n - row0);
-    switch (s->metric) {
-      case kCosHalf: launch_tile<kCosHalf>(s, queries_device, (uint32_t)nq, row0, nr, dmat, (uint32_t)chunk, st); break;
-      case kOneMinusDot: launch_tile<kOneMinusDot>(s, queries_device, (uint32_t)nq, row0, nr, dmat, (uint32_t)chunk, st); break;
-      case kL2Sqrt: launch_tile<kL2Sqrt>(s, queries_device, (uint32_t)nq, row0, nr, dmat, (uint32_t)chunk, st); break;
-      default: launch_tile<kCosClamp>(s, queries_device, (uint32_t)nq, row0, nr, dmat, (uint32_t)chunk, st); break;
-    }
-    size_t smem = (size_t)wpb * k * 8;
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bf_select_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, smem, st>>>(
-        dmat, (uint32_t)chunk, (uint32_t)nq, row0, nr, (uint32_t)k, topk);
-  }
-  bf_emit_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, st>>>(topk, nq * k, out_ids_device,
-                                                                  out_dists_device);
-  e = cudaStreamSynchronize(st);
-  cudaFree(dmat);
   cudaFree(topk);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "bruteforce_knn");
-  return PHNSW_OK;
+  return rc;
 }
 
 phnsw_status phnsw_bruteforce_knn(const phnsw_store *s, const float *queries, uint64_t nq,

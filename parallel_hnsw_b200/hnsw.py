@@ -140,6 +140,16 @@ class BigComparator:
         N.check(N.lib().phnsw_bruteforce_knn(self._h, _ptr(queries), nq, k, _ptr(ids), _ptr(ds)))
         return ids, ds
 
+    @staticmethod
+    def bruteforce_last_stats():
+        """How this thread's last bruteforce_knn ran (path 1 = tcgen05 filter + exact re-rank,
+        0 = CUDA-core scan), the filter kernel's milliseconds and flops, candidate counts."""
+        st = N.BruteforceStats()
+        N.lib().phnsw_bruteforce_last_stats(C.byref(st))
+        return {"path": "tensor" if st.path == 1 else "cuda", "filter_ms": float(st.filter_ms),
+                "filter_flops": float(st.filter_flops), "max_candidates": int(st.max_candidates),
+                "candidate_cap": int(st.candidate_cap), "prefix_rows": int(st.prefix_rows)}
+
     def close(self):
         if getattr(self, "_h", None):
             N.lib().phnsw_store_destroy(self._h)

@@ -1,0 +1,83 @@
+"""GPU parity of the tensor-core brute-force path (tcgen05 GEMM filter + exact re-rank,
+csrc/brute_tc.cu) against the CUDA-core exact scan (csrc/brute.cu): the filter may only skip
+rows that cannot be in the top-k, every distance that is output comes from the re-rank in the
+crate's sequential f32 order -- so ids and distance bits have to be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import clustered, random_normed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ph():
+    import parallel_hnsw_b200 as p
+    if p.device_count() == 0:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return p
+
+
+def _both(ph, comp, q, k):
+    old = os.environ.get("PHNSW_BRUTEFORCE")
+    try:
+        os.environ["PHNSW_BRUTEFORCE"] = "cuda"
+        ci, cd = comp.bruteforce_knn(q, k)
+        assert comp.bruteforce_last_stats()["path"] == "cuda"
+        os.environ["PHNSW_BRUTEFORCE"] = "tensor"
+        ti, td = comp.bruteforce_knn(q, k)
+        st = comp.bruteforce_last_stats()
+    finally:
+        if old is None:
+            os.environ.pop("PHNSW_BRUTEFORCE", None)
+        else:
+            os.environ["PHNSW_BRUTEFORCE"] = old
+    return (ci, cd), (ti, td), st
+
+
+@pytest.mark.parametrize("metric_name,dim,n,nq,k", [
+    ("L2_SQRT", 128, 40000, 300, 10),     # integer-valued SIFT-shaped rows
+    ("L2_SQRT", 96, 50000, 257, 17),      # float rows, ragged query block, dim not a multiple of 64
+    ("L2_SQRT", 30, 20011, 64, 5),        # padded rows (pitch 32), ragged last tile
+    ("COS_HALF", 128, 40000, 200, 10),
+    ("ONE_MINUS_DOT", 100, 33000, 130, 33),
+    ("COS_HALF", 192, 20000, 128, 10),    # three k-blocks
+])
+def test_tensor_path_returns_the_same_bits(ph, metric_name, dim, n, nq, k):
+    metric = getattr(ph, metric_name)
+    if metric_name == "L2_SQRT":
+        rows = clustered(n, dim, 21, n_clusters=256, spread=0.3, integer=(dim == 128))
+        q = clustered(nq, dim, 22, n_clusters=256, spread=0.3, integer=(dim == 128))
+    else:
+        rows = random_normed(n, dim, 23)
+        q = random_normed(nq, dim, 24)
+    comp = ph.BigComparator(rows, metric)
+    (ci, cd), (ti, td), st = _both(ph, comp, q, k)
+    assert st["path"] == "tensor", st
+    assert 0 < st["max_candidates"] <= st["candidate_cap"]
+    assert np.array_equal(ci, ti), "ids differ in %d rows" % int((ci != ti).any(1).sum())
+    assert np.array_equal(cd.view(np.uint32), td.view(np.uint32))
+
+
+def test_tensor_path_with_large_norms_and_duplicates(ph):
+    """Rows far from the origin (large |x|^2 against small distances: the margin of the filter
+    scales with the norms) and exact duplicates (ties ordered by id)."""
+    rng = np.random.default_rng(5)
+    base = (rng.normal(size=(5000, 64)) * 0.05 + 30.0).astype(np.float32)
+    rows = np.ascontiguousarray(base[rng.integers(0, 5000, size=40000)])
+    q = np.ascontiguousarray(base[:200] + np.float32(0.001))
+    comp = ph.BigComparator(rows, ph.L2_SQRT)
+    (ci, cd), (ti, td), st = _both(ph, comp, q, 20)
+    if st["path"] == "tensor":  # an overflowing candidate list falls back, which is also exact
+        assert st["max_candidates"] <= st["candidate_cap"]
+    assert np.array_equal(ci, ti)
+    assert np.array_equal(cd.view(np.uint32), td.view(np.uint32))
+
+
+def test_small_problems_stay_on_the_exact_scan(ph):
+    rows = random_normed(3000, 64, 1)
+    comp = ph.BigComparator(rows, ph.COS_HALF)
+    comp.bruteforce_knn(rows[:10], 5)
+    assert comp.bruteforce_last_stats()["path"] == "cuda"
