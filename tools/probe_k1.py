@@ -22,6 +22,7 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--tag", default="")
 ap.add_argument("--no-improve", action="store_true")
 ap.add_argument("--order", type=int, nargs="+", default=[0], help="0 sequential, 1 tree")
+ap.add_argument("--streams", type=int, default=1)
 ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one launch "
                 "(ncu --profile-from-start off)")
 args = ap.parse_args()
@@ -50,11 +51,29 @@ for order, nq in [(o, n) for o in args.order for n in args.nq]:
         gh.sync(st)
         torch.cuda.profiler.stop()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.reps):
-        gh.search_device(dq, sp, oi, od, oc, stream=st)
-    e1.record()
-    gh.sync(st)
+    if args.streams == 1:
+        e0.record()
+        for _ in range(args.reps):
+            gh.search_device(dq, sp, oi, od, oc, stream=st)
+        e1.record()
+        gh.sync(st)
+    else:
+        ss = [torch.cuda.Stream() for _ in range(args.streams)]
+        outs = [(torch.empty_like(oi), torch.empty_like(od), torch.empty_like(oc)) for _ in ss]
+        for i, s_ in enumerate(ss):  # warm the per-stream workspaces
+            gh.search_device(dq, sp, *outs[i], stream=s_.cuda_stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for s_ in ss:
+            s_.wait_event(e0)
+        for r in range(args.reps):
+            i = r % len(ss)
+            gh.search_device(dq, sp, *outs[i], stream=ss[i].cuda_stream)
+        for s_ in ss:
+            torch.cuda.current_stream().wait_stream(s_)
+        e1.record()
+        torch.cuda.synchronize()
+        oi, od = outs[0][0], outs[0][1]
     ms = e0.elapsed_time(e1) / args.reps
     h = hashlib.sha1(oi.cpu().numpy().tobytes() + od.cpu().numpy().tobytes()).hexdigest()[:12]
     print("PROBE %s order=%d nq=%d: %.3f ms, %.0f QPS, build %.2fs, out sha %s" % (
