@@ -218,8 +218,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")  # any level >= VERSION prints a banner on stdout; keep
+                                          # stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     k = 10
     stream = torch.cuda.current_stream().cuda_stream
