@@ -242,6 +242,16 @@ typedef struct {
   uint64_t prefix_rows;
 } phnsw_bruteforce_stats;
 void phnsw_bruteforce_last_stats(phnsw_bruteforce_stats *out);
+/* How the last nearest-centroid assignment of this thread ran (k-means iteration of
+ * phnsw_pq8_train / encoding of phnsw_pq8_store_create): path 1 = tcgen05 GEMM + exact check of
+ * the undecided rows (same codes), path 0 = CUDA-core exact scan. */
+typedef struct {
+  int path;
+  float kernel_ms;
+  double flops;
+  uint64_t rows, rechecked;
+} phnsw_assign_stats;
+void phnsw_assign_last_stats(phnsw_assign_stats *out);
 
 /* ---- product quantisation: QuantizedHnsw (src/pq.rs:120-477) ----
  * One codebook shared by all sub-spaces, sampled from the data's own sub-vectors

@@ -2,12 +2,12 @@
 terminusdb-labs/parallel-hnsw (see include/phnsw.h for the C ABI, hnsw.py for the host mirror)."""
 from .hnsw import (BigComparator, BuildParameters, COS_CLAMP, COS_HALF, EMPTY, FLT_MAX, Hnsw,
                    L2_SQRT, ONE_MINUS_DOT, PhnswError, Pq8Comparator, PqBuildParameters,
-                   QuantizedHnsw, pq8_train,
+                   QuantizedHnsw, assign_last_stats, pq8_train,
                    SearchParameters, SUM_SEQUENTIAL, SUM_TREE, calculate_partitions,
                    device_count, merge_topk_device)
 
 __all__ = ["BigComparator", "BuildParameters", "COS_CLAMP", "COS_HALF", "EMPTY", "FLT_MAX", "Hnsw",
            "L2_SQRT", "ONE_MINUS_DOT", "PhnswError", "Pq8Comparator", "PqBuildParameters",
-           "QuantizedHnsw", "pq8_train",
+           "QuantizedHnsw", "assign_last_stats", "pq8_train",
            "SearchParameters", "SUM_SEQUENTIAL", "SUM_TREE", "calculate_partitions",
            "device_count", "merge_topk_device"]

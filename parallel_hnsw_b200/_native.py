@@ -58,6 +58,11 @@ class BruteforceStats(C.Structure):
                 ("prefix_rows", C.c_uint64)]
 
 
+class AssignStats(C.Structure):
+    _fields_ = [("path", C.c_int), ("kernel_ms", C.c_float), ("flops", C.c_double),
+                ("rows", C.c_uint64), ("rechecked", C.c_uint64)]
+
+
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_double)
 
 u64p, f32p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p
@@ -113,6 +118,7 @@ SIGNATURES = {
     "phnsw_bruteforce_knn": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
     "phnsw_bruteforce_knn_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
     "phnsw_bruteforce_last_stats": (None, [vp]),
+    "phnsw_assign_last_stats": (None, [vp]),
     "phnsw_default_pq_build_params": (None, [C.POINTER(PqBuildParams)]),
     "phnsw_pq_build": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                  C.POINTER(PqBuildParams), C.c_uint64, PROGRESS_FN, vp,

@@ -30,6 +30,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "internal.h"
 
 namespace phnsw {
@@ -119,6 +121,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "memory");
 #pragma unroll
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
 }
 
 // 8 consecutive floats -> one 16 B chunk of bf16 high parts and one of bf16 low parts
@@ -479,6 +491,269 @@ __global__ void tc_max_u32_kernel(const uint32_t *__restrict__ v, uint32_t n, ui
   if ((threadIdx.x & 31) == 0 && x) atomicMax(out, x);
 }
 
+
+// ============================================================================================
+// K4a: exact nearest-centroid assignment (k-means / PQ encoding) on the tensor cores.
+// BASELINE.json north_star kernel (4): "PQ k-means centroid assignment ... as tcgen05 GEMMs".
+// Replaces the exact CUDA-core scan that pq8.cu runs per k-means iteration (the crate's own
+// assignment is an HNSW search over the centroids, src/pq.rs:61-71; its k-means is dead code,
+// src/pq.rs:216-259 -- the definition kept here is DESIGN.md's: argmin by (sqrt of the
+// sequential f32 sum of squares, centroid id)).
+//
+// Roles are the mirror image of the filter above: the codebook (K <= 256 centroids of cs <= 16
+// floats) is the resident B operand, 128 sub-vectors per tile stream through the A ring.  One
+// K = 64 block per tile:
+//   positions [0, 3cs)   (-2x)h.ch + (-2x)h.cl + (-2x)l.ch       (bf16 hi/lo split, as above)
+//   positions [48, 51)   1 x (three bf16 pieces of |c|^2)
+//   positions [51, 54)   (three bf16 pieces of |x|^2 + bias) x 1
+// so the accumulator IS the squared distance + bias, with bias = 1.5 x the error bound, hence
+// >= 0: its bits order like unsigned integers, the low 8 mantissa bits are replaced by the
+// centroid index and the epilogue is three integer min/max per value (best and runner-up).
+// A row whose runner-up is further away than every rounding error is decided; the few others
+// go to an exact warp-per-row scan (tc_assign_exact_kernel), so the codes are exactly those of
+// the scan.
+constexpr int kAsgThreads = 9 * 32;  // 4 epilogue + 1 MMA + 4 producer warps (one stage each)
+constexpr int kAsgStages = 4;
+constexpr int kAsgN = 256;
+
+struct AssignArgs {
+  const float *sub;       // m x cs f32, consecutive
+  uint64_t m;
+  uint32_t cs;
+  const uint4 *btile;     // 256 x 128 B swizzled bf16 codebook operand (32 KB), built on the host
+  float c;                // relative error bound factor
+  float cmax2;            // max_k |c_k|^2
+  uint8_t *codes;         // m
+  uint32_t *recheck;      // row ids that need the exact scan
+  uint32_t *recheck_cnt;
+  uint32_t recheck_cap;
+};
+
+__device__ __forceinline__ void split3(float v, uint16_t (&p)[3]) {  // v = p0 + p1 + p2 (24 bits)
+  __nv_bfloat16 a = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(a);
+  __nv_bfloat16 b = __float2bfloat16_rn(r);
+  r -= __bfloat162float(b);
+  __nv_bfloat16 cc = __float2bfloat16_rn(r);
+  p[0] = __bfloat16_as_ushort(a);
+  p[1] = __bfloat16_as_ushort(b);
+  p[2] = __bfloat16_as_ushort(cc);
+}
+
+template <int CS>
+__global__ void __launch_bounds__(kAsgThreads, 1) tc_assign_kernel(const AssignArgs a) {
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char *smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t S = kAsgStages;
+  unsigned char *smB = smem;                         // 32 KB
+  unsigned char *smA = smB + kAsgN * 128;            // S x 16 KB
+  float *ering = (float *)(smA + S * kTileA);        // per-row error bound, kWRing tiles
+  uint64_t *full = (uint64_t *)(ering + kWRing * kM);
+  uint64_t *empty = full + 8;
+  uint64_t *tfull = empty + 8;
+  uint64_t *tempty = tfull + 2;
+  uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+  constexpr uint32_t kIdesc = make_idesc(kAsgN);
+  constexpr uint32_t kCols = 2 * kAsgN;
+
+  const uint64_t n_tiles = (a.m + kM - 1) / kM;
+  const uint32_t T = blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < S; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < kAsgN * 8; i += blockDim.x) ((uint4 *)smB)[i] = __ldg(&a.btile[i]);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 5) {
+    // ================= producers: warp g fills stage g; a lane handles 4 rows of the tile
+    const uint32_t g = warp - 5;
+    constexpr uint32_t cs = CS, cs4 = CS / 4;
+    for (uint32_t t = g; t < T; t += S) {
+      mbar_wait(&empty[g], ((t / S) & 1u) ^ 1u);
+      const uint64_t tile = blockIdx.x + (uint64_t)t * gridDim.x;
+      unsigned char *at = smA + (size_t)g * kTileA;
+      float4 f[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint64_t row = tile * kM + lane + 32 * i;
+        const float4 *src = (const float4 *)(a.sub + row * cs);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          f[i][j] = (row < a.m && (uint32_t)j < cs4) ? __ldg(src + (j < (int)cs4 ? j : 0))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t r = lane + 32 * i;
+        // bf16 hi / lo parts of -2x, positions [0, cs) / [cs, 2cs) = hi, [2cs, 3cs) = lo
+        uint16_t h[16], l[16];
+        float nx2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float v[4] = {f[i][j].x, f[i][j].y, f[i][j].z, f[i][j].w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            nx2 = fmaf(v[e], v[e], nx2);
+            const float w = -2.0f * v[e];
+            const __nv_bfloat16 hh = __float2bfloat16_rn(w);
+            h[4 * j + e] = __bfloat16_as_ushort(hh);
+            l[4 * j + e] = __bfloat16_as_ushort(__float2bfloat16_rn(w - __bfloat162float(hh)));
+          }
+        }
+        const float E = a.c * (nx2 + a.cmax2);
+        uint16_t np[3];
+        split3(nx2 + 1.5f * E, np);
+        ering[(t % kWRing) * kM + r] = E;
+        // chunk-wise assembly: 8 chunks of 8 bf16
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+          uint32_t wds[4];
+#pragma unroll
+          for (int k2 = 0; k2 < 4; k2++) {
+            uint32_t pair = 0;
+#pragma unroll
+            for (int hlf = 0; hlf < 2; hlf++) {
+              const uint32_t pos = ch * 8 + k2 * 2 + hlf;
+              uint16_t val = 0;
+              if (pos < cs) val = h[pos & 15];
+              else if (pos < 2 * cs) val = h[(pos - cs) & 15];
+              else if (pos < 3 * cs) val = l[(pos - 2 * cs) & 15];
+              else if (pos >= 48 && pos < 51) val = 0x3F80;  // 1.0 x the |c|^2 pieces
+              else if (pos >= 51 && pos < 54) val = np[pos - 51];
+              pair |= (uint32_t)val << (16 * hlf);
+            }
+            wds[k2] = pair;
+          }
+          *(uint4 *)(at + sw128(r, ch)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[g]);
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer: four K16 steps per tile
+    const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
+    for (uint32_t t = 0; t < T; t++) {
+      const uint32_t b = t & 1u, s = t % S;
+      mbar_wait(&tempty[b], ((t >> 1) & 1u) ^ 1u);
+      mbar_wait(&full[s], (t / S) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t ad = umma_desc(a_base + s * kTileA), bd = umma_desc(b_base);
+        const uint32_t d = tmem_base + b * kAsgN;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) umma_bf16(d, ad + 2 * k, bd + 2 * k, kIdesc, k != 0);
+        umma_commit(&empty[s]);
+        umma_commit(&tfull[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: one sub-vector per thread (TMEM lane), all 256 columns
+    for (uint32_t t = 0; t < T; t++) {
+      const uint32_t b = t & 1u;
+      mbar_wait(&tfull[b], (t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + b * kAsgN;
+      // best and runner-up key, four independent chains (columns j mod 4) merged at the end
+      uint32_t p1[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      uint32_t p2[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll 1
+      for (int c = 0; c < kAsgN / 64; c++) {
+        uint32_t v[64];
+        tmem_ld64(taddr + c * 64, v);
+#pragma unroll
+        for (int j = 0; j < 64; j++) {
+          const uint32_t key = (v[j] & 0xFFFFFF00u) | (uint32_t)(c * 64 + j);
+          p2[j & 3] = min(p2[j & 3], max(p1[j & 3], key));
+          p1[j & 3] = min(p1[j & 3], key);
+        }
+      }
+      uint32_t m1 = p1[0], m2 = p2[0];
+#pragma unroll
+      for (int i = 1; i < 4; i++) {
+        m2 = min(max(m1, p1[i]), min(m2, p2[i]));
+        m1 = min(m1, p1[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+      const uint64_t tile = blockIdx.x + (uint64_t)t * gridDim.x;
+      const uint64_t row = tile * kM + warp * 32 + lane;
+      if (row < a.m) {
+        const float E = ering[(t % kWRing) * kM + warp * 32 + lane];
+        const float v1 = __uint_as_float(m1 & 0xFFFFFF00u), v2 = __uint_as_float(m2 & 0xFFFFFF00u);
+        // truncation: true accumulator in [v, v (1 + 2^-15)); decided iff the runner-up's lower
+        // bound clears the best's upper bound by more than twice the error bound
+        const bool sure = v2 - v1 * (1.0f + 3.1e-5f) > 2.0f * E;
+        a.codes[row] = (uint8_t)(m1 & 0xFFu);
+        if (!sure) {
+          const uint32_t pos = atomicAdd(a.recheck_cnt, 1u);
+          if (pos < a.recheck_cap) a.recheck[pos] = (uint32_t)row;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols)
+                 : "memory");
+  }
+}
+
+// the exact scan for the rows the GEMM could not decide: one warp per row, lanes over centroids,
+// sequential f32 sum of squares, argmin by (sqrt, id) -- the arithmetic of bf_tile_kernel
+__global__ void tc_assign_exact_kernel(const float *__restrict__ sub, uint32_t cs,
+                                       const float *__restrict__ codebook, uint32_t K,
+                                       const uint32_t *__restrict__ rows, uint32_t n,
+                                       uint8_t *__restrict__ codes) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n) return;
+  const uint32_t row = rows[w];
+  const float *x = sub + (size_t)row * cs;
+  uint64_t best = kEmptyKey;
+  for (uint32_t k = lane; k < K; k += 32) {
+    const float *cc = codebook + (size_t)k * cs;
+    float acc = 0.0f;
+    for (uint32_t j = 0; j < cs; j++) {
+      const float t = __fsub_rn(x[j], cc[j]);
+      acc = __fadd_rn(acc, __fmul_rn(t, t));
+    }
+    const uint64_t key = make_key(__fsqrt_rn(acc), k);
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0) codes[row] = (uint8_t)(uint32_t)best;
+}
+
 static thread_local phnsw_bruteforce_stats g_stats;
 
 }  // namespace tc
@@ -625,10 +900,131 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
   return rc;
 }
 
+
+static thread_local phnsw_assign_stats g_assign;
+
+// Exact nearest centroid (L2) of m consecutive cs-float sub-vectors -> u8 codes, on the tensor
+// cores.  *done = 0: shape not covered (or too many undecided rows) -> caller uses the scan.
+phnsw_status assign_tc(const float *sub_dev, uint64_t m, uint32_t cs, const float *codebook_host,
+                       uint32_t K, int device, uint8_t *codes_dev, int *done) {
+  using namespace tc;
+  *done = 0;
+  memset(&g_assign, 0, sizeof(g_assign));
+  g_assign.rows = m;
+  const char *force = getenv("PHNSW_ASSIGN");  // "cuda" / "tensor": developer override
+  if (force && !strcmp(force, "cuda")) return PHNSW_OK;
+  const bool forced = force && !strcmp(force, "tensor");
+  if ((cs != 4 && cs != 8 && cs != 16) || K == 0 || K > 256 || m >= 0xFFFFFF00ull) return PHNSW_OK;
+  if (!forced && m < 65536) return PHNSW_OK;
+  int max_smem = 0, sms = 148;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t smem = (size_t)kAsgN * 128 + (size_t)kAsgStages * kTileA + kWRing * kM * 4 + 256 + 1024;
+  if ((size_t)max_smem < smem) return PHNSW_OK;
+  // the resident operand, built on the host: row k = [ch | cl | ch | pieces of |c|^2 | 1 1 1]
+  std::vector<uint16_t> bt((size_t)kAsgN * 64, 0);
+  auto bf = [](float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); };
+  auto fb = [](uint16_t h) { return __bfloat162float(__ushort_as_bfloat16(h)); };
+  auto put = [&](uint32_t row, uint32_t pos, uint16_t v) {
+    const uint32_t chunk = pos / 8, off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+    bt[off / 2 + pos % 8] = v;
+  };
+  float cmax2 = 0.0f;
+  for (uint32_t k = 0; k < (uint32_t)kAsgN; k++) {
+    float w = 0.0f;
+    if (k < K) {
+      for (uint32_t j = 0; j < cs; j++) {
+        const float v = codebook_host[(size_t)k * cs + j];
+        w = fmaf(v, v, w);
+        const uint16_t h = bf(v), l = bf(v - fb(h));
+        put(k, j, h);
+        put(k, cs + j, l);
+        put(k, 2 * cs + j, h);
+      }
+      cmax2 = std::max(cmax2, w);
+    } else {
+      w = 1e30f;  // padding centroids are never the nearest
+    }
+    const uint16_t p0 = bf(w);
+    float r = w - fb(p0);
+    const uint16_t p1 = bf(r);
+    r -= fb(p1);
+    put(k, 48, p0);
+    put(k, 49, p1);
+    put(k, 50, bf(r));
+    put(k, 51, 0x3F80);
+    put(k, 52, 0x3F80);
+    put(k, 53, 0x3F80);
+  }
+  uint4 *d_bt = nullptr;
+  float *d_cb = nullptr;
+  uint32_t *recheck = nullptr;
+  const uint32_t cap = (uint32_t)std::max<uint64_t>(m / 8, 4096);
+  cudaError_t e = cudaMalloc(&d_bt, bt.size() * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&d_cb, (size_t)K * cs * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&recheck, ((size_t)cap + 1) * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_bt, bt.data(), bt.size() * 2, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_cb, codebook_host, (size_t)K * cs * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(recheck + cap, 0, 4);
+  phnsw_status rc = e == cudaSuccess ? PHNSW_OK : cuda_fail(e, "assign (tensor path) scratch");
+  if (rc == PHNSW_OK) {
+    AssignArgs a;
+    a.sub = sub_dev;
+    a.m = m;
+    a.cs = cs;
+    a.btile = d_bt;
+    a.c = 2e-4f;
+    a.cmax2 = cmax2;
+    a.codes = codes_dev;
+    a.recheck = recheck;
+    a.recheck_cnt = recheck + cap;
+    a.recheck_cap = cap;
+    const uint64_t n_tiles = (m + kM - 1) / kM;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sms);
+    auto kern = cs == 16 ? tc_assign_kernel<16> : cs == 8 ? tc_assign_kernel<8> : tc_assign_kernel<4>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, 0);
+    kern<<<grid, kAsgThreads, smem>>>(a);
+    cudaEventRecord(ev1, 0);
+    uint32_t nre = 0;
+    e = cudaMemcpy(&nre, recheck + cap, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "tc_assign_kernel");
+    if (rc == PHNSW_OK && nre <= cap) {
+      if (nre) {
+        tc_assign_exact_kernel<<<(nre + 7) / 8, 256>>>(sub_dev, cs, d_cb, K, recheck, nre, codes_dev);
+        e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "tc_assign_exact_kernel");
+      }
+      if (rc == PHNSW_OK) *done = 1;
+    }
+    float ms = 0.f;
+    if (rc == PHNSW_OK) cudaEventElapsedTime(&ms, ev0, ev1);
+    g_assign.path = *done ? 1 : 0;
+    g_assign.kernel_ms = ms;
+    g_assign.flops = 2.0 * (double)n_tiles * kM * kAsgN * 64.0;
+    g_assign.rows = m;
+    g_assign.rechecked = nre;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
+  if (d_bt) cudaFree(d_bt);
+  if (d_cb) cudaFree(d_cb);
+  if (recheck) cudaFree(recheck);
+  return rc;
+}
+
 void bruteforce_stats_reset() { memset(&tc::g_stats, 0, sizeof(tc::g_stats)); }
 
 }  // namespace phnsw
 
 extern "C" void phnsw_bruteforce_last_stats(phnsw_bruteforce_stats *out) {
   if (out) *out = phnsw::tc::g_stats;
+}
+extern "C" void phnsw_assign_last_stats(phnsw_assign_stats *out) {
+  if (out) *out = phnsw::g_assign;
 }

@@ -10,8 +10,8 @@
 //   assignment  argmin over centroids of (sqrt of the sequential sum of squares, centroid id)
 //   update      mean of the members, summed in index order, one division at the end
 //   distance    finalize(sum over sub-spaces, in order, of table[s][code_s])
-// Assignment runs on the exact brute-force kernels (brute.cu); a tcgen05 GEMM replaces them in a
-// later round.
+// Assignment runs as a tcgen05 GEMM with an exact check of the undecided rows (brute_tc.cu,
+// tc_assign_kernel) when centroid_size is 4, 8 or 16, else on the exact scan of brute.cu.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,6 +26,10 @@ extern "C" phnsw_status phnsw_bruteforce_knn_device(const phnsw_store *s, const 
                                                     float *out_dists_device, void *cuda_stream);
 
 namespace phnsw {
+
+// brute_tc.cu: nearest-centroid assignment as a tcgen05 GEMM; *done = 0 -> use the exact scan
+phnsw_status assign_tc(const float *sub_dev, uint64_t m, uint32_t cs, const float *codebook_host,
+                       uint32_t K, int device, uint8_t *codes_dev, int *done);
 
 static int blocks_for(size_t n, int b = 256) { return (int)std::max<size_t>(1, (n + b - 1) / b); }
 
@@ -51,7 +55,15 @@ __global__ void kmeans_update_kernel(const float *sub, uint32_t cs, const uint32
   if (b == e) return;  // an empty cluster keeps its centroid
   for (uint32_t t = lane; t < cs; t += 32) {
     float sum = 0.0f;
-    for (uint32_t j = b; j < e; j++) sum = __fadd_rn(sum, sub[(size_t)order[j] * cs + t]);
+    uint32_t j = b;
+    for (; j + 16 <= e; j += 16) {  // 16 independent gathers in flight, added in index order
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; u++) v[u] = __ldg(&sub[(size_t)__ldg(&order[j + u]) * cs + t]);
+#pragma unroll
+      for (int u = 0; u < 16; u++) sum = __fadd_rn(sum, v[u]);
+    }
+    for (; j < e; j++) sum = __fadd_rn(sum, sub[(size_t)order[j] * cs + t]);
     codebook[(size_t)k * cs + t] = __fdiv_rn(sum, (float)(e - b));
   }
 }
@@ -75,6 +87,11 @@ __global__ void unpack_codes_kernel(const uint8_t *in, size_t n, uint32_t Q, uin
 // exact nearest centroid (L2) of `m` consecutive cs-float sub-vectors -> u8 codes (device)
 static phnsw_status assign_device(const float *sub, uint64_t m, uint32_t cs, const float *codebook_host,
                                   uint32_t K, int device, uint8_t *codes_dev) {
+  {  // tensor cores where the shape allows it (same codes), else the exact scan below
+    int done = 0;
+    phnsw_status trc = assign_tc(sub, m, cs, codebook_host, K, device, codes_dev, &done);
+    if (trc != PHNSW_OK || done) return trc;
+  }
   phnsw_store *cst = nullptr;
   phnsw_status rc = phnsw_store_create(PHNSW_METRIC_L2_SQRT, cs, K, codebook_host, device, &cst);
   if (rc != PHNSW_OK) return rc;

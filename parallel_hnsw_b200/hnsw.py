@@ -361,6 +361,15 @@ class Hnsw:
         return float(r.value)
 
 
+def assign_last_stats():
+    """How this thread's last nearest-centroid assignment ran (pq8_train iteration / Pq8Comparator
+    encoding): path "tensor" = tcgen05 GEMM + exact check of the undecided rows, "cuda" = scan."""
+    st = N.AssignStats()
+    N.lib().phnsw_assign_last_stats(C.byref(st))
+    return {"path": "tensor" if st.path == 1 else "cuda", "kernel_ms": float(st.kernel_ms),
+            "flops": float(st.flops), "rows": int(st.rows), "rechecked": int(st.rechecked)}
+
+
 def pq8_train(full_comparator, K, centroid_size, kmeans_iters=5, seed=1):
     """k-means codebook (K <= 256 centroids of centroid_size floats, shared by all sub-spaces):
     random_centroids initialisation (pq.rs:261-285) + Lloyd steps on the device."""

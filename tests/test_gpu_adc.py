@@ -109,3 +109,33 @@ def test_adc_store_is_search_only(ph):
     gh = ph.Hnsw.from_layers(pq, ph.Hnsw.generate(comp, improve=False).layers())
     with pytest.raises(ph.PhnswError):
         gh.knn(3, 2)
+
+
+@pytest.mark.parametrize("n,dim,cs,K,iters", [(6000, 32, 8, 64, 3), (3000, 128, 16, 256, 2),
+                                              (5000, 16, 4, 256, 1), (2500, 48, 16, 200, 3),
+                                              (4000, 64, 16, 7, 2)])
+def test_tensor_core_assignment_gives_the_same_codebook_and_codes(ph, oracle, n, dim, cs, K, iters):
+    """The tcgen05 nearest-centroid kernel (csrc/brute_tc.cu: tc_assign_kernel + exact check of
+    the undecided rows) forced on: k-means codebooks and codes must still be the oracle's bit
+    for bit -- a single wrong assignment changes a centroid mean."""
+    import os
+    rows = clustered(n, dim, 3, n_clusters=32, spread=0.5)
+    rows[::7] = rows[3]  # exact duplicates: distance ties between sub-vectors and centroids
+    comp = ph.BigComparator(rows, ph.L2_SQRT)
+    old = os.environ.get("PHNSW_ASSIGN")
+    try:
+        os.environ["PHNSW_ASSIGN"] = "tensor"
+        cb_g = ph.pq8_train(comp, K, cs, kmeans_iters=iters, seed=2)
+        st = ph.assign_last_stats()
+        assert st["path"] == "tensor" and st["rows"] == n * (dim // cs), st
+        pq = ph.Pq8Comparator(comp, cb_g, cs)
+        assert ph.assign_last_stats()["path"] == "tensor"
+        codes = pq.codes()
+    finally:
+        if old is None:
+            os.environ.pop("PHNSW_ASSIGN", None)
+        else:
+            os.environ["PHNSW_ASSIGN"] = old
+    cb_o = oracle.pq8_train(rows, K, cs, iters=iters, seed=2)
+    assert np.array_equal(cb_g.view(np.uint32), cb_o.view(np.uint32)), "codebooks differ"
+    assert np.array_equal(codes, oracle.pq8_encode(rows, cb_o, cs))
