@@ -1364,7 +1364,11 @@ struct WarpSearch {
   }
 };
 
-template <int METRIC, int PQ, int TREE>
+// MODE: 0 search_layers, 1 knn, 2 threshold_nn -- a template parameter so that each kernel
+// carries one walk driver only (19 k -> 9 k SASS instructions; speed unchanged, compile time
+// halved).  Measured and not kept: a single compaction site (route the end of the walk through
+// the in-loop site) shrinks the hot code by another 9 KB but compacts ~14 % more often: -2 %.
+template <int METRIC, int PQ, int TREE, int MODE>
 __global__ void __launch_bounds__((TREE && !PQ ? kTreeWarps : kSeqWarps) * 32, 1)
     search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1388,8 +1392,8 @@ __global__ void __launch_bounds__((TREE && !PQ ? kTreeWarps : kSeqWarps) * 32, 1
     ws.cap = a.cap;
     ws.len = 0;
     ws.load_query(q);
-    if (a.mode == 0) ws.run_search(q);
-    else if (a.mode == 1) ws.run_knn(q);
+    if (MODE == 0) ws.run_search(q);
+    else if (MODE == 1) ws.run_knn(q);
     else ws.run_threshold(q);
   }
   // hand a clean bitmap to the next launch that uses this slot

@@ -5,20 +5,28 @@
 
 namespace phnsw {
 
-template <int METRIC, int PQ, int TREE>
-static cudaError_t launch_typed(const SearchArgs &a, int grid, int block, size_t smem,
+template <int METRIC, int PQ, int TREE, int MODE>
+static cudaError_t launch_moded(const SearchArgs &a, int grid, int block, size_t smem,
                                 cudaStream_t stream) {
   static thread_local size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 8 || configured[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ, TREE>,
+    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ, TREE, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev < 8) configured[dev] = smem;
   }
-  search_kernel<METRIC, PQ, TREE><<<grid, block, smem, stream>>>(a);
+  search_kernel<METRIC, PQ, TREE, MODE><<<grid, block, smem, stream>>>(a);
   return cudaGetLastError();
+}
+template <int METRIC, int PQ, int TREE>
+static cudaError_t launch_typed(const SearchArgs &a, int grid, int block, size_t smem,
+                                cudaStream_t stream) {
+  if (a.mode == 0) return launch_moded<METRIC, PQ, TREE, 0>(a, grid, block, smem, stream);
+  if (PQ) return cudaErrorInvalidValue;  // the ADC store supports search_layers only
+  if (a.mode == 1) return launch_moded<METRIC, PQ ? 0 : PQ, TREE, PQ ? 0 : 1>(a, grid, block, smem, stream);
+  return launch_moded<METRIC, PQ ? 0 : PQ, TREE, PQ ? 0 : 2>(a, grid, block, smem, stream);
 }
 template <int PQ, int TREE>
 static cudaError_t launch_metric(int metric, const SearchArgs &a, int grid, int block, size_t smem,
