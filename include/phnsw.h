@@ -219,6 +219,13 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
 phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out);
 /* stochastic_recall (src/lib.rs:1463-1505) */
+/* Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): the vectors of layer
+ * `layer_from_top` that do not find themselves (search::match_within_epsilon,
+ * src/search.rs:173-187) when searched over layers[0..=layer] and are not nodes of the layer
+ * above.  *out_ids is malloc'ed (release with phnsw_free), ascending. */
+phnsw_status phnsw_discover_unreachable(const phnsw_index *ix, uint64_t layer_from_top,
+                                        const phnsw_search_params *sp, uint64_t **out_ids,
+                                        uint64_t *out_n);
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix,
                                      const phnsw_optimization_params *op, float *recall_out);
 

@@ -113,6 +113,9 @@ def lib():
                                C.POINTER(BuildParams), C.c_uint64, C.c_int, C.c_int]
     L.orc_improve_index.restype = C.c_float
     L.orc_improve_index.argtypes = [C.c_void_p, C.POINTER(BuildParams), C.c_int]
+    L.orc_discover_unreachable.restype = C.c_uint64
+    L.orc_discover_unreachable.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SearchParams),
+                                           C.POINTER(u64p), C.c_int]
     L.orc_stochastic_recall.restype = C.c_float
     L.orc_stochastic_recall.argtypes = [C.c_void_p, C.POINTER(OptimizationParams), C.c_int]
     L.orc_serialize.restype = C.c_int
@@ -399,6 +402,15 @@ class Hnsw:
     def improve_index(self, bp=None, nthreads=0):
         bp = bp or self.build_parameters
         return float(lib().orc_improve_index(self._h, C.byref(bp), nthreads))
+
+    def discover_unreachable_vectors(self, layer_from_top, sp=None, nthreads=0):
+        """Hnsw::discover_unreachable_vectors (lib.rs:1002-1037)."""
+        sp = sp or default_search_params()
+        p = C.POINTER(C.c_uint64)()
+        n = lib().orc_discover_unreachable(self._h, layer_from_top, C.byref(sp), C.byref(p), nthreads)
+        out = np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.empty(0, np.uint64)
+        lib().orc_free(C.cast(p, C.c_void_p))
+        return out.astype(np.uint64)
 
     def stochastic_recall(self, op=None, nthreads=0):
         op = op or self.build_parameters.optimization

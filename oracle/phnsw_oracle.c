@@ -1397,6 +1397,48 @@ static float stochastic_recall_at(const orc_hnsw *h, uint64_t at,
   return (float)relevant / (float)selection;
 }
 
+/* search::match_within_epsilon (search.rs:173-187), literal */
+static int match_within_epsilon(uint64_t vector, const uint64_t *ids, const float *ds, uint32_t n) {
+  int found = 0;
+  const float epsilon = 1e-5f;
+  for (uint32_t i = 0; i < n; i++) {
+    if (fabsf(ds[i]) < epsilon) {
+      if (ids[i] == vector) found = 1;
+    } else {
+      break;
+    }
+  }
+  return found;
+}
+
+/* Hnsw::discover_unreachable_vectors (lib.rs:1002-1037); out = malloc'ed VectorIds, returns n */
+uint64_t orc_discover_unreachable(const orc_hnsw *h, uint64_t layer_from_top,
+                                  const orc_search_params *sp, uint64_t **out, int nthreads) {
+  *out = NULL;
+  if (layer_from_top >= h->layer_count) return 0;
+  const layer_t *cur = &h->layers[layer_from_top];
+  const layer_t *above = layer_from_top ? &h->layers[layer_from_top - 1] : NULL;
+  const uint64_t n = cur->node_count, ef = sp->number_of_candidates;
+  uint64_t *ids = (uint64_t *)malloc(n * ef * sizeof(uint64_t));
+  float *ds = (float *)malloc(n * ef * sizeof(float));
+  uint32_t *cn = (uint32_t *)malloc(n * sizeof(uint32_t));
+  uint64_t *res = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+  orc_search_batch(h, NULL, cur->nodes, n, sp, layer_from_top + 1, NULL, ef, ids, ds, cn, NULL, NULL,
+                   NULL, nthreads);
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    const uint64_t v = cur->nodes[i];
+    if (match_within_epsilon(v, ids + i * ef, ds + i * ef, cn[i])) continue;
+    if (above && layer_get_node(above, v) >= 0) continue;
+    res[m++] = v;
+  }
+  free(ids);
+  free(ds);
+  free(cn);
+  *out = res;
+  return m;
+}
+
 float orc_stochastic_recall(const orc_hnsw *h, const orc_optimization_params *op, int nthreads) {
   return stochastic_recall_at(h, h->layer_count - 1, op, nthreads);
 }

@@ -158,6 +158,9 @@ orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float
                        const uint64_t *vs, uint64_t n_vs, const orc_build_params *bp,
                        uint64_t seed, int improve, int nthreads);
 float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads);
+/* Hnsw::discover_unreachable_vectors (lib.rs:1002-1037); *out is malloc'ed (orc_free) */
+uint64_t orc_discover_unreachable(const orc_hnsw *h, uint64_t layer_from_top,
+                                  const orc_search_params *sp, uint64_t **out, int nthreads);
 float orc_stochastic_recall(const orc_hnsw *h, const orc_optimization_params *op, int nthreads);
 
 /* serialize.rs:33-209 layout (meta, layer.meta.N, layer.nodes.N, layer.neighbors.N);

@@ -115,6 +115,8 @@ SIGNATURES = {
                                       C.c_int, PROGRESS_FN, vp, C.POINTER(vp)]),
     "phnsw_improve_index": (C.c_int, [vp, C.POINTER(BuildParams), PROGRESS_FN, vp, f32p]),
     "phnsw_stochastic_recall": (C.c_int, [vp, C.POINTER(OptimizationParams), f32p]),
+    "phnsw_discover_unreachable": (C.c_int, [vp, C.c_uint64, C.POINTER(SearchParams),
+                                             C.POINTER(u64p), u64p]),
     "phnsw_bruteforce_knn": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
     "phnsw_bruteforce_knn_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
     "phnsw_bruteforce_last_stats": (None, [vp]),

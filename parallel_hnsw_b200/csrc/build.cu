@@ -914,6 +914,70 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
   return rc;
 }
 
+// Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): every vector of layer
+// `layer_from_top` searches for itself over layers[0..=layer]; it is unreachable when it is not
+// in the leading run of |d| < 1e-5 results (search::match_within_epsilon, search.rs:173-187) and
+// not a node of the layer above.  One batched K1 launch over all nodes of the layer.
+phnsw_status phnsw_discover_unreachable(const phnsw_index *ix, uint64_t layer_from_top,
+                                        const phnsw_search_params *sp, uint64_t **out_ids,
+                                        uint64_t *out_n) {
+  PH_ENTRY();
+  if (!ix || !sp || !out_ids || !out_n || layer_from_top >= ix->layers.size() ||
+      sp->number_of_candidates == 0 || sp->probe_depth == 0) {
+    set_error("discover_unreachable: bad arguments");
+    return PHNSW_ERR_INVALID;
+  }
+  *out_ids = nullptr;
+  *out_n = 0;
+  if (phnsw_device_count() == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return PHNSW_ERR_NO_DEVICE;
+  }
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  const LayerStore &L = ix->layers[layer_from_top];
+  const uint64_t n = L.node_count;
+  std::vector<uint64_t> vecs(L.h_nodes.begin(), L.h_nodes.end());
+  cudaStream_t st = 0;
+  DevMem mem;
+  uint64_t *q_ids;
+  uint32_t *hit;
+  PH_CUDA(mem.alloc(&q_ids, n));
+  PH_CUDA(mem.alloc(&hit, n));
+  PH_CUDA(cudaMemcpyAsync(q_ids, vecs.data(), n * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemsetAsync(hit, 0, n * 4, st));
+  SearchCall c;
+  c.mode = 0;
+  c.stored_ids = q_ids;
+  c.nq = (uint32_t)n;
+  c.cap = (uint32_t)std::min<uint64_t>(sp->number_of_candidates, 0xFFFFFFFFull);
+  c.upper = (uint32_t)std::min<uint64_t>(sp->upper_layer_candidate_count, 0xFFFFFFFFull);
+  c.probe = (uint32_t)std::min<uint64_t>(sp->probe_depth, 0xFFFFFFFFull);
+  c.n_layers = (uint32_t)layer_from_top + 1;
+  c.max_out = 0;
+  c.out_selfhit = hit;
+  c.selfhit_eps = 1;
+  phnsw_status rc = launch_search(ix, c, st);
+  if (rc != PHNSW_OK) return rc;
+  rc = sync_status(ix, st);
+  if (rc != PHNSW_OK) return rc;
+  std::vector<uint32_t> h(n);
+  PH_CUDA(cudaMemcpy(h.data(), hit, n * 4, cudaMemcpyDeviceToHost));
+  const std::vector<uint32_t> *above = layer_from_top ? &ix->layers[layer_from_top - 1].h_nodes : nullptr;
+  std::vector<uint64_t> out;
+  for (uint64_t i = 0; i < n; i++) {
+    if (h[i]) continue;
+    if (above && std::binary_search(above->begin(), above->end(), (uint32_t)vecs[i])) continue;
+    out.push_back(vecs[i]);
+  }
+  if (!out.empty()) {
+    *out_ids = (uint64_t *)malloc(out.size() * 8);
+    if (!*out_ids) return PHNSW_ERR_INVALID;
+    memcpy(*out_ids, out.data(), out.size() * 8);
+  }
+  *out_n = out.size();
+  return PHNSW_OK;
+}
+
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix, const phnsw_optimization_params *op,
                                      float *recall_out) {
   PH_ENTRY();

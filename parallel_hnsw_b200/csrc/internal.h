@@ -142,6 +142,7 @@ struct SearchCall {
   uint64_t *out_ids = nullptr;
   float *out_dists = nullptr;
   uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr, *out_selfhit = nullptr;
+  uint32_t selfhit_eps = 0;  // out_selfhit by search::match_within_epsilon
 };
 
 // the three kernel variants (search_seq.cu, search_tree.cu, search_pq.cu)

@@ -261,6 +261,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.out_ndist = c.out_nd;
   a.out_nexp = c.out_ne;
   a.out_selfhit = c.out_selfhit;
+  a.selfhit_eps = c.selfhit_eps;
   a.stats_stride = (uint32_t)ix->layers.size();
   a.work_counter = ws.ctrl.as<unsigned int>();
   a.status = ws.ctrl.as<uint32_t>() + 1;

@@ -85,6 +85,8 @@ struct SearchArgs {
   uint32_t *out_nexp;
   uint32_t *out_selfhit;   // optional, nq: 1 when stored_ids[q] is among the results
                            // (stochastic_recall_at, lib.rs:1486-1494)
+  uint32_t selfhit_eps;    // 1: search::match_within_epsilon instead (search.rs:173-187): the
+                           // query vector must sit in the leading run of |d| < 1e-5 results
   uint32_t stats_stride;
   unsigned int *work_counter;
   uint32_t *status;
@@ -1230,8 +1232,19 @@ struct WarpSearch {
     if (a.out_selfhit && a.stored_ids) {
       const uint32_t self = (uint32_t)a.stored_ids[q];
       bool hit = false;
-      for (uint32_t i = lane; i < len; i += 32) hit |= ((uint32_t)pool[i] == self);
+      float dmin = 3.4028234663852886e38f;
+      for (uint32_t i = lane; i < len; i += 32) {
+        const uint64_t k = pool[i];
+        const float d = key_dist(k);
+        dmin = fminf(dmin, d);
+        hit |= ((uint32_t)k == self) && (!a.selfhit_eps || fabsf(d) < 1e-5f);
+      }
       hit = __any_sync(kFull, hit);
+      if (a.selfhit_eps) {  // the run ends at the first |d| >= 1e-5: nothing may lie below -1e-5
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(kFull, dmin, o));
+        hit = hit && dmin > -1e-5f;
+      }
       if (lane == 0) a.out_selfhit[q] = hit ? 1u : 0u;
     }
     // candidates.iter().collect() (search.rs:139)

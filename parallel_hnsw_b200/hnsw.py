@@ -353,6 +353,18 @@ class Hnsw:
                                             C.byref(r)))
         return float(r.value)
 
+    def discover_unreachable_vectors(self, layer_from_top, search_parameters=None):
+        """Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): VectorIds of the layer that
+        do not find themselves (match_within_epsilon) and are not in the layer above."""
+        sp = search_parameters or SearchParameters()
+        p, n = C.POINTER(C.c_uint64)(), C.c_uint64()
+        N.check(N.lib().phnsw_discover_unreachable(self._h, layer_from_top, C.byref(sp),
+                                                   C.byref(p), C.byref(n)))
+        out = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.empty(0, np.uint64)
+        if n.value:
+            N.lib().phnsw_free(C.cast(p, C.c_void_p))
+        return out.astype(np.uint64)
+
     def stochastic_recall(self, optimization_parameters=None):
         """Hnsw::stochastic_recall (src/lib.rs:1501-1505)."""
         op = optimization_parameters or self.build_parameters.optimization

@@ -152,3 +152,22 @@ def test_generate_subset_and_errors(ph, oracle):
     with pytest.raises(ph.PhnswError) as e:
         ph.Hnsw.generate(comp, seed=4, progress=stop)
     assert e.value.status == 8 and len(calls) == 3  # Interrupt (src/progress.rs:8-10)
+
+
+def test_discover_unreachable_vectors_matches_oracle(ph, oracle):
+    """Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037) as one batched traversal launch
+    per layer, against the oracle's literal restatement (match_within_epsilon included)."""
+    from tests.helpers import clustered
+    rows = clustered(6000, 32, 17, n_clusters=40, spread=0.4)
+    rows[100:140] = rows[100]  # exact duplicates: several vectors at distance 0 of each other
+    oh = oracle.Hnsw.generate(oracle.L2_SQRT, rows, seed=4, improve=False)
+    comp = ph.BigComparator(rows, ph.L2_SQRT)
+    gh = ph.Hnsw.from_layers(comp, oh.layers())
+    total = 0
+    for layer in range(gh.layer_count()):
+        for ef in (300, 6):
+            g = gh.discover_unreachable_vectors(layer, ph.SearchParameters(ef, ef, 2))
+            o = oh.discover_unreachable_vectors(layer, oracle.search_params(ef, ef, 2))
+            assert np.array_equal(g, o), (layer, ef, len(g), len(o))
+            total += len(o)
+    assert total > 0, "the case should contain unreachable vectors"

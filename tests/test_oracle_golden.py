@@ -309,3 +309,27 @@ def test_tree_sum_order_is_within_the_north_star_tolerance(oracle):
     assert same.mean() >= 0.999, same.mean()
     rel = np.abs(seq[1][same].astype(np.float64) - tree[1][same]) / np.maximum(np.abs(seq[1][same]), 1e-30)
     assert rel.max() <= 1e-5
+
+
+def test_discover_unreachable_vectors_oracle(oracle):
+    """Hnsw::discover_unreachable_vectors (lib.rs:1002-1037) with match_within_epsilon
+    (search.rs:173-187): a node nobody links to cannot find itself unless it is the entry."""
+    from tests.helpers import EMPTY, random_normed
+    rows = random_normed(12, 8, 3)
+    nodes = np.arange(12, dtype=np.uint64)
+    neigh = np.full((12, 4), EMPTY, dtype=np.uint64)
+    for i in range(12):           # a ring over nodes 0..10; node 11 links out but has no in-edge
+        neigh[i, 0] = (i + 1) % 11
+        neigh[i, 1] = (i + 2) % 11
+    h = oracle.Hnsw.from_layers(oracle.COS_HALF, rows, [(nodes, neigh, 4)])
+    un = h.discover_unreachable_vectors(0, oracle.search_params(300, 300, 2))
+    assert un.tolist() == [11]
+    # with a layer above that holds vector 11 it is not reported (lib.rs:1029-1030)
+    top = (np.array([11], np.uint64), np.full((1, 4), EMPTY, np.uint64), 4)
+    h2 = oracle.Hnsw.from_layers(oracle.COS_HALF, rows, [top, (nodes, neigh, 4)])
+    un2 = h2.discover_unreachable_vectors(1, oracle.search_params(300, 300, 2)).tolist()
+    assert 11 not in un2
+    # what is reported must really miss itself (the walk from entry 11 ends on its probe budget)
+    for v in un2:
+        ids = h2.search(stored_ids=np.array([v], np.uint64), sp=oracle.search_params(300, 300, 2))[0][0]
+        assert v not in ids.tolist()
