@@ -322,6 +322,26 @@ def main():
     ms_pipe = p0.elapsed_time(p1) / args.steps
     assert torch.equal(outs2[0][0], oi), "two-stream run disagrees with the single-stream run"
 
+    # ---- secondary: operating points (the metric is QPS at recall@10 >= 0.95; the timed
+    # configuration above is the crate's default 300 / 300 / 2) --------------------------------
+    sweep = []
+    if rank == 0:
+        for ef_s in (300, 200, 150, 100, 64, 32):
+            sp_s = ph.SearchParameters(ef_s, ef_s, 2)
+            gh.search_device(dq, sp_s, oi, od, oc, stream=stream)
+            gh.sync(stream)
+            rec_s = recall_at_k(oi.cpu().numpy(), gt.cpu().numpy(), k)
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            for _ in range(5):
+                gh.search_device(dq, sp_s, oi, od, oc, stream=stream)
+            w1.record()
+            gh.sync(stream)
+            sweep.append({"ef": ef_s, "recall_at_10": rec_s,
+                          "qps": args.nq * 5 / (w0.elapsed_time(w1) * 1e-3)})
+        gh.search_device(dq, sp, oi, od, oc, stream=stream)  # restore the timed run's outputs
+        gh.sync(stream)
+
     # ---- timed region 2: end to end through the host C-ABI call with pinned host buffers --
     q_pin = queries_h.pin_memory().numpy()
     hi = torch.empty((args.nq, k), dtype=torch.int64).pin_memory()
@@ -442,6 +462,11 @@ def main():
                                     / peaks["bf16_tflops"]
                                     if gt_stats["filter_ms"] > 0 and peaks.get("bf16_tflops") else None),
             "max_candidates_per_query": gt_stats["max_candidates"]},
+        "operating_points": {
+            "note": "one GPU, same index, ef = number_of_candidates = upper_layer_candidate_count",
+            "sweep": sweep,
+            "best_qps_at_recall_ge_0.95": max([p_["qps"] for p_ in sweep if p_["recall_at_10"] >= 0.95],
+                                              default=None)},
         "two_streams": {"value": world * args.nq / (ms_pipe * 1e-3), "unit": "queries/s",
                         "ms_per_step": ms_pipe,
                         "note": "steps issued alternately on two streams (tails overlap); "
