@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=2000)
     ap.add_argument("--cpu-queries", type=int, default=2000)
     ap.add_argument("--no-improve", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     ap.add_argument("--sum-order", default="tree", choices=["tree", "sequential"],
                     help="summation order of the traversal kernel's distances (include/phnsw.h)")
     args = ap.parse_args()
@@ -291,11 +293,15 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.nvtx.range_push("timed")
+    if args.profile_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         gh.search_device(dq, sp, oi, od, oc, stream=stream)
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     torch.cuda.nvtx.range_pop()
     gh.sync(stream)
     ms_dev = e0.elapsed_time(e1)
