@@ -281,6 +281,12 @@ phnsw_status phnsw_pq_build(phnsw_store *full, uint64_t number_of_centroids, uin
                             const phnsw_pq_build_params *bp, uint64_t seed,
                             phnsw_progress_fn progress, void *user, phnsw_pq **out);
 void phnsw_pq_destroy(phnsw_pq *pq);
+/* Serializable for QuantizedHnsw / HnswQuantizer (src/pq.rs:94-117, 433-476): <dir>/quantizer/
+ * (centroid Hnsw + pq_build_parameters.json), <dir>/hnsw/ (graph over the codes + the u16 codes),
+ * <dir>/comparator (full-precision vectors).  Load returns the quantizer and a handle on the
+ * full-precision store (destroy both). */
+phnsw_status phnsw_pq_save(const phnsw_pq *pq, const char *dir);
+phnsw_status phnsw_pq_load(const char *dir, int device, phnsw_store **full_out, phnsw_pq **out);
 uint64_t phnsw_pq_centroid_count(const phnsw_pq *pq);
 uint64_t phnsw_pq_quantized_size(const phnsw_pq *pq);   /* QUANTIZED_SIZE */
 uint64_t phnsw_pq_centroid_size(const phnsw_pq *pq);    /* CENTROID_SIZE */

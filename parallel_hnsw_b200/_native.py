@@ -126,6 +126,8 @@ SIGNATURES = {
                                  C.POINTER(PqBuildParams), C.c_uint64, PROGRESS_FN, vp,
                                  C.POINTER(vp)]),
     "phnsw_pq_destroy": (None, [vp]),
+    "phnsw_pq_save": (C.c_int, [vp, C.c_char_p]),
+    "phnsw_pq_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "phnsw_pq_centroid_count": (C.c_uint64, [vp]),
     "phnsw_pq_quantized_size": (C.c_uint64, [vp]),
     "phnsw_pq_centroid_size": (C.c_uint64, [vp]),

@@ -159,6 +159,14 @@ phnsw_status sync_status_bits(const phnsw_index *ix, cudaStream_t stream, uint32
 void store_release(phnsw_store *s);
 phnsw_status upload_layer_tables(phnsw_index *ix);
 phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp, phnsw_index **out);
+// io.cpp: pieces of the serialize.rs layout, shared with the PQ directory layout (pq.cu)
+int io_mkdir_p(const std::string &dir);
+phnsw_status io_save_graph(const phnsw_index *ix, const std::string &dir);
+phnsw_status io_save_store(const phnsw_store *s, const std::string &path);
+phnsw_status io_load_store(const std::string &path, int device, phnsw_store **out);
+phnsw_status io_load_graph(const std::string &dir, phnsw_store *s, phnsw_index **out);
+phnsw_status io_save_pq_params(const std::string &path, const phnsw_pq_build_params &bp);
+phnsw_status io_load_pq_params(const std::string &path, phnsw_pq_build_params *bp);
 // takes ownership of device arrays nodes/neighbors (u32); builds vec2node as needed
 phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint64_t M,
                                      uint32_t *nodes, uint32_t *neighbors);

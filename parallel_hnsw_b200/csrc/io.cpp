@@ -244,6 +244,179 @@ static int mkdir_p(const std::string &dir) {  // create_dir_all (serialize.rs:40
   return 0;
 }
 
+
+int io_mkdir_p(const std::string &dir) { return mkdir_p(dir); }
+
+// <dir>/meta + <dir>/layer.{meta,nodes,neighbors}.N (serialize.rs:33-124 minus the comparator)
+phnsw_status io_save_graph(const phnsw_index *ix, const std::string &d) {
+  if (mkdir_p(d) != 0) {
+    set_error("save: cannot create %s: %s", d.c_str(), strerror(errno));
+    return PHNSW_ERR_IO;
+  }
+  const uint64_t L = ix->layers.size();
+  std::string meta = "{\"layer_count\":" + std::to_string(L) +
+                     ",\"build_parameters\":" + json_build_params(ix->bp) + "}";
+  if (!write_all(d + "/meta", meta.data(), meta.size())) {
+    set_error("save: cannot write %s/meta: %s", d.c_str(), strerror(errno));
+    return PHNSW_ERR_IO;
+  }
+  for (uint64_t i = 0; i < L; i++) {
+    const uint64_t num = L - i - 1;
+    const LayerStore &l = ix->layers[i];
+    std::string lm = "{\"node_count\":" + std::to_string(l.node_count) +
+                     ",\"neighborhood_size\":" + std::to_string(l.M) + "}";
+    std::vector<uint64_t> nodes(l.node_count), nb((size_t)l.node_count * l.M);
+    phnsw_status rc = phnsw_index_export_layer(ix, i, nodes.data(), nb.data());
+    if (rc != PHNSW_OK) return rc;
+    std::string n = std::to_string(num);
+    if (!write_all(d + "/layer.meta." + n, lm.data(), lm.size()) ||
+        !write_all(d + "/layer.nodes." + n, nodes.data(), nodes.size() * 8) ||
+        !write_all(d + "/layer.neighbors." + n, nb.data(), nb.size() * 8)) {
+      set_error("save: cannot write layer %llu under %s: %s", (unsigned long long)num, d.c_str(),
+                strerror(errno));
+      return PHNSW_ERR_IO;
+    }
+  }
+  return PHNSW_OK;
+}
+
+// the comparator file: {tag, metric, dim, count} + raw f32 rows
+phnsw_status io_save_store(const phnsw_store *s, const std::string &path) {
+  std::vector<float> rows((size_t)s->n * s->dim);
+  std::vector<uint64_t> ids(s->n);
+  for (uint64_t i = 0; i < s->n; i++) ids[i] = i;
+  phnsw_status rc = phnsw_store_get_rows(s, ids.data(), s->n, rows.data());
+  if (rc != PHNSW_OK) return rc;
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) {
+    set_error("save: cannot write %s: %s", path.c_str(), strerror(errno));
+    return PHNSW_ERR_IO;
+  }
+  uint64_t hdr[4] = {kComparatorTag, (uint64_t)s->metric, s->dim, s->n};
+  bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1;
+  if (ok && !rows.empty()) ok = fwrite(rows.data(), 4, rows.size(), f) == rows.size();
+  if (fclose(f) != 0) ok = false;
+  if (!ok) {
+    set_error("save: short write on %s", path.c_str());
+    return PHNSW_ERR_IO;
+  }
+  return PHNSW_OK;
+}
+
+phnsw_status io_load_store(const std::string &path, int device, phnsw_store **out) {
+  *out = nullptr;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) {  // serialize.rs:143-145
+    set_error("Index not found");
+    return PHNSW_ERR_NOT_FOUND;
+  }
+  uint64_t hdr[4];
+  if (fread(hdr, sizeof hdr, 1, f) != 1 || hdr[0] != kComparatorTag || hdr[1] > 3 || hdr[2] == 0) {
+    fclose(f);
+    set_error("load: %s has an unknown header", path.c_str());
+    return PHNSW_ERR_FORMAT;
+  }
+  std::vector<float> rows((size_t)hdr[2] * hdr[3]);
+  size_t got = rows.empty() ? 0 : fread(rows.data(), 4, rows.size(), f);
+  fclose(f);
+  if (got != rows.size()) {
+    set_error("load: %s is truncated", path.c_str());
+    return PHNSW_ERR_IO;
+  }
+  return phnsw_store_create((phnsw_metric)hdr[1], hdr[2], hdr[3], rows.data(), device, out);
+}
+
+// layers of <dir> over an existing store
+phnsw_status io_load_graph(const std::string &d, phnsw_store *s, phnsw_index **out) {
+  *out = nullptr;
+  const char *dir = d.c_str();
+  std::vector<char> buf;
+  if (!read_all(d + "/meta", buf)) {
+    set_error("load: cannot read %s/meta: %s", dir, strerror(errno));
+    return PHNSW_ERR_IO;
+  }
+  uint64_t L = 0;
+  phnsw_build_params bp;
+  phnsw_default_build_params(&bp);
+  if (!parse_meta(buf.data(), &L, &bp)) {
+    set_error("load: %s/meta is not a valid HNSWMeta document", dir);
+    return PHNSW_ERR_FORMAT;
+  }
+  std::vector<std::vector<uint64_t>> nodes(L), nbs(L);
+  std::vector<phnsw_layer_desc> descs(L);
+  for (uint64_t i = 0; i < L; i++) {
+    std::string n = std::to_string(L - i - 1);
+    uint64_t nc = 0, M = 0;
+    if (!read_all(d + "/layer.meta." + n, buf)) {
+      set_error("load: cannot read %s/layer.meta.%s: %s", dir, n.c_str(), strerror(errno));
+      return PHNSW_ERR_IO;
+    }
+    if (!parse_layer_meta(buf.data(), &nc, &M)) {
+      set_error("load: %s/layer.meta.%s is not a valid LayerMeta document", dir, n.c_str());
+      return PHNSW_ERR_FORMAT;
+    }
+    nodes[i].resize(nc);
+    nbs[i].resize((size_t)nc * M);
+    for (int which = 0; which < 2; which++) {
+      std::vector<uint64_t> &dst = which ? nbs[i] : nodes[i];
+      std::string p = d + (which ? "/layer.neighbors." : "/layer.nodes.") + n;
+      FILE *g = fopen(p.c_str(), "rb");
+      size_t r = 0;
+      if (g) {
+        r = dst.empty() ? 0 : fread(dst.data(), 8, dst.size(), g);
+        fclose(g);
+      }
+      if (!g || r != dst.size()) {  // read_exact: a short file is an io error
+        set_error("load: cannot read %s", p.c_str());
+        return PHNSW_ERR_IO;
+      }
+    }
+    descs[i].node_count = nc;
+    descs[i].neighborhood_size = M;
+    descs[i].nodes = nodes[i].data();
+    descs[i].neighbors = nbs[i].data();
+  }
+  return phnsw_index_from_layers(s, L, descs.data(), &bp, out);
+}
+
+// pq_build_parameters.json (pq.rs:94-117): serde_json of PqBuildParameters (parameters.rs:66-71)
+phnsw_status io_save_pq_params(const std::string &path, const phnsw_pq_build_params &bp) {
+  std::string j = "{\"centroids\":" + json_build_params(bp.centroids) + ",\"hnsw\":" +
+                  json_build_params(bp.hnsw) + ",\"quantized_search\":" +
+                  json_search_params(bp.quantized_search) + "}";
+  if (!write_all(path, j.data(), j.size())) {
+    set_error("save: cannot write %s: %s", path.c_str(), strerror(errno));
+    return PHNSW_ERR_IO;
+  }
+  return PHNSW_OK;
+}
+phnsw_status io_load_pq_params(const std::string &path, phnsw_pq_build_params *bp) {
+  std::vector<char> buf;
+  if (!read_all(path, buf)) {
+    set_error("load: cannot read %s: %s", path.c_str(), strerror(errno));
+    return PHNSW_ERR_IO;
+  }
+  JsonCur c{buf.data()};
+  int seen = 0;
+  bool ok = c.eat('{');
+  if (ok && !c.eat('}')) {
+    do {
+      std::string k = c.str();
+      if (!c.eat(':')) { ok = false; break; }
+      if (k == "centroids") { ok = parse_build_params(c, &bp->centroids); seen |= 1; }
+      else if (k == "hnsw") { ok = parse_build_params(c, &bp->hnsw); seen |= 2; }
+      else if (k == "quantized_search") { ok = parse_search_params(c, &bp->quantized_search); seen |= 4; }
+      else c.skip();
+    } while (ok && c.ok && c.eat(','));
+    if (ok && !c.eat('}')) ok = false;
+  }
+  if (!ok || !c.ok || seen != 7) {
+    set_error("load: %s is not a valid PqBuildParameters document", path.c_str());
+    return PHNSW_ERR_FORMAT;
+  }
+  return PHNSW_OK;
+}
+
 }  // namespace phnsw
 
 using namespace phnsw;
@@ -266,56 +439,11 @@ phnsw_status phnsw_index_save(const phnsw_index *ix, const char *dir) {
     return PHNSW_ERR_INVALID;
   }
   std::string d(dir);
-  if (mkdir_p(d) != 0) {
-    set_error("save: cannot create %s: %s", dir, strerror(errno));
-    return PHNSW_ERR_IO;
-  }
-  const uint64_t L = ix->layers.size();
-  std::string meta = "{\"layer_count\":" + std::to_string(L) +
-                     ",\"build_parameters\":" + json_build_params(ix->bp) + "}";
-  if (!write_all(d + "/meta", meta.data(), meta.size())) {
-    set_error("save: cannot write %s/meta: %s", dir, strerror(errno));
-    return PHNSW_ERR_IO;
-  }
-  if (L > 0) {  // the comparator entry is only written for a non-empty index (serialize.rs:60-65)
-    const phnsw_store *s = ix->store;
-    std::vector<float> rows((size_t)s->n * s->dim);
-    std::vector<uint64_t> ids(s->n);
-    for (uint64_t i = 0; i < s->n; i++) ids[i] = i;
-    phnsw_status rc = phnsw_store_get_rows(s, ids.data(), s->n, rows.data());
-    if (rc != PHNSW_OK) return rc;
-    FILE *f = fopen((d + "/comparator").c_str(), "wb");
-    if (!f) {
-      set_error("save: cannot write %s/comparator: %s", dir, strerror(errno));
-      return PHNSW_ERR_IO;
-    }
-    uint64_t hdr[4] = {kComparatorTag, (uint64_t)s->metric, s->dim, s->n};
-    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1;
-    if (ok && !rows.empty()) ok = fwrite(rows.data(), 4, rows.size(), f) == rows.size();
-    if (fclose(f) != 0) ok = false;
-    if (!ok) {
-      set_error("save: short write on %s/comparator", dir);
-      return PHNSW_ERR_IO;
-    }
-  }
-  for (uint64_t i = 0; i < L; i++) {
-    const uint64_t num = L - i - 1;
-    const LayerStore &l = ix->layers[i];
-    std::string lm = "{\"node_count\":" + std::to_string(l.node_count) +
-                     ",\"neighborhood_size\":" + std::to_string(l.M) + "}";
-    std::vector<uint64_t> nodes(l.node_count), nb((size_t)l.node_count * l.M);
-    phnsw_status rc = phnsw_index_export_layer(ix, i, nodes.data(), nb.data());
-    if (rc != PHNSW_OK) return rc;
-    std::string n = std::to_string(num);
-    if (!write_all(d + "/layer.meta." + n, lm.data(), lm.size()) ||
-        !write_all(d + "/layer.nodes." + n, nodes.data(), nodes.size() * 8) ||
-        !write_all(d + "/layer.neighbors." + n, nb.data(), nb.size() * 8)) {
-      set_error("save: cannot write layer %llu under %s: %s", (unsigned long long)num, dir,
-                strerror(errno));
-      return PHNSW_ERR_IO;
-    }
-  }
-  return PHNSW_OK;
+  phnsw_status rc = io_save_graph(ix, d);
+  if (rc != PHNSW_OK) return rc;
+  // the comparator entry is only written for a non-empty index (serialize.rs:60-65)
+  if (!ix->layers.empty()) rc = io_save_store(ix->store, d + "/comparator");
+  return rc;
 }
 
 phnsw_status phnsw_index_load(const char *dir, int device, phnsw_store **store_out,
@@ -326,77 +454,15 @@ phnsw_status phnsw_index_load(const char *dir, int device, phnsw_store **store_o
   *index_out = nullptr;
   std::string d(dir);
   std::vector<char> buf;
-  if (!read_all(d + "/meta", buf)) {
+  if (!read_all(d + "/meta", buf)) {  // read before the comparator, as serialize.rs:130-145 does
     set_error("load: cannot read %s/meta: %s", dir, strerror(errno));
     return PHNSW_ERR_IO;
   }
-  uint64_t L = 0;
-  phnsw_build_params bp;
-  phnsw_default_build_params(&bp);
-  if (!parse_meta(buf.data(), &L, &bp)) {
-    set_error("load: %s/meta is not a valid HNSWMeta document", dir);
-    return PHNSW_ERR_FORMAT;
-  }
-  FILE *f = fopen((d + "/comparator").c_str(), "rb");
-  if (!f) {  // serialize.rs:143-145
-    set_error("Index not found");
-    return PHNSW_ERR_NOT_FOUND;
-  }
-  uint64_t hdr[4];
-  if (fread(hdr, sizeof hdr, 1, f) != 1 || hdr[0] != kComparatorTag || hdr[1] > 3 || hdr[2] == 0) {
-    fclose(f);
-    set_error("load: %s/comparator has an unknown header", dir);
-    return PHNSW_ERR_FORMAT;
-  }
-  std::vector<float> rows((size_t)hdr[2] * hdr[3]);
-  size_t got = rows.empty() ? 0 : fread(rows.data(), 4, rows.size(), f);
-  fclose(f);
-  if (got != rows.size()) {
-    set_error("load: %s/comparator is truncated", dir);
-    return PHNSW_ERR_IO;
-  }
   phnsw_store *s = nullptr;
-  phnsw_status rc = phnsw_store_create((phnsw_metric)hdr[1], hdr[2], hdr[3], rows.data(), device, &s);
+  phnsw_status rc = io_load_store(d + "/comparator", device, &s);
   if (rc != PHNSW_OK) return rc;
-  std::vector<std::vector<uint64_t>> nodes(L), nbs(L);
-  std::vector<phnsw_layer_desc> descs(L);
-  for (uint64_t i = 0; i < L; i++) {
-    std::string n = std::to_string(L - i - 1);
-    uint64_t nc = 0, M = 0;
-    if (!read_all(d + "/layer.meta." + n, buf)) {
-      phnsw_store_destroy(s);
-      set_error("load: cannot read %s/layer.meta.%s: %s", dir, n.c_str(), strerror(errno));
-      return PHNSW_ERR_IO;
-    }
-    if (!parse_layer_meta(buf.data(), &nc, &M)) {
-      phnsw_store_destroy(s);
-      set_error("load: %s/layer.meta.%s is not a valid LayerMeta document", dir, n.c_str());
-      return PHNSW_ERR_FORMAT;
-    }
-    nodes[i].resize(nc);
-    nbs[i].resize((size_t)nc * M);
-    for (int which = 0; which < 2; which++) {
-      std::vector<uint64_t> &dst = which ? nbs[i] : nodes[i];
-      std::string p = d + (which ? "/layer.neighbors." : "/layer.nodes.") + n;
-      FILE *g = fopen(p.c_str(), "rb");
-      size_t r = 0;
-      if (g) {
-        r = dst.empty() ? 0 : fread(dst.data(), 8, dst.size(), g);
-        fclose(g);
-      }
-      if (!g || r != dst.size()) {  // read_exact: a short file is an io error
-        phnsw_store_destroy(s);
-        set_error("load: cannot read %s", p.c_str());
-        return PHNSW_ERR_IO;
-      }
-    }
-    descs[i].node_count = nc;
-    descs[i].neighborhood_size = M;
-    descs[i].nodes = nodes[i].data();
-    descs[i].neighbors = nbs[i].data();
-  }
   phnsw_index *ix = nullptr;
-  rc = phnsw_index_from_layers(s, L, descs.data(), &bp, &ix);
+  rc = io_load_graph(d, s, &ix);
   if (rc != PHNSW_OK) {
     phnsw_store_destroy(s);
     return rc;

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "distance.cuh"
@@ -378,6 +379,125 @@ phnsw_status phnsw_pq_build(phnsw_store *full, uint64_t number_of_centroids, uin
     phnsw_pq_destroy(pq);
     return rc;
   }
+  *out = pq;
+  return PHNSW_OK;
+}
+
+// Serializable for QuantizedHnsw (src/pq.rs:433-476) and HnswQuantizer (src/pq.rs:94-117):
+//   <dir>/quantizer/                         the centroid Hnsw (serialize.rs layout, comparator =
+//                                            the centroids) + pq_build_parameters.json
+//   <dir>/hnsw/                              the graph over the codes (serialize.rs layout); its
+//                                            comparator file holds the quantized comparator's data:
+//                                            {tag, metric, SIZE, n, CENTROID_SIZE} + n x Q u16 codes
+//   <dir>/comparator                         the full-precision vectors
+// (the three comparator payloads are user-defined in the crate; the graph files and the JSON are
+// the crate's own formats)
+static const uint64_t kQuantizedTag = 0x3151574e53485042ULL;
+
+phnsw_status phnsw_pq_save(const phnsw_pq *pq, const char *dir) {
+  PH_ENTRY();
+  if (!pq || !dir) return PHNSW_ERR_INVALID;
+  PH_CUDA(cudaSetDevice(pq->full->device));
+  const std::string d(dir);
+  if (io_mkdir_p(d) != 0 || io_mkdir_p(d + "/quantizer") != 0 || io_mkdir_p(d + "/hnsw") != 0) {
+    set_error("pq_save: cannot create %s", dir);
+    return PHNSW_ERR_IO;
+  }
+  phnsw_status rc = phnsw_index_save(pq->centroid_index, (d + "/quantizer").c_str());
+  if (rc == PHNSW_OK) rc = io_save_pq_params(d + "/quantizer/pq_build_parameters.json", pq->bp);
+  if (rc == PHNSW_OK) rc = io_save_graph(pq->index, d + "/hnsw");
+  if (rc == PHNSW_OK) {
+    std::vector<uint16_t> codes((size_t)pq->n * pq->Q);
+    cudaError_t e = cudaMemcpy(codes.data(), pq->codes, codes.size() * 2, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "pq_save codes");
+    FILE *f = fopen((d + "/hnsw/comparator").c_str(), "wb");
+    uint64_t hdr[5] = {kQuantizedTag, (uint64_t)pq->recon_store->metric, pq->size, pq->n, pq->cs};
+    bool ok = f && fwrite(hdr, sizeof hdr, 1, f) == 1 &&
+              (codes.empty() || fwrite(codes.data(), 2, codes.size(), f) == codes.size());
+    if (f && fclose(f) != 0) ok = false;
+    if (!ok) {
+      set_error("pq_save: cannot write %s/hnsw/comparator", dir);
+      return PHNSW_ERR_IO;
+    }
+  }
+  if (rc == PHNSW_OK) rc = io_save_store(pq->full, d + "/comparator");
+  return rc;
+}
+
+phnsw_status phnsw_pq_load(const char *dir, int device, phnsw_store **full_out, phnsw_pq **out) {
+  PH_ENTRY();
+  if (!dir || !full_out || !out) return PHNSW_ERR_INVALID;
+  *full_out = nullptr;
+  *out = nullptr;
+  if (phnsw_device_count() == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return PHNSW_ERR_NO_DEVICE;
+  }
+  PH_CUDA(cudaSetDevice(device));
+  const std::string d(dir);
+  phnsw_pq *pq = new phnsw_pq();
+  phnsw_default_pq_build_params(&pq->bp);
+  phnsw_status rc = phnsw_index_load((d + "/quantizer").c_str(), device, &pq->centroid_store,
+                                     &pq->centroid_index);
+  if (rc == PHNSW_OK) rc = io_load_pq_params(d + "/quantizer/pq_build_parameters.json", &pq->bp);
+  if (rc == PHNSW_OK) rc = io_load_store(d + "/comparator", device, &pq->full);
+  std::vector<uint16_t> codes;
+  uint64_t hdr[5] = {0, 0, 0, 0, 0};
+  if (rc == PHNSW_OK) {
+    FILE *f = fopen((d + "/hnsw/comparator").c_str(), "rb");
+    if (!f) {
+      set_error("Index not found");
+      rc = PHNSW_ERR_NOT_FOUND;
+    } else {
+      if (fread(hdr, sizeof hdr, 1, f) != 1 || hdr[0] != kQuantizedTag || hdr[1] > 3 || hdr[4] == 0 ||
+          hdr[2] % hdr[4] || hdr[2] != pq->full->dim || hdr[3] != pq->full->n ||
+          hdr[4] != pq->centroid_store->dim) {
+        set_error("pq_load: %s/hnsw/comparator does not match the other parts", dir);
+        rc = PHNSW_ERR_FORMAT;
+      } else {
+        codes.resize((size_t)hdr[3] * (hdr[2] / hdr[4]));
+        if (!codes.empty() && fread(codes.data(), 2, codes.size(), f) != codes.size()) {
+          set_error("pq_load: %s/hnsw/comparator is truncated", dir);
+          rc = PHNSW_ERR_IO;
+        }
+      }
+      fclose(f);
+    }
+  }
+  if (rc == PHNSW_OK) {
+    pq->size = hdr[2];
+    pq->n = hdr[3];
+    pq->cs = hdr[4];
+    pq->Q = pq->size / pq->cs;
+    for (uint16_t c : codes)
+      if (c >= pq->centroid_store->n) {
+        set_error("pq_load: a code refers to centroid %u of %llu", (unsigned)c,
+                  (unsigned long long)pq->centroid_store->n);
+        rc = PHNSW_ERR_FORMAT;
+        break;
+      }
+  }
+  if (rc == PHNSW_OK) {
+    cudaError_t e = cudaMalloc(&pq->codes, std::max<size_t>(codes.size(), 1) * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(pq->codes, codes.data(), codes.size() * 2, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "pq_load codes");
+  }
+  if (rc == PHNSW_OK) {  // the quantized comparator's view: reconstructions (pq.rs:73-82)
+    float *tmp = nullptr;
+    cudaError_t e = cudaMalloc(&tmp, std::max<uint64_t>(pq->n * pq->size, 1) * 4);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(reconstructions)");
+    if (rc == PHNSW_OK) rc = reconstruct_device(pq, pq->codes, pq->n, tmp, (uint32_t)pq->size);
+    if (rc == PHNSW_OK)
+      rc = phnsw_store_create_device((phnsw_metric)hdr[1], pq->size, pq->n, tmp, device, &pq->recon_store);
+    if (tmp) cudaFree(tmp);
+  }
+  if (rc == PHNSW_OK) rc = io_load_graph(d + "/hnsw", pq->recon_store, &pq->index);
+  if (rc != PHNSW_OK) {
+    phnsw_pq_destroy(pq);
+    return rc;
+  }
+  pq->full->refs.fetch_add(1);  // one reference for the caller's handle, one for the quantizer
+  *full_out = pq->full;
   *out = pq;
   return PHNSW_OK;
 }

@@ -444,6 +444,18 @@ class QuantizedHnsw:
                                        _progress_cb(progress), None, C.byref(h)))
         return cls(h, full_comparator)
 
+    def serialize(self, path):
+        """Serializable::serialize for QuantizedHnsw (src/pq.rs:433-453): quantizer/, hnsw/,
+        comparator."""
+        N.check(N.lib().phnsw_pq_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def deserialize(cls, path, device=0):
+        """Serializable::deserialize for QuantizedHnsw (src/pq.rs:455-476)."""
+        s, h = C.c_void_p(), C.c_void_p()
+        N.check(N.lib().phnsw_pq_load(os.fsencode(path), device, C.byref(s), C.byref(h)))
+        return cls(h, BigComparator._adopt(s, device))
+
     def close(self):
         if getattr(self, "_h", None):
             N.lib().phnsw_pq_destroy(self._h)

@@ -112,3 +112,35 @@ def test_pq_bad_arguments(ph):
         ph.QuantizedHnsw.new(70000, comp, 4)   # codes are u16
     with pytest.raises(ph.PhnswError):
         ph.QuantizedHnsw.new(10, comp, 5)      # SIZE not a multiple of CENTROID_SIZE
+
+
+def test_pq_serialize_round_trip(ph, oracle, small, tmp_path):
+    """Serializable for QuantizedHnsw (src/pq.rs:433-476): quantizer/ (+ pq_build_parameters.json),
+    hnsw/, comparator.  The reloaded index answers exactly like the original, and the two graph
+    directories are plain serialize.rs layouts (the oracle reads them)."""
+    import json
+    import os
+    rows, g, o = small
+    d = str(tmp_path / "pq")
+    g.serialize(d)
+    assert sorted(os.listdir(d)) == ["comparator", "hnsw", "quantizer"]
+    with open(os.path.join(d, "quantizer", "pq_build_parameters.json")) as f:
+        bp = json.load(f)
+    assert set(bp) == {"centroids", "hnsw", "quantized_search"}
+    assert bp["hnsw"]["zero_layer_neighborhood_size"] == 48 and bp["quantized_search"]["probe_depth"] == 2
+    # the centroid index is an ordinary Hnsw directory
+    oc = oracle.Hnsw.deserialize(os.path.join(d, "quantizer"))
+    _same_graph(g.centroid_hnsw(), oc)
+    g2 = ph.QuantizedHnsw.deserialize(d)
+    assert g2.quantized_size == g.quantized_size and g2.centroid_size == g.centroid_size
+    assert np.array_equal(g2.centroids(), g.centroids())
+    assert np.array_equal(g2.codes(), g.codes())
+    _same_graph(g2.hnsw(), g.hnsw())
+    q = random_normed(200, 16, 77)
+    a, b = g.search(q, max_out=10), g2.search(q, max_out=10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(g2.comparator.lookup([5, 17]), rows[[5, 17]])
+    os.remove(os.path.join(d, "hnsw", "comparator"))
+    with pytest.raises(ph.PhnswError) as e:
+        ph.QuantizedHnsw.deserialize(d)
+    assert e.value.status == 6  # IndexNotFound
