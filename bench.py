@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--n", "--vectors", dest="n", type=int, default=1000000)
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--ef", type=int, default=300)
