@@ -799,7 +799,10 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
   if ((size_t)max_smem < smem) return PHNSW_OK;
 
   const float c = 2e-4f * std::max(1.0f, (float)s->pitch / 128.0f);
-  const uint64_t n_prefix = std::min<uint64_t>(s->n, std::max<uint64_t>(16384, 8 * k));
+  // the prefix that yields tau: 1/64 of the rows keeps the expected candidate count per query
+  // near 64 k (before the margin) whatever the size of the store
+  const uint64_t n_prefix = std::min<uint64_t>(
+      s->n, std::max<uint64_t>(std::min<uint64_t>(s->n / 64, 262144), std::max<uint64_t>(16384, 8 * k)));
   const uint32_t cap = 4096;
   float *w = nullptr, *thr = nullptr;
   uint64_t *topk = nullptr;
