@@ -133,7 +133,10 @@ __host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uin
 }
 // physical pool size for a candidate capacity: room for appends between two compactions
 __host__ __device__ inline uint32_t pool_entries(uint32_t cap) {
-  uint32_t slack = cap / 4 > 64 ? cap / 4 : 64;
+#ifndef PHNSW_SLACK_DIV
+#define PHNSW_SLACK_DIV 2
+#endif
+  uint32_t slack = cap / PHNSW_SLACK_DIV > 64 ? cap / PHNSW_SLACK_DIV : 64;
   return (cap + slack + 31) / 32 * 32;
 }
 
