@@ -350,6 +350,9 @@ struct WarpSearch {
     uint32_t k = cap;  // wanted: the k-th smallest among the keys matching the prefix
     uint64_t T = 0;
     bool found = false;
+    // extra keys an in-walk compaction may keep (0 = exact): half the slack, if that still
+    // leaves room for a 32-key chunk of appends
+    const uint32_t slack_half = (a.cap_pad - cap) / 2 >= 32 ? (a.cap_pad - cap) / 2 : 0;
     for (; d >= 0 && !found; d--) {
       for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
       __syncwarp();
@@ -383,6 +386,15 @@ struct WarpSearch {
       cnt = __shfl_sync(kFull, cnt, L);
       prefix |= (uint64_t)bin << sh;
       pmask |= 0xFFull << sh;
+#ifndef PHNSW_EXACT_COMPACT
+      // In the middle of a walk the pool may hold any superset of the candidate set (ranks are
+      // counted against `cap`, not against `len`): stop refining as soon as keeping the whole
+      // bin leaves room for the next chunk of appends.  One radix pass instead of three or four.
+      if (spill && cnt > 1 && cnt - k <= slack_half) {
+        T = prefix | (sh ? ((1ull << sh) - 1) : 0ull);
+        found = true;
+      } else
+#endif
       if (cnt == 1) {  // a single key carries this prefix: that is the tail
         uint64_t mine = 0;
         for (uint32_t s = lane; s < len; s += 32) {
@@ -396,7 +408,8 @@ struct WarpSearch {
       __syncwarp();
     }
     if (!found) T = prefix;  // all 64 bits decided
-    // partition in place: keys <= T stay (exactly `cap` of them: keys are unique)
+    // partition in place: keys <= T stay (exactly `cap` of them when T is the tail: keys are
+    // unique; up to slack_half more after an early stop)
     const uint32_t old_len = len;
     uint32_t w = 0;
     for (uint32_t r0 = 0; r0 < old_len; r0 += 32) {
