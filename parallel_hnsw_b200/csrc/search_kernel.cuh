@@ -107,8 +107,11 @@ struct SearchArgs {
 };
 
 // per-warp shared memory carve-up (bytes); shared by host (launch size) and device
+constexpr uint32_t kSmallLayerNodes = 8192;  // layers up to this size keep their visited set
+                                             // in a 1 KB shared-memory bitmap
 struct WarpSmemLayout {
-  uint32_t off_q, off_lut, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, total;
+  uint32_t off_q, off_lut, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, off_vsm,
+      total;
 };
 // bytes of the landing zone / scratch area: the sequential-order and ADC variants land rows
 // in it; the tree-order variant reads rows straight into registers and only needs scratch for
@@ -125,9 +128,19 @@ __host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uin
   l.off_stage = o;   o += stage_bytes;
   l.off_pool = o;    o += cap_pad * 8;
   l.off_bkeys = o;   o += kMaxBatch * 8;
-  l.off_bsorted = o; o += kMaxBatch * 8;
   l.off_bid = o;     o += kMaxBatch * 4;
   l.off_mbar = o;    o += kMaxStages * 8;
+  if (stage_bytes == kScratchBytesTree) {
+    // the tree variant lands no rows: its 4 KB scratch area also holds the sorted batch of the
+    // duplicate-row path and the small-layer visited bitmap (histogram of the radix select in
+    // [0, 1 KB), sorted batch in [1 KB, 1.5 KB), bitmap in [3 KB, 4 KB); the pool sort uses the
+    // whole area, but only after a layer's walk is over), which keeps 24 warps resident
+    l.off_bsorted = l.off_stage + 1024;
+    l.off_vsm = l.off_stage + 3072;
+  } else {
+    l.off_bsorted = o; o += kMaxBatch * 8;
+    l.off_vsm = o;     o += kSmallLayerNodes / 8;
+  }
   l.total = ((o + 127) / 128) * 128;
   return l;
 }
@@ -183,6 +196,8 @@ struct WarpSearch {
   uint64_t *ovf;
   uint32_t *bm;
   uint32_t *vlog;
+  uint32_t *vsm;       // shared-memory visited bitmap of a small layer (vis_small)
+  bool vis_small;
   uint64_t *saved;
   const int lane;
   // warp-uniform state
@@ -208,6 +223,8 @@ struct WarpSearch {
     bsorted = (uint64_t *)(smem + l.off_bsorted);
     bid = (uint32_t *)(smem + l.off_bid);
     mbar = (uint64_t *)(smem + l.off_mbar);
+    vsm = (uint32_t *)(smem + l.off_vsm);
+    vis_small = false;
     ovf = a.ovf + (size_t)slot * a.ovf_cap;
     bm = a.bitmap + (size_t)slot * a.bitmap_words;
     vlog = a.vlog + (size_t)slot * a.vlog_cap;
@@ -225,7 +242,11 @@ struct WarpSearch {
   // ------------------------------------------------------------------ visited bitmap
   // clear every bit set since the last reset (by replaying the log, or the whole bitmap if the
   // log overflowed)
-  __device__ void visited_reset() {
+  // Two homes for the visited set: layers of up to kSmallLayerNodes nodes (the upper layers,
+  // where 60 % of all expansions happen) keep it in a 1 KB shared-memory bitmap -- test and mark
+  // at shared-memory latency, nothing to log, cleared with eight stores per lane; larger layers
+  // use the per-warp bitmap in HBM.
+  __device__ void visited_reset(uint32_t next_layer_nodes = 0xffffffffu) {
     __syncwarp();
     if (vlog_over) {
       for (uint32_t w = lane; w < a.bitmap_words; w += 32) bm[w] = 0u;
@@ -244,13 +265,23 @@ struct WarpSearch {
     }
     vlog_n = 0;
     vlog_over = false;
+    vis_small = next_layer_nodes <= kSmallLayerNodes;
+    if (vis_small) {
+      uint4 *z = (uint4 *)vsm;
+      for (uint32_t w = lane; w < kSmallLayerNodes / 128; w += 32) z[w] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncwarp();
   }
   __device__ __forceinline__ bool visited_test(uint32_t id) const {
-    return (ld_cg_u32(&bm[id >> 5]) >> (id & 31)) & 1u;
+    const uint32_t w = vis_small ? vsm[id >> 5] : ld_cg_u32(&bm[id >> 5]);
+    return (w >> (id & 31)) & 1u;
   }
   // all lanes call; lanes with active==true mark their id
   __device__ void visited_set(bool active, uint32_t id) {
+    if (vis_small) {
+      if (active) atomicOr(&vsm[id >> 5], 1u << (id & 31));
+      return;
+    }
     if (active) atomicOr(&bm[id >> 5], 1u << (id & 31));
     uint32_t m = __ballot_sync(kFull, active);
     uint32_t cnt = __popc(m);
@@ -1203,7 +1234,7 @@ struct WarpSearch {
       const uint32_t old_len = len;
       // keep the incoming candidates (VectorId keys) for the merge at search.rs:136, and
       // map VectorId -> NodeId for this layer (lib.rs:258-262)
-      visited_reset();
+      visited_reset(layer.node_count);
       for (uint32_t i0 = 0; i0 < old_len; i0 += 32) {
         uint32_t i = i0 + lane;
         bool act = i < old_len;
