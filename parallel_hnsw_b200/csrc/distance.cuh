@@ -27,22 +27,7 @@ struct RowScorer {
     return kScoreRows * kScoreStride * 4;
   }
 
-  __device__ __forceinline__ float accum4(float acc, const float4 &x, const float4 &q) const {
-    if (METRIC == kL2Sqrt) {
-      float t;
-      t = __fsub_rn(q.x, x.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
-      t = __fsub_rn(q.y, x.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
-      t = __fsub_rn(q.z, x.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
-      t = __fsub_rn(q.w, x.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
-    } else {
-      acc = __fadd_rn(acc, __fmul_rn(q.x, x.x));
-      acc = __fadd_rn(acc, __fmul_rn(q.y, x.y));
-      acc = __fadd_rn(acc, __fmul_rn(q.z, x.z));
-      acc = __fadd_rn(acc, __fmul_rn(q.w, x.w));
-    }
-    return acc;
-  }
-  // per-element terms and their strictly sequential sum: the same roundings as accum4
+  // per-element terms and their strictly sequential sum: the roundings of the crate's loop
   __device__ __forceinline__ float4 terms4(const float4 &x, const float4 &q) const {
     float4 r;
     if (METRIC == kL2Sqrt) {

@@ -9,20 +9,25 @@
 //
 // Design (B200-first, not a transliteration):
 //   * persistent grid, one warp = one query at a time, work handed out by an atomic counter;
-//     per-warp shared memory is kept to ~13 KB (d = 128) so that 16 warps stay resident per SM:
-//     the walk is a chain of dependent latencies and only occupancy hides them;
+//     the walk is a chain of dependent latencies and only occupancy hides them: 24 resident
+//     warps per SM in the tree variant (9.3 KB shared memory, 80 registers), 14-16 in the
+//     sequential variant (row landing zone);
 //   * the candidate set (PriorityQueue of capacity ef) is an UNSORTED pool of 64-bit
-//     (distance,id) keys in shared memory plus its running maximum: "merge" becomes append /
-//     replace-the-maximum, "pop the best unexpanded node" a warp-wide min scan (REDUX), and the
-//     pool is only sorted when an ordered result is actually needed.  The contents are the
-//     exact top-ef of everything merged, which is all the crate's sorted array guarantees;
-//   * the visited set is a per-warp bitmap in HBM (1 bit per node, read through L2, set with
+//     (distance,id) keys in shared memory: "merge" becomes append, "pop the best unexpanded
+//     node" a warp-wide min scan (REDUX), and the pool is only sorted when an ordered result
+//     is actually needed.  Ranks are counted against ef, so the pool may hold any superset of
+//     the top-ef: when its storage (ef + ef/2) runs out a radix select drops the surplus;
+//   * the visited set of a layer of up to 8192 nodes is a 1 KB shared-memory bitmap; larger
+//     layers use a per-warp bitmap in HBM (1 bit per node, read through L2, set with
 //     fire-and-forget REDs) with a log of the set bits so that clearing costs O(visited);
-//   * neighbour rows are fetched with 1-D bulk (TMA) copies -- one per row, issued by up to 16
-//     lanes at once, completion counted on an mbarrier -- into a padded landing zone;
-//   * distances are accumulated lane-per-row in strict left-to-right f32 order with separate
-//     multiply and add (no FMA), i.e. bit-identical to the crate's scalar loops
-//     (src/bigvec.rs:47-53);
+//   * two summation orders for the distances (include/phnsw.h):
+//       TREE = 0  strict left-to-right f32 with separate multiply and add, bit-identical to
+//                 the crate's scalar loops (src/bigvec.rs:47-53); rows are fetched with 1-D
+//                 bulk (TMA) copies into a padded landing zone, all lanes turn them into
+//                 per-element terms in place, then one lane per row adds them in order;
+//       TREE = 1  coalesced 128-bit loads straight into registers, fused per-lane partial
+//                 sums, transposing warp-shuffle butterfly (fixed order, restated by the
+//                 oracle);
 //   * the reference's unbounded frontier (every discovered node stays poppable,
 //     lib.rs:211-220, 243-244) is kept exactly: nodes inside the pool carry an "expanded" bit,
 //     everything else spills to a per-warp list in HBM that is only scanned when it can matter;
@@ -516,23 +521,8 @@ struct WarpSearch {
   }
 
   // ------------------------------------------------------------------ distances
-  __device__ __forceinline__ float accum4(float acc, const float4 &x, const float4 &q) const {
-    if (METRIC == kL2Sqrt) {  // (f1 - f2).powi(2) summed left to right (lib.rs:2431-2437)
-      float t;
-      t = __fsub_rn(q.x, x.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
-      t = __fsub_rn(q.y, x.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
-      t = __fsub_rn(q.z, x.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
-      t = __fsub_rn(q.w, x.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
-    } else {                  // result += f1 * f2 (bigvec.rs:47-52): mul and add NOT fused
-      acc = __fadd_rn(acc, __fmul_rn(q.x, x.x));
-      acc = __fadd_rn(acc, __fmul_rn(q.y, x.y));
-      acc = __fadd_rn(acc, __fmul_rn(q.z, x.z));
-      acc = __fadd_rn(acc, __fmul_rn(q.w, x.w));
-    }
-    return acc;
-  }
-  // per-element terms of the sum, and the strictly sequential sum over them: together the
-  // same roundings as accum4 (every term is rounded to f32 before it is added)
+  // per-element terms of the sum, and the strictly sequential sum over them: the roundings of
+  // the crate's loop (every term is rounded to f32 before it is added, nothing is fused)
   __device__ __forceinline__ float4 terms4(const float4 &x, const float4 &q) const {
     float4 r;
     if (METRIC == kL2Sqrt) {
