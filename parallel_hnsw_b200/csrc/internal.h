@@ -91,6 +91,8 @@ struct LayerStore {
   uint32_t *nodes = nullptr;      // device, node_count
   uint32_t *neighbors = nullptr;  // device, node_count * M
   uint32_t *vec2node = nullptr;   // device, n_vectors (null when nodes[i] == i for all i)
+  float *lrows = nullptr;         // device, node_count x pitch: dense copy of the layer's vectors
+                                  // (null for an identity layer and on a PQ8 store)
   bool identity = false;
   bool row_dups = false;  // some neighbourhood lists an id twice
   std::vector<uint32_t> h_nodes;  // host copy of `nodes` (recall sampling, lib.rs:1468-1481)

@@ -76,6 +76,18 @@ __global__ void row_dups_kernel(const uint32_t *__restrict__ nb, uint32_t n, uin
       if (row[y] == v) { atomicOr(&flags[2], 1u); return; }
   }
 }
+// lrows[i] = rows[nodes[i]] (float4 granularity, pitch4 float4 per row)
+__global__ void gather_rows_kernel(const float4 *__restrict__ rows, uint32_t pitch4,
+                                   const uint32_t *__restrict__ nodes, uint64_t node_count,
+                                   float4 *__restrict__ out) {
+  const uint64_t total = node_count * pitch4;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = t / pitch4;
+    const uint32_t c = (uint32_t)(t - i * pitch4);
+    out[t] = rows[(uint64_t)nodes[i] * pitch4 + c];
+  }
+}
 __global__ void vec2node_kernel(const uint32_t *__restrict__ nodes, uint32_t n,
                                 uint32_t *__restrict__ vec2node) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,6 +349,7 @@ phnsw_status upload_layer_tables(phnsw_index *ix) {
     h[i].nodes = l.identity ? nullptr : l.nodes;
     h[i].neighbors = l.neighbors;
     h[i].vec2node = l.identity ? nullptr : l.vec2node;
+    h[i].lrows = l.identity ? ix->store->rows : l.lrows;
     h[i].node_count = (uint32_t)l.node_count;
     h[i].M = (uint32_t)l.M;
     h[i].row_dups = l.row_dups ? 1u : 0u;
@@ -384,6 +397,14 @@ phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint6
       vec2node_kernel<<<(unsigned)((node_count + 255) / 256), 256>>>(nodes, (uint32_t)node_count,
                                                                     l.vec2node);
     PH_CUDA(cudaGetLastError());
+    if (ix->store->rows && node_count) {  // dense, NodeId-indexed copy of the layer's vectors
+      const uint32_t pitch = ix->store->pitch;
+      PH_CUDA(cudaMalloc(&l.lrows, node_count * (size_t)pitch * 4));
+      gather_rows_kernel<<<(unsigned)std::min<uint64_t>((node_count * (pitch / 4) + 255) / 256, 148 * 32),
+                           256>>>((const float4 *)ix->store->rows, pitch / 4, nodes, node_count,
+                                  (float4 *)l.lrows);
+      PH_CUDA(cudaGetLastError());
+    }
   }
   ix->layers.push_back(l);
   return PHNSW_OK;
@@ -403,6 +424,7 @@ static void free_layer(LayerStore &l) {
   if (l.nodes) cudaFree(l.nodes);
   if (l.neighbors) cudaFree(l.neighbors);
   if (l.vec2node) cudaFree(l.vec2node);
+  if (l.lrows) cudaFree(l.lrows);
   l = LayerStore();
 }
 

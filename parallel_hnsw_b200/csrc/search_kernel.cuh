@@ -58,6 +58,10 @@ struct LayerDev {
   const uint32_t *nodes;      // node -> VectorId, ascending (Layer.nodes); null = identity
   const uint32_t *neighbors;  // node_count * M NodeIds, kEmpty32 padded (Layer.neighbors)
   const uint32_t *vec2node;   // VectorId -> NodeId or kEmpty32 (get_node); null = identity
+  const float *lrows;         // the layer's vectors indexed by NodeId (pitch floats per row): the
+                              // store itself for an identity layer, else a dense copy -- the
+                              // distance path then needs no NodeId -> VectorId lookup and the
+                              // upper layers' rows sit together in L2.  null on a PQ8 store
   uint32_t node_count;
   uint32_t M;
   uint32_t row_dups;          // 1 when some neighbourhood lists the same id twice
@@ -599,20 +603,16 @@ struct WarpSearch {
     const uint32_t fl4 = a.dim_pad / 4;
     const bool in = (uint32_t)lane < fl4;
     const float4 q4 = in ? ((const float4 *)qvec)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 *base = (const float4 *)a.rows + (in ? lane : 0);
+    const float4 *base = (const float4 *)layer.lrows + (in ? lane : 0);
     const uint32_t pitch4 = a.pitch / 4;
-    const uint32_t *nodes = layer.nodes;
     for (uint32_t j0 = 0; j0 < nn; j0 += 8) {
       const uint4 ia = *(const uint4 *)&bid[j0], ib = *(const uint4 *)&bid[j0 + 4];
       uint32_t id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
 #pragma unroll
       for (int r = 1; r < 8; r++) id[r] = j0 + r < nn ? id[r] : id[0];  // stale slots: reuse row 0
-      uint32_t vec[8];
-#pragma unroll
-      for (int r = 0; r < 8; r++) vec[r] = nodes ? __ldg(&nodes[id[r]]) : id[r];
       float4 x[8];
 #pragma unroll
-      for (int r = 0; r < 8; r++) x[r] = __ldg(base + (size_t)vec[r] * pitch4);
+      for (int r = 0; r < 8; r++) x[r] = __ldg(base + (size_t)id[r] * pitch4);
       float acc[8];
 #pragma unroll
       for (int r = 0; r < 8; r++) {
@@ -646,8 +646,7 @@ struct WarpSearch {
       for (int r = 0; r < RB; r++) {
         valid[r] = j0 + r < nn;
         uint32_t node = bid[valid[r] ? j0 + r : j0];
-        uint32_t vec = layer.nodes ? __ldg(&layer.nodes[node]) : node;
-        rp[r] = (const float4 *)(a.rows + (size_t)vec * a.pitch) + lane;
+        rp[r] = (const float4 *)(layer.lrows + (size_t)node * a.pitch) + lane;
       }
       float acc[RB];
 #pragma unroll
@@ -730,8 +729,7 @@ struct WarpSearch {
         __syncwarp();  // also orders the previous readers of the landing zone before the refill
         if (active) {
           node = bid[j];
-          uint32_t vec = layer.nodes ? __ldg(&layer.nodes[node]) : node;
-          bulk_g2s(stage + lane * kRowStride, a.rows + (size_t)vec * a.pitch, a.dim_pad * 4,
+          bulk_g2s(stage + lane * kRowStride, layer.lrows + (size_t)node * a.pitch, a.dim_pad * 4,
                    &mbar[0]);
         }
         mbar_wait(&mbar[0], ph & 1u);
@@ -783,7 +781,7 @@ struct WarpSearch {
         bool active = (uint32_t)lane < R && j < nn;
         if (c == 0 && active) {
           uint32_t node = bid[j];
-          vec_issue = layer.nodes ? __ldg(&layer.nodes[node]) : node;
+          vec_issue = node;  // rows of this layer are indexed by NodeId (LayerDev::lrows)
         }
         uint32_t rows_p = min(R, nn - p * R);
         uint32_t fl = min((uint32_t)kChunk, a.dim_pad - c * kChunk);
@@ -791,7 +789,7 @@ struct WarpSearch {
         __syncwarp();  // also orders the previous readers of this stage before the refill
         if (active)
           bulk_g2s(stage + (s * R + lane) * kRowStride,
-                   a.rows + (size_t)vec_issue * a.pitch + c * kChunk, fl * 4, &mbar[s]);
+                   layer.lrows + (size_t)vec_issue * a.pitch + c * kChunk, fl * 4, &mbar[s]);
       }
       if (t + 1 >= S) {  // ---- consume tile t - (S-1)
         uint32_t tc = t + 1 - S;
