@@ -233,6 +233,10 @@ def main():
     queries_h = sift_like(args.nq, args.dim, 4321 + (rank if world > 1 else 0))
     t_gen = time.perf_counter() - t0
     comp = ph.BigComparator(rows_h.numpy(), ph.L2_SQRT, device=local)
+    # one tiny build first: CUDA module load and allocator warm-up are not build throughput
+    warm = ph.BigComparator(rows_h.numpy()[:4096], ph.L2_SQRT, device=local)
+    ph.Hnsw.generate(warm, seed=1, improve=not args.no_improve).close()
+    warm.close()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     gh = ph.Hnsw.generate(comp, seed=1, improve=not args.no_improve)
