@@ -512,7 +512,8 @@ __global__ void tc_max_u32_kernel(const uint32_t *__restrict__ v, uint32_t n, ui
 // A row whose runner-up is further away than every rounding error is decided; the few others
 // go to an exact warp-per-row scan (tc_assign_exact_kernel), so the codes are exactly those of
 // the scan.
-constexpr int kAsgThreads = 9 * 32;  // 4 epilogue + 1 MMA + 4 producer warps (one stage each)
+constexpr int kAsgEpi = 8;  // epilogue warps: w and w + 4 share TMEM lanes, half the columns each
+constexpr int kAsgThreads = (kAsgEpi + 1 + 4) * 32;  // + 1 MMA + 4 producer warps (one stage each)
 constexpr int kAsgStages = 4;
 constexpr int kAsgN = 256;
 
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(kAsgThreads, 1) tc_assign_kernel(const AssignA
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], kAsgEpi);
     }
     mbar_fence_init();
   }
@@ -585,9 +586,9 @@ __global__ void __launch_bounds__(kAsgThreads, 1) tc_assign_kernel(const AssignA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 5) {
+  if (warp >= kAsgEpi + 1) {
     // ================= producers: warp g fills stage g; a lane handles 4 rows of the tile
-    const uint32_t g = warp - 5;
+    const uint32_t g = warp - (kAsgEpi + 1);
     constexpr uint32_t cs = CS, cs4 = CS / 4;
     for (uint32_t t = g; t < T; t += S) {
       mbar_wait(&empty[g], ((t / S) & 1u) ^ 1u);
@@ -652,7 +653,7 @@ __global__ void __launch_bounds__(kAsgThreads, 1) tc_assign_kernel(const AssignA
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[g]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kAsgEpi) {
     // ================= MMA issuer: four K16 steps per tile
     const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
     for (uint32_t t = 0; t < T; t++) {
@@ -671,22 +672,28 @@ __global__ void __launch_bounds__(kAsgThreads, 1) tc_assign_kernel(const AssignA
       __syncwarp();
     }
   } else {
-    // ================= epilogue: one sub-vector per thread (TMEM lane), all 256 columns
+    // ================= epilogue: warps w and w + 4 own TMEM lanes 32 (w % 4) .. + 31 (one
+    // sub-vector per lane) and 128 of the 256 centroid columns each; the upper half hands its
+    // best / runner-up to the lower half through shared memory (double buffered by tile parity,
+    // one named barrier per tile)
+    const uint32_t quad = warp & 3, half = warp >> 2;
+    uint32_t *comb = (uint32_t *)(tmem_slot + 4);  // [2][128][2]
     for (uint32_t t = 0; t < T; t++) {
       const uint32_t b = t & 1u;
       mbar_wait(&tfull[b], (t >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + b * kAsgN;
+      const uint32_t col0 = half * (kAsgN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * kAsgN + col0;
       // best and runner-up key, four independent chains (columns j mod 4) merged at the end
       uint32_t p1[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       uint32_t p2[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 #pragma unroll 1
-      for (int c = 0; c < kAsgN / 64; c++) {
+      for (int c = 0; c < kAsgN / 2 / 64; c++) {
         uint32_t v[64];
         tmem_ld64(taddr + c * 64, v);
 #pragma unroll
         for (int j = 0; j < 64; j++) {
-          const uint32_t key = (v[j] & 0xFFFFFF00u) | (uint32_t)(c * 64 + j);
+          const uint32_t key = (v[j] & 0xFFFFFF00u) | (col0 + (uint32_t)(c * 64 + j));
           p2[j & 3] = min(p2[j & 3], max(p1[j & 3], key));
           p1[j & 3] = min(p1[j & 3], key);
         }
@@ -700,10 +707,22 @@ __global__ void __launch_bounds__(kAsgThreads, 1) tc_assign_kernel(const AssignA
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
+      uint32_t *slot = comb + ((t & 1u) * kM + quad * 32 + lane) * 2;
+      if (half) {
+        slot[0] = m1;
+        slot[1] = m2;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half) continue;
+      {
+        const uint32_t o1 = slot[0], o2 = slot[1];
+        m2 = min(max(m1, o1), min(m2, o2));
+        m1 = min(m1, o1);
+      }
       const uint64_t tile = blockIdx.x + (uint64_t)t * gridDim.x;
-      const uint64_t row = tile * kM + warp * 32 + lane;
+      const uint64_t row = tile * kM + quad * 32 + lane;
       if (row < a.m) {
-        const float E = ering[(t % kWRing) * kM + warp * 32 + lane];
+        const float E = ering[(t % kWRing) * kM + quad * 32 + lane];
         const float v1 = __uint_as_float(m1 & 0xFFFFFF00u), v2 = __uint_as_float(m2 & 0xFFFFFF00u);
         // truncation: true accumulator in [v, v (1 + 2^-15)); decided iff the runner-up's lower
         // bound clears the best's upper bound by more than twice the error bound
@@ -922,7 +941,8 @@ phnsw_status assign_tc(const float *sub_dev, uint64_t m, uint32_t cs, const floa
   int max_smem = 0, sms = 148;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const size_t smem = (size_t)kAsgN * 128 + (size_t)kAsgStages * kTileA + kWRing * kM * 4 + 256 + 1024;
+  const size_t smem = (size_t)kAsgN * 128 + (size_t)kAsgStages * kTileA + kWRing * kM * 4 + 256 +
+                      2 * kM * 8 + 1024;  // + best / runner-up exchange between the column halves
   if ((size_t)max_smem < smem) return PHNSW_OK;
   // the resident operand, built on the host: row k = [ch | cl | ch | pieces of |c|^2 | 1 1 1]
   std::vector<uint16_t> bt((size_t)kAsgN * 64, 0);
