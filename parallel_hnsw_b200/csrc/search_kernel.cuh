@@ -605,6 +605,20 @@ struct WarpSearch {
     const float4 q4 = in ? ((const float4 *)qvec)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 *base = (const float4 *)layer.lrows + (in ? lane : 0);
     const uint32_t pitch4 = a.pitch / 4;
+#ifndef PHNSW_NO_L2_PREFETCH
+    // DRAM-resident layer (identity node map = the bottom layer): the rows of the later batches
+    // are pulled into L2 while the first batch is in flight -- one prefetch instruction covers
+    // eight rows (lane l touches 128-byte line l & 3 of row l >> 2); no registers, no barrier
+    if (!layer.nodes && nn > 8) {
+      for (uint32_t j0 = 8; j0 < nn; j0 += 8) {
+        const uint32_t j = j0 + ((uint32_t)lane >> 2);
+        if (j < nn && (uint32_t)(lane & 3) * 32 < a.dim_pad) {
+          const float *p = layer.lrows + (size_t)bid[j] * a.pitch + (lane & 3) * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+      }
+    }
+#endif
     for (uint32_t j0 = 0; j0 < nn; j0 += 8) {
       const uint4 ia = *(const uint4 *)&bid[j0], ib = *(const uint4 *)&bid[j0 + 4];
       uint32_t id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
