@@ -1043,6 +1043,14 @@ struct WarpSearch {
       if (!did) {                                // lib.rs:233-238: cumulative, never reset
         if (--probe == 0) break;
       }
+#ifndef PHNSW_NO_VIS_PREFETCH
+      // the neighbour row of the next pop was requested before the merge and has arrived by
+      // now: pull the visited-bitmap words of its entries towards L2 (HBM-resident bitmaps only)
+      if (pf_id != kEmpty32 && !vis_small) {
+        if (pf_n0 < layer.node_count) asm volatile("prefetch.global.L2 [%0];" ::"l"(&bm[pf_n0 >> 5]));
+        if (pf_n1 < layer.node_count) asm volatile("prefetch.global.L2 [%0];" ::"l"(&bm[pf_n1 >> 5]));
+      }
+#endif
     }
     compact(false);
   }
