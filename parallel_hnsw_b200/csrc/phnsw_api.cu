@@ -874,6 +874,28 @@ phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
   }
   PH_CUDA(cudaSetDevice(ix->store->device));
   cudaStream_t st = 0;  // legacy default stream of this thread's context
+  // Page-locked host buffers are used in place: the kernel reads each query once straight from
+  // host memory and writes its results straight back (unified addressing), so neither copy sits
+  // on the critical path in front of or behind the launch.
+  {
+    auto pinned = [](const void *p) {
+      if (!p) return true;
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      return at.type == cudaMemoryTypeHost && at.devicePointer == p;
+    };
+    if (!getenv("PHNSW_NO_ZERO_COPY") && queries && !exclude && !out_ndist && !out_nexp &&
+        pinned(queries) && pinned(out_ids) && pinned(out_dists) && pinned(out_counts)) {
+      phnsw_status rc = phnsw_search_batch_device(ix, queries, nullptr, nq, sp, upto_layers_from_top,
+                                                  nullptr, max_out, out_ids, out_dists, out_counts,
+                                                  nullptr, nullptr, (void *)st);
+      if (rc != PHNSW_OK) return rc;
+      return sync_status(ix, st);
+    }
+  }
   Workspace *wsp;
   {
     std::lock_guard<std::mutex> g(ix->mu);

@@ -424,3 +424,28 @@ def test_other_shapes_tree_order(ph, oracle, metric_name, dim, n):
     _tree_same(gh.search(queries, stats=True), oh.search(queries=queries, stats=True),
                metric_name + " tree", metric == ph.L2_SQRT)
     _assert_same(gh.knn(5, 2), oh.knn(5, 2), "tree knn")
+
+
+def test_pinned_host_buffers_are_used_in_place(ph, oracle, cfg1):
+    """phnsw_search_batch with page-locked host buffers (zero-copy: the kernel reads the queries
+    from and writes the results to host memory) returns exactly what the staged path returns."""
+    import ctypes as C
+
+    import torch
+    from parallel_hnsw_b200 import _native as N
+    rows, oh, gh, queries = cfg1
+    q = np.ascontiguousarray(queries[:700])
+    k = 10
+    sp = ph.SearchParameters()
+    staged = gh.search(q, sp, max_out=k)  # pageable numpy buffers: staging copies
+    qp = torch.from_numpy(q).pin_memory()
+    hi = torch.empty((700, k), dtype=torch.int64).pin_memory()
+    hd = torch.empty((700, k), dtype=torch.float32).pin_memory()
+    hc = torch.empty((700,), dtype=torch.int32).pin_memory()
+    N.check(N.lib().phnsw_search_batch(gh._h, C.c_void_p(qp.data_ptr()), None, 700, C.byref(sp), 0,
+                                       None, k, C.c_void_p(hi.data_ptr()), C.c_void_p(hd.data_ptr()),
+                                       C.c_void_p(hc.data_ptr()), None, None))
+    assert np.array_equal(hi.numpy().astype(np.uint64), staged[0])
+    assert np.array_equal(hd.numpy().view(np.uint32), staged[1].view(np.uint32))
+    assert np.array_equal(hc.numpy().astype(np.uint32), staged[2].astype(np.uint32))
+    _assert_same(staged, oh.search(queries=q, max_out=k), "staged vs oracle")
