@@ -178,6 +178,8 @@ phnsw_status phnsw_index_load(const char *dir, int device, phnsw_store **store_o
  * (distance, id); unused slots hold PHNSW_EMPTY_ID / FLT_MAX.
  * out_ndist / out_nexp (optional, nq x layer_count u32): distance evaluations and
  * expansions per layer (the algorithmic-bytes counters of SURVEY section 8d).
+ * Host buffers: page-locked ones (cudaHostAlloc / cudaHostRegister) are read and written in
+ * place by the kernel; pageable ones are staged through device buffers.  Same results.
  */
 phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
                                 const uint64_t *stored_ids, uint64_t nq,
