@@ -116,6 +116,16 @@ def lib():
     L.orc_discover_unreachable.restype = C.c_uint64
     L.orc_discover_unreachable.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SearchParams),
                                            C.POINTER(u64p), C.c_int]
+    L.orc_extend_layer.restype = C.c_int
+    L.orc_extend_layer.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_uint64]
+    L.orc_filter_promotion_candidates.restype = C.c_uint64
+    L.orc_filter_promotion_candidates.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_uint64,
+                                                  C.POINTER(SearchParams), u64p, u64p, C.c_uint64,
+                                                  C.POINTER(u64p), C.c_int]
+    L.orc_promote_at_layer.restype = C.c_int
+    L.orc_promote_at_layer.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(BuildParams), C.c_int]
+    L.orc_improve_index_promote.restype = C.c_float
+    L.orc_improve_index_promote.argtypes = [C.c_void_p, C.POINTER(BuildParams), C.c_uint64, C.c_int]
     L.orc_stochastic_recall.restype = C.c_float
     L.orc_stochastic_recall.argtypes = [C.c_void_p, C.POINTER(OptimizationParams), C.c_int]
     L.orc_serialize.restype = C.c_int
@@ -272,7 +282,7 @@ class Hnsw:
         bp = bp or default_build_params()
         h = lib().orc_generate(metric, rows.shape[1], rows.shape[0], _p(rows, C.c_float),
                                _p(vs, C.c_uint64), vs.size, C.byref(bp), seed,
-                               1 if improve else 0, nthreads)
+                               int(improve), nthreads)
         if not h:
             raise ValueError("generate: empty vector list")
         return cls(h, rows)
@@ -402,6 +412,47 @@ class Hnsw:
     def improve_index(self, bp=None, nthreads=0):
         bp = bp or self.build_parameters
         return float(lib().orc_improve_index(self._h, C.byref(bp), nthreads))
+
+    def improve_index_with_promotion(self, bp=None, seed=1, nthreads=0):
+        """Hnsw::improve_index (lib.rs:1661-1685) with promote_at_layer live."""
+        bp = bp or self.build_parameters
+        return float(lib().orc_improve_index_promote(self._h, C.byref(bp), seed, nthreads))
+
+    def extend_layer(self, layer_id, vecs):
+        """Hnsw::extend_layer (lib.rs:1039-1068); layer_id counts from the bottom as in the crate."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint64)
+        rc = lib().orc_extend_layer(self._h, self.layer_count - layer_id - 1, _p(vecs, C.c_uint64),
+                                    vecs.size)
+        if rc == -2:
+            raise ValueError("tried to insert vector that already exists in this layer")
+        if rc:
+            raise IndexError("no such layer")
+
+    def filter_promotion_candidates(self, layer_from_top, vecs, sp=None, nthreads=0):
+        """Hnsw::filter_promotion_candidates (lib.rs:1176-1268) -> [(order, [VectorId])]."""
+        sp = sp or default_search_params()
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint64)
+        orders = np.zeros(64, np.uint64)
+        counts = np.zeros(64, np.uint64)
+        p = C.POINTER(C.c_uint64)()
+        g = lib().orc_filter_promotion_candidates(self._h, layer_from_top, _p(vecs, C.c_uint64),
+                                                  vecs.size, C.byref(sp), _p(orders, C.c_uint64),
+                                                  _p(counts, C.c_uint64), 64, C.byref(p), nthreads)
+        out, off = [], 0
+        for i in range(g):
+            c = int(counts[i])
+            out.append((int(orders[i]), [int(p[off + k]) for k in range(c)]))
+            off += c
+        lib().orc_free(C.cast(p, C.c_void_p))
+        return out
+
+    def promote_at_layer(self, layer_from_top, bp=None, nthreads=0):
+        """Hnsw::promote_at_layer (lib.rs:1270-1427)."""
+        bp = bp or self.build_parameters
+        rc = lib().orc_promote_at_layer(self._h, layer_from_top, C.byref(bp), nthreads)
+        if rc < 0:
+            raise RuntimeError("promote_at_layer: the crate would panic here (%d)" % rc)
+        return bool(rc)
 
     def discover_unreachable_vectors(self, layer_from_top, sp=None, nthreads=0):
         """Hnsw::discover_unreachable_vectors (lib.rs:1002-1037)."""

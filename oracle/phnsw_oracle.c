@@ -315,6 +315,8 @@ struct orc_hnsw {
   const float *pq_codebook;
   uint64_t pq_Q, pq_K, pq_cs;
   int sum_order; /* 0 = the crate's sequential loop, 1 = orc_distance_tree (search paths only) */
+  uint64_t seed;        /* seed this index was generated with (nested re-top generates derive theirs) */
+  uint64_t promo_count; /* number of nested generates so far */
 };
 
 orc_hnsw *orc_hnsw_new(int metric, uint64_t dim, uint64_t n, const float *rows) {
@@ -1458,10 +1460,252 @@ static float improve_neighbors_upto(orc_hnsw *h, uint64_t upto,
   return last_recall;
 }
 
-/* improve_index_at (lib.rs:1546-1603), promotion treated as "nothing to promote" */
-static float improve_index_at(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
-                              int nthreads) {
+/* ---------------------------------------------------------------- promotion (lib.rs:1039-1068,
+ * 1167-1427, 1726-1812).  Where the crate's outcome depends on HashMap iteration order (ties in
+ * the in-link histogram, lib.rs:1226-1233) the order here is (count, NodeId) ascending, popped
+ * from the end: one of the orders the crate itself can produce. */
+
+/* Hnsw::extend_layer (lib.rs:1039-1068): generate_node_maps (:1763-1812) merges the sorted new
+ * VectorIds into `nodes`, copy_old_neighborhoods_into_layer (:1736-1761) rewrites every old
+ * neighbourhood through the old->new NodeId map, initialize_new_neighborhoods_into_layer
+ * (:1726-1734) fills the new rows with !0.  Returns -2 where the crate panics ("tried to insert
+ * vector that already exists in this layer"). */
+int orc_extend_layer(orc_hnsw *h, uint64_t layer_from_top, const uint64_t *vecs_in, uint64_t n) {
+  if (layer_from_top >= h->layer_count) return -1;
+  layer_t *l = &h->layers[layer_from_top];
+  const uint64_t on = l->node_count, M = l->M, nn = on + n;
+  uint64_t *vecs = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+  memcpy(vecs, vecs_in, n * sizeof(uint64_t));
+  qsort(vecs, n, sizeof(uint64_t), u64_cmp);
+  uint64_t *nodes = (uint64_t *)malloc((nn ? nn : 1) * sizeof(uint64_t));
+  uint64_t *old_map = (uint64_t *)malloc((on ? on : 1) * sizeof(uint64_t));
+  uint8_t *is_new = (uint8_t *)calloc(nn ? nn : 1, 1);
+  uint64_t a = 0, b = 0, w = 0;
+  while (a < on || b < n) {
+    if (b >= n || (a < on && l->nodes[a] < vecs[b])) {
+      old_map[a] = w;
+      nodes[w++] = l->nodes[a++];
+    } else if (a < on && l->nodes[a] == vecs[b]) {
+      free(vecs); free(nodes); free(old_map); free(is_new);
+      return -2;
+    } else {
+      is_new[w] = 1;
+      nodes[w++] = vecs[b++];
+    }
+  }
+  uint64_t *nb = (uint64_t *)malloc((nn * M ? nn * M : 1) * sizeof(uint64_t));
+  for (uint64_t i = 0; i < nn; i++)
+    if (is_new[i])
+      for (uint64_t k = 0; k < M; k++) nb[i * M + k] = ORC_EMPTY;
+  for (uint64_t o = 0; o < on; o++) {
+    const uint64_t *src = l->neighbors + o * M;
+    uint64_t *dst = nb + old_map[o] * M;
+    for (uint64_t k = 0; k < M; k++) dst[k] = src[k] == ORC_EMPTY ? ORC_EMPTY : old_map[src[k]];
+  }
+  free(l->nodes);
+  free(l->neighbors);
+  l->nodes = nodes;
+  l->neighbors = nb;
+  l->node_count = nn;
+  free(vecs); free(old_map); free(is_new);
+  return 0;
+}
+
+/* discover_order_from_top (lib.rs:1167-1174) */
+static int64_t discover_order_from_top(const orc_hnsw *h, uint64_t v) {
+  for (uint64_t i = 0; i < h->layer_count; i++)
+    if (layer_get_node(&h->layers[i], v) >= 0) return (int64_t)i;
+  return -1; /* the crate panics */
+}
+
+typedef struct { uint64_t node, count; } histo_t;
+static int histo_cmp(const void *a, const void *b) {
+  const histo_t *x = (const histo_t *)a, *y = (const histo_t *)b;
+  if (x->count != y->count) return x->count < y->count ? -1 : 1;
+  return x->node < y->node ? -1 : x->node > y->node;
+}
+
+/* filter_promotion_candidates (lib.rs:1176-1268).  Output: for every order (ascending) that has
+ * a histogram, the selected VectorIds in selection order.  orders[g], counts[g], and the
+ * concatenated selections in *sel (malloc'ed).  Returns the number of groups. */
+uint64_t orc_filter_promotion_candidates(const orc_hnsw *h, uint64_t layer_from_top,
+                                         const uint64_t *vecs_in, uint64_t n,
+                                         const orc_search_params *sp, uint64_t *orders,
+                                         uint64_t *counts, uint64_t max_groups, uint64_t **sel,
+                                         int nthreads) {
+  *sel = NULL;
+  if (layer_from_top == 0 || n == 0) return 0;
+  uint64_t *vecs = (uint64_t *)malloc(n * sizeof(uint64_t));
+  memcpy(vecs, vecs_in, n * sizeof(uint64_t));
+  qsort(vecs, n, sizeof(uint64_t), u64_cmp);
+  uint64_t **histo = (uint64_t **)calloc(h->layer_count, sizeof(uint64_t *));
+  for (uint64_t i = 0; i < n; i++) {
+    int64_t order = discover_order_from_top(h, vecs[i]);
+    if (order <= 0) continue;
+    const layer_t *ol = &h->layers[order];
+    if (!histo[order]) histo[order] = (uint64_t *)calloc(ol->node_count ? ol->node_count : 1, 8);
+    uint64_t node = (uint64_t)layer_get_node(ol, vecs[i]);
+    const uint64_t end = orc_get_final_neighbor_idx(ol->M, ol->neighbors, node);
+    for (uint64_t k = node * ol->M; k < end; k++) {
+      uint64_t nbr = ol->neighbors[k];
+      uint64_t nv = ol->nodes[nbr];
+      uint64_t lo = 0, hi = n; /* vecs.binary_search(&neighbor_vector) */
+      while (lo < hi) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (vecs[mid] < nv) lo = mid + 1; else hi = mid;
+      }
+      if (lo < n && vecs[lo] == nv) histo[order][nbr]++;
+    }
+  }
+  uint64_t *out = (uint64_t *)malloc(n * sizeof(uint64_t));
+  uint64_t n_out = 0, groups = 0;
+  for (uint64_t order = 0; order < h->layer_count && groups < max_groups; order++) {
+    if (!histo[order]) continue;
+    const layer_t *ol = &h->layers[order];
+    uint64_t hn = 0;
+    for (uint64_t i = 0; i < ol->node_count; i++) hn += histo[order][i] != 0;
+    histo_t *hs = (histo_t *)malloc((hn ? hn : 1) * sizeof(histo_t));
+    hn = 0;
+    for (uint64_t i = 0; i < ol->node_count; i++)
+      if (histo[order][i]) { hs[hn].node = i; hs[hn].count = histo[order][i]; hn++; }
+    qsort(hs, hn, sizeof(histo_t), histo_cmp);
+    /* the radius of a candidate does not depend on the selection: search them all at once */
+    uint64_t *qv = (uint64_t *)malloc((hn ? hn : 1) * 8), *rid = (uint64_t *)malloc((hn ? hn : 1) * 8);
+    float *rd = (float *)malloc((hn ? hn : 1) * 4);
+    uint32_t *rc = (uint32_t *)malloc((hn ? hn : 1) * 4);
+    for (uint64_t i = 0; i < hn; i++) qv[i] = ol->nodes[hs[i].node];
+    orc_search_batch(h, NULL, qv, hn, sp, layer_from_top, NULL, 1, rid, rd, rc, NULL, NULL, NULL,
+                     nthreads);
+    float *radius = (float *)malloc((hn ? hn : 1) * 4);
+    const uint64_t start = n_out;
+    for (uint64_t i = hn; i-- > 0;) { /* histogram.pop() */
+      const uint64_t vec = qv[i];
+      int covered = 0;
+      for (uint64_t j = start; j < n_out && !covered; j++)
+        covered = orc_distance(h->metric, h->dim, h->rows + out[j] * h->dim,
+                               h->rows + vec * h->dim) < radius[j - start];
+      if (covered) continue;
+      radius[n_out - start] = rc[i] ? rd[i] : 0.0f; /* result[0].1 (panics when empty) */
+      out[n_out++] = vec;
+    }
+    orders[groups] = order;
+    counts[groups] = n_out - start;
+    groups++;
+    free(hs); free(qv); free(rid); free(rd); free(rc); free(radius);
+  }
+  for (uint64_t i = 0; i < h->layer_count; i++) free(histo[i]);
+  free(histo);
+  free(vecs);
+  *sel = out;
+  return groups;
+}
+
+static uint64_t partitions_from_bottom(uint64_t total, uint64_t order, uint64_t *out) {
+  uint64_t top_first[64];
+  uint64_t n = orc_calculate_partitions(total, order, top_first, 64);
+  for (uint64_t i = 0; i < n; i++) out[i] = top_first[n - 1 - i];
+  return n;
+}
+
+static float improve_index_promote(orc_hnsw *h, const orc_build_params *bp, int nthreads);
+
+/* the crate's nested Self::generate(comparator, vecs, new_bp, progress) (lib.rs:1316, 1377):
+ * a fresh layer stack over `vecs` whose bottom layer uses neighborhood_size */
+static orc_hnsw *nested_generate(orc_hnsw *h, const uint64_t *vecs, uint64_t n,
+                                 const orc_build_params *bp, int nthreads) {
+  orc_build_params nbp = *bp;
+  nbp.zero_layer_neighborhood_size = bp->neighborhood_size;
+  uint64_t seed = h->seed ^ (0x9E3779B97F4A7C15ull * ++h->promo_count);
+  orc_hnsw *t = orc_generate(h->metric, h->dim, h->n_vectors, h->rows, vecs, n, &nbp, seed, 2,
+                             nthreads);
+  return t;
+}
+
+/* Hnsw::promote_at_layer (lib.rs:1270-1427).  Returns 1 = promoted (true), 0 = false,
+ * negative where the crate would panic. */
+int orc_promote_at_layer(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
+                         int nthreads) {
+  uint64_t *vecs = NULL;
+  uint64_t n = orc_discover_unreachable(h, layer_from_top, &bp->optimization.search, &vecs, nthreads);
+  if (n == 0) { free(vecs); return 0; }
+  if (bp->optimization.promotion_proportion < 1.0f) {
+    n = (uint64_t)((float)n * bp->optimization.promotion_proportion);
+    if (n == 0) { free(vecs); return 0; }
+  }
+  uint64_t orders[64], counts[64], *sel = NULL;
+  uint64_t groups = orc_filter_promotion_candidates(h, layer_from_top, vecs, n,
+                                                    &bp->optimization.search, orders, counts, 64,
+                                                    &sel, nthreads);
+  free(vecs);
+  int rc = 1;
+  uint64_t off = 0;
+  for (uint64_t g = 0; g < groups && rc == 1; g++) {
+    const uint64_t lft = orders[g];
+    if (lft == 0 || lft > 64) continue; /* order 0 never enters the histogram */
+    const uint64_t *pv = sel + off;
+    const uint64_t pn = counts[g];
+    off += pn;
+    uint64_t sizes[64], new_sizes[64], promo[64];
+    uint64_t ns = lft; /* layers above, bottom-most first */
+    for (uint64_t i = 0; i < ns; i++) sizes[i] = h->layers[lft - 1 - i].node_count;
+    uint64_t nn = partitions_from_bottom(sizes[0] + pn, h->bp.order, new_sizes);
+    while (nn < ns) new_sizes[nn++] = 0;
+    const uint64_t retop_upto = nn - ns;
+    for (uint64_t i = 0; i < ns; i++) promo[i] = new_sizes[i] > sizes[i] ? new_sizes[i] - sizes[i] : 0;
+    uint64_t np = ns, offset = 0;
+    if (retop_upto != 0) {
+      if (retop_upto > ns) { rc = -3; break; } /* usize underflow in the crate */
+      const uint64_t ridx = ns - retop_upto;
+      const uint64_t into_top = promo[ridx];
+      np = ridx;
+      if (into_top > pn) { rc = -3; break; } /* slice index out of range in the crate */
+      const layer_t *tl = &h->layers[retop_upto - 1];
+      uint64_t tn = tl->node_count + into_top;
+      uint64_t *tv = (uint64_t *)malloc((tn ? tn : 1) * 8);
+      memcpy(tv, tl->nodes, tl->node_count * 8);
+      memcpy(tv + tl->node_count, pv, into_top * 8);
+      qsort(tv, tn, 8, u64_cmp);
+      uint64_t w = 0;
+      for (uint64_t i = 0; i < tn; i++)
+        if (w == 0 || tv[w - 1] != tv[i]) tv[w++] = tv[i];
+      orc_hnsw *t = nested_generate(h, tv, w, bp, nthreads);
+      free(tv);
+      if (!t) { rc = -4; break; }
+      /* self.layers = new top layers ++ self.layers[retop_upto..] */
+      const uint64_t keep = h->layer_count - retop_upto, tl_n = t->layer_count;
+      layer_t *nl = (layer_t *)malloc((tl_n + keep) * sizeof(layer_t));
+      memcpy(nl, t->layers, tl_n * sizeof(layer_t));
+      memcpy(nl + tl_n, h->layers + retop_upto, keep * sizeof(layer_t));
+      for (uint64_t i = 0; i < retop_upto; i++) { free(h->layers[i].nodes); free(h->layers[i].neighbors); }
+      free(h->layers);
+      h->layers = nl;
+      h->layer_count = h->layer_cap = tl_n + keep;
+      t->layer_count = 0; /* layers moved out */
+      orc_hnsw_free(t);
+      offset = tl_n;
+    }
+    for (uint64_t i = 0; i < np && rc == 1; i++) { /* promotion_sizes.reverse(): top first */
+      const uint64_t size = promo[np - 1 - i];
+      const uint64_t cur = offset + i;
+      const layer_t *l = &h->layers[cur];
+      uint64_t *tp = (uint64_t *)malloc((pn ? pn : 1) * 8);
+      uint64_t c = 0;
+      for (uint64_t k = 0; k < pn && c < size; k++)
+        if (layer_get_node(l, pv[k]) < 0) tp[c++] = pv[k];
+      if (orc_extend_layer(h, cur, tp, c) != 0) rc = -2;
+      free(tp);
+    }
+  }
+  free(sel);
+  return rc;
+}
+
+/* improve_index_at (lib.rs:1546-1603); promote = 0 treats promote_at_layer as "nothing to
+ * promote" (the default of the build entry points), promote = 1 is the crate's full loop */
+static float improve_index_at_ex(orc_hnsw *h, uint64_t *layer_from_top_io,
+                                 const orc_build_params *bp, int promote, int nthreads) {
   const orc_optimization_params *op = &bp->optimization;
+  uint64_t layer_from_top = *layer_from_top_io;
   float recall = stochastic_recall_at(h, layer_from_top, op, nthreads);
   float improvement = 1.0f;
   int bailout = 1;
@@ -1469,19 +1713,49 @@ static float improve_index_at(orc_hnsw *h, uint64_t layer_from_top, const orc_bu
     float last_recall = recall;
     uint64_t cur = 0;
     while (cur <= layer_from_top && bailout != 0) {
+      const uint64_t layer_count = h->layer_count;
       recall = improve_neighbors_upto(h, cur + 1, op, 0, 0.0f, nthreads);
-      cur += 1; /* recall == 1.0 -> continue; else promote_at_layer (skipped) -> +1 */
+      if (recall == 1.0f) { cur += 1; continue; }
+      if (promote && orc_promote_at_layer(h, cur, bp, nthreads) == 1) {
+        const uint64_t delta = h->layer_count - layer_count;
+        cur += delta;
+        layer_from_top += delta;
+        recall = improve_neighbors_upto(h, cur + 1, op, 1, recall, nthreads);
+      }
+      cur += 1;
     }
     bailout -= 1;
     improvement = recall - last_recall;
   }
+  *layer_from_top_io = layer_from_top;
   return recall;
 }
 
 float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
   float recall = orc_stochastic_recall(h, &bp->optimization, nthreads); /* lib.rs:1671 */
-  for (uint64_t l = 0; l < h->layer_count; l++) recall = improve_index_at(h, l, bp, nthreads);
+  for (uint64_t l = 0; l < h->layer_count; l++) {
+    uint64_t lft = l;
+    recall = improve_index_at_ex(h, &lft, bp, 0, nthreads);
+  }
   return recall;
+}
+
+/* improve_index (lib.rs:1661-1685) with promotion, as the crate runs it */
+static float improve_index_promote(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
+  float recall = orc_stochastic_recall(h, &bp->optimization, nthreads);
+  uint64_t lft = 0;
+  while (lft < h->layer_count) {
+    recall = improve_index_at_ex(h, &lft, bp, 1, nthreads);
+    lft += 1;
+  }
+  return recall;
+}
+
+float orc_improve_index_promote(orc_hnsw *h, const orc_build_params *bp, uint64_t seed,
+                                int nthreads) {
+  h->seed = seed;
+  h->promo_count = 0;
+  return improve_index_promote(h, bp, nthreads);
 }
 
 orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float *rows,
@@ -1490,6 +1764,7 @@ orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float
   if (n_vs == 0) return NULL; /* assert!(total_size > 0) lib.rs:837 */
   orc_hnsw *h = orc_hnsw_new(metric, dim, n_vectors, rows);
   h->bp = *bp;
+  h->seed = seed;
   uint64_t *vs = (uint64_t *)malloc(n_vs * sizeof(uint64_t));
   memcpy(vs, vs_in, n_vs * sizeof(uint64_t));
   rng_t rng;
@@ -1505,7 +1780,8 @@ orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float
     memcpy(slice, vs, len * sizeof(uint64_t));
     generate_layer(h, slice, len, M, &bp->initial_partition_search, nthreads);
     free(slice);
-    if (improve) orc_improve_index(h, bp, nthreads); /* lib.rs:876 */
+    if (improve == 2) improve_index_promote(h, bp, nthreads);
+    else if (improve) orc_improve_index(h, bp, nthreads); /* lib.rs:876 */
   }
   free(vs);
   return h;

@@ -158,6 +158,20 @@ orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float
                        const uint64_t *vs, uint64_t n_vs, const orc_build_params *bp,
                        uint64_t seed, int improve, int nthreads);
 float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads);
+/* Promotion / layer surgery (lib.rs:1039-1068, 1167-1427, 1726-1812).  orc_generate with
+ * improve = 2 and orc_improve_index_promote run improve_index as the crate does, promotion
+ * included; improve = 1 / orc_improve_index leave it out (the default of the build entry points).
+ * Histogram ties, which the crate breaks by HashMap iteration order, are broken by NodeId. */
+int orc_extend_layer(orc_hnsw *h, uint64_t layer_from_top, const uint64_t *vecs, uint64_t n);
+uint64_t orc_filter_promotion_candidates(const orc_hnsw *h, uint64_t layer_from_top,
+                                         const uint64_t *vecs, uint64_t n,
+                                         const orc_search_params *sp, uint64_t *orders,
+                                         uint64_t *counts, uint64_t max_groups, uint64_t **sel,
+                                         int nthreads);
+int orc_promote_at_layer(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
+                         int nthreads);
+float orc_improve_index_promote(orc_hnsw *h, const orc_build_params *bp, uint64_t seed,
+                                int nthreads);
 /* Hnsw::discover_unreachable_vectors (lib.rs:1002-1037); *out is malloc'ed (orc_free) */
 uint64_t orc_discover_unreachable(const orc_hnsw *h, uint64_t layer_from_top,
                                   const orc_search_params *sp, uint64_t **out, int nthreads);
