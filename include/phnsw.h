@@ -214,13 +214,38 @@ void phnsw_free(void *p);
 phnsw_status phnsw_generate(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
                             const phnsw_build_params *bp, uint64_t seed,
                             phnsw_progress_fn progress, void *user, phnsw_index **out);
-/* same; improve = 0 skips the improve_index call after every layer (src/lib.rs:876) */
+/* same; improve = 0 skips the improve_index call after every layer (src/lib.rs:876),
+ * improve = 2 runs it with promotion (see below) */
 phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
                                  const phnsw_build_params *bp, uint64_t seed, int improve,
                                  phnsw_progress_fn progress, void *user, phnsw_index **out);
 phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out);
-/* stochastic_recall (src/lib.rs:1463-1505) */
+/* Promotion / layer surgery (src/lib.rs:1039-1068 extend_layer, 1167-1268
+ * discover_order_from_top + filter_promotion_candidates, 1273-1427 promote_at_layer, 1726-1812
+ * node maps and neighbourhood rewrite).  Opt-in: phnsw_generate_with(improve = 2) and
+ * phnsw_improve_index_promote run improve_index as the crate does, promote_at_layer live;
+ * improve = 1 / phnsw_improve_index treat it as "nothing to promote".  Ties of the in-link
+ * histogram, which the crate breaks by HashMap iteration order, are broken by NodeId; nested
+ * re-top generates derive their seed from `seed`.  Exclusive access (&mut self).
+ *   phnsw_extend_layer: `layer_from_top` (the crate counts from the bottom: layer_count-1-id);
+ *     PHNSW_ERR_INVALID where the crate panics on a vector already in the layer.
+ *   phnsw_filter_promotion_candidates: groups (order ascending) with the selected VectorIds in
+ *     selection order, concatenated in *selected (malloc'ed, phnsw_free).
+ *   phnsw_promote_at_layer: *promoted_out = the crate's bool. */
+phnsw_status phnsw_extend_layer(phnsw_index *ix, uint64_t layer_from_top, const uint64_t *vecs,
+                                uint64_t n);
+phnsw_status phnsw_filter_promotion_candidates(const phnsw_index *ix, uint64_t layer_from_top,
+                                               const uint64_t *vecs, uint64_t n,
+                                               const phnsw_search_params *sp, uint64_t *orders,
+                                               uint64_t *counts, uint64_t max_groups,
+                                               uint64_t **selected, uint64_t *n_groups);
+phnsw_status phnsw_promote_at_layer(phnsw_index *ix, uint64_t layer_from_top,
+                                    const phnsw_build_params *bp, phnsw_progress_fn progress,
+                                    void *user, int *promoted_out);
+phnsw_status phnsw_improve_index_promote(phnsw_index *ix, const phnsw_build_params *bp,
+                                         uint64_t seed, phnsw_progress_fn progress, void *user,
+                                         float *recall_out);
 /* Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): the vectors of layer
  * `layer_from_top` that do not find themselves (search::match_within_epsilon,
  * src/search.rs:173-187) when searched over layers[0..=layer] and are not nodes of the layer
@@ -228,6 +253,7 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
 phnsw_status phnsw_discover_unreachable(const phnsw_index *ix, uint64_t layer_from_top,
                                         const phnsw_search_params *sp, uint64_t **out_ids,
                                         uint64_t *out_n);
+/* stochastic_recall (src/lib.rs:1463-1505) */
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix,
                                      const phnsw_optimization_params *op, float *recall_out);
 

@@ -115,6 +115,14 @@ SIGNATURES = {
                                       C.c_int, PROGRESS_FN, vp, C.POINTER(vp)]),
     "phnsw_improve_index": (C.c_int, [vp, C.POINTER(BuildParams), PROGRESS_FN, vp, f32p]),
     "phnsw_stochastic_recall": (C.c_int, [vp, C.POINTER(OptimizationParams), f32p]),
+    "phnsw_extend_layer": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64]),
+    "phnsw_filter_promotion_candidates": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64,
+                                                    C.POINTER(SearchParams), vp, vp, C.c_uint64,
+                                                    C.POINTER(u64p), u64p]),
+    "phnsw_promote_at_layer": (C.c_int, [vp, C.c_uint64, C.POINTER(BuildParams), PROGRESS_FN, vp,
+                                         C.POINTER(C.c_int)]),
+    "phnsw_improve_index_promote": (C.c_int, [vp, C.POINTER(BuildParams), C.c_uint64, PROGRESS_FN,
+                                              vp, f32p]),
     "phnsw_discover_unreachable": (C.c_int, [vp, C.c_uint64, C.POINTER(SearchParams),
                                              C.POINTER(u64p), u64p]),
     "phnsw_bruteforce_knn": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),

@@ -9,8 +9,10 @@
 //   link_nodes_in_layer_to_better_neighbors src/lib.rs:1084-1154
 //   stochastic_recall_at                   src/lib.rs:1463-1499
 //   improve_neighbors_upto / improve_index_at / improve_index   src/lib.rs:1515-1603, 1664-1685
-// promote_at_layer (src/lib.rs:1273-1427) is not built yet: it is treated as "nothing to promote"
-// (out-of-scope table).
+//   extend_layer / generate_node_maps / copy_old_neighborhoods_into_layer   src/lib.rs:1039-1068, 1726-1812
+//   discover_order_from_top / filter_promotion_candidates / promote_at_layer src/lib.rs:1167-1427
+// Promotion is opt-in (improve = 2 in phnsw_generate_with, phnsw_improve_index_promote): the
+// default build entry points treat promote_at_layer as "nothing to promote" (DESIGN.md).
 //
 // Design.  The crate mutates neighbourhoods under per-node RwLocks from rayon workers
 // (lib.rs:789-815, 1102-1148); every such mutation is "insert (node, d) into a bounded list
@@ -757,9 +759,9 @@ static phnsw_status stochastic_recall_at(const phnsw_index *ix, uint32_t at,
 // improve_neighbors_upto (lib.rs:1515-1544)
 static phnsw_status improve_neighbors_upto(phnsw_index *ix, uint32_t upto,
                                            const phnsw_build_params &bp, Progress &pg,
-                                           float *recall_out) {
+                                           float *recall_out, const float *last_recall_in = nullptr) {
   const phnsw_optimization_params &op = bp.optimization;
-  float last_recall = 0.0f, last_improvement = 1.0f;
+  float last_recall = last_recall_in ? *last_recall_in : 0.0f, last_improvement = 1.0f;
   while (last_improvement >= op.neighborhood_threshold && last_recall < 1.0f) {
     for (uint32_t l = 0; l < upto; l++) {
       phnsw_status rc = link_layer(ix, l, op.search, bp.neighborhood_size);
@@ -776,10 +778,350 @@ static phnsw_status improve_neighbors_upto(phnsw_index *ix, uint32_t upto,
   return PHNSW_OK;
 }
 
-// improve_index_at (lib.rs:1546-1603) with promote_at_layer = "nothing to promote"
-static phnsw_status improve_index_at(phnsw_index *ix, uint32_t layer_from_top,
-                                     const phnsw_build_params &bp, Progress &pg, float *recall_out) {
+// ------------------------------------------------------------------ promotion / layer surgery
+// copy_old_neighborhoods_into_layer (lib.rs:1736-1761): every old row moves to its new NodeId and
+// its entries are rewritten through the same map; rows of new nodes stay !0 (memset before)
+__global__ void extend_remap_kernel(const uint32_t *__restrict__ old_nb, uint32_t old_n, uint32_t M,
+                                    const uint32_t *__restrict__ old_map, uint32_t *__restrict__ nb) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)old_n * M) return;
+  uint32_t o = (uint32_t)(i / M), k = (uint32_t)(i - (size_t)o * M);
+  uint32_t v = old_nb[i];
+  nb[(size_t)old_map[o] * M + k] = v == 0xFFFFFFFFu ? v : (v < old_n ? old_map[v] : 0xFFFFFFFFu);
+}
+
+__global__ void gather_nb_rows_kernel(const uint32_t *__restrict__ nb, uint32_t M,
+                                      const uint32_t *__restrict__ node_ids, uint32_t n,
+                                      uint32_t *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * M) return;
+  uint32_t r = (uint32_t)(i / M), k = (uint32_t)(i - (size_t)r * M);
+  out[i] = nb[(size_t)node_ids[r] * M + k];
+}
+
+__device__ __forceinline__ float pair_distance_seq(const float *x, const float *y, uint32_t dim,
+                                                   int metric) {
+  float acc = 0.0f;  // Comparator::compare_vec(Stored, Stored), strict left-to-right f32
+  if (metric == kL2Sqrt) {
+    for (uint32_t k = 0; k < dim; k++) {
+      float t = __fsub_rn(x[k], y[k]);
+      acc = __fadd_rn(acc, __fmul_rn(t, t));
+    }
+    return __fsqrt_rn(acc);
+  }
+  for (uint32_t k = 0; k < dim; k++) acc = __fadd_rn(acc, __fmul_rn(x[k], y[k]));
+  if (metric == kCosHalf) return __fdiv_rn(__fsub_rn(1.0f, acc), 2.0f);
+  if (metric == kOneMinusDot) return __fsub_rn(1.0f, acc);
+  float r = __fdiv_rn(__fsub_rn(acc, 1.0f), -2.0f);
+  r = r < 0.0f ? 0.0f : r;
+  return r > 1.0f ? 1.0f : r;
+}
+
+// the hypersphere selection of filter_promotion_candidates (lib.rs:1243-1262): candidates in pop
+// order; one is kept unless an earlier kept vector lies closer to it than that vector's radius.
+// The loop is sequential in the candidates; one CTA spreads the kept list over its threads.
+__global__ void __launch_bounds__(1024)
+promo_select_kernel(const float *__restrict__ rows, uint32_t pitch, uint32_t dim, int metric,
+                    const uint64_t *__restrict__ cand, const float *__restrict__ radius,
+                    const uint32_t *__restrict__ found, uint32_t n, uint32_t *sel_idx,
+                    float *sel_radius, uint32_t *n_sel_out) {
+  __shared__ uint32_t n_sel;
+  if (threadIdx.x == 0) n_sel = 0;
+  __syncthreads();
+  for (uint32_t i = 0; i < n; i++) {
+    const float *y = rows + cand[i] * pitch;
+    int covered = 0;
+    const uint32_t ns = n_sel;
+    for (uint32_t j = threadIdx.x; j < ns && !covered; j += blockDim.x)
+      covered = pair_distance_seq(rows + cand[sel_idx[j]] * pitch, y, dim, metric) < sel_radius[j];
+    covered = __syncthreads_or(covered);
+    if (!covered && threadIdx.x == 0) {
+      sel_idx[ns] = i;
+      sel_radius[ns] = found[i] ? radius[i] : 0.0f;  // result[0].1
+      n_sel = ns + 1;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_sel_out = n_sel;
+}
+
+// Hnsw::extend_layer (lib.rs:1039-1068); the node merge of generate_node_maps (:1763-1812) runs
+// on the host copy of `nodes`, the neighbourhood rewrite on the device
+static phnsw_status extend_layer(phnsw_index *ix, uint32_t lft, std::vector<uint32_t> vecs) {
+  if (lft >= ix->layers.size()) return PHNSW_ERR_INVALID;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  const LayerStore &L = ix->layers[lft];
+  const uint32_t on = (uint32_t)L.node_count, M = (uint32_t)L.M;
+  std::sort(vecs.begin(), vecs.end());
+  const uint32_t nn = on + (uint32_t)vecs.size();
+  std::vector<uint32_t> nodes(nn), old_map(on);
+  uint32_t a = 0, b = 0, w = 0;
+  while (a < on || b < vecs.size()) {
+    if (b >= vecs.size() || (a < on && L.h_nodes[a] < vecs[b])) {
+      old_map[a] = w;
+      nodes[w++] = L.h_nodes[a++];
+    } else if (a < on && L.h_nodes[a] == vecs[b]) {
+      set_error("extend_layer: tried to insert vector that already exists in this layer");
+      return PHNSW_ERR_INVALID;  // panic at lib.rs:1795
+    } else {
+      if (vecs[b] >= ix->store->n) {
+        set_error("extend_layer: VectorId %u is not in the store", vecs[b]);
+        return PHNSW_ERR_INVALID;
+      }
+      nodes[w++] = vecs[b++];
+    }
+  }
+  uint32_t *d_nodes = nullptr, *d_nb = nullptr, *d_map = nullptr;
+  PH_CUDA(cudaMalloc(&d_nodes, std::max<size_t>(nn, 1) * 4));
+  PH_CUDA(cudaMalloc(&d_nb, std::max<size_t>((size_t)nn * M, 1) * 4));
+  PH_CUDA(cudaMalloc(&d_map, std::max<size_t>(on, 1) * 4));
+  PH_CUDA(cudaMemcpy(d_nodes, nodes.data(), (size_t)nn * 4, cudaMemcpyHostToDevice));
+  PH_CUDA(cudaMemcpy(d_map, old_map.data(), (size_t)on * 4, cudaMemcpyHostToDevice));
+  PH_CUDA(cudaMemset(d_nb, 0xFF, (size_t)nn * M * 4));
+  if (on && M)
+    extend_remap_kernel<<<blocks_for((size_t)on * M), 256>>>(L.neighbors, on, M, d_map, d_nb);
+  PH_CUDA(cudaGetLastError());
+  PH_CUDA(cudaDeviceSynchronize());
+  cudaFree(d_map);
+  return index_replace_layer(ix, lft, nn, M, d_nodes, d_nb);
+}
+
+// discover_order_from_top (lib.rs:1167-1174)
+static int64_t discover_order_from_top(const phnsw_index *ix, uint32_t v) {
+  for (size_t i = 0; i < ix->layers.size(); i++) {
+    const std::vector<uint32_t> &hn = ix->layers[i].h_nodes;
+    if (std::binary_search(hn.begin(), hn.end(), v)) return (int64_t)i;
+  }
+  return -1;
+}
+
+// filter_promotion_candidates (lib.rs:1176-1268) -> [(order, selected VectorIds)].  The in-link
+// histogram is built on the host from the gathered neighbourhoods of the unreachable vectors; ties
+// of the count (HashMap order in the crate) are broken by NodeId.  All radius searches of an
+// order run as one traversal launch, the hypersphere selection as one kernel.
+static phnsw_status filter_promotion_candidates(
+    const phnsw_index *ix, uint32_t layer_from_top, std::vector<uint32_t> vecs,
+    const phnsw_search_params &sp, std::vector<std::pair<uint32_t, std::vector<uint32_t>>> *out) {
+  out->clear();
+  if (layer_from_top == 0 || vecs.empty()) return PHNSW_OK;
+  std::sort(vecs.begin(), vecs.end());
+  cudaStream_t st = 0;
+  std::vector<std::vector<uint32_t>> by_order(ix->layers.size());  // node ids per order
+  for (uint32_t v : vecs) {
+    int64_t order = discover_order_from_top(ix, v);
+    if (order <= 0) continue;
+    const std::vector<uint32_t> &hn = ix->layers[order].h_nodes;
+    by_order[order].push_back((uint32_t)(std::lower_bound(hn.begin(), hn.end(), v) - hn.begin()));
+  }
+  for (uint32_t order = 1; order < ix->layers.size(); order++) {
+    const std::vector<uint32_t> &src = by_order[order];
+    if (src.empty()) continue;
+    const LayerStore &L = ix->layers[order];
+    const uint32_t M = (uint32_t)L.M, ns = (uint32_t)src.size();
+    DevMem mem;
+    uint32_t *d_src, *d_rows;
+    PH_CUDA(mem.alloc(&d_src, ns));
+    PH_CUDA(mem.alloc(&d_rows, (size_t)ns * M));
+    PH_CUDA(cudaMemcpyAsync(d_src, src.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    gather_nb_rows_kernel<<<blocks_for((size_t)ns * M), 256, 0, st>>>(L.neighbors, M, d_src, ns, d_rows);
+    std::vector<uint32_t> nbrows((size_t)ns * M);
+    PH_CUDA(cudaMemcpy(nbrows.data(), d_rows, (size_t)ns * M * 4, cudaMemcpyDeviceToHost));
+    std::vector<std::pair<uint32_t, uint32_t>> histo;  // (count, node), filled through a map
+    {
+      std::vector<uint32_t> hit;
+      for (uint32_t r = 0; r < ns; r++) {
+        uint32_t end = M;  // get_neighbors trims trailing sentinels only (lib.rs:114-125)
+        while (end > 0 && nbrows[(size_t)r * M + end - 1] == 0xFFFFFFFFu) end--;
+        for (uint32_t k = 0; k < end; k++) {
+          uint32_t nbr = nbrows[(size_t)r * M + k];
+          if (nbr >= L.node_count) {
+            set_error("filter_promotion_candidates: interior sentinel in a neighbourhood");
+            return PHNSW_ERR_GRAPH;  // get_vector(!0) panics in the crate
+          }
+          if (std::binary_search(vecs.begin(), vecs.end(), L.h_nodes[nbr])) hit.push_back(nbr);
+        }
+      }
+      std::sort(hit.begin(), hit.end());
+      for (size_t i = 0; i < hit.size();) {
+        size_t j = i;
+        while (j < hit.size() && hit[j] == hit[i]) j++;
+        histo.push_back({(uint32_t)(j - i), hit[i]});
+        i = j;
+      }
+      std::sort(histo.begin(), histo.end());  // (count, NodeId) ascending; popped from the end
+    }
+    const uint32_t hn = (uint32_t)histo.size();
+    std::vector<uint32_t> sel;
+    if (hn) {
+      std::vector<uint64_t> cand(hn);  // pop order
+      for (uint32_t i = 0; i < hn; i++) cand[i] = L.h_nodes[histo[hn - 1 - i].second];
+      uint64_t *d_cand, *d_ids;
+      float *d_rad, *d_selrad;
+      uint32_t *d_cnt, *d_sel, *d_nsel;
+      PH_CUDA(mem.alloc(&d_cand, hn));
+      PH_CUDA(mem.alloc(&d_ids, hn));
+      PH_CUDA(mem.alloc(&d_rad, hn));
+      PH_CUDA(mem.alloc(&d_selrad, hn));
+      PH_CUDA(mem.alloc(&d_cnt, hn));
+      PH_CUDA(mem.alloc(&d_sel, hn));
+      PH_CUDA(mem.alloc(&d_nsel, 1));
+      PH_CUDA(cudaMemcpyAsync(d_cand, cand.data(), (size_t)hn * 8, cudaMemcpyHostToDevice, st));
+      SearchCall c;  // self.search_upto(Stored(vec), search_parameters, layer_from_top)
+      c.mode = 0;
+      c.stored_ids = d_cand;
+      c.nq = hn;
+      c.cap = (uint32_t)std::min<uint64_t>(sp.number_of_candidates, 0xFFFFFFFFull);
+      c.upper = (uint32_t)std::min<uint64_t>(sp.upper_layer_candidate_count, 0xFFFFFFFFull);
+      c.probe = (uint32_t)std::min<uint64_t>(sp.probe_depth, 0xFFFFFFFFull);
+      c.n_layers = layer_from_top;
+      c.max_out = 1;
+      c.out_ids = d_ids;
+      c.out_dists = d_rad;
+      c.out_counts = d_cnt;
+      phnsw_status rc = launch_search(ix, c, st);
+      if (rc != PHNSW_OK) return rc;
+      rc = sync_status(ix, st);
+      if (rc != PHNSW_OK) return rc;
+      promo_select_kernel<<<1, 1024, 0, st>>>(ix->store->rows, ix->store->pitch,
+                                              (uint32_t)ix->store->dim, ix->store->metric, d_cand,
+                                              d_rad, d_cnt, hn, d_sel, d_selrad, d_nsel);
+      PH_CUDA(cudaGetLastError());
+      uint32_t nsel = 0;
+      PH_CUDA(cudaMemcpy(&nsel, d_nsel, 4, cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> idx(nsel);
+      if (nsel) PH_CUDA(cudaMemcpy(idx.data(), d_sel, (size_t)nsel * 4, cudaMemcpyDeviceToHost));
+      for (uint32_t i : idx) sel.push_back((uint32_t)cand[i]);
+    }
+    out->push_back({order, sel});
+  }
+  return PHNSW_OK;
+}
+
+static uint64_t partitions_from_bottom(uint64_t total, uint64_t order, uint64_t *out) {
+  uint64_t top_first[64];
+  uint64_t n = phnsw_calculate_partitions(total, order, top_first, 64);
+  for (uint64_t i = 0; i < n; i++) out[i] = top_first[n - 1 - i];
+  return n;
+}
+
+// Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): every vector of layer
+// `layer_from_top` searches for itself over layers[0..=layer]; it is unreachable when it is not
+// in the leading run of |d| < 1e-5 results (search::match_within_epsilon, search.rs:173-187) and
+// not a node of the layer above.  One batched K1 launch over all nodes of the layer.
+static phnsw_status discover_unreachable(const phnsw_index *ix, uint64_t layer_from_top,
+                                         const phnsw_search_params &sp, std::vector<uint32_t> *out) {
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  const LayerStore &L = ix->layers[layer_from_top];
+  const uint64_t n = L.node_count;
+  std::vector<uint64_t> vecs(L.h_nodes.begin(), L.h_nodes.end());
+  cudaStream_t st = 0;
+  DevMem mem;
+  uint64_t *q_ids;
+  uint32_t *hit;
+  PH_CUDA(mem.alloc(&q_ids, n));
+  PH_CUDA(mem.alloc(&hit, n));
+  PH_CUDA(cudaMemcpyAsync(q_ids, vecs.data(), n * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemsetAsync(hit, 0, n * 4, st));
+  SearchCall c;
+  c.mode = 0;
+  c.stored_ids = q_ids;
+  c.nq = (uint32_t)n;
+  c.cap = (uint32_t)std::min<uint64_t>(sp.number_of_candidates, 0xFFFFFFFFull);
+  c.upper = (uint32_t)std::min<uint64_t>(sp.upper_layer_candidate_count, 0xFFFFFFFFull);
+  c.probe = (uint32_t)std::min<uint64_t>(sp.probe_depth, 0xFFFFFFFFull);
+  c.n_layers = (uint32_t)layer_from_top + 1;
+  c.max_out = 0;
+  c.out_selfhit = hit;
+  c.selfhit_eps = 1;
+  phnsw_status rc = launch_search(ix, c, st);
+  if (rc != PHNSW_OK) return rc;
+  rc = sync_status(ix, st);
+  if (rc != PHNSW_OK) return rc;
+  std::vector<uint32_t> h(n);
+  PH_CUDA(cudaMemcpy(h.data(), hit, n * 4, cudaMemcpyDeviceToHost));
+  const std::vector<uint32_t> *above = layer_from_top ? &ix->layers[layer_from_top - 1].h_nodes : nullptr;
+  out->clear();
+  for (uint64_t i = 0; i < n; i++) {
+    if (h[i]) continue;
+    if (above && std::binary_search(above->begin(), above->end(), (uint32_t)vecs[i])) continue;
+    out->push_back((uint32_t)vecs[i]);
+  }
+  return PHNSW_OK;
+}
+
+// Hnsw::promote_at_layer (lib.rs:1273-1427)
+static phnsw_status promote_at_layer(phnsw_index *ix, uint32_t layer_from_top,
+                                     const phnsw_build_params &bp, Progress &pg, bool *promoted) {
+  *promoted = false;
+  std::vector<uint32_t> vecs;
+  phnsw_status rc = discover_unreachable(ix, layer_from_top, bp.optimization.search, &vecs);
+  if (rc != PHNSW_OK) return rc;
+  if (vecs.empty()) return PHNSW_OK;
+  if (bp.optimization.promotion_proportion < 1.0f) {
+    vecs.resize((size_t)((float)vecs.size() * bp.optimization.promotion_proportion));
+    if (vecs.empty()) return PHNSW_OK;
+  }
+  std::vector<std::pair<uint32_t, std::vector<uint32_t>>> groups;
+  rc = filter_promotion_candidates(ix, layer_from_top, vecs, bp.optimization.search, &groups);
+  if (rc != PHNSW_OK) return rc;
+  for (auto &g : groups) {
+    const uint32_t lft = g.first;  // >= 1: order 0 never enters the histogram
+    const std::vector<uint32_t> &pv = g.second;
+    if (lft == 0 || lft > 64) continue;
+    uint64_t sizes[64], new_sizes[64], promo[64];
+    const uint64_t ns = lft;  // layers above, bottom-most first
+    for (uint64_t i = 0; i < ns; i++) sizes[i] = ix->layers[lft - 1 - i].node_count;
+    uint64_t nn = partitions_from_bottom(sizes[0] + pv.size(), ix->bp.order, new_sizes);
+    while (nn < ns) new_sizes[nn++] = 0;
+    const uint64_t retop_upto = nn - ns;
+    for (uint64_t i = 0; i < ns; i++) promo[i] = new_sizes[i] > sizes[i] ? new_sizes[i] - sizes[i] : 0;
+    uint64_t np = ns, offset = 0;
+    if (retop_upto != 0) {
+      if (retop_upto > ns || promo[ns - retop_upto] > pv.size()) {
+        set_error("promote_at_layer: layer stack too unbalanced to re-top (the crate panics here)");
+        return PHNSW_ERR_GRAPH;
+      }
+      const uint64_t ridx = ns - retop_upto, into_top = promo[ridx];
+      np = ridx;
+      const std::vector<uint32_t> &tl = ix->layers[retop_upto - 1].h_nodes;
+      std::vector<uint64_t> tv(tl.begin(), tl.end());
+      tv.insert(tv.end(), pv.begin(), pv.begin() + into_top);
+      std::sort(tv.begin(), tv.end());
+      tv.erase(std::unique(tv.begin(), tv.end()), tv.end());
+      phnsw_build_params nbp = bp;  // "our zero layer is not a real zero" (lib.rs:1313-1315)
+      nbp.zero_layer_neighborhood_size = bp.neighborhood_size;
+      const uint64_t seed = ix->seed ^ (0x9E3779B97F4A7C15ull * ++ix->promo_count);
+      phnsw_index *t = nullptr;
+      rc = phnsw_generate_with(ix->store, tv.data(), tv.size(), &nbp, seed, 2, pg.fn, pg.user, &t);
+      if (rc != PHNSW_OK) return rc;
+      offset = t->layers.size();
+      rc = index_retop(ix, retop_upto, t);
+      phnsw_index_destroy(t);
+      if (rc != PHNSW_OK) return rc;
+    }
+    for (uint64_t i = 0; i < np; i++) {  // promotion_sizes.reverse(): top first
+      const uint64_t size = promo[np - 1 - i], cur = offset + i;
+      const std::vector<uint32_t> &hn = ix->layers[cur].h_nodes;
+      std::vector<uint32_t> tp;
+      for (uint32_t v : pv) {
+        if (tp.size() >= size) break;
+        if (!std::binary_search(hn.begin(), hn.end(), v)) tp.push_back(v);
+      }
+      rc = extend_layer(ix, (uint32_t)cur, tp);
+      if (rc != PHNSW_OK) return rc;
+    }
+  }
+  *promoted = true;
+  return PHNSW_OK;
+}
+
+// improve_index_at (lib.rs:1546-1603); promote = false treats promote_at_layer as "nothing to
+// promote" (the default of the build entry points)
+static phnsw_status improve_index_at(phnsw_index *ix, uint32_t *layer_from_top_io,
+                                     const phnsw_build_params &bp, Progress &pg, bool promote,
+                                     float *recall_out) {
   const phnsw_optimization_params &op = bp.optimization;
+  uint32_t layer_from_top = *layer_from_top_io;
   float recall;
   phnsw_status rc = stochastic_recall_at(ix, layer_from_top, op, &recall);
   if (rc != PHNSW_OK) return rc;
@@ -789,19 +1131,38 @@ static phnsw_status improve_index_at(phnsw_index *ix, uint32_t layer_from_top,
     float last_recall = recall;
     uint32_t cur = 0;
     while (cur <= layer_from_top && bailout != 0) {
+      const size_t layer_count = ix->layers.size();
       rc = improve_neighbors_upto(ix, cur + 1, bp, pg, &recall);
       if (rc != PHNSW_OK) return rc;
+      if (recall == 1.0f) {
+        cur += 1;
+        continue;
+      }
+      bool promoted = false;
+      if (promote) {
+        rc = promote_at_layer(ix, cur, bp, pg, &promoted);
+        if (rc != PHNSW_OK) return rc;
+      }
+      if (promoted) {
+        const uint32_t delta = (uint32_t)(ix->layers.size() - layer_count);
+        cur += delta;
+        layer_from_top += delta;
+        const float before = recall;
+        rc = improve_neighbors_upto(ix, cur + 1, bp, pg, &recall, &before);
+        if (rc != PHNSW_OK) return rc;
+      }
       cur += 1;
     }
     bailout -= 1;
     improvement = recall - last_recall;
   }
+  *layer_from_top_io = layer_from_top;
   *recall_out = recall;
   return PHNSW_OK;
 }
 
 static phnsw_status improve_index(phnsw_index *ix, const phnsw_build_params &bp, Progress &pg,
-                                  float *recall_out) {
+                                  float *recall_out, bool promote = false) {
   float recall = 0.0f;
   if (ix->layers.empty()) {
     *recall_out = 1.0f;
@@ -810,9 +1171,19 @@ static phnsw_status improve_index(phnsw_index *ix, const phnsw_build_params &bp,
   phnsw_status rc = stochastic_recall_at(ix, (uint32_t)ix->layers.size() - 1, bp.optimization,
                                          &recall);  // lib.rs:1671
   if (rc != PHNSW_OK) return rc;
-  for (uint32_t l = 0; l < ix->layers.size(); l++) {
-    rc = improve_index_at(ix, l, bp, pg, &recall);
-    if (rc != PHNSW_OK) return rc;
+  if (!promote) {
+    for (uint32_t l = 0; l < ix->layers.size(); l++) {
+      uint32_t lft = l;
+      rc = improve_index_at(ix, &lft, bp, pg, false, &recall);
+      if (rc != PHNSW_OK) return rc;
+    }
+  } else {  // lib.rs:1673-1682: the layer cursor follows the layers a re-top inserts
+    uint32_t lft = 0;
+    while (lft < ix->layers.size()) {
+      rc = improve_index_at(ix, &lft, bp, pg, true, &recall);
+      if (rc != PHNSW_OK) return rc;
+      lft += 1;
+    }
   }
   *recall_out = recall;
   return PHNSW_OK;
@@ -864,6 +1235,7 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
   phnsw_index *ix = nullptr;
   phnsw_status rc = index_create_empty(s, &bp, &ix);
   if (rc != PHNSW_OK) return rc;
+  ix->seed = seed;
   Progress pg{progress, user};
   for (uint64_t i = 0; i < np && rc == PHNSW_OK; i++) {
     const uint64_t level = np - i - 1;
@@ -881,7 +1253,7 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
     rc = build_layer(ix, slice, M, bp.initial_partition_search, pg);
     if (rc == PHNSW_OK && improve) {
       float recall;
-      rc = improve_index(ix, bp, pg, &recall);  // lib.rs:876
+      rc = improve_index(ix, bp, pg, &recall, improve == 2);  // lib.rs:876
     }
   }
   if (rc != PHNSW_OK) {
@@ -914,10 +1286,6 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
   return rc;
 }
 
-// Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): every vector of layer
-// `layer_from_top` searches for itself over layers[0..=layer]; it is unreachable when it is not
-// in the leading run of |d| < 1e-5 results (search::match_within_epsilon, search.rs:173-187) and
-// not a node of the layer above.  One batched K1 launch over all nodes of the layer.
 phnsw_status phnsw_discover_unreachable(const phnsw_index *ix, uint64_t layer_from_top,
                                         const phnsw_search_params *sp, uint64_t **out_ids,
                                         uint64_t *out_n) {
@@ -933,49 +1301,115 @@ phnsw_status phnsw_discover_unreachable(const phnsw_index *ix, uint64_t layer_fr
     set_error("no CUDA device: this library has no CPU fallback");
     return PHNSW_ERR_NO_DEVICE;
   }
-  PH_CUDA(cudaSetDevice(ix->store->device));
-  const LayerStore &L = ix->layers[layer_from_top];
-  const uint64_t n = L.node_count;
-  std::vector<uint64_t> vecs(L.h_nodes.begin(), L.h_nodes.end());
-  cudaStream_t st = 0;
-  DevMem mem;
-  uint64_t *q_ids;
-  uint32_t *hit;
-  PH_CUDA(mem.alloc(&q_ids, n));
-  PH_CUDA(mem.alloc(&hit, n));
-  PH_CUDA(cudaMemcpyAsync(q_ids, vecs.data(), n * 8, cudaMemcpyHostToDevice, st));
-  PH_CUDA(cudaMemsetAsync(hit, 0, n * 4, st));
-  SearchCall c;
-  c.mode = 0;
-  c.stored_ids = q_ids;
-  c.nq = (uint32_t)n;
-  c.cap = (uint32_t)std::min<uint64_t>(sp->number_of_candidates, 0xFFFFFFFFull);
-  c.upper = (uint32_t)std::min<uint64_t>(sp->upper_layer_candidate_count, 0xFFFFFFFFull);
-  c.probe = (uint32_t)std::min<uint64_t>(sp->probe_depth, 0xFFFFFFFFull);
-  c.n_layers = (uint32_t)layer_from_top + 1;
-  c.max_out = 0;
-  c.out_selfhit = hit;
-  c.selfhit_eps = 1;
-  phnsw_status rc = launch_search(ix, c, st);
+  std::vector<uint32_t> out;
+  phnsw_status rc = discover_unreachable(ix, layer_from_top, *sp, &out);
   if (rc != PHNSW_OK) return rc;
-  rc = sync_status(ix, st);
-  if (rc != PHNSW_OK) return rc;
-  std::vector<uint32_t> h(n);
-  PH_CUDA(cudaMemcpy(h.data(), hit, n * 4, cudaMemcpyDeviceToHost));
-  const std::vector<uint32_t> *above = layer_from_top ? &ix->layers[layer_from_top - 1].h_nodes : nullptr;
-  std::vector<uint64_t> out;
-  for (uint64_t i = 0; i < n; i++) {
-    if (h[i]) continue;
-    if (above && std::binary_search(above->begin(), above->end(), (uint32_t)vecs[i])) continue;
-    out.push_back(vecs[i]);
-  }
   if (!out.empty()) {
     *out_ids = (uint64_t *)malloc(out.size() * 8);
     if (!*out_ids) return PHNSW_ERR_INVALID;
-    memcpy(*out_ids, out.data(), out.size() * 8);
+    for (size_t i = 0; i < out.size(); i++) (*out_ids)[i] = out[i];
   }
   *out_n = out.size();
   return PHNSW_OK;
+}
+
+static phnsw_status promo_entry_check(const phnsw_index *ix, const char *what) {
+  if (!ix) return PHNSW_ERR_INVALID;
+  if (!ix->store->rows) {
+    set_error("%s: not available on a PQ8 store", what);
+    return PHNSW_ERR_INVALID;
+  }
+  if (phnsw_device_count() == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return PHNSW_ERR_NO_DEVICE;
+  }
+  return PHNSW_OK;
+}
+
+phnsw_status phnsw_extend_layer(phnsw_index *ix, uint64_t layer_from_top, const uint64_t *vecs,
+                                uint64_t n) {
+  PH_ENTRY();
+  phnsw_status rc = promo_entry_check(ix, "extend_layer");
+  if (rc != PHNSW_OK) return rc;
+  if (layer_from_top >= ix->layers.size() || (n && !vecs)) return PHNSW_ERR_INVALID;
+  std::vector<uint32_t> v(n);
+  for (uint64_t i = 0; i < n; i++) {
+    if (vecs[i] >= ix->store->n) {
+      set_error("extend_layer: VectorId %llu is not in the store", (unsigned long long)vecs[i]);
+      return PHNSW_ERR_INVALID;
+    }
+    v[i] = (uint32_t)vecs[i];
+  }
+  return extend_layer(ix, (uint32_t)layer_from_top, v);
+}
+
+phnsw_status phnsw_filter_promotion_candidates(const phnsw_index *ix, uint64_t layer_from_top,
+                                               const uint64_t *vecs, uint64_t n,
+                                               const phnsw_search_params *sp, uint64_t *orders,
+                                               uint64_t *counts, uint64_t max_groups,
+                                               uint64_t **selected, uint64_t *n_groups) {
+  PH_ENTRY();
+  phnsw_status rc = promo_entry_check(ix, "filter_promotion_candidates");
+  if (rc != PHNSW_OK) return rc;
+  if (!sp || !orders || !counts || !selected || !n_groups || (n && !vecs) ||
+      layer_from_top >= ix->layers.size())
+    return PHNSW_ERR_INVALID;
+  *selected = nullptr;
+  *n_groups = 0;
+  std::vector<uint32_t> v(n);
+  for (uint64_t i = 0; i < n; i++) v[i] = (uint32_t)vecs[i];
+  std::vector<std::pair<uint32_t, std::vector<uint32_t>>> groups;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  rc = filter_promotion_candidates(ix, (uint32_t)layer_from_top, v, *sp, &groups);
+  if (rc != PHNSW_OK) return rc;
+  size_t total = 0;
+  for (auto &g : groups) total += g.second.size();
+  uint64_t *sel = (uint64_t *)malloc(std::max<size_t>(total, 1) * 8);
+  if (!sel) return PHNSW_ERR_INVALID;
+  size_t off = 0, ng = 0;
+  for (auto &g : groups) {
+    if (ng >= max_groups) break;
+    orders[ng] = g.first;
+    counts[ng] = g.second.size();
+    for (uint32_t x : g.second) sel[off++] = x;
+    ng++;
+  }
+  *selected = sel;
+  *n_groups = ng;
+  return PHNSW_OK;
+}
+
+phnsw_status phnsw_promote_at_layer(phnsw_index *ix, uint64_t layer_from_top,
+                                    const phnsw_build_params *bp, phnsw_progress_fn progress,
+                                    void *user, int *promoted_out) {
+  PH_ENTRY();
+  phnsw_status rc = promo_entry_check(ix, "promote_at_layer");
+  if (rc != PHNSW_OK) return rc;
+  if (layer_from_top >= ix->layers.size()) return PHNSW_ERR_INVALID;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  phnsw_build_params b = bp ? *bp : ix->bp;
+  Progress pg{progress, user};
+  bool promoted = false;
+  rc = promote_at_layer(ix, (uint32_t)layer_from_top, b, pg, &promoted);
+  if (rc == PHNSW_OK && promoted_out) *promoted_out = promoted ? 1 : 0;
+  return rc;
+}
+
+phnsw_status phnsw_improve_index_promote(phnsw_index *ix, const phnsw_build_params *bp,
+                                         uint64_t seed, phnsw_progress_fn progress, void *user,
+                                         float *recall_out) {
+  PH_ENTRY();
+  phnsw_status rc = promo_entry_check(ix, "improve_index_promote");
+  if (rc != PHNSW_OK) return rc;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  phnsw_build_params b = bp ? *bp : ix->bp;
+  Progress pg{progress, user};
+  ix->seed = seed;
+  ix->promo_count = 0;
+  float recall = 0.0f;
+  rc = improve_index(ix, b, pg, &recall, true);
+  if (rc == PHNSW_OK && recall_out) *recall_out = recall;
+  return rc;
 }
 
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix, const phnsw_optimization_params *op,

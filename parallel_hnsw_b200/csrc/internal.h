@@ -126,6 +126,8 @@ struct phnsw_index {
   int max_smem = 0;
   uint32_t vlog_cap = 8192, ovf_cap = 8192;  // per-query device scratch (entries)
   int sum_order = 0;  // PHNSW_SUM_SEQUENTIAL / PHNSW_SUM_TREE: traversal distance summation
+  uint64_t seed = 0;         // seed of the generate call (nested re-top generates derive theirs)
+  uint64_t promo_count = 0;  // nested generates so far
   mutable std::mutex mu;
   mutable std::map<cudaStream_t, phnsw::Workspace> ws;
 };
@@ -172,5 +174,10 @@ phnsw_status io_load_pq_params(const std::string &path, phnsw_pq_build_params *b
 // takes ownership of device arrays nodes/neighbors (u32); builds vec2node as needed
 phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint64_t M,
                                      uint32_t *nodes, uint32_t *neighbors);
+// layer surgery (promotion): replace layer `idx` (ownership of the device arrays is taken);
+// layers = t.layers ++ layers[retop_upto..], leaving `t` without layers
+phnsw_status index_replace_layer(phnsw_index *ix, size_t idx, uint64_t node_count, uint64_t M,
+                                 uint32_t *nodes, uint32_t *neighbors);
+phnsw_status index_retop(phnsw_index *ix, size_t retop_upto, phnsw_index *t);
 
 }  // namespace phnsw

@@ -428,6 +428,27 @@ static void free_layer(LayerStore &l) {
   l = LayerStore();
 }
 
+phnsw_status index_replace_layer(phnsw_index *ix, size_t idx, uint64_t node_count, uint64_t M,
+                                 uint32_t *nodes, uint32_t *neighbors) {
+  if (idx >= ix->layers.size()) return PHNSW_ERR_INVALID;
+  phnsw_status rc = index_push_layer_device(ix, node_count, M, nodes, neighbors);
+  if (rc != PHNSW_OK) return rc;
+  LayerStore nl = ix->layers.back();
+  ix->layers.pop_back();
+  free_layer(ix->layers[idx]);
+  ix->layers[idx] = nl;
+  return upload_layer_tables(ix);
+}
+
+phnsw_status index_retop(phnsw_index *ix, size_t retop_upto, phnsw_index *t) {
+  if (retop_upto > ix->layers.size() || t->store != ix->store) return PHNSW_ERR_INVALID;
+  for (size_t i = 0; i < retop_upto; i++) free_layer(ix->layers[i]);
+  ix->layers.erase(ix->layers.begin(), ix->layers.begin() + retop_upto);
+  ix->layers.insert(ix->layers.begin(), t->layers.begin(), t->layers.end());
+  t->layers.clear();
+  return upload_layer_tables(ix);
+}
+
 phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp,
                                 phnsw_index **out) {
   if (!s || !out) return PHNSW_ERR_INVALID;

@@ -193,7 +193,8 @@ class Hnsw:
     def generate(cls, comparator, vs=None, build_parameters=None, progress=None, seed=1,
                  improve=True):
         """Hnsw::generate(c, vs, bp, progress) (src/lib.rs:825-893) on the device.
-        improve=False skips the improve_index call the crate makes after every layer."""
+        improve=False skips the improve_index call the crate makes after every layer;
+        improve=2 runs it with promote_at_layer live (src/lib.rs:1273-1427)."""
         if vs is None:
             vs = np.arange(len(comparator), dtype=np.uint64)
         vs = _host(vs, np.uint64)
@@ -201,7 +202,7 @@ class Hnsw:
         cb = _progress_cb(progress)
         h = C.c_void_p()
         N.check(N.lib().phnsw_generate_with(comparator._h, _ptr(vs), vs.size, C.byref(bp), seed,
-                                            1 if improve else 0, cb, None, C.byref(h)))
+                                            int(improve), cb, None, C.byref(h)))
         return cls(h, comparator)
 
     @classmethod
@@ -352,6 +353,49 @@ class Hnsw:
         N.check(N.lib().phnsw_improve_index(self._h, C.byref(bp), _progress_cb(progress), None,
                                             C.byref(r)))
         return float(r.value)
+
+    def improve_index_with_promotion(self, build_parameters=None, seed=1, progress=None):
+        """Hnsw::improve_index (src/lib.rs:1664-1685) with promote_at_layer live."""
+        bp = build_parameters or self.build_parameters
+        r = C.c_float()
+        N.check(N.lib().phnsw_improve_index_promote(self._h, C.byref(bp), seed,
+                                                    _progress_cb(progress), None, C.byref(r)))
+        return float(r.value)
+
+    def extend_layer(self, layer_id, vecs):
+        """Hnsw::extend_layer (src/lib.rs:1039-1068); layer_id counts from the bottom."""
+        vecs = _host(np.atleast_1d(np.asarray(vecs, dtype=np.uint64)), np.uint64)
+        lft = self.layer_count() - layer_id - 1
+        if lft < 0:
+            raise IndexError(layer_id)
+        N.check(N.lib().phnsw_extend_layer(self._h, lft, _ptr(vecs), vecs.size))
+
+    def filter_promotion_candidates(self, layer_from_top, vecs, search_parameters=None):
+        """Hnsw::filter_promotion_candidates (src/lib.rs:1176-1268) -> [(order, [VectorId])]."""
+        sp = search_parameters or SearchParameters()
+        vecs = _host(np.atleast_1d(np.asarray(vecs, dtype=np.uint64)), np.uint64)
+        orders = np.zeros(64, np.uint64)
+        counts = np.zeros(64, np.uint64)
+        p, g = C.POINTER(C.c_uint64)(), C.c_uint64()
+        N.check(N.lib().phnsw_filter_promotion_candidates(
+            self._h, layer_from_top, _ptr(vecs), vecs.size, C.byref(sp), _ptr(orders),
+            _ptr(counts), 64, C.byref(p), C.byref(g)))
+        out, off = [], 0
+        for i in range(g.value):
+            c = int(counts[i])
+            out.append((int(orders[i]), [int(p[off + k]) for k in range(c)]))
+            off += c
+        if p:
+            N.lib().phnsw_free(C.cast(p, C.c_void_p))
+        return out
+
+    def promote_at_layer(self, layer_from_top, build_parameters=None, progress=None):
+        """Hnsw::promote_at_layer (src/lib.rs:1273-1427)."""
+        bp = build_parameters or self.build_parameters
+        r = C.c_int()
+        N.check(N.lib().phnsw_promote_at_layer(self._h, layer_from_top, C.byref(bp),
+                                               _progress_cb(progress), None, C.byref(r)))
+        return bool(r.value)
 
     def discover_unreachable_vectors(self, layer_from_top, search_parameters=None):
         """Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037): VectorIds of the layer that
