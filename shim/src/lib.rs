@@ -1,0 +1,300 @@
+//! Forwarding layer: `parallel-hnsw`'s public types over the C ABI of `include/phnsw.h`.
+//!
+//! Mirrors the crate's names and argument meaning (paths relative to the reference crate):
+//! `SearchParameters` / `BuildParameters` (src/parameters.rs:3-64), `VectorId` (src/types.rs:3-14),
+//! `AbstractVector` (src/types.rs:41-75), `ProgressMonitor` (src/progress.rs:12-29),
+//! `BigComparator` (src/bigvec.rs:36-57), `Hnsw::{generate, search, search_upto, knn,
+//! threshold_nn, improve_index, promote_at_layer, extend_layer, discover_unreachable_vectors,
+//! stochastic_recall, serialize, deserialize}` (src/lib.rs:653-1699).
+//!
+//! NOT COMPILED in this repository's environment (no Rust toolchain); `ffi.rs` is generated from
+//! the header and checked by `tests/test_rust_shim.py`, this file is reviewed by hand against it.
+pub mod ffi;
+
+use ffi::*;
+use rayon::prelude::*;
+use std::ffi::{CStr, CString};
+use std::os::raw::{c_char, c_int, c_void};
+use std::path::Path;
+use std::ptr;
+use std::sync::Arc;
+
+#[derive(Clone, Copy, Debug, PartialEq, Eq, PartialOrd, Ord, Hash)]
+pub struct VectorId(pub usize);
+
+pub enum AbstractVector<'a> {
+    Stored(VectorId),
+    Unstored(&'a [f32]),
+}
+
+pub type SearchParameters = phnsw_search_params;
+pub type OptimizationParameters = phnsw_optimization_params;
+pub type BuildParameters = phnsw_build_params;
+
+impl Default for phnsw_search_params {
+    fn default() -> Self {
+        let mut sp = phnsw_search_params { number_of_candidates: 0, upper_layer_candidate_count: 0, probe_depth: 0 };
+        unsafe { phnsw_default_search_params(&mut sp) };
+        sp
+    }
+}
+
+impl Default for phnsw_build_params {
+    fn default() -> Self {
+        let mut bp = std::mem::MaybeUninit::<phnsw_build_params>::uninit();
+        unsafe {
+            phnsw_default_build_params(bp.as_mut_ptr());
+            bp.assume_init()
+        }
+    }
+}
+
+/// src/serialize.rs:11-19 plus the conditions the crate reports by panicking
+#[derive(Debug)]
+pub enum Error {
+    Io(String),
+    Serde(String),
+    IndexNotFound,
+    Interrupted,
+    Other(c_int, String),
+}
+
+fn check(rc: c_int) -> Result<(), Error> {
+    if rc == PHNSW_OK {
+        return Ok(());
+    }
+    let msg = unsafe { CStr::from_ptr(phnsw_last_error()) }.to_string_lossy().into_owned();
+    Err(match rc {
+        PHNSW_ERR_IO => Error::Io(msg),
+        PHNSW_ERR_FORMAT => Error::Serde(msg),
+        PHNSW_ERR_NOT_FOUND => Error::IndexNotFound,
+        PHNSW_ERR_INTERRUPTED => Error::Interrupted,
+        _ => Error::Other(rc, msg),
+    })
+}
+
+/// the crate panics where the library returns a status (src/lib.rs:181, 261; src/types.rs:86)
+fn check_or_panic(rc: c_int) {
+    if let Err(e) = check(rc) {
+        panic!("phnsw: {e:?}");
+    }
+}
+
+/// src/progress.rs:12-29
+pub struct Interrupt;
+pub trait ProgressMonitor: Send {
+    fn alive(&mut self) -> Result<(), Interrupt>;
+    fn update(&mut self, phase: &str, fraction: f64) -> Result<(), Interrupt>;
+}
+impl ProgressMonitor for () {
+    fn alive(&mut self) -> Result<(), Interrupt> { Ok(()) }
+    fn update(&mut self, _phase: &str, _fraction: f64) -> Result<(), Interrupt> { Ok(()) }
+}
+
+unsafe extern "C" fn progress_trampoline(user: *mut c_void, phase: *const c_char, fraction: f64) -> c_int {
+    let monitor = &mut *(user as *mut &mut dyn ProgressMonitor);
+    let phase = CStr::from_ptr(phase).to_string_lossy();
+    match monitor.alive().and_then(|_| monitor.update(&phase, fraction)) {
+        Ok(()) => 0,
+        Err(Interrupt) => 1,
+    }
+}
+
+struct StoreHandle(*mut phnsw_store);
+unsafe impl Send for StoreHandle {}
+unsafe impl Sync for StoreHandle {}
+impl Drop for StoreHandle {
+    fn drop(&mut self) { unsafe { phnsw_store_destroy(self.0) } }
+}
+
+/// src/bigvec.rs:36-57: the comparator is a device-resident store; `metric` picks the crate's
+/// distance body (0 bigvec.rs:47-53, 1 lib.rs:1985-1991, 2 lib.rs:2431-2437, 3 pq.rs:481-497)
+#[derive(Clone)]
+pub struct BigComparator {
+    store: Arc<StoreHandle>,
+    dim: usize,
+}
+
+impl BigComparator {
+    pub fn new(data: &[Vec<f32>], metric: c_int, device: c_int) -> Result<Self, Error> {
+        let dim = data.first().map_or(0, |v| v.len());
+        let flat: Vec<f32> = data.iter().flat_map(|v| v.iter().copied()).collect();
+        let mut s = ptr::null_mut();
+        check(unsafe { phnsw_store_create(metric, dim as u64, data.len() as u64, flat.as_ptr(), device, &mut s) })?;
+        Ok(Self { store: Arc::new(StoreHandle(s)), dim })
+    }
+    pub fn len(&self) -> usize { unsafe { phnsw_store_len(self.store.0) as usize } }
+    /// Comparator::compare_vec(Stored(a), Stored(b)) for a batch of pairs (src/lib.rs:69-73)
+    pub fn compare_vec(&self, a: &[VectorId], b: &[VectorId]) -> Vec<f32> {
+        assert_eq!(a.len(), b.len());
+        let (a, b): (Vec<u64>, Vec<u64>) = (a.iter().map(|v| v.0 as u64).collect(), b.iter().map(|v| v.0 as u64).collect());
+        let mut out = vec![0f32; a.len()];
+        check_or_panic(unsafe { phnsw_store_compare(self.store.0, a.as_ptr(), b.as_ptr(), a.len() as u64, out.as_mut_ptr()) });
+        out
+    }
+}
+
+struct IndexHandle(*mut phnsw_index);
+unsafe impl Send for IndexHandle {}
+unsafe impl Sync for IndexHandle {}
+impl Drop for IndexHandle {
+    fn drop(&mut self) { unsafe { phnsw_index_destroy(self.0) } }
+}
+
+pub struct Hnsw {
+    comparator: BigComparator,
+    index: IndexHandle,
+    seed: u64,
+}
+
+impl Hnsw {
+    /// src/lib.rs:825-893; `seed` replaces the crate's thread_rng
+    pub fn generate(c: BigComparator, vs: Vec<VectorId>, bp: BuildParameters, seed: u64,
+                    mut progress: &mut dyn ProgressMonitor) -> Result<Self, Error> {
+        let ids: Vec<u64> = vs.iter().map(|v| v.0 as u64).collect();
+        let mut ix = ptr::null_mut();
+        // improve = 2: improve_index after every layer with promote_at_layer live, as the crate
+        check(unsafe {
+            phnsw_generate_with(c.store.0, ids.as_ptr(), ids.len() as u64, &bp, seed, 2, Some(progress_trampoline),
+                                &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut ix)
+        })?;
+        Ok(Self { comparator: c, index: IndexHandle(ix), seed })
+    }
+
+    pub fn layer_count(&self) -> usize { unsafe { phnsw_index_layer_count(self.index.0) as usize } }
+    pub fn vector_count(&self) -> usize { unsafe { phnsw_index_vector_count(self.index.0) as usize } }
+    pub fn entry_vector(&self) -> VectorId { VectorId(unsafe { phnsw_index_entry_vector(self.index.0) } as usize) }
+    pub fn comparator(&self) -> &BigComparator { &self.comparator }
+
+    /// src/lib.rs:654-665 for a batch: one launch; `upto_layer_from_top` = 0 searches every layer
+    pub fn search_batch(&self, vs: &[AbstractVector], sp: SearchParameters, upto_layer_from_top: usize)
+                        -> Vec<Vec<(VectorId, f32)>> {
+        let nq = vs.len();
+        let ef = sp.number_of_candidates as usize;
+        let stored = vs.iter().all(|v| matches!(v, AbstractVector::Stored(_)));
+        let mut ids: Vec<u64> = Vec::new();
+        let mut rows: Vec<f32> = Vec::new();
+        if stored {
+            ids = vs.iter().map(|v| match v { AbstractVector::Stored(id) => id.0 as u64, _ => unreachable!() }).collect();
+        } else {
+            // mixed batches: stored queries are fetched as rows first
+            for v in vs {
+                match v {
+                    AbstractVector::Unstored(r) => rows.extend_from_slice(r),
+                    AbstractVector::Stored(id) => {
+                        let mut r = vec![0f32; self.comparator.dim];
+                        let id = id.0 as u64;
+                        check_or_panic(unsafe { phnsw_store_get_rows(self.comparator.store.0, &id, 1, r.as_mut_ptr()) });
+                        rows.extend_from_slice(&r);
+                    }
+                }
+            }
+        }
+        let (mut out_ids, mut out_ds, mut cnt) = (vec![0u64; nq * ef], vec![0f32; nq * ef], vec![0u32; nq]);
+        check_or_panic(unsafe {
+            phnsw_search_batch(self.index.0, if stored { ptr::null() } else { rows.as_ptr() },
+                               if stored { ids.as_ptr() } else { ptr::null() }, nq as u64, &sp,
+                               upto_layer_from_top as u64, ptr::null(), ef as u64, out_ids.as_mut_ptr(),
+                               out_ds.as_mut_ptr(), cnt.as_mut_ptr(), ptr::null_mut(), ptr::null_mut())
+        });
+        (0..nq).map(|q| (0..cnt[q] as usize).map(|i| (VectorId(out_ids[q * ef + i] as usize), out_ds[q * ef + i])).collect()).collect()
+    }
+    pub fn search(&self, v: AbstractVector, sp: SearchParameters) -> Vec<(VectorId, f32)> {
+        self.search_batch(&[v], sp, 0).pop().unwrap()
+    }
+    pub fn search_upto(&self, v: AbstractVector, sp: SearchParameters, upto_layer_from_top: usize) -> Vec<(VectorId, f32)> {
+        self.search_batch(&[v], sp, upto_layer_from_top).pop().unwrap()
+    }
+
+    /// src/lib.rs:905-928: rows follow bottom-layer node order
+    pub fn knn(&self, k: usize, probe_depth: usize) -> impl ParallelIterator<Item = (VectorId, Vec<(VectorId, f32)>)> {
+        let n = self.vector_count();
+        let (mut ids, mut ds, mut cnt) = (vec![0u64; n * k], vec![0f32; n * k], vec![0u32; n]);
+        check_or_panic(unsafe { phnsw_knn(self.index.0, k as u64, probe_depth as u64, ids.as_mut_ptr(), ds.as_mut_ptr(), cnt.as_mut_ptr()) });
+        let (mut nc, mut m) = (0u64, 0u64);
+        let bottom = self.layer_count() as u64 - 1;
+        check_or_panic(unsafe { phnsw_index_layer_info(self.index.0, bottom, &mut nc, &mut m) });
+        let mut nodes = vec![0u64; nc as usize];
+        let mut nb = vec![0u64; (nc * m) as usize];
+        check_or_panic(unsafe { phnsw_index_export_layer(self.index.0, bottom, nodes.as_mut_ptr(), nb.as_mut_ptr()) });
+        (0..n).into_par_iter().map(move |i| {
+            let row = (0..cnt[i] as usize).map(|j| (VectorId(ids[i * k + j] as usize), ds[i * k + j])).collect();
+            (VectorId(nodes[i] as usize), row)
+        })
+    }
+
+    /// src/lib.rs:930-962
+    pub fn threshold_nn(&self, threshold: f32, probe_depth: usize, initial_search_depth: usize)
+                        -> Vec<(VectorId, Vec<(VectorId, f32)>)> {
+        let n = self.vector_count();
+        let (mut off, mut ids, mut ds) = (ptr::null_mut::<u64>(), ptr::null_mut::<u64>(), ptr::null_mut::<f32>());
+        check_or_panic(unsafe {
+            phnsw_threshold_nn(self.index.0, threshold, probe_depth as u64, initial_search_depth as u64, &mut off, &mut ids, &mut ds)
+        });
+        let out = unsafe {
+            let off = std::slice::from_raw_parts(off, n + 1);
+            (0..n).map(|i| {
+                let (a, b) = (off[i] as usize, off[i + 1] as usize);
+                (VectorId(i), (a..b).map(|j| (VectorId(*ids.add(j) as usize), *ds.add(j))).collect())
+            }).collect()
+        };
+        unsafe {
+            phnsw_free(off as *mut c_void);
+            phnsw_free(ids as *mut c_void);
+            phnsw_free(ds as *mut c_void);
+        }
+        out
+    }
+
+    /// src/lib.rs:1664-1685 (promotion live)
+    pub fn improve_index(&mut self, bp: BuildParameters, mut progress: &mut dyn ProgressMonitor) -> f32 {
+        let mut recall = 0f32;
+        check_or_panic(unsafe {
+            phnsw_improve_index_promote(self.index.0, &bp, self.seed, Some(progress_trampoline),
+                                        &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut recall)
+        });
+        recall
+    }
+    /// src/lib.rs:1273-1427
+    pub fn promote_at_layer(&mut self, layer_from_top: usize, bp: BuildParameters, mut progress: &mut dyn ProgressMonitor) -> bool {
+        let mut promoted: c_int = 0;
+        check_or_panic(unsafe {
+            phnsw_promote_at_layer(self.index.0, layer_from_top as u64, &bp, Some(progress_trampoline),
+                                   &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut promoted)
+        });
+        promoted != 0
+    }
+    /// src/lib.rs:1039-1068 (`layer_id` counts from the bottom)
+    pub fn extend_layer(&mut self, layer_id: usize, vecs: Vec<VectorId>) {
+        let ids: Vec<u64> = vecs.iter().map(|v| v.0 as u64).collect();
+        let from_top = (self.layer_count() - layer_id - 1) as u64;
+        check_or_panic(unsafe { phnsw_extend_layer(self.index.0, from_top, ids.as_ptr(), ids.len() as u64) });
+    }
+    /// src/lib.rs:1002-1037
+    pub fn discover_unreachable_vectors(&self, layer_id_from_top: usize, sp: SearchParameters) -> Vec<VectorId> {
+        let (mut p, mut n) = (ptr::null_mut::<u64>(), 0u64);
+        check_or_panic(unsafe { phnsw_discover_unreachable(self.index.0, layer_id_from_top as u64, &sp, &mut p, &mut n) });
+        let out = (0..n as usize).map(|i| VectorId(unsafe { *p.add(i) } as usize)).collect();
+        unsafe { phnsw_free(p as *mut c_void) };
+        out
+    }
+    /// src/lib.rs:1501-1505
+    pub fn stochastic_recall(&self, op: OptimizationParameters) -> f32 {
+        let mut r = 0f32;
+        check_or_panic(unsafe { phnsw_stochastic_recall(self.index.0, &op, &mut r) });
+        r
+    }
+
+    /// src/lib.rs:1688-1699, src/serialize.rs:33-209 (the crate's own directory layout)
+    pub fn serialize<P: AsRef<Path>>(&self, path: P) -> Result<(), Error> {
+        let dir = CString::new(path.as_ref().to_string_lossy().as_bytes()).map_err(|e| Error::Io(e.to_string()))?;
+        check(unsafe { phnsw_index_save(self.index.0, dir.as_ptr()) })
+    }
+    pub fn deserialize<P: AsRef<Path>>(path: P, device: c_int) -> Result<Self, Error> {
+        let dir = CString::new(path.as_ref().to_string_lossy().as_bytes()).map_err(|e| Error::Io(e.to_string()))?;
+        let (mut s, mut ix) = (ptr::null_mut(), ptr::null_mut());
+        check(unsafe { phnsw_index_load(dir.as_ptr(), device, &mut s, &mut ix) })?;
+        let dim = unsafe { phnsw_store_dim(s) } as usize;
+        Ok(Self { comparator: BigComparator { store: Arc::new(StoreHandle(s)), dim }, index: IndexHandle(ix), seed: 0 })
+    }
+}
