@@ -253,6 +253,19 @@ phnsw_status phnsw_improve_index_promote(phnsw_index *ix, const phnsw_build_para
 phnsw_status phnsw_discover_unreachable(const phnsw_index *ix, uint64_t layer_from_top,
                                         const phnsw_search_params *sp, uint64_t **out_ids,
                                         uint64_t *out_n);
+/* Graph diagnostics.  Layer::node_distances (src/lib.rs:425-489): level-synchronous walk from
+ * `supers` (VectorIds that must be nodes of the layer); per node hops (BFS level) and index_sum
+ * (smallest sum of neighbourhood positions + 1 over the relaxations received, in the crate's
+ * in-order queue semantics), UINT64_MAX = never reached (NodeDistance::MAX).  Outputs hold
+ * node_count entries.  Layer::discover_nodes_to_promote (src/lib.rs:510-536): the never-reached
+ * NodeIds, ascending; *out_nodes malloc'ed (phnsw_free).  Hnsw::node_distances_for_layer
+ * (src/lib.rs:986-990) = this with supers_for_layer (:977-984). */
+phnsw_status phnsw_node_distances(const phnsw_index *ix, uint64_t layer_from_top,
+                                  const uint64_t *supers, uint64_t n_supers, uint64_t *hops_out,
+                                  uint64_t *index_sum_out);
+phnsw_status phnsw_discover_nodes_to_promote(const phnsw_index *ix, uint64_t layer_from_top,
+                                             const uint64_t *supers, uint64_t n_supers,
+                                             uint64_t **out_nodes, uint64_t *out_n);
 /* stochastic_recall (src/lib.rs:1463-1505) */
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix,
                                      const phnsw_optimization_params *op, float *recall_out);

@@ -126,6 +126,14 @@ def lib():
     L.orc_promote_at_layer.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(BuildParams), C.c_int]
     L.orc_improve_index_promote.restype = C.c_float
     L.orc_improve_index_promote.argtypes = [C.c_void_p, C.POINTER(BuildParams), C.c_uint64, C.c_int]
+    L.orc_node_distances.restype = C.c_int
+    L.orc_node_distances.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_uint64, u64p, u64p]
+    L.orc_discover_nodes_to_promote.restype = C.c_int64
+    L.orc_discover_nodes_to_promote.argtypes = [C.c_void_p, C.c_uint64, u64p, C.c_uint64,
+                                                C.POINTER(u64p)]
+    L.orc_reachables_from.restype = C.c_uint64
+    L.orc_reachables_from.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u64p, C.c_uint64, u64p,
+                                      u64p]
     L.orc_stochastic_recall.restype = C.c_float
     L.orc_stochastic_recall.argtypes = [C.c_void_p, C.POINTER(OptimizationParams), C.c_int]
     L.orc_serialize.restype = C.c_int
@@ -412,6 +420,47 @@ class Hnsw:
     def improve_index(self, bp=None, nthreads=0):
         bp = bp or self.build_parameters
         return float(lib().orc_improve_index(self._h, C.byref(bp), nthreads))
+
+    def supers_for_layer(self, layer_id):
+        """Hnsw::supers_for_layer (lib.rs:977-984); layer_id counts from the bottom."""
+        if self.layer_count == layer_id + 1:
+            return self.layer(0)[0][:1]
+        return self.layer(self.layer_count - layer_id - 2)[0]
+
+    def node_distances(self, layer_from_top, supers):
+        """Layer::node_distances (lib.rs:425-489) -> (hops u64[n], index_sum u64[n])."""
+        supers = np.ascontiguousarray(supers, dtype=np.uint64)
+        n = self.layer(layer_from_top)[0].size
+        hops, isum = np.empty(n, np.uint64), np.empty(n, np.uint64)
+        rc = lib().orc_node_distances(self._h, layer_from_top, _p(supers, C.c_uint64), supers.size,
+                                      _p(hops, C.c_uint64), _p(isum, C.c_uint64))
+        if rc:
+            raise ValueError("node_distances: the crate would panic here")
+        return hops, isum
+
+    def node_distances_for_layer(self, layer_id):
+        """Hnsw::node_distances_for_layer (lib.rs:986-990); layer_id counts from the bottom."""
+        return self.node_distances(self.layer_count - layer_id - 1, self.supers_for_layer(layer_id))
+
+    def discover_nodes_to_promote(self, layer_from_top, supers):
+        """Layer::discover_nodes_to_promote (lib.rs:510-536)."""
+        supers = np.ascontiguousarray(supers, dtype=np.uint64)
+        p = C.POINTER(C.c_uint64)()
+        n = lib().orc_discover_nodes_to_promote(self._h, layer_from_top, _p(supers, C.c_uint64),
+                                                supers.size, C.byref(p))
+        if n < 0:
+            raise ValueError("discover_nodes_to_promote: the crate would panic here")
+        out = np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.empty(0, np.uint64)
+        lib().orc_free(C.cast(p, C.c_void_p))
+        return out
+
+    def reachables_from(self, layer_from_top, node, check):
+        """Layer::reachables_from (lib.rs:491-508) -> [(NodeId, index distance)]."""
+        check = np.ascontiguousarray(check, dtype=np.uint64)
+        on, od = np.empty(check.size + 1, np.uint64), np.empty(check.size + 1, np.uint64)
+        m = lib().orc_reachables_from(self._h, layer_from_top, node, _p(check, C.c_uint64),
+                                      check.size, _p(on, C.c_uint64), _p(od, C.c_uint64))
+        return list(zip(on[:m].tolist(), od[:m].tolist()))
 
     def improve_index_with_promotion(self, bp=None, seed=1, nthreads=0):
         """Hnsw::improve_index (lib.rs:1661-1685) with promote_at_layer live."""

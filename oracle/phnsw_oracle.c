@@ -1460,6 +1460,115 @@ static float improve_neighbors_upto(orc_hnsw *h, uint64_t upto,
   return last_recall;
 }
 
+/* ---------------------------------------------------------------- graph diagnostics
+ * Layer::node_distances (lib.rs:425-489), literal: a level-synchronous walk from the supers whose
+ * queue is consumed in order (Vec::into_iter().flat_map, sequential).  hops = BFS level;
+ * index_sum = the smallest sum of (position in the neighbourhood + 1) seen when the node's
+ * in-neighbours were processed -- order dependent inside a level, hence the literal loop.
+ * Returns -1 where the crate panics (super not in the layer, interior sentinel). */
+int orc_node_distances(const orc_hnsw *h, uint64_t layer_from_top, const uint64_t *supers,
+                       uint64_t n_supers, uint64_t *hops, uint64_t *index_sum) {
+  if (layer_from_top >= h->layer_count) return -1;
+  const layer_t *l = &h->layers[layer_from_top];
+  const uint64_t n = l->node_count, M = l->M;
+  uint64_t cap = n_supers > 16 ? n_supers : 16, qn = 0;
+  uint64_t *queue = (uint64_t *)malloc(cap * 8);
+  for (uint64_t i = 0; i < n_supers; i++) {
+    int64_t node = layer_get_node(l, supers[i]);
+    if (node < 0) { free(queue); return -1; }
+    queue[qn++] = (uint64_t)node;
+  }
+  for (uint64_t i = 0; i < n; i++) hops[i] = index_sum[i] = UINT64_MAX;
+  for (uint64_t i = 0; i < qn; i++) index_sum[queue[i]] = 0;
+  uint64_t generation = 0;
+  int rc = 0;
+  for (;;) {
+    uint64_t ncap = 16, nn = 0;
+    uint64_t *next = (uint64_t *)malloc(ncap * 8);
+    for (uint64_t qi = 0; qi < qn && rc == 0; qi++) {
+      const uint64_t node = queue[qi];
+      const int swapped = hops[node] == UINT64_MAX; /* compare_exchange(MAX, generation) */
+      if (swapped) hops[node] = generation;
+      if (hops[node] != generation) continue;
+      const uint64_t end = orc_get_final_neighbor_idx(M, l->neighbors, node);
+      for (uint64_t k = node * M; k < end; k++) {
+        const uint64_t nb = l->neighbors[k];
+        if (nb >= n) { rc = -1; break; } /* result[neighbor.0] out of bounds */
+        const uint64_t total = index_sum[node] + (k - node * M) + 1;
+        if (total < index_sum[nb]) index_sum[nb] = total;
+      }
+      if (swapped) {
+        if (nn + (end - node * M) > ncap) {
+          while (nn + (end - node * M) > ncap) ncap *= 2;
+          next = (uint64_t *)realloc(next, ncap * 8);
+        }
+        for (uint64_t k = node * M; k < end; k++) next[nn++] = l->neighbors[k];
+      }
+    }
+    free(queue);
+    queue = next;
+    qn = nn;
+    if (qn == 0 || rc) break;
+    generation++;
+  }
+  free(queue);
+  return rc;
+}
+
+/* Layer::discover_nodes_to_promote (lib.rs:510-536): sorted by (MAX - index_sum, MAX - hops,
+ * node), the leading run with hops == MAX, i.e. the unreachable nodes ascending; *out malloc'ed */
+int64_t orc_discover_nodes_to_promote(const orc_hnsw *h, uint64_t layer_from_top,
+                                      const uint64_t *supers, uint64_t n_supers, uint64_t **out) {
+  *out = NULL;
+  if (layer_from_top >= h->layer_count) return -1;
+  const uint64_t n = h->layers[layer_from_top].node_count;
+  uint64_t *hops = (uint64_t *)malloc((n ? n : 1) * 8), *is = (uint64_t *)malloc((n ? n : 1) * 8);
+  if (orc_node_distances(h, layer_from_top, supers, n_supers, hops, is) != 0) {
+    free(hops); free(is);
+    return -1;
+  }
+  /* the sort key puts (index_sum MAX, hops MAX) first; an unreached node has both */
+  uint64_t *res = (uint64_t *)malloc((n ? n : 1) * 8), m = 0;
+  for (uint64_t i = 0; i < n; i++)
+    if (is[i] == UINT64_MAX && hops[i] == UINT64_MAX) res[m++] = i;
+  free(hops); free(is);
+  *out = res;
+  return (int64_t)m;
+}
+
+/* Layer::reachables_from (lib.rs:491-508), literal: depth-first over a stack, `check` is the set
+ * of nodes still to be found; out arrays sized n_check + 1; returns the number of entries */
+uint64_t orc_reachables_from(const orc_hnsw *h, uint64_t layer_from_top, uint64_t node,
+                             const uint64_t *check, uint64_t n_check, uint64_t *out_nodes,
+                             uint64_t *out_dist) {
+  if (layer_from_top >= h->layer_count) return 0;
+  const layer_t *l = &h->layers[layer_from_top];
+  const uint64_t M = l->M;
+  uint8_t *alive = (uint8_t *)calloc(l->node_count ? l->node_count : 1, 1);
+  for (uint64_t i = 0; i < n_check; i++)
+    if (check[i] < l->node_count) alive[check[i]] = 1;
+  uint64_t *stack_n = (uint64_t *)malloc((n_check + 1) * 8), *stack_d = (uint64_t *)malloc((n_check + 1) * 8);
+  uint64_t sp = 0, m = 0;
+  out_nodes[m] = node; out_dist[m++] = 0;
+  stack_n[sp] = node; stack_d[sp++] = 0;
+  while (sp) {
+    sp--;
+    const uint64_t cur = stack_n[sp], dist = stack_d[sp];
+    const uint64_t end = orc_get_final_neighbor_idx(M, l->neighbors, cur);
+    for (uint64_t k = cur * M; k < end; k++) {
+      const uint64_t nb = l->neighbors[k];
+      if (nb < l->node_count && alive[nb]) { /* set.remove(n) */
+        alive[nb] = 0;
+        const uint64_t nd = dist + (k - cur * M) + 1;
+        stack_n[sp] = nb; stack_d[sp++] = nd;
+        out_nodes[m] = nb; out_dist[m++] = nd;
+      }
+    }
+  }
+  free(alive); free(stack_n); free(stack_d);
+  return m;
+}
+
 /* ---------------------------------------------------------------- promotion (lib.rs:1039-1068,
  * 1167-1427, 1726-1812).  Where the crate's outcome depends on HashMap iteration order (ties in
  * the in-link histogram, lib.rs:1226-1233) the order here is (count, NodeId) ascending, popped

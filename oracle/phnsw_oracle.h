@@ -176,6 +176,14 @@ float orc_improve_index_promote(orc_hnsw *h, const orc_build_params *bp, uint64_
 uint64_t orc_discover_unreachable(const orc_hnsw *h, uint64_t layer_from_top,
                                   const orc_search_params *sp, uint64_t **out, int nthreads);
 float orc_stochastic_recall(const orc_hnsw *h, const orc_optimization_params *op, int nthreads);
+/* graph diagnostics (lib.rs:425-536): node_distances, discover_nodes_to_promote, reachables_from */
+int orc_node_distances(const orc_hnsw *h, uint64_t layer_from_top, const uint64_t *supers,
+                       uint64_t n_supers, uint64_t *hops, uint64_t *index_sum);
+int64_t orc_discover_nodes_to_promote(const orc_hnsw *h, uint64_t layer_from_top,
+                                      const uint64_t *supers, uint64_t n_supers, uint64_t **out);
+uint64_t orc_reachables_from(const orc_hnsw *h, uint64_t layer_from_top, uint64_t node,
+                             const uint64_t *check, uint64_t n_check, uint64_t *out_nodes,
+                             uint64_t *out_dist);
 
 /* serialize.rs:33-209 layout (meta, layer.meta.N, layer.nodes.N, layer.neighbors.N);
  * the `comparator` entry is user-defined in the reference -- here a small file with

@@ -354,6 +354,40 @@ class Hnsw:
                                             C.byref(r)))
         return float(r.value)
 
+    # ---- graph diagnostics --------------------------------------------------------------
+    def supers_for_layer(self, layer_id):
+        """Hnsw::supers_for_layer (src/lib.rs:977-984); layer_id counts from the bottom."""
+        if self.layer_count() == layer_id + 1:
+            return self.get_layer_from_top(0)[0][:1]
+        return self.get_layer_from_top(self.layer_count() - layer_id - 2)[0]
+
+    def node_distances(self, layer_from_top, supers):
+        """Layer::node_distances (src/lib.rs:425-489) -> (hops u64[n], index_sum u64[n]);
+        EMPTY (usize::MAX) marks a node the walk never reached."""
+        supers = _host(np.atleast_1d(np.asarray(supers, dtype=np.uint64)), np.uint64)
+        nc, M = C.c_uint64(), C.c_uint64()
+        N.check(N.lib().phnsw_index_layer_info(self._h, layer_from_top, C.byref(nc), C.byref(M)))
+        hops = np.empty(nc.value, dtype=np.uint64)
+        isum = np.empty(nc.value, dtype=np.uint64)
+        N.check(N.lib().phnsw_node_distances(self._h, layer_from_top, _ptr(supers), supers.size,
+                                             _ptr(hops), _ptr(isum)))
+        return hops, isum
+
+    def node_distances_for_layer(self, layer_id):
+        """Hnsw::node_distances_for_layer (src/lib.rs:986-990); layer_id counts from the bottom."""
+        return self.node_distances(self.layer_count() - layer_id - 1, self.supers_for_layer(layer_id))
+
+    def discover_nodes_to_promote(self, layer_from_top, supers):
+        """Layer::discover_nodes_to_promote (src/lib.rs:510-536): never-reached NodeIds."""
+        supers = _host(np.atleast_1d(np.asarray(supers, dtype=np.uint64)), np.uint64)
+        p, n = C.POINTER(C.c_uint64)(), C.c_uint64()
+        N.check(N.lib().phnsw_discover_nodes_to_promote(self._h, layer_from_top, _ptr(supers),
+                                                        supers.size, C.byref(p), C.byref(n)))
+        out = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.empty(0, np.uint64)
+        if n.value:
+            N.lib().phnsw_free(C.cast(p, C.c_void_p))
+        return out
+
     def improve_index_with_promotion(self, build_parameters=None, seed=1, progress=None):
         """Hnsw::improve_index (src/lib.rs:1664-1685) with promote_at_layer live."""
         bp = build_parameters or self.build_parameters

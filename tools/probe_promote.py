@@ -55,4 +55,15 @@ for improve in (1, 2):
     rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(ids, gt)])
     print("PROMOTE improve=%d: build %.2fs, layers %s, unreachable(bottom) %d, recall@10 %.4f, "
           "%.0f QPS" % (improve, tb, sizes, un, rec, args.nq / ms * 1e3), flush=True)
+    if improve == 1:
+        for layer_id in (1, 0):
+            torch.cuda.synchronize()
+            t = time.time()
+            hops, isum = gh.node_distances_for_layer(layer_id)
+            dt = time.time() - t
+            reached = hops != np.uint64(ph.EMPTY)
+            print("DIAG node_distances_for_layer(%d): %.3fs, %d nodes, %d unreached, max hops %d, "
+                  "mean index_sum %.1f" % (layer_id, dt, hops.size, int((~reached).sum()),
+                                           int(hops[reached].max()), float(isum[reached].mean())),
+                  flush=True)
     gh.close()
