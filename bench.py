@@ -445,7 +445,7 @@ def main():
                    "search": {"number_of_candidates": args.ef, "upper_layer_candidate_count": args.ef,
                               "probe_depth": 2},
                    "sum_order": args.sum_order,
-                   "layers_top_first": [int(x) for x in ph.calculate_partitions(args.n, 12)],
+                   "layers_top_first": gh.layer_sizes(),
                    "cache": "inputs larger than L2 (rows %.0f MB + graph %.0f MB vs 126 MB L2)" % (
                        args.n * args.dim * 4 / 1e6, args.n * 48 * 4 / 1e6),
                    "parallelism": "replicas x%d (queries split)" % world if world > 1 else "single GPU"},

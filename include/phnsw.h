@@ -214,8 +214,8 @@ void phnsw_free(void *p);
 phnsw_status phnsw_generate(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
                             const phnsw_build_params *bp, uint64_t seed,
                             phnsw_progress_fn progress, void *user, phnsw_index **out);
-/* same; improve = 0 skips the improve_index call after every layer (src/lib.rs:876),
- * improve = 2 runs it with promotion (see below) */
+/* same; improve = 1 is phnsw_generate, improve = 0 skips the improve_index call after every layer
+ * (src/lib.rs:876), improve = 2 runs it with promote_at_layer treated as "nothing to promote" */
 phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
                                  const phnsw_build_params *bp, uint64_t seed, int improve,
                                  phnsw_progress_fn progress, void *user, phnsw_index **out);
@@ -223,9 +223,9 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out);
 /* Promotion / layer surgery (src/lib.rs:1039-1068 extend_layer, 1167-1268
  * discover_order_from_top + filter_promotion_candidates, 1273-1427 promote_at_layer, 1726-1812
- * node maps and neighbourhood rewrite).  Opt-in: phnsw_generate_with(improve = 2) and
- * phnsw_improve_index_promote run improve_index as the crate does, promote_at_layer live;
- * improve = 1 / phnsw_improve_index treat it as "nothing to promote".  Ties of the in-link
+ * node maps and neighbourhood rewrite).  phnsw_generate and phnsw_improve_index run improve_index
+ * as the crate does, promote_at_layer live (phnsw_improve_index continues the index's seed
+ * sequence, phnsw_improve_index_promote restarts it from `seed`).  Ties of the in-link
  * histogram, which the crate breaks by HashMap iteration order, are broken by NodeId; nested
  * re-top generates derive their seed from `seed`.  Exclusive access (&mut self).
  *   phnsw_extend_layer: `layer_from_top` (the crate counts from the bottom: layer_count-1-id);

@@ -463,7 +463,7 @@ class Hnsw:
         return list(zip(on[:m].tolist(), od[:m].tolist()))
 
     def improve_index_with_promotion(self, bp=None, seed=1, nthreads=0):
-        """Hnsw::improve_index (lib.rs:1661-1685) with promote_at_layer live."""
+        """Hnsw::improve_index (lib.rs:1661-1685), nested-generate seeds restarted from `seed`."""
         bp = bp or self.build_parameters
         return float(lib().orc_improve_index_promote(self._h, C.byref(bp), seed, nthreads))
 

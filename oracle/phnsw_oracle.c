@@ -317,6 +317,7 @@ struct orc_hnsw {
   int sum_order; /* 0 = the crate's sequential loop, 1 = orc_distance_tree (search paths only) */
   uint64_t seed;        /* seed this index was generated with (nested re-top generates derive theirs) */
   uint64_t promo_count; /* number of nested generates so far */
+  int promo_failed;     /* promote_at_layer hit a state where the crate panics */
 };
 
 orc_hnsw *orc_hnsw_new(int metric, uint64_t dim, uint64_t n, const float *rows) {
@@ -1725,7 +1726,7 @@ static orc_hnsw *nested_generate(orc_hnsw *h, const uint64_t *vecs, uint64_t n,
   orc_build_params nbp = *bp;
   nbp.zero_layer_neighborhood_size = bp->neighborhood_size;
   uint64_t seed = h->seed ^ (0x9E3779B97F4A7C15ull * ++h->promo_count);
-  orc_hnsw *t = orc_generate(h->metric, h->dim, h->n_vectors, h->rows, vecs, n, &nbp, seed, 2,
+  orc_hnsw *t = orc_generate(h->metric, h->dim, h->n_vectors, h->rows, vecs, n, &nbp, seed, 1,
                              nthreads);
   return t;
 }
@@ -1825,7 +1826,13 @@ static float improve_index_at_ex(orc_hnsw *h, uint64_t *layer_from_top_io,
       const uint64_t layer_count = h->layer_count;
       recall = improve_neighbors_upto(h, cur + 1, op, 0, 0.0f, nthreads);
       if (recall == 1.0f) { cur += 1; continue; }
-      if (promote && orc_promote_at_layer(h, cur, bp, nthreads) == 1) {
+      const int pr = promote ? orc_promote_at_layer(h, cur, bp, nthreads) : 0;
+      if (pr < 0) {
+        h->promo_failed = 1;
+        *layer_from_top_io = layer_from_top;
+        return recall;
+      }
+      if (pr == 1) {
         const uint64_t delta = h->layer_count - layer_count;
         cur += delta;
         layer_from_top += delta;
@@ -1840,7 +1847,8 @@ static float improve_index_at_ex(orc_hnsw *h, uint64_t *layer_from_top_io,
   return recall;
 }
 
-float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
+/* improve_index with promote_at_layer treated as "nothing to promote" (orc_generate improve = 2) */
+static float improve_index_no_promotion(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
   float recall = orc_stochastic_recall(h, &bp->optimization, nthreads); /* lib.rs:1671 */
   for (uint64_t l = 0; l < h->layer_count; l++) {
     uint64_t lft = l;
@@ -1849,15 +1857,19 @@ float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
   return recall;
 }
 
-/* improve_index (lib.rs:1661-1685) with promotion, as the crate runs it */
+/* improve_index (lib.rs:1661-1685) as the crate runs it, promotion included */
 static float improve_index_promote(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
   float recall = orc_stochastic_recall(h, &bp->optimization, nthreads);
   uint64_t lft = 0;
-  while (lft < h->layer_count) {
+  while (lft < h->layer_count && !h->promo_failed) {
     recall = improve_index_at_ex(h, &lft, bp, 1, nthreads);
     lft += 1;
   }
-  return recall;
+  return h->promo_failed ? -1.0f : recall;
+}
+
+float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
+  return improve_index_promote(h, bp, nthreads);
 }
 
 float orc_improve_index_promote(orc_hnsw *h, const orc_build_params *bp, uint64_t seed,
@@ -1889,10 +1901,15 @@ orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float
     memcpy(slice, vs, len * sizeof(uint64_t));
     generate_layer(h, slice, len, M, &bp->initial_partition_search, nthreads);
     free(slice);
-    if (improve == 2) improve_index_promote(h, bp, nthreads);
-    else if (improve) orc_improve_index(h, bp, nthreads); /* lib.rs:876 */
+    if (improve == 2) improve_index_no_promotion(h, bp, nthreads);
+    else if (improve) improve_index_promote(h, bp, nthreads); /* lib.rs:876 */
+    if (h->promo_failed) break;
   }
   free(vs);
+  if (h->promo_failed) { /* the crate panics */
+    orc_hnsw_free(h);
+    return NULL;
+  }
   return h;
 }
 

@@ -149,18 +149,18 @@ int orc_compare_all(const orc_hnsw *h, uint64_t v, const uint64_t *vs, uint64_t 
 /*
  * Reference-style build (lib.rs:675-893 generate/generate_layer, :1070-1154
  * link_nodes_in_layer_to_better_neighbors, :1463-1544 stochastic recall +
- * improve_neighbors_upto, :1546-1685 improve_index[_at] WITHOUT promotion --
- * promote_at_layer is treated as "nothing to promote").  The RNG is our own
+ * improve_neighbors_upto, :1546-1685 improve_index[_at], promotion included).  The RNG is our own
  * (splitmix64), seeded by `seed`: parity unpinned for the shuffles/picks.
- * improve = 0 skips improve_index after each layer.
+ * improve = 0 skips improve_index after each layer, improve = 2 runs it with promote_at_layer
+ * treated as "nothing to promote".
  */
 orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float *rows,
                        const uint64_t *vs, uint64_t n_vs, const orc_build_params *bp,
                        uint64_t seed, int improve, int nthreads);
 float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads);
-/* Promotion / layer surgery (lib.rs:1039-1068, 1167-1427, 1726-1812).  orc_generate with
- * improve = 2 and orc_improve_index_promote run improve_index as the crate does, promotion
- * included; improve = 1 / orc_improve_index leave it out (the default of the build entry points).
+/* Promotion / layer surgery (lib.rs:1039-1068, 1167-1427, 1726-1812), part of improve_index;
+ * orc_improve_index continues the index's seed sequence for nested re-top generates,
+ * orc_improve_index_promote restarts it from `seed`.
  * Histogram ties, which the crate breaks by HashMap iteration order, are broken by NodeId. */
 int orc_extend_layer(orc_hnsw *h, uint64_t layer_from_top, const uint64_t *vecs, uint64_t n);
 uint64_t orc_filter_promotion_candidates(const orc_hnsw *h, uint64_t layer_from_top,

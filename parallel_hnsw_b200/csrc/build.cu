@@ -11,8 +11,8 @@
 //   improve_neighbors_upto / improve_index_at / improve_index   src/lib.rs:1515-1603, 1664-1685
 //   extend_layer / generate_node_maps / copy_old_neighborhoods_into_layer   src/lib.rs:1039-1068, 1726-1812
 //   discover_order_from_top / filter_promotion_candidates / promote_at_layer src/lib.rs:1167-1427
-// Promotion is opt-in (improve = 2 in phnsw_generate_with, phnsw_improve_index_promote): the
-// default build entry points treat promote_at_layer as "nothing to promote" (DESIGN.md).
+// improve_index runs with promote_at_layer live, as in the crate; phnsw_generate_with(improve = 2)
+// is the variant that treats promote_at_layer as "nothing to promote" (kept for A/B runs).
 //
 // Design.  The crate mutates neighbourhoods under per-node RwLocks from rayon workers
 // (lib.rs:789-815, 1102-1148); every such mutation is "insert (node, d) into a bounded list
@@ -1092,7 +1092,7 @@ static phnsw_status promote_at_layer(phnsw_index *ix, uint32_t layer_from_top,
       nbp.zero_layer_neighborhood_size = bp.neighborhood_size;
       const uint64_t seed = ix->seed ^ (0x9E3779B97F4A7C15ull * ++ix->promo_count);
       phnsw_index *t = nullptr;
-      rc = phnsw_generate_with(ix->store, tv.data(), tv.size(), &nbp, seed, 2, pg.fn, pg.user, &t);
+      rc = phnsw_generate_with(ix->store, tv.data(), tv.size(), &nbp, seed, 1, pg.fn, pg.user, &t);
       if (rc != PHNSW_OK) return rc;
       offset = t->layers.size();
       rc = index_retop(ix, retop_upto, t);
@@ -1116,7 +1116,7 @@ static phnsw_status promote_at_layer(phnsw_index *ix, uint32_t layer_from_top,
 }
 
 // improve_index_at (lib.rs:1546-1603); promote = false treats promote_at_layer as "nothing to
-// promote" (the default of the build entry points)
+// promote" (phnsw_generate_with(improve = 2))
 static phnsw_status improve_index_at(phnsw_index *ix, uint32_t *layer_from_top_io,
                                      const phnsw_build_params &bp, Progress &pg, bool promote,
                                      float *recall_out) {
@@ -1253,7 +1253,7 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
     rc = build_layer(ix, slice, M, bp.initial_partition_search, pg);
     if (rc == PHNSW_OK && improve) {
       float recall;
-      rc = improve_index(ix, bp, pg, &recall, improve == 2);  // lib.rs:876
+      rc = improve_index(ix, bp, pg, &recall, improve != 2);  // lib.rs:876
     }
   }
   if (rc != PHNSW_OK) {
@@ -1281,7 +1281,7 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
   phnsw_build_params b = bp ? *bp : ix->bp;
   Progress pg{progress, user};
   float recall = 0.0f;
-  phnsw_status rc = improve_index(ix, b, pg, &recall);
+  phnsw_status rc = improve_index(ix, b, pg, &recall, true);
   if (rc == PHNSW_OK && recall_out) *recall_out = recall;
   return rc;
 }

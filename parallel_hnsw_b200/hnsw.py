@@ -194,7 +194,8 @@ class Hnsw:
                  improve=True):
         """Hnsw::generate(c, vs, bp, progress) (src/lib.rs:825-893) on the device.
         improve=False skips the improve_index call the crate makes after every layer;
-        improve=2 runs it with promote_at_layer live (src/lib.rs:1273-1427)."""
+        improve=2 runs it with promote_at_layer (src/lib.rs:1273-1427) treated as "nothing to
+        promote" (A/B runs)."""
         if vs is None:
             vs = np.arange(len(comparator), dtype=np.uint64)
         vs = _host(vs, np.uint64)
@@ -267,6 +268,15 @@ class Hnsw:
 
     def layers(self):
         return [self.get_layer_from_top(i) for i in range(self.layer_count())]
+
+    def layer_sizes(self):
+        """node_count of every layer, top first (Layer::node_count, src/lib.rs:150-152)."""
+        out = []
+        for i in range(self.layer_count()):
+            nc, M = C.c_uint64(), C.c_uint64()
+            N.check(N.lib().phnsw_index_layer_info(self._h, i, C.byref(nc), C.byref(M)))
+            out.append(int(nc.value))
+        return out
 
     def set_scratch(self, visited_log=0, frontier_spill=0):
         N.check(N.lib().phnsw_index_set_scratch(self._h, visited_log, 0, frontier_spill))
@@ -389,7 +399,8 @@ class Hnsw:
         return out
 
     def improve_index_with_promotion(self, build_parameters=None, seed=1, progress=None):
-        """Hnsw::improve_index (src/lib.rs:1664-1685) with promote_at_layer live."""
+        """Hnsw::improve_index (src/lib.rs:1664-1685) with the seed sequence of the nested
+        re-top generates restarted from `seed` (improve_index continues the index's own)."""
         bp = build_parameters or self.build_parameters
         r = C.c_float()
         N.check(N.lib().phnsw_improve_index_promote(self._h, C.byref(bp), seed,

@@ -153,9 +153,9 @@ impl Hnsw {
                     mut progress: &mut dyn ProgressMonitor) -> Result<Self, Error> {
         let ids: Vec<u64> = vs.iter().map(|v| v.0 as u64).collect();
         let mut ix = ptr::null_mut();
-        // improve = 2: improve_index after every layer with promote_at_layer live, as the crate
+        // improve = 1: improve_index after every layer, promote_at_layer live, as the crate
         check(unsafe {
-            phnsw_generate_with(c.store.0, ids.as_ptr(), ids.len() as u64, &bp, seed, 2, Some(progress_trampoline),
+            phnsw_generate_with(c.store.0, ids.as_ptr(), ids.len() as u64, &bp, seed, 1, Some(progress_trampoline),
                                 &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut ix)
         })?;
         Ok(Self { comparator: c, index: IndexHandle(ix), seed })
@@ -246,12 +246,12 @@ impl Hnsw {
         out
     }
 
-    /// src/lib.rs:1664-1685 (promotion live)
+    /// src/lib.rs:1664-1685
     pub fn improve_index(&mut self, bp: BuildParameters, mut progress: &mut dyn ProgressMonitor) -> f32 {
         let mut recall = 0f32;
         check_or_panic(unsafe {
-            phnsw_improve_index_promote(self.index.0, &bp, self.seed, Some(progress_trampoline),
-                                        &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut recall)
+            phnsw_improve_index(self.index.0, &bp, Some(progress_trampoline),
+                                &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut recall)
         });
         recall
     }

@@ -28,9 +28,15 @@ def big():
 
 def test_layer_sizes_and_nesting(big):
     ph, rows, comp, gh, queries = big
-    sizes = [gh.get_layer_from_top(i)[0].shape[0] for i in range(gh.layer_count())]
-    assert sizes == [int(x) for x in ph.calculate_partitions(1000000, 12)]  # lib.rs:1883-1899
-    assert sizes == [4, 48, 578, 6944, 83333, 1000000]
+    sizes = gh.layer_sizes()
+    parts = [int(x) for x in ph.calculate_partitions(1000000, 12)]       # lib.rs:1883-1899
+    assert parts == [4, 48, 578, 6944, 83333, 1000000]
+    # generate_layer fills the partitions; promote_at_layer (lib.rs:1273-1427) may add a few supers
+    assert len(sizes) == len(parts) and sizes[-1] == parts[-1]
+    assert all(p <= s <= p + p // 100 + 4 for s, p in zip(sizes, parts)), sizes
+    base = ph.Hnsw.generate(comp, seed=1, improve=2)                     # promotion left out
+    assert base.layer_sizes() == parts
+    base.close()
     prev = None
     for i in range(gh.layer_count()):
         nodes, neigh, M = gh.get_layer_from_top(i)

@@ -101,14 +101,14 @@ def test_generate_with_promotion_matches_oracle(ph, oracle, n, dim, M, ef, seed)
     generate) and the relinking after it reproduce the oracle's layer stack exactly."""
     rows = random_normed(n, dim, seed)
     bp, obp = _bp_pair(ph, oracle, 8, M, ef)
-    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=obp, seed=7, improve=2)
-    base = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=obp, seed=7, improve=1)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=obp, seed=7, improve=True)
+    base = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=obp, seed=7, improve=2)  # no promotion
     comp = ph.BigComparator(rows, ph.COS_HALF)
-    gh = ph.Hnsw.generate(comp, build_parameters=bp, seed=7, improve=2)
+    gh = ph.Hnsw.generate(comp, build_parameters=bp, seed=7, improve=True)
     _same_layers(gh.layers(), oh.layers())
     assert sum(l[0].size for l in oh.layers()) > sum(l[0].size for l in base.layers())
-    # the default entry point is unchanged by the opt-in
-    gb = ph.Hnsw.generate(comp, build_parameters=bp, seed=7, improve=True)
+    # the A/B variant that leaves promotion out
+    gb = ph.Hnsw.generate(comp, build_parameters=bp, seed=7, improve=2)
     _same_layers(gb.layers(), base.layers())
 
 

@@ -152,8 +152,8 @@ def test_generate_with_promotion_keeps_invariants(oracle, n, dim, M, ef, grows_a
     bp.zero_layer_neighborhood_size = 2 * M
     bp.optimization.search = oracle.search_params(ef, ef, 2)
     bp.initial_partition_search = oracle.search_params(ef, ef, 2)
-    base = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=bp, seed=7, improve=1)
-    full = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=bp, seed=7, improve=2)
+    base = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=bp, seed=7, improve=2)   # no promotion
+    full = oracle.Hnsw.generate(oracle.COS_HALF, rows, bp=bp, seed=7, improve=True)
     check_layer_invariants(full)
     assert full.layer(full.layer_count - 1)[0].size == n
     sizes = lambda h: [l[0].size for l in h.layers()]

@@ -1,5 +1,5 @@
 """Developer probe (not part of the product): the bench index built with and without promotion
-(improve = 1 / 2): build time, layer sizes, unreachable vectors of the bottom layer, recall@10
+(improve = 2 / 1): build time, layer sizes, unreachable vectors of the bottom layer, recall@10
 and queries/s at the bench operating point.
 usage: python tools/probe_promote.py [--n N] [--nq NQ]"""
 import argparse
@@ -27,7 +27,7 @@ q = sift_like(args.nq, args.dim, 4321)
 gt, _ = comp.bruteforce_knn(q.numpy(), 10)
 sp = ph.SearchParameters(args.ef, args.ef, 2)
 st = torch.cuda.current_stream().cuda_stream
-for improve in (1, 2):
+for improve in (2, 1):
     torch.cuda.synchronize()
     t = time.time()
     gh = ph.Hnsw.generate(comp, seed=1, improve=improve)
