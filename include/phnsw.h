@@ -221,6 +221,13 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
                                  phnsw_progress_fn progress, void *user, phnsw_index **out);
 phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out);
+/* Hnsw::improve_neighbors_upto (src/lib.rs:1515-1544): link passes over layers[0..upto) until the
+ * stochastic recall stops improving by neighborhood_threshold; improve_neighbors (:1507-1513) is
+ * upto = layer_count.  has_last_recall / last_recall = the crate's Option<f32>.  op NULL = the
+ * index's own build parameters. */
+phnsw_status phnsw_improve_neighbors_upto(phnsw_index *ix, uint64_t upto,
+                                          const phnsw_optimization_params *op, int has_last_recall,
+                                          float last_recall, float *recall_out);
 /* Promotion / layer surgery (src/lib.rs:1039-1068 extend_layer, 1167-1268
  * discover_order_from_top + filter_promotion_candidates, 1273-1427 promote_at_layer, 1726-1812
  * node maps and neighbourhood rewrite).  phnsw_generate and phnsw_improve_index run improve_index

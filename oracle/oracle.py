@@ -134,6 +134,9 @@ def lib():
     L.orc_reachables_from.restype = C.c_uint64
     L.orc_reachables_from.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u64p, C.c_uint64, u64p,
                                       u64p]
+    L.orc_improve_neighbors_upto.restype = C.c_float
+    L.orc_improve_neighbors_upto.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OptimizationParams),
+                                             C.c_int, C.c_float, C.c_int]
     L.orc_stochastic_recall.restype = C.c_float
     L.orc_stochastic_recall.argtypes = [C.c_void_p, C.POINTER(OptimizationParams), C.c_int]
     L.orc_serialize.restype = C.c_int
@@ -420,6 +423,19 @@ class Hnsw:
     def improve_index(self, bp=None, nthreads=0):
         bp = bp or self.build_parameters
         return float(lib().orc_improve_index(self._h, C.byref(bp), nthreads))
+
+    def improve_neighbors_upto(self, upto, op=None, last_recall=None, nthreads=0):
+        """Hnsw::improve_neighbors_upto (lib.rs:1515-1544)."""
+        op = op or self.build_parameters.optimization
+        r = lib().orc_improve_neighbors_upto(self._h, upto, C.byref(op), last_recall is not None,
+                                             float(last_recall or 0.0), nthreads)
+        if r < 0:
+            raise ValueError("improve_neighbors_upto: upto must be in 1..=layer_count")
+        return float(r)
+
+    def improve_neighbors(self, op=None, last_recall=None, nthreads=0):
+        """Hnsw::improve_neighbors (lib.rs:1507-1513)."""
+        return self.improve_neighbors_upto(self.layer_count, op, last_recall, nthreads)
 
     def supers_for_layer(self, layer_id):
         """Hnsw::supers_for_layer (lib.rs:977-984); layer_id counts from the bottom."""

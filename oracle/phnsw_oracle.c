@@ -1461,6 +1461,14 @@ static float improve_neighbors_upto(orc_hnsw *h, uint64_t upto,
   return last_recall;
 }
 
+/* Hnsw::improve_neighbors_upto / improve_neighbors (lib.rs:1507-1544); returns -1 on the crate's
+ * asserts (upto in 1..=layer_count) */
+float orc_improve_neighbors_upto(orc_hnsw *h, uint64_t upto, const orc_optimization_params *op,
+                                 int has_last, float last_recall, int nthreads) {
+  if (upto < 1 || upto > h->layer_count) return -1.0f;
+  return improve_neighbors_upto(h, upto, op, has_last, last_recall, nthreads);
+}
+
 /* ---------------------------------------------------------------- graph diagnostics
  * Layer::node_distances (lib.rs:425-489), literal: a level-synchronous walk from the supers whose
  * queue is consumed in order (Vec::into_iter().flat_map, sequential).  hops = BFS level;

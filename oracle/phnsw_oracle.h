@@ -158,6 +158,9 @@ orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float
                        const uint64_t *vs, uint64_t n_vs, const orc_build_params *bp,
                        uint64_t seed, int improve, int nthreads);
 float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads);
+/* improve_neighbors_upto (lib.rs:1515-1544); improve_neighbors = upto layer_count (:1507-1513) */
+float orc_improve_neighbors_upto(orc_hnsw *h, uint64_t upto, const orc_optimization_params *op,
+                                 int has_last, float last_recall, int nthreads);
 /* Promotion / layer surgery (lib.rs:1039-1068, 1167-1427, 1726-1812), part of improve_index;
  * orc_improve_index continues the index's seed sequence for nested re-top generates,
  * orc_improve_index_promote restarts it from `seed`.

@@ -116,6 +116,8 @@ SIGNATURES = {
     "phnsw_improve_index": (C.c_int, [vp, C.POINTER(BuildParams), PROGRESS_FN, vp, f32p]),
     "phnsw_stochastic_recall": (C.c_int, [vp, C.POINTER(OptimizationParams), f32p]),
     "phnsw_extend_layer": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64]),
+    "phnsw_improve_neighbors_upto": (C.c_int, [vp, C.c_uint64, C.POINTER(OptimizationParams),
+                                               C.c_int, C.c_float, f32p]),
     "phnsw_node_distances": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "phnsw_discover_nodes_to_promote": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64, C.POINTER(u64p),
                                                   u64p]),

@@ -1326,6 +1326,28 @@ static phnsw_status promo_entry_check(const phnsw_index *ix, const char *what) {
   return PHNSW_OK;
 }
 
+// Hnsw::improve_neighbors_upto / improve_neighbors (src/lib.rs:1507-1544)
+phnsw_status phnsw_improve_neighbors_upto(phnsw_index *ix, uint64_t upto,
+                                          const phnsw_optimization_params *op, int has_last_recall,
+                                          float last_recall, float *recall_out) {
+  PH_ENTRY();
+  phnsw_status rc = promo_entry_check(ix, "improve_neighbors_upto");
+  if (rc != PHNSW_OK) return rc;
+  if (upto < 1 || upto > ix->layers.size()) {  // the crate's asserts (lib.rs:1521-1522)
+    set_error("improve_neighbors_upto: upto must be in 1..=layer_count");
+    return PHNSW_ERR_INVALID;
+  }
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  phnsw_build_params b = ix->bp;
+  if (op) b.optimization = *op;
+  Progress pg{nullptr, nullptr};
+  float recall = 0.0f;
+  rc = improve_neighbors_upto(ix, (uint32_t)upto, b, pg, &recall,
+                              has_last_recall ? &last_recall : nullptr);
+  if (rc == PHNSW_OK && recall_out) *recall_out = recall;
+  return rc;
+}
+
 phnsw_status phnsw_extend_layer(phnsw_index *ix, uint64_t layer_from_top, const uint64_t *vecs,
                                 uint64_t n) {
   PH_ENTRY();

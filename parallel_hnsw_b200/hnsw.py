@@ -364,6 +364,27 @@ class Hnsw:
                                             C.byref(r)))
         return float(r.value)
 
+    def improve_neighbors_upto(self, upto, optimization_parameters=None, last_recall=None):
+        """Hnsw::improve_neighbors_upto (src/lib.rs:1515-1544)."""
+        op = optimization_parameters or self.build_parameters.optimization
+        r = C.c_float()
+        N.check(N.lib().phnsw_improve_neighbors_upto(self._h, upto, C.byref(op),
+                                                     int(last_recall is not None),
+                                                     float(last_recall or 0.0), C.byref(r)))
+        return float(r.value)
+
+    def improve_neighbors(self, optimization_parameters=None, last_recall=None):
+        """Hnsw::improve_neighbors (src/lib.rs:1507-1513)."""
+        return self.improve_neighbors_upto(self.layer_count(), optimization_parameters, last_recall)
+
+    def neighborhood_size(self):
+        """src/lib.rs:596-598"""
+        return int(self.build_parameters.neighborhood_size)
+
+    def zero_neighborhood_size(self):
+        """src/lib.rs:600-602"""
+        return int(self.build_parameters.zero_layer_neighborhood_size)
+
     # ---- graph diagnostics --------------------------------------------------------------
     def supers_for_layer(self, layer_id):
         """Hnsw::supers_for_layer (src/lib.rs:977-984); layer_id counts from the bottom."""
@@ -601,6 +622,28 @@ class QuantizedHnsw:
         out = np.empty((codes.shape[0], self.quantized_size * self.centroid_size), dtype=np.float32)
         N.check(N.lib().phnsw_pq_reconstruct(self._h, _ptr(codes), codes.shape[0], _ptr(out)))
         return out
+
+    # the crate forwards these to the graph over the codes (src/pq.rs:366-410)
+    def improve_index(self, build_parameters=None, progress=None):
+        return self.hnsw().improve_index(build_parameters, progress)
+
+    def improve_neighbors(self, optimization_parameters=None, last_recall=None):
+        return self.hnsw().improve_neighbors(optimization_parameters, last_recall)
+
+    def promote_at_layer(self, layer_from_top, build_parameters=None, progress=None):
+        return self.hnsw().promote_at_layer(layer_from_top, build_parameters, progress)
+
+    def zero_neighborhood_size(self):
+        return self.hnsw().zero_neighborhood_size()
+
+    def threshold_nn(self, threshold, probe_depth, initial_search_depth):
+        return self.hnsw().threshold_nn(threshold, probe_depth, initial_search_depth)
+
+    def stochastic_recall(self, optimization_parameters=None):
+        return self.hnsw().stochastic_recall(optimization_parameters)
+
+    def build_parameters_for_improve_index(self):
+        return self.hnsw().build_parameters
 
     def search(self, queries=None, sp=None, stored_ids=None, max_out=None):
         """QuantizedHnsw::search (pq.rs:346-364), batched."""

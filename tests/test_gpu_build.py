@@ -154,6 +154,24 @@ def test_generate_subset_and_errors(ph, oracle):
     assert e.value.status == 8 and len(calls) == 3  # Interrupt (src/progress.rs:8-10)
 
 
+def test_improve_neighbors_matches_oracle(ph, oracle):
+    """Hnsw::improve_neighbors_upto / improve_neighbors (src/lib.rs:1507-1544), Option<f32>
+    last_recall included, on a graph uploaded from the oracle."""
+    rows = random_normed(5000, 32, 6)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, seed=2, improve=False)
+    gh = ph.Hnsw.from_layers(ph.BigComparator(rows, ph.COS_HALF), oh.layers())
+    ro, rg = oh.improve_neighbors_upto(2), gh.improve_neighbors_upto(2)
+    assert rg == ro
+    _same_layers(gh.layers(), oh.layers())
+    ro2, rg2 = oh.improve_neighbors(last_recall=ro), gh.improve_neighbors(last_recall=rg)
+    assert rg2 == ro2
+    _same_layers(gh.layers(), oh.layers())
+    assert gh.neighborhood_size() == 24 and gh.zero_neighborhood_size() == 48
+    for bad in (0, gh.layer_count() + 1):           # the crate's asserts (lib.rs:1521-1522)
+        with pytest.raises(ph.PhnswError):
+            gh.improve_neighbors_upto(bad)
+
+
 def test_discover_unreachable_vectors_matches_oracle(ph, oracle):
     """Hnsw::discover_unreachable_vectors (src/lib.rs:1002-1037) as one batched traversal launch
     per layer, against the oracle's literal restatement (match_within_epsilon included)."""

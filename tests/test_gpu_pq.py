@@ -144,3 +144,22 @@ def test_pq_serialize_round_trip(ph, oracle, small, tmp_path):
     with pytest.raises(ph.PhnswError) as e:
         ph.QuantizedHnsw.deserialize(d)
     assert e.value.status == 6  # IndexNotFound
+
+
+def test_pq_forwards_the_graph_methods(ph, oracle, small):
+    """QuantizedHnsw::{improve_neighbors, stochastic_recall, zero_neighborhood_size, threshold_nn,
+    promote_at_layer, build_parameters_for_improve_index} (pq.rs:366-410) forward to the graph
+    over the codes; run last in this module because improve_neighbors mutates that graph."""
+    rows, g, o = small
+    bp = g.build_parameters_for_improve_index()
+    assert g.zero_neighborhood_size() == bp.zero_layer_neighborhood_size == 48
+    assert g.stochastic_recall() == o.hnsw().stochastic_recall()
+    off, ids, ds = g.threshold_nn(0.05, 2, 10)
+    off2, ids2, ds2 = g.hnsw().threshold_nn(0.05, 2, 10)
+    assert np.array_equal(off, off2) and np.array_equal(ids, ids2) and np.array_equal(ds, ds2)
+    rg = g.improve_neighbors()
+    ro = o.hnsw().improve_neighbors()
+    assert rg == ro
+    _same_graph(g.hnsw(), o.hnsw())
+    assert g.promote_at_layer(1) == o.hnsw().promote_at_layer(1)
+    _same_graph(g.hnsw(), o.hnsw())
