@@ -62,7 +62,8 @@ def _check_invariants(ph, comp, layers):
                                                      ("L2_SQRT", 6000, 96, 12),
                                                      ("COS_HALF", 5000, 32, 100),
                                                      ("ONE_MINUS_DOT", 700, 20, 6),
-                                                     ("COS_HALF", 9, 8, 6), ("COS_HALF", 1, 8, 12)])
+                                                     ("COS_HALF", 9, 8, 6), ("COS_HALF", 1, 8, 12),
+                                                     ("COS_HALF", 2500, 1536, 12)])
 def test_generate_matches_oracle_without_improve(ph, oracle, metric_name, n, dim, order):
     metric = getattr(ph, metric_name)
     rows = clustered(n, dim, 7, integer=True) if metric_name == "L2_SQRT" else random_normed(n, dim, 7)
@@ -152,6 +153,14 @@ def test_generate_subset_and_errors(ph, oracle):
     with pytest.raises(ph.PhnswError) as e:
         ph.Hnsw.generate(comp, seed=4, progress=stop)
     assert e.value.status == 8 and len(calls) == 3  # Interrupt (src/progress.rs:8-10)
+
+
+def test_generate_with_improve_matches_oracle_at_embedding_width(ph, oracle):
+    """BASELINE configs[2] row width (1536 f32 = 6 KB rows): whole build incl. improve_index."""
+    rows = random_normed(2000, 1536, 8)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, seed=5, improve=True)
+    gh = ph.Hnsw.generate(ph.BigComparator(rows, ph.COS_HALF), seed=5, improve=True)
+    _same_layers(gh.layers(), oh.layers())
 
 
 def test_improve_neighbors_matches_oracle(ph, oracle):

@@ -14,14 +14,19 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 dim, cs, K, k = 1536, 16, 256, 10
 g = torch.Generator(device="cuda").manual_seed(2024)
-basis = torch.randn(64, dim, generator=g, device="cuda") / 8.0
+# embedding-shaped: 2048 topic clusters on a 24-d manifold (local intrinsic dimension of text
+# embeddings is a few tens), small isotropic noise, unit norm
+basis = torch.randn(24, dim, generator=g, device="cuda") / 5.0
+centers = torch.randn(2048, 24, generator=g, device="cuda") * 2.0
 
 
 def gen(m):
     out = torch.empty((m, dim), dtype=torch.float32, device="cuda")
     for s in range(0, m, 1 << 16):
         c = min(1 << 16, m - s)
-        x = torch.randn(c, 64, generator=g, device="cuda") @ basis + 0.05 * torch.randn(c, dim, generator=g, device="cuda")
+        cl = torch.randint(0, 2048, (c,), generator=g, device="cuda")
+        z = centers[cl] + torch.randn(c, 24, generator=g, device="cuda")
+        x = z @ basis + 0.01 * torch.randn(c, dim, generator=g, device="cuda")
         out[s:s + c] = x / x.norm(dim=1, keepdim=True)
     return out
 
