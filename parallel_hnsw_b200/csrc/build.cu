@@ -1379,7 +1379,14 @@ phnsw_status phnsw_filter_promotion_candidates(const phnsw_index *ix, uint64_t l
   *selected = nullptr;
   *n_groups = 0;
   std::vector<uint32_t> v(n);
-  for (uint64_t i = 0; i < n; i++) v[i] = (uint32_t)vecs[i];
+  for (uint64_t i = 0; i < n; i++) {
+    if (vecs[i] >= ix->store->n) {
+      set_error("filter_promotion_candidates: VectorId %llu is not in the store",
+                (unsigned long long)vecs[i]);
+      return PHNSW_ERR_INVALID;
+    }
+    v[i] = (uint32_t)vecs[i];
+  }
   std::vector<std::pair<uint32_t, std::vector<uint32_t>>> groups;
   PH_CUDA(cudaSetDevice(ix->store->device));
   rc = filter_promotion_candidates(ix, (uint32_t)layer_from_top, v, *sp, &groups);
