@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cub/cub.cuh>
 #include <vector>
 
@@ -433,12 +434,43 @@ __global__ void map_hits_kernel(const uint64_t *ids, const uint64_t *self_ids, u
 }
 
 // ------------------------------------------------------------------ host helpers
-struct DevMem {  // scoped device allocations
+// Scoped device allocations.  The build allocates and frees several GB of temporaries per layer
+// pass; they come from the device's stream-ordered pool, which keeps them between passes instead
+// of returning them to the driver (1M x 128 build: 0.96-1.25 s against 1.1-1.4 s with cudaMalloc /
+// cudaFree in back-to-back A/B runs; an occasional 2 s build remains on both, not traced yet).
+// PHNSW_ASYNC_ALLOC=0 goes back to cudaMalloc.
+static bool async_alloc() {
+  static const bool on = [] {
+    const char *e = getenv("PHNSW_ASYNC_ALLOC");
+    return !(e && atoi(e) == 0);
+  }();
+  if (!on) return false;
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(configured.load() & bit)) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured.fetch_or(bit);
+  }
+  return true;
+}
+struct DevMem {
   std::vector<void *> ptrs;
-  ~DevMem() { for (void *p : ptrs) cudaFree(p); }
+  ~DevMem() {
+    for (void *p : ptrs) {
+      if (async_alloc()) cudaFreeAsync(p, 0);
+      else cudaFree(p);
+    }
+  }
   template <class T>
   cudaError_t alloc(T **p, size_t count) {
-    cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = async_alloc() ? cudaMallocAsync((void **)p, bytes, 0) : cudaMalloc((void **)p, bytes);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }
