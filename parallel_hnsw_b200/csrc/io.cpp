@@ -8,6 +8,10 @@
 // N counts from the bottom (serialize.rs:67) while layers[0] is the top.  The JSON is emitted
 // field for field in serde's declaration order, f32 in shortest round-trip form, so a `meta`
 // written here is byte-identical to the crate's for the same parameters.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <errno.h>
 #include <math.h>
 #include <stdio.h>
@@ -342,7 +346,15 @@ phnsw_status io_load_graph(const std::string &d, phnsw_store *s, phnsw_index **o
     set_error("load: %s/meta is not a valid HNSWMeta document", dir);
     return PHNSW_ERR_FORMAT;
   }
-  std::vector<std::vector<uint64_t>> nodes(L), nbs(L);
+  // layer.nodes.N / layer.neighbors.N are raw little-endian u64 arrays (serialize.rs:88-121):
+  // they are mapped read-only and handed to the uploader as they lie in the page cache, which
+  // compacts them to u32 on the device -- no intermediate host copy
+  struct Mapping {
+    void *p = nullptr;
+    size_t len = 0;
+    ~Mapping() { if (p) munmap(p, len); }
+  };
+  std::vector<Mapping> maps(2 * L);
   std::vector<phnsw_layer_desc> descs(L);
   for (uint64_t i = 0; i < L; i++) {
     std::string n = std::to_string(L - i - 1);
@@ -355,26 +367,33 @@ phnsw_status io_load_graph(const std::string &d, phnsw_store *s, phnsw_index **o
       set_error("load: %s/layer.meta.%s is not a valid LayerMeta document", dir, n.c_str());
       return PHNSW_ERR_FORMAT;
     }
-    nodes[i].resize(nc);
-    nbs[i].resize((size_t)nc * M);
+    const uint64_t *ptr[2] = {nullptr, nullptr};
     for (int which = 0; which < 2; which++) {
-      std::vector<uint64_t> &dst = which ? nbs[i] : nodes[i];
+      const size_t want = (size_t)(which ? nc * M : nc) * 8;
       std::string p = d + (which ? "/layer.neighbors." : "/layer.nodes.") + n;
-      FILE *g = fopen(p.c_str(), "rb");
-      size_t r = 0;
-      if (g) {
-        r = dst.empty() ? 0 : fread(dst.data(), 8, dst.size(), g);
-        fclose(g);
+      int fd = open(p.c_str(), O_RDONLY);
+      struct stat sb;
+      bool ok = fd >= 0 && fstat(fd, &sb) == 0 && (size_t)sb.st_size >= want;  // read_exact
+      if (ok && want) {
+        Mapping &m = maps[2 * i + which];
+        void *q = mmap(nullptr, want, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (q == MAP_FAILED) ok = false;
+        else {
+          m.p = q;
+          m.len = want;
+          ptr[which] = (const uint64_t *)q;
+        }
       }
-      if (!g || r != dst.size()) {  // read_exact: a short file is an io error
+      if (fd >= 0) close(fd);
+      if (!ok) {  // a missing or short file is an io error
         set_error("load: cannot read %s", p.c_str());
         return PHNSW_ERR_IO;
       }
     }
     descs[i].node_count = nc;
     descs[i].neighborhood_size = M;
-    descs[i].nodes = nodes[i].data();
-    descs[i].neighbors = nbs[i].data();
+    descs[i].nodes = ptr[0];
+    descs[i].neighbors = ptr[1];
   }
   return phnsw_index_from_layers(s, L, descs.data(), &bp, out);
 }
