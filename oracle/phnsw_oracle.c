@@ -1466,7 +1466,11 @@ static float improve_neighbors_upto(orc_hnsw *h, uint64_t upto,
 float orc_improve_neighbors_upto(orc_hnsw *h, uint64_t upto, const orc_optimization_params *op,
                                  int has_last, float last_recall, int nthreads) {
   if (upto < 1 || upto > h->layer_count) return -1.0f;
-  return improve_neighbors_upto(h, upto, op, has_last, last_recall, nthreads);
+  const int saved = h->sum_order;
+  h->sum_order = 0;
+  float r = improve_neighbors_upto(h, upto, op, has_last, last_recall, nthreads);
+  h->sum_order = saved;
+  return r;
 }
 
 /* ---------------------------------------------------------------- graph diagnostics
@@ -1741,8 +1745,18 @@ static orc_hnsw *nested_generate(orc_hnsw *h, const uint64_t *vecs, uint64_t n,
 
 /* Hnsw::promote_at_layer (lib.rs:1270-1427).  Returns 1 = promoted (true), 0 = false,
  * negative where the crate would panic. */
+static int promote_at_layer_impl(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
+                                 int nthreads);
 int orc_promote_at_layer(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
                          int nthreads) {
+  const int saved = h->sum_order;
+  h->sum_order = 0;
+  int r = promote_at_layer_impl(h, layer_from_top, bp, nthreads);
+  h->sum_order = saved;
+  return r;
+}
+static int promote_at_layer_impl(orc_hnsw *h, uint64_t layer_from_top, const orc_build_params *bp,
+                                 int nthreads) {
   uint64_t *vecs = NULL;
   uint64_t n = orc_discover_unreachable(h, layer_from_top, &bp->optimization.search, &vecs, nthreads);
   if (n == 0) { free(vecs); return 0; }
@@ -1876,15 +1890,20 @@ static float improve_index_promote(orc_hnsw *h, const orc_build_params *bp, int 
   return h->promo_failed ? -1.0f : recall;
 }
 
+/* construction always runs in the crate's sequential summation order (see orc_hnsw_set_sum_order) */
 float orc_improve_index(orc_hnsw *h, const orc_build_params *bp, int nthreads) {
-  return improve_index_promote(h, bp, nthreads);
+  const int saved = h->sum_order;
+  h->sum_order = 0;
+  float r = improve_index_promote(h, bp, nthreads);
+  h->sum_order = saved;
+  return r;
 }
 
 float orc_improve_index_promote(orc_hnsw *h, const orc_build_params *bp, uint64_t seed,
                                 int nthreads) {
   h->seed = seed;
   h->promo_count = 0;
-  return improve_index_promote(h, bp, nthreads);
+  return orc_improve_index(h, bp, nthreads);
 }
 
 orc_hnsw *orc_generate(int metric, uint64_t dim, uint64_t n_vectors, const float *rows,

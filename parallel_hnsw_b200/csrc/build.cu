@@ -1227,6 +1227,16 @@ static phnsw_status improve_index(phnsw_index *ix, const phnsw_build_params &bp,
 
 using namespace phnsw;
 
+// Construction always runs in the crate's sequential summation order, whatever order the index
+// serves queries in: neighbourhood updates compare distances from the traversal with stored
+// ones, which only works when both come from one order (and it keeps the graphs the crate's).
+struct SequentialScope {
+  phnsw_index *ix;
+  int saved;
+  explicit SequentialScope(phnsw_index *i) : ix(i), saved(i->sum_order) { ix->sum_order = PHNSW_SUM_SEQUENTIAL; }
+  ~SequentialScope() { ix->sum_order = saved; }
+};
+
 extern "C" {
 
 phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uint64_t n,
@@ -1325,6 +1335,7 @@ phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
     set_error("improve_index: not available on a PQ8 store");
     return PHNSW_ERR_INVALID;
   }
+  SequentialScope seq(ix);
   phnsw_build_params b = bp ? *bp : ix->bp;
   Progress pg{progress, user};
   float recall = 0.0f;
@@ -1388,6 +1399,7 @@ phnsw_status phnsw_improve_neighbors_upto(phnsw_index *ix, uint64_t upto,
   phnsw_build_params b = ix->bp;
   if (op) b.optimization = *op;
   Progress pg{nullptr, nullptr};
+  SequentialScope seq(ix);
   float recall = 0.0f;
   rc = improve_neighbors_upto(ix, (uint32_t)upto, b, pg, &recall,
                               has_last_recall ? &last_recall : nullptr);
@@ -1465,6 +1477,7 @@ phnsw_status phnsw_promote_at_layer(phnsw_index *ix, uint64_t layer_from_top,
   PH_CUDA(cudaSetDevice(ix->store->device));
   phnsw_build_params b = bp ? *bp : ix->bp;
   Progress pg{progress, user};
+  SequentialScope seq(ix);
   bool promoted = false;
   rc = promote_at_layer(ix, (uint32_t)layer_from_top, b, pg, &promoted);
   if (rc == PHNSW_OK && promoted_out) *promoted_out = promoted ? 1 : 0;
@@ -1480,6 +1493,7 @@ phnsw_status phnsw_improve_index_promote(phnsw_index *ix, const phnsw_build_para
   PH_CUDA(cudaSetDevice(ix->store->device));
   phnsw_build_params b = bp ? *bp : ix->bp;
   Progress pg{progress, user};
+  SequentialScope seq(ix);
   ix->seed = seed;
   ix->promo_count = 0;
   float recall = 0.0f;

@@ -155,6 +155,25 @@ def test_generate_subset_and_errors(ph, oracle):
     assert e.value.status == 8 and len(calls) == 3  # Interrupt (src/progress.rs:8-10)
 
 
+def test_improve_index_on_a_tree_order_index_builds_in_the_sequential_order(ph, oracle):
+    """Construction runs in the crate's sequential order whatever order the index serves queries
+    in (a link pass compares traversal distances with stored ones): improve_index on an index
+    switched to the tree order yields the graph of the sequential run, and the order is kept."""
+    rows = clustered(4000, 64, 3, n_clusters=32, spread=0.5, normalise=True)
+    oh = oracle.Hnsw.generate(oracle.COS_HALF, rows, seed=2, improve=False)
+    ref = oracle.Hnsw.from_layers(oracle.COS_HALF, rows, oh.layers())
+    gh = ph.Hnsw.from_layers(ph.BigComparator(rows, ph.COS_HALF), oh.layers())
+    oh.set_sum_order(1)
+    gh.set_sum_order(ph.SUM_TREE)
+    rg, ro, rr = gh.improve_index(), oh.improve_index(), ref.improve_index()
+    assert rg == ro == rr
+    assert gh.sum_order() == ph.SUM_TREE
+    _same_layers(gh.layers(), oh.layers())
+    _same_layers(gh.layers(), ref.layers())
+    assert gh.promote_at_layer(gh.layer_count() - 1) == oh.promote_at_layer(oh.layer_count - 1)
+    _same_layers(gh.layers(), oh.layers())
+
+
 def test_generate_with_improve_matches_oracle_at_embedding_width(ph, oracle):
     """BASELINE configs[2] row width (1536 f32 = 6 KB rows): whole build incl. improve_index."""
     rows = random_normed(2000, 1536, 8)
