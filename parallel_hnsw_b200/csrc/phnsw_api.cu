@@ -184,7 +184,15 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     return PHNSW_ERR_INVALID;
   }
   const bool tree = !pq8 && ix->sum_order == PHNSW_SUM_TREE;
-  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, pq8 ? s->pq_Q * s->pq_K : 0,
+  // ADC: a per-query table of Q x K partial distances is the cheapest per candidate, but at the
+  // embedding shape (96 x 256 x 4 B = 96 KB) it leaves room for two warps per SM; above 24 KB the
+  // entries are recomputed from the (L1-resident) codebook instead.  PHNSW_ADC_TABLE=0/1 forces.
+  bool pq_table = pq8 && (size_t)s->pq_Q * s->pq_K * 4 <= 24 * 1024;
+  if (pq8) {
+    static const char *force = getenv("PHNSW_ADC_TABLE");
+    if (force) pq_table = atoi(force) != 0;
+  }
+  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, pq_table ? s->pq_Q * s->pq_K : 0,
                                         tree ? kScratchBytesTree : kLandingBytes);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
@@ -253,6 +261,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.pq_Q = s->pq_Q;
   a.pq_K = s->pq_K;
   a.pq_cs = s->pq_cs;
+  a.pq_table = pq_table ? 1u : 0u;
   a.layers = ix->d_layers;
   a.n_layers = c.n_layers;
   a.mode = c.mode;

@@ -111,6 +111,9 @@ struct SearchArgs {
   uint32_t cpitch;
   const float *codebook;   // pq_K x pq_cs f32 (one codebook shared by all sub-spaces)
   uint32_t pq_Q, pq_K, pq_cs;
+  uint32_t pq_table;       // 1: per-query table in shared memory; 0: entries recomputed from the
+                           // codebook where they are used (large Q x K: the table would leave
+                           // room for two warps per SM)
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
   uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
 };
@@ -223,7 +226,8 @@ struct WarpSearch {
 
   __device__ WarpSearch(const SearchArgs &args, unsigned char *smem, uint32_t slot, int lane_)
       : a(args), lane(lane_) {
-    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0, kStageBytes);
+    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, PQ && a.pq_table ? a.pq_Q * a.pq_K : 0,
+                                        kStageBytes);
     qvec = (float *)(smem + l.off_q);
     lut = (float *)(smem + l.off_lut);
     stage = (float *)(smem + l.off_stage);
@@ -709,7 +713,51 @@ struct WarpSearch {
         }
         mbar_wait(&mbar[0], ph & 1u);
         ph ^= 1u;
-        if (active) {
+        if (active && !a.pq_table) {
+          // the table entry of (sub-space s, code c) recomputed on the spot: the same sequential
+          // f32 sum over the sub-vector that load_query() would have stored
+          const unsigned char *cb = land + lane * rstride;
+          const uint32_t cs = a.pq_cs;
+          float acc = 0.0f;
+          for (uint32_t s = 0; s < a.pq_Q; s++) {
+            const float *qs = qvec + s * cs;
+            const float *c = a.codebook + (size_t)cb[s] * cs;
+            float r = 0.0f;
+            if ((cs & 3u) == 0) {
+              for (uint32_t t = 0; t < cs; t += 4) {
+                const float4 cv = __ldg((const float4 *)(c + t));
+                const float4 qv = *(const float4 *)(qs + t);
+                if (METRIC == kL2Sqrt) {
+                  float d0 = __fsub_rn(qv.x, cv.x), d1 = __fsub_rn(qv.y, cv.y);
+                  float d2 = __fsub_rn(qv.z, cv.z), d3 = __fsub_rn(qv.w, cv.w);
+                  r = __fadd_rn(r, __fmul_rn(d0, d0));
+                  r = __fadd_rn(r, __fmul_rn(d1, d1));
+                  r = __fadd_rn(r, __fmul_rn(d2, d2));
+                  r = __fadd_rn(r, __fmul_rn(d3, d3));
+                } else {
+                  r = __fadd_rn(r, __fmul_rn(qv.x, cv.x));
+                  r = __fadd_rn(r, __fmul_rn(qv.y, cv.y));
+                  r = __fadd_rn(r, __fmul_rn(qv.z, cv.z));
+                  r = __fadd_rn(r, __fmul_rn(qv.w, cv.w));
+                }
+              }
+            } else {
+              for (uint32_t t = 0; t < cs; t++) {
+                const float cv = __ldg(&c[t]);
+                if (METRIC == kL2Sqrt) {
+                  float dlt = __fsub_rn(qs[t], cv);
+                  r = __fadd_rn(r, __fmul_rn(dlt, dlt));
+                } else {
+                  r = __fadd_rn(r, __fmul_rn(qs[t], cv));
+                }
+              }
+            }
+            acc = __fadd_rn(acc, r);
+          }
+          float d = finalize(acc);
+          if (d != d) stat |= kStatNaN;
+          bkeys[j] = make_key(d, node);
+        } else if (active) {
           const uint32_t *cw = (const uint32_t *)(land + lane * rstride);
           float acc = 0.0f;
           for (uint32_t s = 0; s < a.pq_Q; s += 4) {
@@ -1076,7 +1124,7 @@ struct WarpSearch {
       }
       __syncwarp();
       // table of partial distances: lut[s * K + k] = partial(q_s, centroid k), sequential f32
-      const uint32_t entries = a.pq_Q * a.pq_K;
+      const uint32_t entries = a.pq_table ? a.pq_Q * a.pq_K : 0;
       for (uint32_t e = lane; e < entries; e += 32) {
         const uint32_t s = e / a.pq_K, k = e - s * a.pq_K;
         const float *qs = qvec + s * a.pq_cs;
@@ -1445,7 +1493,7 @@ __global__ void __launch_bounds__((TREE && !PQ ? kTreeWarps : kSeqWarps) * 32, 1
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t warps_per_cta = blockDim.x >> 5;
-  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, PQ ? a.pq_Q * a.pq_K : 0,
+  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, PQ && a.pq_table ? a.pq_Q * a.pq_K : 0,
                                         WarpSearch<METRIC, PQ, TREE>::kStageBytes);
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
   WarpSearch<METRIC, PQ, TREE> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);

@@ -48,7 +48,11 @@ def test_kmeans_codebook_and_codes_match_oracle(ph, oracle, n, dim, cs, K, iters
 
 
 @pytest.mark.parametrize("metric_name,dim,cs,K", [("L2_SQRT", 128, 8, 256), ("COS_HALF", 64, 8, 128),
-                                                  ("ONE_MINUS_DOT", 32, 4, 256), ("COS_CLAMP", 48, 16, 32)])
+                                                  ("ONE_MINUS_DOT", 32, 4, 256), ("COS_CLAMP", 48, 16, 32),
+                                                  # Q x K x 4 B > 24 KB: no per-query table, the
+                                                  # entries are recomputed from the codebook
+                                                  ("COS_HALF", 256, 8, 256), ("L2_SQRT", 192, 4, 256),
+                                                  ("ONE_MINUS_DOT", 330, 6, 200)])
 def test_adc_search_matches_oracle(ph, oracle, metric_name, dim, cs, K):
     metric = getattr(ph, metric_name)
     n = 6000
