@@ -52,7 +52,7 @@ def test_kmeans_codebook_and_codes_match_oracle(ph, oracle, n, dim, cs, K, iters
                                                   # Q x K x 4 B > 24 KB: no per-query table, the
                                                   # entries are recomputed from the codebook
                                                   ("COS_HALF", 256, 8, 256), ("L2_SQRT", 192, 4, 256),
-                                                  ("ONE_MINUS_DOT", 330, 6, 200)])
+                                                  ("ONE_MINUS_DOT", 360, 6, 200)])
 def test_adc_search_matches_oracle(ph, oracle, metric_name, dim, cs, K):
     metric = getattr(ph, metric_name)
     n = 6000
