@@ -12,7 +12,9 @@ import parallel_hnsw_b200 as ph  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
-dim, cs, K, k = 1536, 16, 256, 10
+dim = int(sys.argv[3]) if len(sys.argv) > 3 else 1536
+cs = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+K, k = 256, 10
 g = torch.Generator(device="cuda").manual_seed(2024)
 # embedding-shaped: 2048 topic clusters on a 24-d manifold (local intrinsic dimension of text
 # embeddings is a few tens), small isotropic noise, unit norm
