@@ -130,6 +130,12 @@ phnsw_status phnsw_store_get_rows(const phnsw_store *s, const uint64_t *ids, uin
 phnsw_status phnsw_index_from_layers(phnsw_store *s, uint64_t layer_count,
                                      const phnsw_layer_desc *layers,
                                      const phnsw_build_params *bp, phnsw_index **out);
+/* The same layers over another store that holds the same VectorIds on the same device -- e.g. the
+ * PQ8-coded view (phnsw_pq8_store_create) of the vectors the graph was built on; the crate's
+ * analogue is constructing Hnsw{layers, ..} with a different Comparator over the same ids
+ * (QuantizedHnsw keeps one graph and two comparators, src/pq.rs:120-131).  Layer arrays are
+ * copied device to device; `src` stays valid. */
+phnsw_status phnsw_index_rebind(const phnsw_index *src, phnsw_store *s, phnsw_index **out);
 void phnsw_index_destroy(phnsw_index *ix);
 uint64_t phnsw_index_layer_count(const phnsw_index *ix);          /* lib.rs:644-646 */
 uint64_t phnsw_index_vector_count(const phnsw_index *ix);         /* lib.rs:592-594 */
@@ -376,11 +382,70 @@ phnsw_status phnsw_pq8_store_create(const phnsw_store *full, const float *codebo
 /* the codes, n x QUANTIZED_SIZE u8 */
 phnsw_status phnsw_pq8_store_codes(const phnsw_store *s, uint8_t *codes_out);
 
+/* QuantizedHnsw::search (src/pq.rs:346-364) on a PQ8 index as ONE call: the ADC walk over the
+ * code graph (per-query tables of partial distances in shared memory) followed by the exact
+ * re-rank of its hits with the full-precision comparator (pq.rs:354-363: compare_vec(Stored(id),
+ * v), sequential f32) and the sort by (d, id).  `ix_codes` is an index over a PQ8 store, `full`
+ * the f32 store holding the same vectors (NULL: no re-rank, ADC distances are returned).
+ * rerank_k: how many of the walk's hits are re-scored (0 = all number_of_candidates, which is
+ * what the crate does); output: up to min(hits, max_out) pairs per query, ascending (d, id).
+ * The _device variant takes HBM buffers and is asynchronous on `cuda_stream` (errors surface at
+ * phnsw_index_sync(ix_codes, stream)); the host variant stages, runs and copies back. */
+phnsw_status phnsw_pq8_search_batch(const phnsw_index *ix_codes, const phnsw_store *full,
+                                    const float *queries, uint64_t nq,
+                                    const phnsw_search_params *sp, uint64_t rerank_k,
+                                    uint64_t max_out, uint64_t *out_ids, float *out_dists,
+                                    uint32_t *out_counts);
+phnsw_status phnsw_pq8_search_batch_device(const phnsw_index *ix_codes, const phnsw_store *full,
+                                           const float *queries_device, uint64_t nq,
+                                           const phnsw_search_params *sp, uint64_t rerank_k,
+                                           uint64_t max_out, uint64_t *out_ids, float *out_dists,
+                                           uint32_t *out_counts, void *cuda_stream);
+
 /* cross-shard top-k merge by (distance, id): `shards` lists of nq x k pairs laid out
  * shard-major (the all-gather receive buffer); no reference analogue (single index) */
 phnsw_status phnsw_merge_topk_device(const uint64_t *ids, const float *dists, uint64_t shards,
                                      uint64_t nq, uint64_t k, uint64_t *out_ids,
                                      float *out_dists, void *cuda_stream);
+
+
+/* ---- multi-GPU: sharded sub-indexes (no reference analogue: the crate is one process, one
+ * index; the merged order is its result order (OrderedFloat(d), id), src/search.rs:139) ----
+ * One process per GPU, each rank owning a complete Hnsw over its own slice of the vectors.
+ * phnsw_comm wraps one NCCL communicator (NCCL is bound with dlopen at the first comm call, so
+ * single-GPU users never need it).  Rank 0 obtains an id with phnsw_comm_unique_id, the host
+ * distributes its PHNSW_COMM_ID_BYTES bytes by any means (the Rust host: its own channel; the
+ * Python host: torch.distributed / a file), every rank calls phnsw_comm_init. */
+#define PHNSW_COMM_ID_BYTES 128
+typedef struct phnsw_comm phnsw_comm;
+phnsw_status phnsw_comm_unique_id(void *id_out, uint64_t id_bytes);
+phnsw_status phnsw_comm_init(int nranks, int rank, const void *unique_id, int device,
+                             phnsw_comm **out);
+void phnsw_comm_destroy(phnsw_comm *c);
+int phnsw_comm_rank(const phnsw_comm *c);
+int phnsw_comm_nranks(const phnsw_comm *c);
+int phnsw_comm_nccl_version(void); /* NCCL_VERSION_CODE of the bound library, 0 = unavailable */
+/* bytes one rank contributes to the all-gather for nq queries x k results (ids then distances,
+ * each padded to 16 B) */
+uint64_t phnsw_comm_slice_bytes(uint64_t nq, uint64_t k);
+/* in-place sum over ranks of `count` floats in HBM (k-means across shards: centroid sums and
+ * counts); asynchronous on the stream */
+phnsw_status phnsw_comm_allreduce_sum_f32(phnsw_comm *c, float *buf_device, uint64_t count,
+                                          void *cuda_stream);
+/* One sharded search step, entirely on `cuda_stream`, no host synchronisation:
+ *   root >= 0: ncclBroadcast of queries_device (nq x dim f32, valid on `root`) to every rank;
+ *   this rank's shard is searched (Hnsw::search with `sp`; on a PQ8 index the ADC walk + exact
+ *   re-rank of phnsw_pq8_search_batch with rerank_store / rerank_k) and the kernel epilogue writes
+ *   (id + id_offset, distance) records for the best k straight into this rank's slice of the
+ *   exchange buffer; ONE ncclAllGather; merge of nranks ascending lists per query by
+ *   (distance, id) into out_ids_device / out_dists_device (nq x k, identical on every rank).
+ * Errors raised by kernels surface at phnsw_index_sync(ix, cuda_stream). */
+phnsw_status phnsw_search_batch_sharded(phnsw_comm *c, const phnsw_index *ix,
+                                        const phnsw_store *rerank_store, float *queries_device,
+                                        uint64_t nq, const phnsw_search_params *sp,
+                                        uint64_t rerank_k, uint64_t k, uint64_t id_offset, int root,
+                                        uint64_t *out_ids_device, float *out_dists_device,
+                                        void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -285,6 +285,20 @@ class Hnsw:
         return self
 
     @classmethod
+    def from_layers_codes(cls, metric, dim, n, layers, codes, codebook, cs):
+        """An index whose stored vectors exist only as PQ8 codes (ADC view, see attach_pq8): no
+        f32 rows are held, so only Unstored queries can be searched."""
+        h = lib().orc_hnsw_new(metric, dim, n, None)
+        self = cls(h, None)
+        for nodes, neighbors, M in layers:
+            nodes = np.ascontiguousarray(nodes, dtype=np.uint64)
+            neighbors = np.ascontiguousarray(neighbors, dtype=np.uint64).reshape(-1)
+            assert neighbors.size == nodes.size * M
+            lib().orc_hnsw_push_layer(h, nodes.size, M, _p(nodes, C.c_uint64),
+                                      _p(neighbors, C.c_uint64))
+        return attach_pq8(self, codes, codebook, cs)
+
+    @classmethod
     def generate(cls, metric, rows, vs=None, bp=None, seed=1, improve=True, nthreads=0):
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         if vs is None:

@@ -87,6 +87,7 @@ SIGNATURES = {
     "phnsw_store_get_rows": (C.c_int, [vp, vp, C.c_uint64, vp]),
     "phnsw_index_from_layers": (C.c_int, [vp, C.c_uint64, C.POINTER(LayerDesc),
                                           C.POINTER(BuildParams), C.POINTER(vp)]),
+    "phnsw_index_rebind": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "phnsw_index_destroy": (None, [vp]),
     "phnsw_index_layer_count": (C.c_uint64, [vp]),
     "phnsw_index_set_sum_order": (C.c_int, [vp, C.c_int]),
@@ -156,7 +157,22 @@ SIGNATURES = {
     "phnsw_pq8_store_create": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "phnsw_pq8_store_codes": (C.c_int, [vp, vp]),
     "phnsw_merge_topk_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
+    "phnsw_pq8_search_batch": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams), C.c_uint64,
+                                         C.c_uint64, vp, vp, vp]),
+    "phnsw_pq8_search_batch_device": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams),
+                                                C.c_uint64, C.c_uint64, vp, vp, vp, vp]),
+    "phnsw_comm_unique_id": (C.c_int, [vp, C.c_uint64]),
+    "phnsw_comm_init": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, C.POINTER(vp)]),
+    "phnsw_comm_destroy": (None, [vp]),
+    "phnsw_comm_rank": (C.c_int, [vp]),
+    "phnsw_comm_nranks": (C.c_int, [vp]),
+    "phnsw_comm_nccl_version": (C.c_int, []),
+    "phnsw_comm_slice_bytes": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "phnsw_comm_allreduce_sum_f32": (C.c_int, [vp, vp, C.c_uint64, vp]),
+    "phnsw_search_batch_sharded": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.POINTER(SearchParams),
+                                             C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]),
 }
+COMM_ID_BYTES = 128
 
 _lib = None
 

@@ -18,7 +18,8 @@ enum : uint32_t {
   kStatOverflowVisited = 2u,   // per-query visited spill table exhausted
   kStatMissingNode = 4u,       // candidate vector is not a node of the next layer (lib.rs:261)
   kStatNaN = 8u,               // NaN distance (OrderedFloat would panic, types.rs:83-88)
-  kStatBadNeighbor = 16u       // neighbour id out of range
+  kStatBadNeighbor = 16u,      // neighbour id out of range
+  kStatBadQuery = 32u          // stored_ids entry names no stored vector (the crate panics)
 };
 
 // A (distance, id) pair as one ordered 64-bit key: the f32 is mapped to an unsigned that

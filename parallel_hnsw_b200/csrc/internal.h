@@ -78,11 +78,13 @@ struct DevBuf {
 struct Workspace {
   DevBuf ovf, bitmap, vlog, saved, ctrl;  // ctrl: [0] work counter, [1] status
   DevBuf stage_q, stage_ids, stage_excl, out_ids, out_dists, out_counts, out_nd, out_ne;
+  DevBuf hit_ids, hit_dists, hit_counts;  // ADC hits handed from the walk to the re-rank kernel
   uint32_t slots = 0, ovf_cap = 0, vlog_cap = 0, bitmap_words = 0, cap_pad = 0;
   void release() {
     ovf.release(); bitmap.release(); vlog.release(); saved.release(); ctrl.release();
     stage_q.release(); stage_ids.release(); stage_excl.release();
     out_ids.release(); out_dists.release(); out_counts.release(); out_nd.release(); out_ne.release();
+    hit_ids.release(); hit_dists.release(); hit_counts.release();
   }
 };
 
@@ -130,7 +132,11 @@ struct phnsw_index {
                              // bitmap is allocated once and not regrown layer by layer
   uint64_t seed = 0;         // seed of the generate call (nested re-top generates derive theirs)
   uint64_t promo_count = 0;  // nested generates so far
-  mutable std::mutex mu;
+  mutable std::mutex mu;       // guards `ws` and every launch's workspace set-up
+  mutable std::mutex host_mu;  // serialises the host-staged calls (phnsw_search_batch, phnsw_knn,
+                               // phnsw_threshold_nn, ...): they share stream 0's staging buffers
+                               // and status word, and `search(&self)` may be called from many
+                               // threads at once (the crate's callers use rayon par_iter)
   mutable std::map<cudaStream_t, phnsw::Workspace> ws;
 };
 
@@ -149,6 +155,7 @@ struct SearchCall {
   float *out_dists = nullptr;
   uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr, *out_selfhit = nullptr;
   uint32_t selfhit_eps = 0;  // out_selfhit by search::match_within_epsilon
+  uint64_t id_offset = 0;    // added to every emitted VectorId (sharded search)
 };
 
 // the three kernel variants (search_seq.cu, search_tree.cu, search_pq.cu)

@@ -215,12 +215,11 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   if (ix->expect_nodes < 0x7FFFFFFFull) max_nodes = std::max(max_nodes, ix->expect_nodes);
   const uint32_t need_words = (uint32_t)((max_nodes + 31) / 32);
 
-  Workspace *wsp;
-  {
-    std::lock_guard<std::mutex> g(ix->mu);
-    wsp = &ix->ws[stream];
-  }
-  Workspace &ws = *wsp;
+  // the workspace of a stream is set up and handed to the kernel under the index lock: launches
+  // from different host threads (different streams, or the serialised host-staged calls) never
+  // see a half-grown buffer
+  std::lock_guard<std::mutex> g(ix->mu);
+  Workspace &ws = ix->ws[stream];
   if (!ws.ctrl.p) {
     PH_CUDA(ws.ctrl.reserve(64));
     PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64, stream));
@@ -295,6 +294,8 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.vlog_cap = ix->vlog_cap;
   a.saved = ws.saved.as<uint64_t>();
   a.cap_pad = cap_pad;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
+  a.n_vectors = (uint32_t)s->n;
+  a.out_id_offset = c.id_offset;
 
   const size_t smem = (size_t)lay.total * w;
   cudaError_t e = pq8    ? launch_search_pq(s->metric, a, grid, w * 32, smem, stream)
@@ -338,6 +339,10 @@ static phnsw_status status_from_bits(uint32_t st) {
   }
   if (st & kStatNaN) {
     set_error("search: NaN distance (OrderedFloat would panic, types.rs:83-88)");
+    return PHNSW_ERR_INVALID;
+  }
+  if (st & kStatBadQuery) {
+    set_error("search: a stored_ids entry names no stored vector (Comparator::lookup would panic)");
     return PHNSW_ERR_INVALID;
   }
   set_error("search: per-query scratch overflow (status 0x%x); raise it with "
@@ -757,6 +762,47 @@ phnsw_status phnsw_index_from_layers(phnsw_store *s, uint64_t layer_count,
   return PHNSW_OK;
 }
 
+// the same graph over another store of the same vectors: layer arrays copied device to device
+phnsw_status phnsw_index_rebind(const phnsw_index *src, phnsw_store *s, phnsw_index **out) {
+  PH_ENTRY();
+  if (!src || !s || !out) return PHNSW_ERR_INVALID;
+  *out = nullptr;
+  if (s->n != src->store->n || s->device != src->store->device) {
+    set_error("index_rebind: the new store must hold the same %llu vectors on the same device",
+              (unsigned long long)src->store->n);
+    return PHNSW_ERR_INVALID;
+  }
+  phnsw_index *ix = nullptr;
+  phnsw_status rc = index_create_empty(s, &src->bp, &ix);
+  if (rc != PHNSW_OK) return rc;
+  for (size_t i = 0; i < src->layers.size() && rc == PHNSW_OK; i++) {
+    const LayerStore &l = src->layers[i];
+    const size_t nn = (size_t)l.node_count * l.M;
+    uint32_t *d_nodes = nullptr, *d_nb = nullptr;
+    cudaError_t e = cudaMalloc(&d_nodes, std::max<size_t>(l.node_count, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_nb, std::max<size_t>(nn, 1) * 4);
+    if (e == cudaSuccess && l.node_count)
+      e = cudaMemcpy(d_nodes, l.nodes, l.node_count * 4, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess && nn) e = cudaMemcpy(d_nb, l.neighbors, nn * 4, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "index_rebind copy");
+    if (rc == PHNSW_OK) rc = index_push_layer_device(ix, l.node_count, l.M, d_nodes, d_nb);
+    if (rc != PHNSW_OK) {
+      if (d_nodes) cudaFree(d_nodes);
+      if (d_nb) cudaFree(d_nb);
+    }
+  }
+  if (rc == PHNSW_OK) rc = upload_layer_tables(ix);
+  if (rc != PHNSW_OK) {
+    phnsw_index_destroy(ix);
+    return rc;
+  }
+  ix->sum_order = src->sum_order;
+  ix->vlog_cap = src->vlog_cap;
+  ix->ovf_cap = src->ovf_cap;
+  *out = ix;
+  return PHNSW_OK;
+}
+
 void phnsw_index_destroy(phnsw_index *ix) {
   PH_ENTRY();
   if (!ix) return;
@@ -904,6 +950,7 @@ phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
     return PHNSW_ERR_NO_DEVICE;
   }
   PH_CUDA(cudaSetDevice(ix->store->device));
+  std::lock_guard<std::mutex> host_guard(ix->host_mu);
   cudaStream_t st = 0;  // legacy default stream of this thread's context
   // Page-locked host buffers are used in place: the kernel reads each query once straight from
   // host memory and writes its results straight back (unified addressing), so neither copy sits
@@ -992,6 +1039,7 @@ phnsw_status phnsw_knn(const phnsw_index *ix, uint64_t k, uint64_t probe_depth, 
     return PHNSW_ERR_INVALID;
   }
   PH_CUDA(cudaSetDevice(ix->store->device));
+  std::lock_guard<std::mutex> host_guard(ix->host_mu);
   cudaStream_t st = 0;
   Workspace *wsp;
   {
@@ -1047,6 +1095,7 @@ phnsw_status phnsw_threshold_nn(const phnsw_index *ix, float threshold, uint64_t
   if (!offs) return PHNSW_ERR_INVALID;
   std::vector<uint64_t> ids;
   std::vector<float> ds;
+  std::lock_guard<std::mutex> host_guard(ix->host_mu);
   if (initial_search_depth > 0) {
     PH_CUDA(cudaSetDevice(ix->store->device));
     cudaStream_t st = 0;

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128)
 rerank_kernel(const float *rows, uint32_t pitch, const float *queries, uint32_t qdim,
               const uint64_t *hit_ids, const uint32_t *hit_cnt, uint32_t hit_pitch, uint32_t nq,
               uint32_t max_out, uint64_t *out_ids, float *out_dists, uint32_t *out_counts,
-              uint32_t P /* pow2 >= hit_pitch */, uint32_t *status) {
+              uint32_t P /* pow2 >= hit_pitch */, uint32_t *status, uint64_t id_offset) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -133,7 +133,7 @@ rerank_kernel(const float *rows, uint32_t pitch, const float *queries, uint32_t 
   const uint32_t n_out = min(cnt, max_out);
   for (uint32_t i = lane; i < max_out; i += 32) {
     uint64_t k = i < n_out ? keys[i] : 0;
-    out_ids[(size_t)q * max_out + i] = i < n_out ? (uint64_t)(uint32_t)k : ~0ull;
+    out_ids[(size_t)q * max_out + i] = i < n_out ? (uint64_t)(uint32_t)k + id_offset : ~0ull;
     out_dists[(size_t)q * max_out + i] = i < n_out ? key_dist(k) : 3.4028234663852886e38f;
   }
   if (out_counts && lane == 0) out_counts[q] = n_out;
@@ -232,7 +232,8 @@ template <int METRIC>
 static cudaError_t launch_rerank(const phnsw_store *full, const float *queries, const uint64_t *hit_ids,
                                  const uint32_t *hit_cnt, uint32_t hit_pitch, uint32_t nq,
                                  uint32_t max_out, uint64_t *out_ids, float *out_dists,
-                                 uint32_t *out_counts, uint32_t *status, int max_smem) {
+                                 uint32_t *out_counts, uint32_t *status, int max_smem,
+                                 cudaStream_t st = 0, uint64_t id_offset = 0) {
   uint32_t P = 32;
   while (P < hit_pitch) P <<= 1;
   const uint32_t qb = (full->pitch * 4 + 15) / 16 * 16;
@@ -243,10 +244,95 @@ static cudaError_t launch_rerank(const phnsw_store *full, const float *queries, 
   cudaError_t e = cudaFuncSetAttribute(rerank_kernel<METRIC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  rerank_kernel<METRIC><<<(nq + w - 1) / w, w * 32, smem>>>(
+  rerank_kernel<METRIC><<<(nq + w - 1) / w, w * 32, smem, st>>>(
       full->rows, full->pitch, queries, (uint32_t)full->dim, hit_ids, hit_cnt, hit_pitch, nq, max_out,
-      out_ids, out_dists, out_counts, P, status);
+      out_ids, out_dists, out_counts, P, status, id_offset);
   return cudaGetLastError();
+}
+
+// ADC walk over a PQ8 index + exact re-rank of its first `rerank_k` hits against `full` -- the
+// second half of QuantizedHnsw::search (pq.rs:354-363) -- as one stream-ordered sequence: the
+// walk writes its hits into the stream's workspace, the re-rank kernel reads them there.
+// rerank_k = 0 re-ranks every hit (number_of_candidates, as the crate does); full = null skips
+// the re-rank (ADC distances out).  `id_offset` is added to every emitted id.
+phnsw_status pq8_search_device(const phnsw_index *ix, const phnsw_store *full, const float *queries,
+                               uint64_t nq, const phnsw_search_params *sp, uint64_t rerank_k,
+                               uint64_t max_out, uint64_t id_offset, uint64_t *out_ids,
+                               float *out_dists, uint32_t *out_counts, cudaStream_t st) {
+  if (!ix || !sp || !queries || !out_ids || !out_dists || max_out == 0 || ix->layers.empty() ||
+      sp->number_of_candidates == 0 || sp->number_of_candidates > 4096 || sp->probe_depth == 0) {
+    set_error("pq8_search: bad arguments (1 <= number_of_candidates <= 4096)");
+    return PHNSW_ERR_INVALID;
+  }
+  const phnsw_store *cs = ix->store;
+  if (!cs->is_pq8()) {
+    set_error("pq8_search: the index is not built over a PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
+  if (full && (!full->rows || full->n != cs->n || full->dim != cs->dim || full->device != cs->device)) {
+    set_error("pq8_search: the re-rank store must hold the same vectors as the PQ8 store");
+    return PHNSW_ERR_INVALID;
+  }
+  if (nq == 0) return PHNSW_OK;
+  PH_CUDA(cudaSetDevice(cs->device));
+  const uint32_t ef = (uint32_t)sp->number_of_candidates;
+  SearchCall c;
+  c.mode = 0;
+  c.queries = queries;
+  c.qpitch = (uint32_t)cs->dim;
+  c.nq = (uint32_t)nq;
+  c.cap = ef;
+  c.upper = (uint32_t)std::min<uint64_t>(sp->upper_layer_candidate_count, 0xFFFFFFFFull);
+  c.probe = (uint32_t)std::min<uint64_t>(sp->probe_depth, 0xFFFFFFFFull);
+  c.n_layers = (uint32_t)ix->layers.size();
+  if (!full) {
+    c.max_out = (uint32_t)max_out;
+    c.out_ids = out_ids;
+    c.out_dists = out_dists;
+    c.out_counts = out_counts;
+    c.id_offset = id_offset;
+    return launch_search(ix, c, st);
+  }
+  const uint32_t hits = (uint32_t)std::min<uint64_t>(ef, rerank_k ? rerank_k : ef);
+  uint64_t *hi;
+  float *hd;
+  uint32_t *hc, *status;
+  {
+    std::lock_guard<std::mutex> g(ix->mu);
+    Workspace &ws = ix->ws[st];
+    if (ws.hit_ids.bytes < nq * hits * 8 || ws.hit_dists.bytes < nq * hits * 4 ||
+        ws.hit_counts.bytes < nq * 4 || !ws.ctrl.p) {
+      PH_CUDA(cudaStreamSynchronize(st));
+      PH_CUDA(ws.hit_ids.reserve(nq * hits * 8));
+      PH_CUDA(ws.hit_dists.reserve(nq * hits * 4));
+      PH_CUDA(ws.hit_counts.reserve(nq * 4));
+      if (!ws.ctrl.p) {
+        PH_CUDA(ws.ctrl.reserve(64));
+        PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64, st));
+      }
+    }
+    hi = ws.hit_ids.as<uint64_t>();
+    hd = ws.hit_dists.as<float>();
+    hc = ws.hit_counts.as<uint32_t>();
+    status = ws.ctrl.as<uint32_t>() + 1;
+  }
+  c.max_out = hits;
+  c.out_ids = hi;
+  c.out_dists = hd;
+  c.out_counts = hc;
+  phnsw_status rc = launch_search(ix, c, st);
+  if (rc != PHNSW_OK) return rc;
+  cudaError_t e;
+  const int max_smem = ix->max_smem;
+  const uint32_t mo = (uint32_t)max_out;
+  switch (full->metric) {
+    case kCosHalf: e = launch_rerank<kCosHalf>(full, queries, hi, hc, hits, (uint32_t)nq, mo, out_ids, out_dists, out_counts, status, max_smem, st, id_offset); break;
+    case kOneMinusDot: e = launch_rerank<kOneMinusDot>(full, queries, hi, hc, hits, (uint32_t)nq, mo, out_ids, out_dists, out_counts, status, max_smem, st, id_offset); break;
+    case kL2Sqrt: e = launch_rerank<kL2Sqrt>(full, queries, hi, hc, hits, (uint32_t)nq, mo, out_ids, out_dists, out_counts, status, max_smem, st, id_offset); break;
+    default: e = launch_rerank<kCosClamp>(full, queries, hi, hc, hits, (uint32_t)nq, mo, out_ids, out_dists, out_counts, status, max_smem, st, id_offset); break;
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "rerank_kernel launch");
+  return PHNSW_OK;
 }
 
 }  // namespace phnsw
@@ -571,6 +657,8 @@ phnsw_status phnsw_pq_search_batch(const phnsw_pq *pq, const float *queries, con
   if (!nq) return PHNSW_OK;
   const phnsw_store *full = pq->full;
   PH_CUDA(cudaSetDevice(full->device));
+  // one host-staged call at a time per quantized index (shared stream-0 status word)
+  std::lock_guard<std::mutex> host_guard(pq->index->host_mu);
   const uint32_t ef = (uint32_t)sp->number_of_candidates;
   float *raw = nullptr, *recon = nullptr, *hd = nullptr, *od = nullptr;
   uint64_t *sid = nullptr, *hi = nullptr, *oi = nullptr;
@@ -634,6 +722,63 @@ phnsw_status phnsw_pq_search_batch(const phnsw_pq *pq, const float *queries, con
   for (void *b : bufs)
     if (b) cudaFree(b);
   return rc;
+}
+
+// ADC search over a PQ8 index + exact re-rank, every buffer in HBM, asynchronous on `cuda_stream`
+phnsw_status phnsw_pq8_search_batch_device(const phnsw_index *ix_codes, const phnsw_store *full,
+                                           const float *queries_device, uint64_t nq,
+                                           const phnsw_search_params *sp, uint64_t rerank_k,
+                                           uint64_t max_out, uint64_t *out_ids, float *out_dists,
+                                           uint32_t *out_counts, void *cuda_stream) {
+  PH_ENTRY();
+  return pq8_search_device(ix_codes, full, queries_device, nq, sp, rerank_k, max_out, 0, out_ids,
+                           out_dists, out_counts, (cudaStream_t)cuda_stream);
+}
+
+// same from host buffers (staged through the index's stream-0 workspace), synchronous
+phnsw_status phnsw_pq8_search_batch(const phnsw_index *ix_codes, const phnsw_store *full,
+                                    const float *queries, uint64_t nq,
+                                    const phnsw_search_params *sp, uint64_t rerank_k,
+                                    uint64_t max_out, uint64_t *out_ids, float *out_dists,
+                                    uint32_t *out_counts) {
+  PH_ENTRY();
+  if (!ix_codes || !queries || !out_ids || !out_dists || !sp || max_out == 0) {
+    set_error("pq8_search_batch: bad arguments");
+    return PHNSW_ERR_INVALID;
+  }
+  if (nq == 0) return PHNSW_OK;
+  if (phnsw_device_count() == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return PHNSW_ERR_NO_DEVICE;
+  }
+  const phnsw_index *ix = ix_codes;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  std::lock_guard<std::mutex> host_guard(ix->host_mu);
+  cudaStream_t st = 0;
+  const uint64_t dim = ix->store->dim;
+  float *dq;
+  uint64_t *oi;
+  float *od;
+  uint32_t *oc;
+  {
+    std::lock_guard<std::mutex> g(ix->mu);
+    Workspace &ws = ix->ws[st];
+    PH_CUDA(ws.stage_q.reserve(nq * dim * 4));
+    PH_CUDA(ws.out_ids.reserve(nq * max_out * 8));
+    PH_CUDA(ws.out_dists.reserve(nq * max_out * 4));
+    PH_CUDA(ws.out_counts.reserve(nq * 4));
+    dq = ws.stage_q.as<float>();
+    oi = ws.out_ids.as<uint64_t>();
+    od = ws.out_dists.as<float>();
+    oc = ws.out_counts.as<uint32_t>();
+  }
+  PH_CUDA(cudaMemcpyAsync(dq, queries, nq * dim * 4, cudaMemcpyHostToDevice, st));
+  phnsw_status rc = pq8_search_device(ix, full, dq, nq, sp, rerank_k, max_out, 0, oi, od, oc, st);
+  if (rc != PHNSW_OK) return rc;
+  PH_CUDA(cudaMemcpyAsync(out_ids, oi, nq * max_out * 8, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaMemcpyAsync(out_dists, od, nq * max_out * 4, cudaMemcpyDeviceToHost, st));
+  if (out_counts) PH_CUDA(cudaMemcpyAsync(out_counts, oc, nq * 4, cudaMemcpyDeviceToHost, st));
+  return sync_status(ix, st);
 }
 
 }  // extern "C"

@@ -116,6 +116,9 @@ struct SearchArgs {
                            // room for two warps per SM)
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
   uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
+  uint32_t n_vectors;      // rows of the store: stored_ids / exclude are checked against it
+  uint64_t out_id_offset;  // added to every emitted VectorId (sharded search: shard-local ->
+                           // global ids straight from the kernel epilogue); empty slots stay !0
 };
 
 // per-warp shared memory carve-up (bytes); shared by host (launch size) and device
@@ -1104,7 +1107,13 @@ struct WarpSearch {
   }
 
   // ------------------------------------------------------------------ whole-query drivers
-  __device__ void load_query(uint32_t q) {
+  // false: the query names a stored vector that does not exist (the crate panics on an unknown
+  // VectorId); the status word is raised and the query is skipped
+  __device__ bool load_query(uint32_t q) {
+    if (a.stored_ids && a.stored_ids[q] >= (uint64_t)a.n_vectors) {
+      stat |= kStatBadQuery;
+      return false;
+    }
     if (PQ) {
       if (a.queries) {
         const float *src = a.queries + (size_t)q * a.qpitch;
@@ -1142,7 +1151,7 @@ struct WarpSearch {
         lut[e] = r;
       }
       __syncwarp();
-      return;
+      return true;
     }
     const float *src;
     if (a.queries) {
@@ -1159,6 +1168,17 @@ struct WarpSearch {
       for (uint32_t i = lane; i < a.dim_pad; i += 32) qvec[i] = src[i];
     }
     __syncwarp();
+    return true;
+  }
+  // outputs of a skipped query: no results
+  __device__ void emit_nothing(uint32_t q) {
+    if (a.out_ids)
+      for (uint32_t i = lane; i < a.max_out; i += 32) {
+        a.out_ids[(size_t)q * a.max_out + i] = ~0ull;
+        a.out_dists[(size_t)q * a.max_out + i] = 3.4028234663852886e38f;
+      }
+    if (a.out_counts && lane == 0) a.out_counts[q] = 0;
+    if (a.out_selfhit && lane == 0) a.out_selfhit[q] = 0;
   }
 
   // emit the `want` smallest pool entries in ascending order through f(rank, key); entries are
@@ -1270,8 +1290,11 @@ struct WarpSearch {
 
   // search_layers_instrumented, src/search.rs:93-140
   __device__ void run_search(uint32_t q) {
+    // an excluded id that names no stored vector matches nothing (and must not alias one by
+    // truncation to 32 bits)
     const uint32_t excl =
-        a.exclude ? (a.exclude[q] == ~0ull ? kEmpty32 : (uint32_t)a.exclude[q]) : kEmpty32;
+        a.exclude ? (a.exclude[q] >= (uint64_t)a.n_vectors ? kEmpty32 : (uint32_t)a.exclude[q])
+                  : kEmpty32;
     uint32_t nd_l = 0, ne_l = 0;
     // entry vector = first node of the top layer (search.rs:9-11, 101-111)
     {
@@ -1357,8 +1380,9 @@ struct WarpSearch {
     if (a.out_ids) {
       uint64_t *oi = a.out_ids + (size_t)q * a.max_out;
       float *od = a.out_dists + (size_t)q * a.max_out;
+      const uint64_t idoff = a.out_id_offset;
       n_out = emit_smallest(a.max_out, [&](uint32_t r, uint64_t k) {
-        oi[r] = (uint64_t)(uint32_t)k;
+        oi[r] = (uint64_t)(uint32_t)k + idoff;
         od[r] = key_dist(k);
       });
       for (uint32_t i = n_out + lane; i < a.max_out; i += 32) {
@@ -1509,7 +1533,10 @@ __global__ void __launch_bounds__((TREE && !PQ ? kTreeWarps : kSeqWarps) * 32, 1
     if (q >= a.nq) break;
     ws.cap = a.cap;
     ws.len = 0;
-    ws.load_query(q);
+    if (!ws.load_query(q)) {
+      ws.emit_nothing(q);
+      continue;
+    }
     if (MODE == 0) ws.run_search(q);
     else if (MODE == 1) ws.run_knn(q);
     else ws.run_threshold(q);

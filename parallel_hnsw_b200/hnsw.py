@@ -206,6 +206,13 @@ class Hnsw:
                                             int(improve), cb, None, C.byref(h)))
         return cls(h, comparator)
 
+    def rebind(self, comparator):
+        """The same layers over another comparator holding the same VectorIds (e.g. the
+        Pq8Comparator view of this index's vectors); copies device to device."""
+        h = C.c_void_p()
+        N.check(N.lib().phnsw_index_rebind(self._h, comparator._h, C.byref(h)))
+        return Hnsw(h, comparator)
+
     @classmethod
     def deserialize(cls, path, device=0):
         """Hnsw::deserialize (src/lib.rs:1693-1699, src/serialize.rs:126-209)."""
@@ -331,6 +338,32 @@ class Hnsw:
 
     def sync(self, stream=None):
         N.check(N.lib().phnsw_index_sync(self._h, C.c_void_p(stream or 0)))
+
+    def adc_search(self, queries, sp=None, rerank=None, rerank_k=0, max_out=None):
+        """QuantizedHnsw::search (src/pq.rs:346-364) on an index over a Pq8Comparator, one
+        library call: ADC walk of the code graph, exact re-rank of its first `rerank_k` hits
+        (0 = all, as the crate does) against `rerank` (the f32 BigComparator of the same vectors;
+        None = ADC distances out), sorted by (d, id).  Host numpy in -> host numpy out."""
+        sp = sp or SearchParameters()
+        queries = _host(np.atleast_2d(queries), np.float32)
+        nq = queries.shape[0]
+        max_out = int(max_out or sp.number_of_candidates)
+        ids = np.empty((nq, max_out), dtype=np.uint64)
+        ds = np.empty((nq, max_out), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        N.check(N.lib().phnsw_pq8_search_batch(
+            self._h, rerank._h if rerank is not None else None, _ptr(queries), nq, C.byref(sp),
+            rerank_k, max_out, _ptr(ids), _ptr(ds), _ptr(cnt)))
+        return ids, ds, cnt
+
+    def adc_search_device(self, queries, sp, out_ids, out_dists, out_counts=None, rerank=None,
+                          rerank_k=0, max_out=None, stream=None):
+        """Asynchronous variant of adc_search: every buffer is a CUDA tensor."""
+        max_out = int(max_out or out_ids.shape[1])
+        N.check(N.lib().phnsw_pq8_search_batch_device(
+            self._h, rerank._h if rerank is not None else None, _ptr(queries), queries.shape[0],
+            C.byref(sp), rerank_k, max_out, _ptr(out_ids), _ptr(out_dists), _ptr(out_counts),
+            C.c_void_p(stream or 0)))
 
     def knn(self, k, probe_depth):
         """Hnsw::knn (src/lib.rs:905-928): rows follow bottom-layer node order."""

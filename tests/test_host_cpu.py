@@ -85,6 +85,21 @@ def test_no_device_is_loud_not_a_fallback(ph):
     assert "no CPU fallback" in str(e.value)
 
 
+def test_comm_entry_points_without_a_device(ph):
+    """Layout arithmetic needs no device; creating a communicator without one is loud."""
+    from parallel_hnsw_b200 import _native as N
+    L = N.lib()
+    # ids (nq*k u64) then distances (nq*k f32), each padded to 16 B
+    assert L.phnsw_comm_slice_bytes(10000, 10) == 10000 * 10 * 12
+    assert L.phnsw_comm_slice_bytes(3, 1) == 32 + 16
+    assert L.phnsw_comm_rank(None) == -1 and L.phnsw_comm_nranks(None) == 0
+    if ph.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    assert L.phnsw_comm_init(1, 0, None, 0, C.byref(h)) == 2  # PHNSW_ERR_NO_DEVICE
+    assert L.phnsw_comm_init(2, 5, None, 0, C.byref(h)) == 1  # bad rank: PHNSW_ERR_INVALID
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "parallel_hnsw_b200")
     for dirpath, _, files in os.walk(pkg):
@@ -124,6 +139,9 @@ def _worker(rank, world, port, tmp):
     d[3, 7:] = np.float32(3.4028235e38)
     gid = sharded.to_global_ids(torch.from_numpy(ids), rank * n_shard)
     assert int(gid[3, 8]) == -1 and int(gid[0, 0]) == int(ids[0, 0]) + rank * n_shard
+    # the NCCL unique id of the library's communicator travels over the host's process group
+    uid = sharded.exchange_unique_id(lambda: bytes(range(128)), rank, world)
+    assert uid == bytes(range(128))
     gi, gd = sharded.gather_topk(gid, torch.from_numpy(d), world)
     assert gi.shape == (world, nq, k)
     assert np.array_equal(gi[rank].numpy(), gid.numpy())  # shard-major layout
