@@ -353,6 +353,12 @@ def main():
                     help="secondary blocks: auto | none | comma list of config3,sharded,config5")
     ap.add_argument("--block-timeout", type=int, default=700,
                     help="seconds the secondary blocks may take before the headline line is printed without them")
+    ap.add_argument("--adc-table", default="q8", choices=["q8", "f32"],
+                    help="per-query ADC table form of the timed ADC blocks (include/phnsw.h "
+                         "phnsw_pq8_store_set_adc_table); the other form is reported beside it")
+    ap.add_argument("--c5-rerank", type=int, default=300,
+                    help="config 5: ADC hits re-scored exactly per shard (300 = all candidates, "
+                         "what the crate's QuantizedHnsw::search does)")
     ap.add_argument("--c3-n", type=int, default=1000000)
     ap.add_argument("--c4-n", type=int, default=10000000, help="config 4: total vectors over all ranks")
     ap.add_argument("--c5-n", type=int, default=12500000, help="config 5: vectors per rank")
@@ -771,6 +777,8 @@ def run_config3(ctx):
     torch.cuda.synchronize()
     t_encode = time.perf_counter() - t0
     enc_stats = ph.assign_last_stats()
+    table = ph.ADC_TABLE_Q8 if args.adc_table == "q8" else ph.ADC_TABLE_F32
+    pq.set_adc_table(table)
     gh = full.rebind(pq)
     full.set_sum_order(ph.SUM_TREE)
     L = gh.layer_count()
@@ -827,6 +835,14 @@ def run_config3(ctx):
         e2e()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
     assert np.array_equal(hi.numpy(), rr_ids), "config3: host path and device path disagree"
+    # the other table form, same call (secondary)
+    other = ph.ADC_TABLE_F32 if table == ph.ADC_TABLE_Q8 else ph.ADC_TABLE_Q8
+    pq.set_adc_table(other)
+    oi2, od2 = torch.empty_like(oi), torch.empty_like(od)
+    ms_other = tm.run(lambda: gh.adc_search_device(q, sp, oi2, od2, oc, rerank=comp, rerank_k=rerank_k,
+                                                   stream=stream), steps, 3, lambda: gh.sync(stream))
+    rec_other = recall_at_k(oi2.cpu().numpy(), gt, k)
+    pq.set_adc_table(table)
 
     # parity sample against the CPU oracle: the ADC walk (oracle's ADC definition on the same
     # graph, codes and codebook) bit for bit, and the re-ranked distances against the crate's
@@ -845,7 +861,13 @@ def run_config3(ctx):
         "queries_per_step": nq,
         "value": nq / (ms_adc * 1e-3), "unit": "queries/s", "ms_per_step": ms_adc,
         "what": "phnsw_pq8_search_batch_device: ADC walk + exact re-rank inside the timed region",
+        "adc_table": args.adc_table + (" (per-query tables quantised to u8 by a pre-pass kernel, "
+                                       "24 KB per query in flight, integer sums)" if table == ph.ADC_TABLE_Q8
+                                       else " (exact f32 entries)"),
         "recall_at_10": rec_adc,
+        "other_table_form": {"adc_table": "f32" if table == ph.ADC_TABLE_Q8 else "q8",
+                             "value": nq / (ms_other * 1e-3), "ms_per_step": ms_other,
+                             "recall_at_10": rec_other},
         "adc_walk_only": {"value": nq / (ms_walk * 1e-3), "ms_per_step": ms_walk,
                           "recall_at_10_before_rerank": rec_adc_raw},
         "full_precision": {"value": nq / (ms_full * 1e-3), "ms_per_step": ms_full,
@@ -861,6 +883,7 @@ def run_config3(ctx):
                      "n_dist_per_query": float(ndist.sum() / nq),
                      "n_exp_per_query": float(nexp.sum() / nq),
                      "lut_flops_per_query": 2.0 * dim * K,
+                     "walk_includes": "the table pre-pass kernel (adc_lut_q8_kernel) when adc_table = q8",
                      "note": "96 B of codes per distance: the walk is bound by dependent latencies "
                              "and table arithmetic, not by HBM"},
         "build": {"graph_seconds": t_build, "graph_vectors_per_s": n / t_build,
@@ -891,6 +914,7 @@ def config3_parity(ctx, gh, pq, cb, cs, dim, n, q, sp, adc_ids, adc_ds, ndist, n
     sq = min(200, q.shape[0])
     codes = pq.codes()
     oh = orc.Hnsw.from_layers_codes(orc.COS_HALF, dim, n, gh.layers(), codes, cb, cs)
+    orc.attach_pq8(oh, codes, cb, cs, table=pq.adc_table())
     qh = q[:sq].cpu().numpy()
     o = oh.search(queries=qh, sp=orc.search_params(args.ef, args.ef, 2), max_out=rerank_k,
                   stats=True, nthreads=host_cores())
@@ -1153,13 +1177,13 @@ def run_config5(ctx):
     """BASELINE configs[4]: world x 12.5M x 128 (100M over 8 GPUs), generated shard by shard in
     HBM, PQ8-coded (centroid_size 8 -> 16 u8 codes per vector, K = 256).  Per rank: f32 rows are
     kept (6.4 GB of 180 GB) for the graph build and for the exact re-rank; the search walks the
-    16 B/vector codes with per-query tables in shared memory (ADC), re-ranks 100 hits against
+    16 B/vector codes with per-query tables in shared memory (ADC), re-ranks its hits against
     the f32 rows, and the sharded exchange merges the per-shard top-10.  One batch of 10 000
     queries per step."""
     torch, dist, ph, dev, k = ctx["torch"], ctx["dist"], ctx["ph"], ctx["dev"], ctx["k"]
     args, stream, rank, world, peaks = ctx["args"], ctx["stream"], ctx["rank"], ctx["world"], ctx["peaks"]
     from parallel_hnsw_b200.sharded import ShardedHnsw
-    n_shard, dim, cs, K, nq, rerank_k = args.c5_n, 128, 8, 256, args.nq, 100
+    n_shard, dim, cs, K, nq, rerank_k = args.c5_n, 128, 8, 256, args.nq, args.c5_rerank
     mix = mixture_for("sift", dev)
     t0 = time.perf_counter()
     rows = mix.rows(n_shard, 100 + rank)
@@ -1181,6 +1205,7 @@ def run_config5(ctx):
     torch.cuda.synchronize()
     t_encode = time.perf_counter() - t0
     enc_stats = ph.assign_last_stats()
+    pq.set_adc_table(ph.ADC_TABLE_Q8 if args.adc_table == "q8" else ph.ADC_TABLE_F32)
     gh = full.rebind(pq)
     full.close()
     sp = ph.SearchParameters(args.ef, args.ef, 2)
@@ -1233,6 +1258,7 @@ def run_config5(ctx):
                          "codes %.2f GB, graph (u32) %.1f GB" % (
                              n_shard * dim * 4 / 1e9, n_shard * 16 / 1e9, n_shard * 48 * 4 / 1e9),
             "shards": world, "vectors_total": n_shard * world, "queries_per_step": nq,
+            "adc_table": args.adc_table,
             "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
             "recall_at_10": rec,
             "single_shard": {"value": nq / (ms_local_max * 1e-3), "ms_per_step": ms_local_max,
@@ -1267,7 +1293,9 @@ def shard_parity_adc(ctx, gh, pq, cb, cs, dim, n, q_h, adc_ids, adc_ds, ndist, n
     from oracle import oracle as orc
     args = ctx["args"]
     sq = min(200, q_h.shape[0])
-    oh = orc.Hnsw.from_layers_codes(orc.L2_SQRT, dim, n, gh.layers(), pq.codes(), cb, cs)
+    codes = pq.codes()
+    oh = orc.Hnsw.from_layers_codes(orc.L2_SQRT, dim, n, gh.layers(), codes, cb, cs)
+    orc.attach_pq8(oh, codes, cb, cs, table=pq.adc_table())
     o = oh.search(queries=q_h[:sq], sp=orc.search_params(args.ef, args.ef, 2), max_out=adc_ids.shape[1],
                   stats=True, nthreads=host_cores())
     return {"sample_queries": sq, "shard": 0,

@@ -381,6 +381,20 @@ phnsw_status phnsw_pq8_store_create(const phnsw_store *full, const float *codebo
                                     uint64_t centroid_size, phnsw_store **out);
 /* the codes, n x QUANTIZED_SIZE u8 */
 phnsw_status phnsw_pq8_store_codes(const phnsw_store *s, uint8_t *codes_out);
+/* Form of the per-query table the ADC walk keeps in shared memory (set before searching; not
+ * while a search on the store is in flight).  No crate analogue; both forms are defined by the
+ * oracle (adc_build_lut / adc_build_lut_q8) and reproduced bit for bit.
+ *   PHNSW_ADC_TABLE_F32 (default): table[s][k] = partial distance, sequential f32; a distance is
+ *     the in-order f32 sum of QUANTIZED_SIZE entries.  Q x K x 4 bytes per query in flight.
+ *   PHNSW_ADC_TABLE_Q8: the same entries quantised per query to u8 ("fast scan"): lo[s] = row
+ *     minimum, delta = (largest row range) / 255, table[s][k] = rint((entry - lo[s]) / delta),
+ *     distance = finalize(sum_s lo[s] + delta * (integer sum of the entries)).  Q x K bytes per
+ *     query in flight -- 24 KB instead of 96 KB at 96 sub-spaces x 256 centroids -- and integer
+ *     sums; meant to be followed by the exact re-rank of phnsw_pq8_search_batch. */
+#define PHNSW_ADC_TABLE_F32 0
+#define PHNSW_ADC_TABLE_Q8 1
+phnsw_status phnsw_pq8_store_set_adc_table(phnsw_store *s, int table);
+int phnsw_pq8_store_adc_table(const phnsw_store *s); /* -1: not a PQ8 store */
 
 /* QuantizedHnsw::search (src/pq.rs:346-364) on a PQ8 index as ONE call: the ADC walk over the
  * code graph (per-query tables of partial distances in shared memory) followed by the exact

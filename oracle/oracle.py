@@ -173,6 +173,7 @@ def lib():
     L.orc_pq8_train.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                 C.c_uint64, f32p, C.c_int]
     L.orc_hnsw_set_pq8.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint64, f32p]
+    L.orc_hnsw_set_adc_table.argtypes = [C.c_void_p, C.c_int]
     L.orc_pq_search.restype = C.c_int
     L.orc_pq_search.argtypes = [C.c_void_p, f32p, u64p, C.c_uint64, C.POINTER(SearchParams),
                                 C.c_uint64, u64p, f32p, u32p, C.c_int]
@@ -644,12 +645,14 @@ def pq8_encode(rows, codebook, cs, nthreads=0):
     return codes
 
 
-def attach_pq8(hnsw, codes, codebook, cs):
+def attach_pq8(hnsw, codes, codebook, cs, table=0):
     """ADC view: `hnsw` (built over any rows with the same ids) scores stored vectors through
-    the u8 codes from now on.  Keeps the arrays alive on the handle."""
+    the u8 codes from now on.  Keeps the arrays alive on the handle.  table: 0 = exact f32
+    per-query tables, 1 = tables quantised per query to u8 (adc_build_lut_q8)."""
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     codebook = np.ascontiguousarray(codebook, dtype=np.float32)
     hnsw._pq8 = (codes, codebook)
     lib().orc_hnsw_set_pq8(hnsw._h, _p(codes, C.c_uint8), codes.shape[1], codebook.shape[0], cs,
                            _p(codebook, C.c_float))
+    lib().orc_hnsw_set_adc_table(hnsw._h, int(table))
     return hnsw

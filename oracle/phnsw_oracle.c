@@ -314,6 +314,7 @@ struct orc_hnsw {
   const uint8_t *pq_codes;
   const float *pq_codebook;
   uint64_t pq_Q, pq_K, pq_cs;
+  int adc_table; /* 0 = exact f32 table, 1 = quantised u8 table (adc_build_lut_q8) */
   int sum_order; /* 0 = the crate's sequential loop, 1 = orc_distance_tree (search paths only) */
   uint64_t seed;        /* seed this index was generated with (nested re-top generates derive theirs) */
   uint64_t promo_count; /* number of nested generates so far */
@@ -395,6 +396,9 @@ typedef struct {
   const orc_hnsw *h;
   const float *qvec;
   const float *lut; /* ADC: Q x K partial distances of this query, or NULL */
+  /* ADC with quantised tables (orc_hnsw_set_adc_table(h, 1)): the same entries as u8 */
+  const uint8_t *qlut;
+  float q8_bias, q8_delta;
 } query_t;
 
 /* finish a distance from the accumulated sum; the ADC path is our own definition and uses the
@@ -414,6 +418,15 @@ static inline float adc_finalize(int metric, float r) {
 }
 
 static inline float dist_to_stored(const query_t *q, uint64_t vid) {
+  if (q->qlut) { /* quantised table: integer sum of u8 entries, then bias + delta * sum */
+    const orc_hnsw *h = q->h;
+    const uint8_t *code = h->pq_codes + vid * h->pq_Q;
+    uint32_t isum = 0;
+    for (uint64_t s = 0; s < h->pq_Q; s++) isum += q->qlut[s * h->pq_K + code[s]];
+    float scaled = q->q8_delta * (float)isum;
+    float r = q->q8_bias + scaled;
+    return adc_finalize(h->metric, r);
+  }
   if (q->lut) { /* asymmetric distance: sum the query's table entries selected by the codes */
     const orc_hnsw *h = q->h;
     const uint8_t *code = h->pq_codes + vid * h->pq_Q;
@@ -442,6 +455,53 @@ static void adc_build_lut(const orc_hnsw *h, const float *qvec, float *lut) {
         for (uint64_t t = 0; t < h->pq_cs; t++) r += a[t] * c[t];
       lut[s * h->pq_K + k] = r;
     }
+}
+
+/* The same table quantised per query to u8 ("fast scan" form; our own definition, no crate
+ * analogue -- parity unpinned): lo[s] = row minimum, range = largest (row maximum - row
+ * minimum), inv = 255 / range, delta = range / 255 (both 0 for a flat table),
+ * tab[s][k] = min(255, rint((lut[s][k] - lo[s]) * inv)) (round half to even), bias = lo[0] +
+ * lo[1] + ... in order.  A NaN or infinite entry makes bias NaN (every distance NaN). */
+static void adc_build_lut_q8(const orc_hnsw *h, const float *lut, uint8_t *tab, float *bias_out,
+                             float *delta_out) {
+  const uint64_t Q = h->pq_Q, K = h->pq_K;
+  float range = 0.0f, bias = 0.0f;
+  int bad = 0;
+  float *lo = (float *)malloc(Q * sizeof(float));
+  for (uint64_t s = 0; s < Q; s++) {
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (uint64_t k = 0; k < K; k++) {
+      float v = lut[s * K + k];
+      if (v != v) bad = 1;
+      if (v < mn) mn = v;
+      if (v > mx) mx = v;
+    }
+    lo[s] = mn;
+    float d = mx - mn;
+    if (d > range) range = d;
+    bias = bias + mn;
+  }
+  float inv = 0.0f, delta = 0.0f;
+  if (range > 0.0f) {
+    inv = 255.0f / range;
+    delta = range / 255.0f;
+  }
+  if (bad || !(range < FLT_MAX)) {
+    bias = NAN;
+    inv = 0.0f;
+    delta = 0.0f;
+  }
+  for (uint64_t s = 0; s < Q; s++)
+    for (uint64_t k = 0; k < K; k++) {
+      float x = (lut[s * K + k] - lo[s]) * inv;
+      long v = lrintf(x); /* default rounding mode: to nearest, ties to even */
+      if (v < 0) v = 0;
+      if (v > 255) v = 255;
+      tab[s * K + k] = (uint8_t)v;
+    }
+  free(lo);
+  *bias_out = bias;
+  *delta_out = delta;
 }
 
 /* ---------------------------------------------------- visited set (HashSet) */
@@ -779,6 +839,7 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
     uint64_t *nd = (uint64_t *)calloc(h->layer_count + 1, sizeof(uint64_t));
     uint64_t *ne = (uint64_t *)calloc(h->layer_count + 1, sizeof(uint64_t));
     float *lut = NULL, *recon = NULL;
+    uint8_t *qtab = NULL;
 #pragma omp for schedule(dynamic, 8)
     for (int64_t qi = 0; qi < (int64_t)nq; qi++) {
       for (uint64_t i = 0; i < ef; i++) {
@@ -790,6 +851,7 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
       query_t q;
       q.h = h;
       q.lut = NULL;
+      q.qlut = NULL;
       if (h->pq_codes) {
         if (!lut) {
           lut = (float *)malloc(h->pq_Q * h->pq_K * sizeof(float));
@@ -806,6 +868,11 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
         }
         adc_build_lut(h, q.qvec, lut);
         q.lut = lut;
+        if (h->adc_table == 1) {
+          if (!qtab) qtab = (uint8_t *)malloc(h->pq_Q * h->pq_K);
+          adc_build_lut_q8(h, lut, qtab, &q.q8_bias, &q.q8_delta);
+          q.qlut = qtab;
+        }
       } else {
         q.qvec = queries ? queries + (uint64_t)qi * h->dim : h->rows + stored_ids[qi] * h->dim;
       }
@@ -837,6 +904,7 @@ int orc_search_batch(const orc_hnsw *h, const float *queries, const uint64_t *st
     free(ne);
     free(lut);
     free(recon);
+    free(qtab);
     free(cand.data);
     free(cand.pri);
     scratch_free(&s);
@@ -873,6 +941,7 @@ int orc_knn(const orc_hnsw *h, uint64_t k, uint64_t probe_depth, uint64_t *out_i
       query_t q;
       q.h = h;
       q.lut = NULL;
+      q.qlut = NULL;
       q.qvec = h->rows + layer->nodes[i] * h->dim;
       closest_nodes(layer, &q, &pq, probe_depth, &s, NULL, NULL);
       uint64_t cnt = 0;
@@ -925,6 +994,7 @@ int orc_threshold_nn(const orc_hnsw *h, float threshold, uint64_t probe_depth,
       query_t q;
       q.h = h;
       q.lut = NULL;
+      q.qlut = NULL;
       q.qvec = h->rows + layer->nodes[i] * h->dim;
       float last = 0.0f;
       uint64_t last_size = 0;
@@ -1138,6 +1208,7 @@ static void generate_layer(orc_hnsw *h, uint64_t *vs, uint64_t n, uint64_t M,
         query_t q;
         q.h = h;
         q.lut = NULL;
+        q.qlut = NULL;
         q.qvec = h->rows + vs[i] * h->dim;
         search_layers(h, h->layers, n_above, &q, isp, ORC_EMPTY, &cand, &s, NULL, NULL, NULL);
         uint64_t c = 0;
@@ -1313,6 +1384,7 @@ static uint64_t link_layer(orc_hnsw *h, uint64_t layer_from_top, const orc_searc
       query_t q;
       q.h = h;
       q.lut = NULL;
+      q.qlut = NULL;
       q.qvec = h->rows + vector * h->dim;
       search_layers(h, stack, layer_from_top + 1, &q, sp, vector, &cand, &s, NULL, NULL, NULL);
       uint32_t c = 0;
@@ -2444,3 +2516,6 @@ void orc_hnsw_set_pq8(orc_hnsw *h, const uint8_t *codes, uint64_t Q, uint64_t K,
   h->pq_cs = cs;
   h->pq_codebook = codebook;
 }
+
+/* form of the ADC table used by searches over the codes: 0 exact f32, 1 quantised u8 */
+void orc_hnsw_set_adc_table(orc_hnsw *h, int table) { h->adc_table = table; }

@@ -229,6 +229,8 @@ uint64_t orc_pq8_train(const float *rows, uint64_t n, uint64_t size, uint64_t cs
                        uint64_t iters, uint64_t seed, float *codebook_out, int nthreads);
 void orc_hnsw_set_pq8(orc_hnsw *h, const uint8_t *codes, uint64_t Q, uint64_t K, uint64_t cs,
                       const float *codebook);
+/* form of the ADC table: 0 = exact f32 entries, 1 = quantised per query to u8 (adc_build_lut_q8) */
+void orc_hnsw_set_adc_table(orc_hnsw *h, int table);
 
 int orc_num_threads(void);
 

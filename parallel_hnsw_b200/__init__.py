@@ -3,11 +3,12 @@ terminusdb-labs/parallel-hnsw (see include/phnsw.h for the C ABI, hnsw.py for th
 from .hnsw import (BigComparator, BuildParameters, COS_CLAMP, COS_HALF, EMPTY, FLT_MAX, Hnsw,
                    L2_SQRT, ONE_MINUS_DOT, PhnswError, Pq8Comparator, PqBuildParameters,
                    QuantizedHnsw, assign_last_stats, pq8_train,
-                   SearchParameters, SUM_SEQUENTIAL, SUM_TREE, calculate_partitions,
-                   device_count, merge_topk_device)
+                   SearchParameters, SUM_SEQUENTIAL, SUM_TREE, ADC_TABLE_F32, ADC_TABLE_Q8,
+                   calculate_partitions, device_count, merge_topk_device)
 
 __all__ = ["BigComparator", "BuildParameters", "COS_CLAMP", "COS_HALF", "EMPTY", "FLT_MAX", "Hnsw",
            "L2_SQRT", "ONE_MINUS_DOT", "PhnswError", "Pq8Comparator", "PqBuildParameters",
            "QuantizedHnsw", "assign_last_stats", "pq8_train",
-           "SearchParameters", "SUM_SEQUENTIAL", "SUM_TREE", "calculate_partitions",
+           "SearchParameters", "SUM_SEQUENTIAL", "SUM_TREE", "ADC_TABLE_F32", "ADC_TABLE_Q8",
+           "calculate_partitions",
            "device_count", "merge_topk_device"]

@@ -16,6 +16,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_IO, ERR_FORMAT, ERR_NOT_FOUND, ERR
 
 METRIC_COS_HALF, METRIC_ONE_MINUS_DOT, METRIC_L2_SQRT, METRIC_COS_CLAMP = 0, 1, 2, 3
 SUM_SEQUENTIAL, SUM_TREE = 0, 1
+ADC_TABLE_F32, ADC_TABLE_Q8 = 0, 1
 
 
 class SearchParams(C.Structure):  # src/parameters.rs:3-18
@@ -156,6 +157,8 @@ SIGNATURES = {
     "phnsw_pq8_train": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, u64p]),
     "phnsw_pq8_store_create": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "phnsw_pq8_store_codes": (C.c_int, [vp, vp]),
+    "phnsw_pq8_store_set_adc_table": (C.c_int, [vp, C.c_int]),
+    "phnsw_pq8_store_adc_table": (C.c_int, [vp]),
     "phnsw_merge_topk_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
     "phnsw_pq8_search_batch": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams), C.c_uint64,
                                          C.c_uint64, vp, vp, vp]),

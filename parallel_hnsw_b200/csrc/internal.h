@@ -79,12 +79,13 @@ struct Workspace {
   DevBuf ovf, bitmap, vlog, saved, ctrl;  // ctrl: [0] work counter, [1] status
   DevBuf stage_q, stage_ids, stage_excl, out_ids, out_dists, out_counts, out_nd, out_ne;
   DevBuf hit_ids, hit_dists, hit_counts;  // ADC hits handed from the walk to the re-rank kernel
+  DevBuf qlut;                            // quantised ADC tables of the batch (adc_lut.cu)
   uint32_t slots = 0, ovf_cap = 0, vlog_cap = 0, bitmap_words = 0, cap_pad = 0;
   void release() {
     ovf.release(); bitmap.release(); vlog.release(); saved.release(); ctrl.release();
     stage_q.release(); stage_ids.release(); stage_excl.release();
     out_ids.release(); out_dists.release(); out_counts.release(); out_nd.release(); out_ne.release();
-    hit_ids.release(); hit_dists.release(); hit_counts.release();
+    hit_ids.release(); hit_dists.release(); hit_counts.release(); qlut.release();
   }
 };
 
@@ -116,6 +117,7 @@ struct phnsw_store {
   uint32_t cpitch = 0;         // bytes per code row (QUANTIZED_SIZE rounded up to 16)
   float *codebook = nullptr;   // device, pq_K x pq_cs
   uint32_t pq_Q = 0, pq_K = 0, pq_cs = 0;
+  int adc_table = 0;           // PHNSW_ADC_TABLE_F32 / PHNSW_ADC_TABLE_Q8 (phnsw_pq8_store_set_adc_table)
   bool is_pq8() const { return codes8 != nullptr; }
 };
 
@@ -165,6 +167,12 @@ cudaError_t launch_search_tree(int metric, const SearchArgs &a, int grid, int bl
                                cudaStream_t stream);
 cudaError_t launch_search_pq(int metric, const SearchArgs &a, int grid, int block, size_t smem,
                              cudaStream_t stream);
+cudaError_t launch_search_pq8q(int metric, const SearchArgs &a, int grid, int block, size_t smem,
+                               cudaStream_t stream);
+// adc_lut.cu: quantised per-query ADC tables of a batch into `out` (nq blobs), async on `st`
+phnsw_status launch_adc_lut_q8(const phnsw_store *s, const float *queries, uint32_t qpitch,
+                               const uint64_t *stored_ids, uint32_t nq, uint8_t *out,
+                               int max_smem, cudaStream_t st);
 // launches the traversal kernel on `stream` (asynchronous); status word is read by sync_status
 phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStream_t stream);
 phnsw_status sync_status(const phnsw_index *ix, cudaStream_t stream);

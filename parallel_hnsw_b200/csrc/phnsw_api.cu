@@ -179,28 +179,49 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   const uint32_t cap_max = std::max(c.cap, c.cap_max);
   const uint32_t cap_pad = pool_entries(std::max(cap_max, 1u));
   const bool pq8 = s->is_pq8();
-  if (pq8 && (c.mode != 0 || (s->cpitch + 16) * 32 > kLandingRows * kRowStride * 4)) {
-    set_error("search: a PQ8 (ADC) store supports search_layers only, with at most 248 codes per vector");
-    return PHNSW_ERR_INVALID;
-  }
   const bool tree = !pq8 && ix->sum_order == PHNSW_SUM_TREE;
   // ADC: a per-query table of Q x K partial distances is the cheapest per candidate, but at the
   // embedding shape (96 x 256 x 4 B = 96 KB) it leaves room for two warps per SM; above 24 KB the
   // entries are recomputed from the (L1-resident) codebook instead.  PHNSW_ADC_TABLE=0/1 forces.
-  bool pq_table = pq8 && (size_t)s->pq_Q * s->pq_K * 4 <= 24 * 1024;
-  if (pq8) {
+  // With quantised tables (phnsw_pq8_store_set_adc_table) the table is Q x K bytes, written by a
+  // pre-pass kernel, and the walk keeps no query vector at all.
+  const bool q8 = pq8 && s->adc_table == PHNSW_ADC_TABLE_Q8;
+  if (pq8 && (c.mode != 0 || (!q8 && (s->cpitch + 16) * 32 > kLandingRows * kRowStride * 4))) {
+    set_error("search: a PQ8 (ADC) store supports search_layers only, with at most 248 codes per vector");
+    return PHNSW_ERR_INVALID;
+  }
+  bool pq_table = pq8 && !q8 && (size_t)s->pq_Q * s->pq_K * 4 <= 24 * 1024;
+  if (pq8 && !q8) {
     static const char *force = getenv("PHNSW_ADC_TABLE");
     if (force) pq_table = atoi(force) != 0;
   }
-  WarpSmemLayout lay = warp_smem_layout(s->pitch, cap_pad, pq_table ? s->pq_Q * s->pq_K : 0,
-                                        tree ? kScratchBytesTree : kLandingBytes);
+  const int variant = q8 ? 2 : (pq8 ? 1 : 0);
+  WarpSmemLayout lay = warp_smem_layout(variant_q_floats(variant, s->pitch), cap_pad,
+                                        variant_lut_floats(variant, pq_table, s->pq_Q, s->pq_K),
+                                        (tree || q8) ? kScratchBytesTree : kLandingBytes);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
     set_error("search: per-query shared memory %u B exceeds %zu B (dim %llu, capacity %u)",
               lay.total, avail, (unsigned long long)s->dim, cap_max);
     return PHNSW_ERR_INVALID;
   }
-  uint32_t wmax = (uint32_t)std::min<size_t>(tree ? kTreeWarps : kSeqWarps, avail / lay.total);
+  uint32_t wmax = (uint32_t)std::min<size_t>((tree || q8) ? kTreeWarps : kSeqWarps, avail / lay.total);
+  uint32_t cap_pad_used = cap_pad;
+  if (q8 && wmax < (uint32_t)kTreeWarps && c.cap_max <= c.cap) {
+    // the table dominates the footprint: give up one 32-key chunk of pool slack (never below 64
+    // keys of slack) when that lets one more query per SM stay in flight
+    const uint32_t trimmed = cap_pad - 32;
+    if (trimmed >= cap_max + 64) {
+      WarpSmemLayout l2 = warp_smem_layout(variant_q_floats(variant, s->pitch), trimmed,
+                                           variant_lut_floats(variant, pq_table, s->pq_Q, s->pq_K),
+                                           kScratchBytesTree);
+      if (avail / l2.total > wmax) {
+        lay = l2;
+        cap_pad_used = trimmed;
+        wmax = (uint32_t)std::min<size_t>(kTreeWarps, avail / l2.total);
+      }
+    }
+  }
   // spread small batches over all SMs before stacking warps on one SM
   uint32_t w = std::min<uint32_t>(wmax, (c.nq + ix->sm_count - 1) / ix->sm_count);
   if (w < 1) w = 1;
@@ -292,13 +313,26 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.bitmap_words = ws.bitmap_words;
   a.vlog = ws.vlog.as<uint32_t>();
   a.vlog_cap = ix->vlog_cap;
+  if (q8) {
+    const uint32_t blob = adc_q8_blob_bytes(s->pq_Q, s->pq_K);
+    if (ws.qlut.bytes < (size_t)c.nq * blob) {
+      PH_CUDA(cudaStreamSynchronize(stream));
+      PH_CUDA(ws.qlut.reserve((size_t)c.nq * blob));
+    }
+    phnsw_status rq = launch_adc_lut_q8(s, c.queries, c.qpitch, c.stored_ids, c.nq,
+                                        ws.qlut.as<uint8_t>(), ix->max_smem, stream);
+    if (rq != PHNSW_OK) return rq;
+    a.qlut = ws.qlut.as<uint8_t>();
+    a.qlut_stride = blob;
+  }
   a.saved = ws.saved.as<uint64_t>();
-  a.cap_pad = cap_pad;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
+  a.cap_pad = cap_pad_used;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
   a.n_vectors = (uint32_t)s->n;
   a.out_id_offset = c.id_offset;
 
   const size_t smem = (size_t)lay.total * w;
-  cudaError_t e = pq8    ? launch_search_pq(s->metric, a, grid, w * 32, smem, stream)
+  cudaError_t e = q8     ? launch_search_pq8q(s->metric, a, grid, w * 32, smem, stream)
+                  : pq8  ? launch_search_pq(s->metric, a, grid, w * 32, smem, stream)
                   : tree ? launch_search_tree(s->metric, a, grid, w * 32, smem, stream)
                          : launch_search_seq(s->metric, a, grid, w * 32, smem, stream);
   if (e != cudaSuccess) return cuda_fail(e, "search_kernel launch");
@@ -364,7 +398,8 @@ phnsw_status upload_layer_tables(phnsw_index *ix) {
     h[i].nodes = l.identity ? nullptr : l.nodes;
     h[i].neighbors = l.neighbors;
     h[i].vec2node = l.identity ? nullptr : l.vec2node;
-    h[i].lrows = l.identity ? ix->store->rows : l.lrows;
+    h[i].lrows = l.identity ? (ix->store->rows ? ix->store->rows : (const float *)ix->store->codes8)
+                            : l.lrows;
     h[i].node_count = (uint32_t)l.node_count;
     h[i].M = (uint32_t)l.M;
     h[i].row_dups = l.row_dups ? 1u : 0u;
@@ -412,12 +447,15 @@ phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint6
       vec2node_kernel<<<(unsigned)((node_count + 255) / 256), 256>>>(nodes, (uint32_t)node_count,
                                                                     l.vec2node);
     PH_CUDA(cudaGetLastError());
-    if (ix->store->rows && node_count) {  // dense, NodeId-indexed copy of the layer's vectors
-      const uint32_t pitch = ix->store->pitch;
-      PH_CUDA(cudaMalloc(&l.lrows, node_count * (size_t)pitch * 4));
-      gather_rows_kernel<<<(unsigned)std::min<uint64_t>((node_count * (pitch / 4) + 255) / 256, 148 * 32),
-                           256>>>((const float4 *)ix->store->rows, pitch / 4, nodes, node_count,
-                                  (float4 *)l.lrows);
+    if ((ix->store->rows || ix->store->codes8) && node_count) {
+      // dense, NodeId-indexed copy of the layer's vectors (f32 rows, or code rows on a PQ8 store:
+      // cpitch is a multiple of 16 B, so the same 16-byte gather serves both)
+      const bool pq8 = !ix->store->rows;
+      const uint32_t pitch4 = pq8 ? ix->store->cpitch / 16 : ix->store->pitch / 4;
+      const float4 *src = pq8 ? (const float4 *)ix->store->codes8 : (const float4 *)ix->store->rows;
+      PH_CUDA(cudaMalloc(&l.lrows, node_count * (size_t)pitch4 * 16));
+      gather_rows_kernel<<<(unsigned)std::min<uint64_t>((node_count * pitch4 + 255) / 256, 148 * 32),
+                           256>>>(src, pitch4, nodes, node_count, (float4 *)l.lrows);
       PH_CUDA(cudaGetLastError());
     }
   }

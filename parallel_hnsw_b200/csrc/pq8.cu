@@ -300,4 +300,16 @@ phnsw_status phnsw_pq8_store_codes(const phnsw_store *s, uint8_t *codes_out) {
   return PHNSW_OK;
 }
 
+phnsw_status phnsw_pq8_store_set_adc_table(phnsw_store *s, int table) {
+  PH_ENTRY();
+  if (!s || !s->codes8 || (table != PHNSW_ADC_TABLE_F32 && table != PHNSW_ADC_TABLE_Q8)) {
+    set_error("pq8_store_set_adc_table: a PQ8 store and PHNSW_ADC_TABLE_F32 / _Q8 required");
+    return PHNSW_ERR_INVALID;
+  }
+  s->adc_table = table;
+  return PHNSW_OK;
+}
+
+int phnsw_pq8_store_adc_table(const phnsw_store *s) { return s && s->codes8 ? s->adc_table : -1; }
+
 }  // extern "C"

@@ -61,7 +61,8 @@ struct LayerDev {
   const float *lrows;         // the layer's vectors indexed by NodeId (pitch floats per row): the
                               // store itself for an identity layer, else a dense copy -- the
                               // distance path then needs no NodeId -> VectorId lookup and the
-                              // upper layers' rows sit together in L2.  null on a PQ8 store
+                              // upper layers' rows sit together in L2.  On a PQ8 store: the
+                              // layer's code rows (cpitch bytes each), same arrangement
   uint32_t node_count;
   uint32_t M;
   uint32_t row_dups;          // 1 when some neighbourhood lists the same id twice
@@ -114,6 +115,10 @@ struct SearchArgs {
   uint32_t pq_table;       // 1: per-query table in shared memory; 0: entries recomputed from the
                            // codebook where they are used (large Q x K: the table would leave
                            // room for two warps per SM)
+  // ADC with quantised tables (PQ == 2): one blob per query written by adc_lut_q8_kernel
+  // (adc_lut.cu): pq_Q x pq_K u8 entries, padded to 16 B, then {bias, delta} f32
+  const uint8_t *qlut;
+  uint32_t qlut_stride;    // bytes per query blob (adc_q8_blob_bytes)
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
   uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
   uint32_t n_vectors;      // rows of the store: stored_ids / exclude are checked against it
@@ -168,6 +173,21 @@ __host__ __device__ inline uint32_t pool_entries(uint32_t cap) {
   return (cap + slack + 31) / 32 * 32;
 }
 
+// ADC with quantised tables: bytes of one query's blob (u8 table, 16 B aligned, + bias/delta)
+__host__ __device__ inline uint32_t adc_q8_blob_bytes(uint32_t Q, uint32_t K) {
+  return (Q * K + 15) / 16 * 16 + 16;
+}
+// per-warp query area (floats) and table area (floats) of a kernel variant: the exact ADC walk
+// keeps the query (table entries are built from it), the quantised one only its table blob
+__host__ __device__ inline uint32_t variant_q_floats(int pq, uint32_t dim_pad) {
+  return pq == 2 ? 0u : dim_pad;
+}
+__host__ __device__ inline uint32_t variant_lut_floats(int pq, uint32_t pq_table, uint32_t Q,
+                                                       uint32_t K) {
+  if (pq == 2) return adc_q8_blob_bytes(Q, K) / 4;
+  return pq && pq_table ? Q * K : 0u;
+}
+
 #ifdef __CUDACC__
 
 constexpr uint32_t kFull = 0xffffffffu;
@@ -197,7 +217,8 @@ __device__ __forceinline__ uint64_t warp_max_key(uint64_t v) {
 //           sequential order to a few ulp.
 template <int METRIC, int PQ, int TREE>
 struct WarpSearch {
-  static constexpr uint32_t kStageBytes = (TREE && !PQ) ? kScratchBytesTree : kLandingBytes;
+  static constexpr uint32_t kStageBytes =
+      ((TREE && !PQ) || PQ == 2) ? kScratchBytesTree : kLandingBytes;
   static constexpr uint32_t kSortScratch = kStageBytes / 8;  // u64 keys the scratch can hold
   const SearchArgs &a;
   float *qvec;
@@ -226,10 +247,12 @@ struct WarpSearch {
   bool vlog_over;
   uint32_t ph;    // mbarrier phase bits, one per stage
   uint32_t stat;  // status bits raised by this warp
+  float q8_bias, q8_delta;  // PQ == 2: distance = finalize(bias + delta * sum of u8 entries)
 
   __device__ WarpSearch(const SearchArgs &args, unsigned char *smem, uint32_t slot, int lane_)
       : a(args), lane(lane_) {
-    WarpSmemLayout l = warp_smem_layout(a.dim_pad, a.cap_pad, PQ && a.pq_table ? a.pq_Q * a.pq_K : 0,
+    WarpSmemLayout l = warp_smem_layout(variant_q_floats(PQ, a.dim_pad), a.cap_pad,
+                                        variant_lut_floats(PQ, a.pq_table, a.pq_Q, a.pq_K),
                                         kStageBytes);
     qvec = (float *)(smem + l.off_q);
     lut = (float *)(smem + l.off_lut);
@@ -697,6 +720,62 @@ struct WarpSearch {
   // result bkeys[j] = key(distance, bid[j]).  Tiles of R rows x one 512 B chunk are copied
   // by the bulk-copy engine into stage t % S and consumed lane-per-row.
   __device__ void compute_distances(const LayerDev &layer, uint32_t nn) {
+    if (PQ == 2) {
+      // ADC over the query's quantised table (adc_lut.cu; oracle adc_build_lut_q8): a group of
+      // `gl` lanes scores one candidate -- lane t owns the code words t, t + gl, ... (four
+      // sub-spaces each), looks its u8 entries up in shared memory and the group adds the
+      // integers (exact, so the order is free); 32 / gl candidates per pass, four passes'
+      // code words in flight at once.  distance = finalize(bias + delta * sum).
+      const uint8_t *tab = (const uint8_t *)lut;
+      const uint32_t Q = a.pq_Q, K = a.pq_K, W4 = (Q + 3) / 4;
+      uint32_t gl = 1;
+      while (gl < W4 && gl < 32) gl <<= 1;
+      const uint32_t G = 32 / gl, t = lane & (gl - 1), g = lane / gl;
+      constexpr int R = 4;
+      for (uint32_t j0 = 0; j0 < nn; j0 += R * G) {
+        uint32_t node[R], sum[R];
+        const uint32_t *row[R];
+        bool ok[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const uint32_t j = j0 + r * G + g;
+          ok[r] = j < nn;
+          node[r] = bid[ok[r] ? j : j0];
+          row[r] = (const uint32_t *)((const uint8_t *)layer.lrows + (size_t)node[r] * a.cpitch);
+          sum[r] = 0;
+        }
+        for (uint32_t w = t; w < W4; w += gl) {
+          uint32_t cw[R];
+#pragma unroll
+          for (int r = 0; r < R; r++) cw[r] = __ldg(row[r] + w);
+          const uint8_t *tb = tab + (size_t)(4 * w) * K;
+          const bool f1 = 4 * w + 1 < Q, f2 = 4 * w + 2 < Q, f3 = 4 * w + 3 < Q;
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            uint32_t v = tb[cw[r] & 255u];
+            if (f1) v += tb[K + ((cw[r] >> 8) & 255u)];
+            if (f2) v += tb[2 * K + ((cw[r] >> 16) & 255u)];
+            if (f3) v += tb[3 * K + (cw[r] >> 24)];
+            sum[r] += v;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (gl == 32) {
+            sum[r] = __reduce_add_sync(kFull, sum[r]);
+          } else {
+            for (uint32_t o = gl >> 1; o > 0; o >>= 1) sum[r] += __shfl_xor_sync(kFull, sum[r], o);
+          }
+          if (t == 0 && ok[r]) {
+            float d = finalize(__fadd_rn(q8_bias, __fmul_rn(q8_delta, (float)sum[r])));
+            if (d != d) stat |= kStatNaN;
+            bkeys[j0 + r * G + g] = make_key(d, node[r]);
+          }
+        }
+      }
+      __syncwarp();
+      return;
+    }
     if (PQ) {
       // ADC: code rows (cpitch bytes each) land 32 at a time; each lane sums its row's table
       // entries in sub-space order, which is the order the oracle defines
@@ -1102,6 +1181,22 @@ struct WarpSearch {
         if (pf_n1 < layer.node_count) asm volatile("prefetch.global.L2 [%0];" ::"l"(&bm[pf_n1 >> 5]));
       }
 #endif
+#ifndef PHNSW_NO_CODE_PREFETCH
+      // quantised ADC: the code rows of that row's entries as well (the bottom layer's codes are
+      // DRAM-resident; a row may straddle two 128-byte lines)
+      if (PQ == 2 && pf_id != kEmpty32 && !layer.nodes) {
+        if (pf_n0 < layer.node_count) {
+          const uint8_t *p = a.codes + (size_t)pf_n0 * a.cpitch;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          if (a.cpitch & 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + a.cpitch - 1));
+        }
+        if (pf_n1 < layer.node_count) {
+          const uint8_t *p = a.codes + (size_t)pf_n1 * a.cpitch;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          if (a.cpitch & 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + a.cpitch - 1));
+        }
+      }
+#endif
     }
     compact(false);
   }
@@ -1113,6 +1208,22 @@ struct WarpSearch {
     if (a.stored_ids && a.stored_ids[q] >= (uint64_t)a.n_vectors) {
       stat |= kStatBadQuery;
       return false;
+    }
+    if (PQ == 2) {
+      // the query's table blob (u8 entries + {bias, delta}) was written by the pre-pass kernel:
+      // one bulk (TMA) copy into this warp's table area
+      const uint32_t bytes = a.qlut_stride;
+      __syncwarp();  // the previous query's table reads are over
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&mbar[0], bytes);
+        bulk_g2s(lut, a.qlut + (size_t)q * bytes, bytes, &mbar[0]);
+      }
+      mbar_wait(&mbar[0], ph & 1u);
+      ph ^= 1u;
+      const float *tr = (const float *)((const uint8_t *)lut + bytes - 16);
+      q8_bias = tr[0];
+      q8_delta = tr[1];
+      return true;
     }
     if (PQ) {
       if (a.queries) {
@@ -1511,13 +1622,14 @@ struct WarpSearch {
 // halved).  Measured and not kept: a single compaction site (route the end of the walk through
 // the in-loop site) shrinks the hot code by another 9 KB but compacts ~14 % more often: -2 %.
 template <int METRIC, int PQ, int TREE, int MODE>
-__global__ void __launch_bounds__((TREE && !PQ ? kTreeWarps : kSeqWarps) * 32, 1)
+__global__ void __launch_bounds__(((TREE && !PQ) || PQ == 2 ? kTreeWarps : kSeqWarps) * 32, 1)
     search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t warps_per_cta = blockDim.x >> 5;
-  WarpSmemLayout lay = warp_smem_layout(a.dim_pad, a.cap_pad, PQ && a.pq_table ? a.pq_Q * a.pq_K : 0,
+  WarpSmemLayout lay = warp_smem_layout(variant_q_floats(PQ, a.dim_pad), a.cap_pad,
+                                        variant_lut_floats(PQ, a.pq_table, a.pq_Q, a.pq_K),
                                         WarpSearch<METRIC, PQ, TREE>::kStageBytes);
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
   WarpSearch<METRIC, PQ, TREE> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);

@@ -2,20 +2,27 @@
 // metrics; included by search_seq.cu / search_tree.cu / search_pq.cu.
 #pragma once
 #include "internal.h"
+#include <mutex>
 
 namespace phnsw {
 
 template <int METRIC, int PQ, int TREE, int MODE>
 static cudaError_t launch_moded(const SearchArgs &a, int grid, int block, size_t smem,
                                 cudaStream_t stream) {
-  static thread_local size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // the attribute belongs to the function (per device), not to the calling thread: keep one
+  // high-water mark per device for all host threads, and only ever raise it
+  static std::mutex mu;
+  static size_t configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 8 || configured[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ, TREE, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (dev < 8) configured[dev] = smem;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (dev >= 16 || configured[dev] < smem) {
+      cudaError_t e = cudaFuncSetAttribute(search_kernel<METRIC, PQ, TREE, MODE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if (dev < 16) configured[dev] = smem;
+    }
   }
   search_kernel<METRIC, PQ, TREE, MODE><<<grid, block, smem, stream>>>(a);
   return cudaGetLastError();

@@ -22,6 +22,7 @@ FLT_MAX = np.float32(3.4028235e38)
 
 COS_HALF, ONE_MINUS_DOT, L2_SQRT, COS_CLAMP = 0, 1, 2, 3
 SUM_SEQUENTIAL, SUM_TREE = N.SUM_SEQUENTIAL, N.SUM_TREE
+ADC_TABLE_F32, ADC_TABLE_Q8 = N.ADC_TABLE_F32, N.ADC_TABLE_Q8
 
 
 def SearchParameters(number_of_candidates=300, upper_layer_candidate_count=300, probe_depth=2):
@@ -553,6 +554,15 @@ class Pq8Comparator(BigComparator):
         out = np.empty((self.n, self.quantized_size), dtype=np.uint8)
         N.check(N.lib().phnsw_pq8_store_codes(self._h, _ptr(out)))
         return out
+
+    def set_adc_table(self, table):
+        """ADC_TABLE_F32 (exact f32 entries, default) or ADC_TABLE_Q8 (entries quantised per
+        query to u8, integer sums; include/phnsw.h phnsw_pq8_store_set_adc_table)."""
+        N.check(N.lib().phnsw_pq8_store_set_adc_table(self._h, int(table)))
+        return self
+
+    def adc_table(self):
+        return int(N.lib().phnsw_pq8_store_adc_table(self._h))
 
 
 def PqBuildParameters():

@@ -79,6 +79,56 @@ def test_adc_search_matches_oracle(ph, oracle, metric_name, dim, cs, K):
           oh.search(stored_ids=ids, exclude=ids, max_out=20))
 
 
+@pytest.mark.parametrize("metric_name,dim,cs,K,n", [
+    ("L2_SQRT", 128, 8, 256, 6000),         # BASELINE configs[4] shape: 16 codes, 4 KB table
+    ("COS_HALF", 64, 8, 128, 5000),         # K < 256: table rows of 128 bytes
+    ("ONE_MINUS_DOT", 60, 6, 200, 4000),    # 10 codes: a partial last code word, 4 lanes / candidate
+    ("COS_CLAMP", 48, 16, 32, 3000),        # 3 codes: one lane per candidate
+    ("L2_SQRT", 1144, 8, 160, 1500),        # 143 codes: more than 32 code words per row
+    ("COS_HALF", 1536, 16, 256, 2500),      # BASELINE configs[2] shape: 96 codes, 24 KB table
+])
+def test_adc_quantised_table_matches_oracle(ph, oracle, metric_name, dim, cs, K, n):
+    """PHNSW_ADC_TABLE_Q8: per-query tables quantised to u8 by the pre-pass kernel, integer sums
+    in the walk; ids, distance bits, counts and work counters equal the oracle's definition
+    (adc_build_lut_q8), coarse-table distance ties included."""
+    metric = getattr(ph, metric_name)
+    rows = clustered(n, dim, 5, n_clusters=64, spread=0.6, normalise=(metric_name != "L2_SQRT"))
+    comp = ph.BigComparator(rows, metric)
+    cb = ph.pq8_train(comp, K, cs, kmeans_iters=2, seed=7)
+    pq = ph.Pq8Comparator(comp, cb, cs).set_adc_table(ph.ADC_TABLE_Q8)
+    assert pq.adc_table() == ph.ADC_TABLE_Q8
+    oh = oracle.Hnsw.generate(metric, rows, seed=1, improve=False)
+    gh = ph.Hnsw.from_layers(pq, oh.layers())
+    oracle.attach_pq8(oh, pq.codes(), cb, cs, table=1)
+    queries = rows[::23] + np.float32(0.02)
+    for ef, max_out in ((300, 300), (40, 10), (1, 1)):
+        g = gh.search(queries, ph.SearchParameters(ef, ef, 2), max_out=max_out, stats=True)
+        o = oh.search(queries=queries, sp=oracle.search_params(ef, ef, 2), max_out=max_out,
+                      stats=True)
+        _same(g, o)
+        assert np.array_equal(g[3].astype(np.uint64), o[3]) and np.array_equal(g[4].astype(np.uint64), o[4])
+    ids = np.arange(0, n, 41, dtype=np.uint64)  # Stored: the query is its own reconstruction
+    _same(gh.search(stored_ids=ids, max_out=20), oh.search(stored_ids=ids, max_out=20))
+    _same(gh.search(stored_ids=ids, exclude=ids, max_out=20),
+          oh.search(stored_ids=ids, exclude=ids, max_out=20))
+    # a flat table (all-zero query against a dot metric: every entry 0) and the f32 form again
+    if metric_name == "ONE_MINUS_DOT":
+        z = np.zeros((3, dim), np.float32)
+        _same(gh.search(z, max_out=5), oh.search(queries=z, max_out=5))
+    pq.set_adc_table(ph.ADC_TABLE_F32)
+    oracle.attach_pq8(oh, pq.codes(), cb, cs, table=0)
+    _same(gh.search(queries[:40], max_out=10), oh.search(queries=queries[:40], max_out=10))
+    with pytest.raises(ph.PhnswError):
+        ph.Pq8Comparator.set_adc_table(comp, ph.ADC_TABLE_Q8)   # not a PQ8 store
+    # NaN in a query is loud in either form
+    pq.set_adc_table(ph.ADC_TABLE_Q8)
+    bad = queries[:2].copy()
+    bad[1, 3] = np.nan
+    with pytest.raises(ph.PhnswError):
+        gh.search(bad, max_out=5)
+    _same(gh.search(queries[:5], max_out=5), gh.search(queries[:5], max_out=5))
+
+
 def test_adc_recall_with_rerank(ph, oracle):
     """ADC candidates re-ranked with the exact comparator recover most of the exact top-10."""
     rows = clustered(20000, 128, 9, n_clusters=256, spread=0.7)
