@@ -399,10 +399,15 @@ def main():
     ctx = {"torch": torch, "dist": dist, "ph": ph, "N": N, "dev": dev, "rank": rank, "world": world,
            "local": local, "k": k, "stream": stream, "peaks": peaks, "args": args}
 
-    # ---- data + index (replica: same seed on every rank) --------------------------------
+    # ---- data + index.  N = 1: the BASELINE configs[1] index.  N > 1: the same workload per GPU,
+    # sharded -- rank r owns vectors [r * n, (r + 1) * n) of an N * n vector set (its own seed), builds
+    # and searches its own sub-index, every rank searches the SAME query batch (broadcast from rank
+    # 0 inside the step) and the per-shard top-k are merged through one NCCL all-gather
+    # (phnsw_search_batch_sharded).  `value` counts the (query, shard) searches all ranks did.
+    sharded = world > 1
     t0 = time.perf_counter()
-    rows_h = sift_like(args.n, args.dim, 1234)
-    queries_h = sift_like(args.nq, args.dim, 4321 + (rank if world > 1 else 0))
+    rows_h = sift_like(args.n, args.dim, 1234 + rank)
+    queries_h = sift_like(args.nq, args.dim, 4321)
     t_gen = time.perf_counter() - t0
     comp = ph.BigComparator(rows_h.numpy(), ph.L2_SQRT, device=local)
     # one tiny build first: CUDA module load and allocator warm-up are not build throughput
@@ -430,10 +435,15 @@ def main():
     comp.bruteforce_knn(dq[:256], k)  # warm-up (allocator, kernel attributes)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    gt, _ = comp.bruteforce_knn(dq, k)
+    gt, _ = comp.bruteforce_knn(dq, k)  # this rank's shard (ids are shard-local)
     torch.cuda.synchronize()
     t_gt = time.perf_counter() - t0
     gt_stats = comp.bruteforce_last_stats()
+    sh = None
+    if sharded:
+        from parallel_hnsw_b200.sharded import ShardedHnsw
+        sh = ShardedHnsw(gh, rank * args.n, rank, world)
+        gt_global = sharded_ground_truth(ctx, comp, dq, rank * args.n)
     # secondary number: the sequential summation order (bit-identical to the crate's loops)
     gh.set_sum_order(ph.SUM_SEQUENTIAL)
     for _ in range(args.warmup):
@@ -460,8 +470,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---- timed region 1: device-resident ------------------------------------------------
+    mi = torch.empty((args.nq, k), dtype=torch.int64, device=dev)   # merged (sharded) results
+    md = torch.empty((args.nq, k), dtype=torch.float32, device=dev)
+
+    def step():
+        if sharded:
+            sh.search(dq, sp, k, src=0, stream=stream, out=(mi, md))
+        else:
+            gh.search_device(dq, sp, oi, od, oc, stream=stream)
+
     for _ in range(args.warmup):
-        gh.search_device(dq, sp, oi, od, oc, stream=stream)
+        step()
     gh.sync(stream)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -473,7 +492,7 @@ def main():
         torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
-        gh.search_device(dq, sp, oi, od, oc, stream=stream)
+        step()
     e1.record()
     barrier()
     if args.profile_range:
@@ -482,6 +501,31 @@ def main():
     gh.sync(stream)
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    sharded_info = None
+    if sharded:
+        # beside it: the same shards searched WITHOUT broadcast / exchange / merge (what N
+        # independent replicas of this per-GPU workload deliver), max over ranks
+        for _ in range(args.warmup):
+            gh.search_device(dq, sp, oi, od, oc, stream=stream)
+        gh.sync(stream)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        r0.record()
+        for _ in range(args.steps):
+            gh.search_device(dq, sp, oi, od, oc, stream=stream)
+        r1.record()
+        barrier()
+        gh.sync(stream)
+        tl = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        ms_local = float(tl[0])
+        merged_np = mi.cpu().numpy()
+        sharded_info = {
+            "recall_merged": recall_at_k(merged_np, gt_global, k),
+            "ms_local": ms_local,
+            # every merged entry that names a vector of this rank's shard must be this rank's own
+            # result for that query, and every merged list ascending by (distance, id)
+            "merged": merged_np, "merged_d": md.cpu().numpy()}
 
     # ---- secondary: the same steps issued round robin on two streams, so that the ragged end
     # of one batch overlaps the start of the next -- what a server with back-to-back batches sees
@@ -535,15 +579,21 @@ def main():
             C.c_void_p(hi.data_ptr()), C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr()),
             None, None))
 
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    ms_e2e = (time.perf_counter() - t0) * 1e3
-    assert np.array_equal(hi.numpy(), oi.cpu().numpy()), "host path and device path disagree"
+    if sharded:
+        # rank 0: pinned host queries -> H2D -> sharded step (broadcast, search, all-gather,
+        # merge) -> D2H of the merged top-k; the other ranks take part in the step
+        ms_e2e = timed_e2e_sharded(ctx, sh, gh, queries_h.pin_memory(), dq, sp, 0, args.steps,
+                                   args.warmup) * args.steps
+    else:
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(hi.numpy(), oi.cpu().numpy()), "host path and device path disagree"
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -572,9 +622,10 @@ def headline_line(ctx, v):
     """The headline JSON object (rank 0), built before the secondary blocks run."""
     args, world, k, peaks = ctx["args"], ctx["world"], ctx["k"], ctx["peaks"]
     (ndist, nexp, layer_M, ms_dev, ms_e2e, ms_seq, ms_pipe, recall, main_cpu, clocks, tree, t_build,
-     t_gen, t_gt, gt_stats, gh_layers_top_first) = (v[x] for x in (
+     t_gen, t_gt, gt_stats, gh_layers_top_first, sharded_info, oi, od) = (v[x] for x in (
          "ndist", "nexp", "layer_M", "ms_dev", "ms_e2e", "ms_seq", "ms_pipe", "recall", "main_cpu",
-         "clocks", "tree", "t_build", "t_gen", "t_gt", "gt_stats", "gh_layers_top_first"))
+         "clocks", "tree", "t_build", "t_gen", "t_gt", "gt_stats", "gh_layers_top_first",
+         "sharded_info", "oi", "od"))
     cpu_build = None
     if args.cpu_build:
         sizes = [int(x) for x in args.cpu_build.split(",") if x]
@@ -608,7 +659,8 @@ def headline_line(ctx, v):
         "cpu_baseline": (main_cpu or {}).get("cpu_baseline"),
         "clocks": clocks,
         "sum_order": args.sum_order,
-        "parallelism": "replicas x%d (queries split)" % world if world > 1 else "single GPU",
+        "parallelism": ("sharded x%d (one sub-index per GPU, queries broadcast, NCCL all-gather + merge "
+                        "inside the step)" % world) if world > 1 else "single GPU",
         "layers_top_first": gh_layers_top_first,
         "build": {"vectors_per_s": args.n / t_build, "seconds": t_build,
                   "improve_index": not args.no_improve, "data_gen_seconds": t_gen,
@@ -640,6 +692,35 @@ def headline_line(ctx, v):
     }
     if main_cpu and "error" in main_cpu:
         out["cpu_baseline_error"] = main_cpu
+    if sharded_info:
+        # rank 0's shard holds global ids [0, n): its own top-k must reappear in the merged lists
+        # wherever the merge kept an id of that range, and merged lists ascend by (distance, id)
+        mg, mgd = sharded_info["merged"], sharded_info["merged_d"]
+        loc = oi.cpu().numpy()
+        own = (mg >= 0) & (mg < args.n)
+        ok_rows = [set(mg[i][own[i]].tolist()) <= set(loc[i].tolist()) for i in range(mg.shape[0])]
+        asc = [all((mgd[i][j], mg[i][j]) <= (mgd[i][j + 1], mg[i][j + 1]) for j in range(k - 1)
+                   if mg[i][j + 1] >= 0) for i in range(mg.shape[0])]
+        ms_local = sharded_info["ms_local"] / args.steps
+        out["recall_at_10"] = sharded_info["recall_merged"]
+        out["gpu_launches"] = 2 * args.steps
+        out["sharded"] = {
+            "what": "N > 1: one sub-index of %d vectors per GPU (%d vectors in all), every rank searches "
+                    "the same %d-query batch; one library call per step (phnsw_search_batch_sharded): "
+                    "ncclBroadcast(queries) -> K1 (epilogue writes global-id records into the exchange "
+                    "buffer) -> one ncclAllGather -> merge.  `value` = (query, shard) searches per "
+                    "second over all ranks = N x merged queries/s" % (args.n, args.n * world, args.nq),
+            "merged_queries_per_s": args.nq / (kernel_ms * 1e-3),
+            "vectors_total": args.n * world,
+            "recall_at_10_merged_vs_exact_over_all_shards": sharded_info["recall_merged"],
+            "recall_at_10_rank0_shard_alone": recall,
+            "without_exchange": {"value": world * args.nq / (ms_local * 1e-3), "ms_per_step": ms_local,
+                                 "what": "the same shards searched with no broadcast / all-gather / merge "
+                                         "(N independent replicas of the per-GPU workload), max over ranks"},
+            "exchange_overhead_frac": kernel_ms / ms_local - 1.0,
+            "exchange_bytes_per_rank_per_step": int(args.nq * k * 12),
+            "merge_parity": {"merged_entries_of_rank0_shard_match_frac": float(np.mean(ok_rows)),
+                             "merged_ascending_frac": float(np.mean(asc))}}
     return out
 
 

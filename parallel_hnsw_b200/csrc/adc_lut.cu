@@ -18,7 +18,7 @@
 //
 // One CTA per query: phase A computes the f32 entries into shared memory, phase B the per-row
 // minima / maxima, phase C quantises and writes the blob the traversal kernel pulls with one
-// bulk copy: [Q*K u8, padded to 16 B][bias f32][delta f32][8 B pad].
+// bulk copy: [4*ceil(Q/4) x K u8 (rows >= Q zero), padded to 16 B][bias f32][delta f32][8 B pad].
 #include "internal.h"
 
 namespace phnsw {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kLutThreads)
     v = v < 0 ? 0 : (v > 255 ? 255 : v);
     blob[e] = (uint8_t)v;
   }
-  const uint32_t tab_bytes = (total + 15) / 16 * 16;
+  const uint32_t tab_bytes = stride - 16;  // rows up to 4 * ceil(Q / 4) and the 16 B padding: zero
   for (uint32_t e = total + tid; e < tab_bytes; e += kLutThreads) blob[e] = 0;
   if (tid == 0) {
     float *tr = (float *)(blob + tab_bytes);

@@ -175,7 +175,7 @@ __host__ __device__ inline uint32_t pool_entries(uint32_t cap) {
 
 // ADC with quantised tables: bytes of one query's blob (u8 table, 16 B aligned, + bias/delta)
 __host__ __device__ inline uint32_t adc_q8_blob_bytes(uint32_t Q, uint32_t K) {
-  return (Q * K + 15) / 16 * 16 + 16;
+  return ((Q + 3) / 4 * 4 * K + 15) / 16 * 16 + 16;  // rows padded to a multiple of four (zeros)
 }
 // per-warp query area (floats) and table area (floats) of a kernel variant: the exact ADC walk
 // keeps the query (table entries are built from it), the quantised one only its table blob
@@ -248,6 +248,7 @@ struct WarpSearch {
   uint32_t ph;    // mbarrier phase bits, one per stage
   uint32_t stat;  // status bits raised by this warp
   float q8_bias, q8_delta;  // PQ == 2: distance = finalize(bias + delta * sum of u8 entries)
+  uint32_t q8_gl;           // PQ == 2: lanes that share one candidate (power of two, <= 32)
 
   __device__ WarpSearch(const SearchArgs &args, unsigned char *smem, uint32_t slot, int lane_)
       : a(args), lane(lane_) {
@@ -578,10 +579,11 @@ struct WarpSearch {
     return __fadd_rn(acc, t.w);
   }
   __device__ __forceinline__ float finalize(float acc) const {
-    if (METRIC == kCosHalf) return __fdiv_rn(__fsub_rn(1.0f, acc), 2.0f);
+    // x / 2 and x * 0.5 round the same real number once: identical bits, no division sequence
+    if (METRIC == kCosHalf) return __fmul_rn(__fsub_rn(1.0f, acc), 0.5f);
     if (METRIC == kOneMinusDot) return __fsub_rn(1.0f, acc);
     if (METRIC == kL2Sqrt) return __fsqrt_rn(acc);
-    float x = __fdiv_rn(__fsub_rn(acc, 1.0f), -2.0f);  // kCosClamp (pq.rs:481-487)
+    float x = __fmul_rn(__fsub_rn(acc, 1.0f), -0.5f);  // kCosClamp (pq.rs:481-487): / -2.0
     x = x < 0.0f ? 0.0f : x;
     x = x > 1.0f ? 1.0f : x;
     return x;
@@ -722,55 +724,73 @@ struct WarpSearch {
   __device__ void compute_distances(const LayerDev &layer, uint32_t nn) {
     if (PQ == 2) {
       // ADC over the query's quantised table (adc_lut.cu; oracle adc_build_lut_q8): a group of
-      // `gl` lanes scores one candidate -- lane t owns the code words t, t + gl, ... (four
-      // sub-spaces each), looks its u8 entries up in shared memory and the group adds the
-      // integers (exact, so the order is free); 32 / gl candidates per pass, four passes'
-      // code words in flight at once.  distance = finalize(bias + delta * sum).
+      // `gl` lanes scores one candidate -- lane t owns the code word t (four sub-spaces; words
+      // t + gl, ... as well when a row has more than 32 words), looks its u8 entries up in
+      // shared memory and the group adds the integers (exact, so the order is free).  The table
+      // has 4 * ceil(Q / 4) rows, the extra ones zero, so a word needs no per-byte guard.  The
+      // code words of the next eight passes are requested before the current eight are summed;
+      // lane c of a batch of 32 keeps candidate c's sum and the batch is finished with one
+      // distance = finalize(bias + delta * sum) per lane.
       const uint8_t *tab = (const uint8_t *)lut;
-      const uint32_t Q = a.pq_Q, K = a.pq_K, W4 = (Q + 3) / 4;
-      uint32_t gl = 1;
-      while (gl < W4 && gl < 32) gl <<= 1;
-      const uint32_t G = 32 / gl, t = lane & (gl - 1), g = lane / gl;
-      constexpr int R = 4;
-      for (uint32_t j0 = 0; j0 < nn; j0 += R * G) {
-        uint32_t node[R], sum[R];
-        const uint32_t *row[R];
-        bool ok[R];
+      const uint32_t K = a.pq_K, W4 = (a.pq_Q + 3) / 4;
+      const uint32_t gl = q8_gl, G = 32 / gl, t = lane & (gl - 1), g = lane / gl;
+      const uint8_t *tb = tab + (size_t)(4 * t) * K;
+      const bool has = t < W4;
+      const uint8_t *base = (const uint8_t *)layer.lrows + (has ? t : 0) * 4;
+      constexpr int R = 8;
+      for (uint32_t p0 = 0; p0 < nn; p0 += 32) {
+        const uint32_t np = min(32u, nn - p0);
+        uint32_t mysum = 0;
+        uint32_t cwn[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          const uint32_t j = j0 + r * G + g;
-          ok[r] = j < nn;
-          node[r] = bid[ok[r] ? j : j0];
-          row[r] = (const uint32_t *)((const uint8_t *)layer.lrows + (size_t)node[r] * a.cpitch);
-          sum[r] = 0;
+          const uint32_t c = r * G + g;
+          cwn[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
         }
-        for (uint32_t w = t; w < W4; w += gl) {
+        for (uint32_t c0 = 0; c0 < np; c0 += R * G) {
           uint32_t cw[R];
 #pragma unroll
-          for (int r = 0; r < R; r++) cw[r] = __ldg(row[r] + w);
-          const uint8_t *tb = tab + (size_t)(4 * w) * K;
-          const bool f1 = 4 * w + 1 < Q, f2 = 4 * w + 2 < Q, f3 = 4 * w + 3 < Q;
+          for (int r = 0; r < R; r++) cw[r] = cwn[r];
+          if (c0 + R * G < np) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const uint32_t c = c0 + R * G + r * G + g;
+              cwn[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
+            }
+          }
 #pragma unroll
           for (int r = 0; r < R; r++) {
-            uint32_t v = tb[cw[r] & 255u];
-            if (f1) v += tb[K + ((cw[r] >> 8) & 255u)];
-            if (f2) v += tb[2 * K + ((cw[r] >> 16) & 255u)];
-            if (f3) v += tb[3 * K + (cw[r] >> 24)];
-            sum[r] += v;
+            if (c0 + r * G >= np) break;  // warp-uniform
+            uint32_t v = 0;
+            if (has)
+              v = (uint32_t)tb[cw[r] & 255u] + tb[K + ((cw[r] >> 8) & 255u)] +
+                  tb[2 * K + ((cw[r] >> 16) & 255u)] + tb[3 * K + (cw[r] >> 24)];
+            if (W4 > gl) {  // rows of more than 32 code words (Q > 128)
+              const uint32_t c = c0 + r * G + g;
+              const uint8_t *rowp = (const uint8_t *)layer.lrows + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch;
+              for (uint32_t w = t + gl; w < W4; w += gl) {
+                const uint32_t x = __ldg((const uint32_t *)(rowp + 4 * w));
+                const uint8_t *tw = tab + (size_t)(4 * w) * K;
+                v += (uint32_t)tw[x & 255u] + tw[K + ((x >> 8) & 255u)] + tw[2 * K + ((x >> 16) & 255u)] +
+                     tw[3 * K + (x >> 24)];
+              }
+            }
+            if (gl == 32) {
+              v = __reduce_add_sync(kFull, v);
+              if ((uint32_t)lane == c0 + r) mysum = v;
+            } else {
+              for (uint32_t o = gl >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+              // lane L keeps candidate L: it sits in group L - (c0 + r * G) of this pass
+              const uint32_t gi = (uint32_t)lane - (c0 + r * G);
+              const uint32_t got = __shfl_sync(kFull, v, (gi * gl) & 31u);
+              if (gi < G) mysum = got;
+            }
           }
         }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          if (gl == 32) {
-            sum[r] = __reduce_add_sync(kFull, sum[r]);
-          } else {
-            for (uint32_t o = gl >> 1; o > 0; o >>= 1) sum[r] += __shfl_xor_sync(kFull, sum[r], o);
-          }
-          if (t == 0 && ok[r]) {
-            float d = finalize(__fadd_rn(q8_bias, __fmul_rn(q8_delta, (float)sum[r])));
-            if (d != d) stat |= kStatNaN;
-            bkeys[j0 + r * G + g] = make_key(d, node[r]);
-          }
+        if ((uint32_t)lane < np) {
+          float d = finalize(__fadd_rn(q8_bias, __fmul_rn(q8_delta, (float)mysum)));
+          if (d != d) stat |= kStatNaN;
+          bkeys[p0 + lane] = make_key(d, bid[p0 + lane]);
         }
       }
       __syncwarp();
@@ -1223,6 +1243,8 @@ struct WarpSearch {
       const float *tr = (const float *)((const uint8_t *)lut + bytes - 16);
       q8_bias = tr[0];
       q8_delta = tr[1];
+      q8_gl = 1;
+      while (q8_gl < (a.pq_Q + 3) / 4 && q8_gl < 32) q8_gl <<= 1;
       return true;
     }
     if (PQ) {
