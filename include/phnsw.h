@@ -153,6 +153,20 @@ void phnsw_index_build_params(const phnsw_index *ix, phnsw_build_params *bp);
 typedef enum { PHNSW_SUM_SEQUENTIAL = 0, PHNSW_SUM_TREE = 1 } phnsw_sum_order;
 phnsw_status phnsw_index_set_sum_order(phnsw_index *ix, int order);
 int phnsw_index_sum_order(const phnsw_index *ix);
+/* Batch overlap for back-to-back phnsw_search_batch_device calls on ONE stream (a server
+ * draining a queue of batches).  A launch of the traversal kernel ends ragged: its last queries
+ * finish one by one while most SMs already idle (about 12 % of a 10 000-query launch).  With
+ * overlap on, a launch that fills the machine is issued as a programmatic dependent launch: its
+ * CTAs start on the SMs the previous launch of that stream has already left, on a second set of
+ * per-query scratch.  Completion stays in stream order (a launch does not finish before the one
+ * it overtook), so everything that FOLLOWS a call on the stream still sees its results.  The
+ * contract the caller accepts: the inputs of a call (queries, stored_ids, exclude) must not be
+ * produced by the operation issued on that stream immediately before the call -- they must be
+ * complete by the time the previous operation STARTS (true for a pre-filled queue of batches,
+ * and for inputs uploaded or computed on another stream with the usual event wait).  Off by
+ * default.  No reference analogue (the crate is synchronous). */
+phnsw_status phnsw_index_set_batch_overlap(phnsw_index *ix, int on);
+int phnsw_index_batch_overlap(const phnsw_index *ix);
 phnsw_status phnsw_index_layer_info(const phnsw_index *ix, uint64_t layer_from_top,
                                     uint64_t *node_count, uint64_t *neighborhood_size);
 /* copy one layer out as u64 (the exact content of layer.nodes.N / layer.neighbors.N) */
@@ -227,6 +241,12 @@ phnsw_status phnsw_generate_with(phnsw_store *s, const uint64_t *vector_ids, uin
                                  phnsw_progress_fn progress, void *user, phnsw_index **out);
 phnsw_status phnsw_improve_index(phnsw_index *ix, const phnsw_build_params *bp,
                                  phnsw_progress_fn progress, void *user, float *recall_out);
+/* Construction temporaries (several GB per layer pass at 1M vectors) come from a stream-ordered
+ * memory pool owned by the library (one per device, NOT the device's default pool) and stay
+ * cached there between builds, so that a second build does not pay the driver's allocation
+ * cost again.  This hands the cached memory of `device` back to the driver (synchronises the
+ * device).  No reference analogue. */
+phnsw_status phnsw_release_build_memory(int device);
 /* Hnsw::improve_neighbors_upto (src/lib.rs:1515-1544): link passes over layers[0..upto) until the
  * stochastic recall stops improving by neighborhood_threshold; improve_neighbors (:1507-1513) is
  * upto = layer_count.  has_last_recall / last_recall = the crate's Option<f32>.  op NULL = the

@@ -81,6 +81,8 @@ struct Workspace {
   DevBuf hit_ids, hit_dists, hit_counts;  // ADC hits handed from the walk to the re-rank kernel
   DevBuf qlut;                            // quantised ADC tables of the batch (adc_lut.cu)
   uint32_t slots = 0, ovf_cap = 0, vlog_cap = 0, bitmap_words = 0, cap_pad = 0;
+  uint64_t chain_seq = 0;   // batch overlap: launches of the current chain so far
+  bool chained = false;     // the last launch on this stream followed the overlap protocol
   void release() {
     ovf.release(); bitmap.release(); vlog.release(); saved.release(); ctrl.release();
     stage_q.release(); stage_ids.release(); stage_excl.release();
@@ -130,6 +132,7 @@ struct phnsw_index {
   int max_smem = 0;
   uint32_t vlog_cap = 8192, ovf_cap = 8192;  // per-query device scratch (entries)
   int sum_order = 0;  // PHNSW_SUM_SEQUENTIAL / PHNSW_SUM_TREE: traversal distance summation
+  int batch_overlap = 0;  // phnsw_index_set_batch_overlap
   uint64_t expect_nodes = 0; // generate: size of the final bottom layer, so that the visited
                              // bitmap is allocated once and not regrown layer by layer
   uint64_t seed = 0;         // seed of the generate call (nested re-top generates derive theirs)
@@ -158,6 +161,9 @@ struct SearchCall {
   uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr, *out_selfhit = nullptr;
   uint32_t selfhit_eps = 0;  // out_selfhit by search::match_within_epsilon
   uint64_t id_offset = 0;    // added to every emitted VectorId (sharded search)
+  bool allow_overlap = false;  // batch overlap may apply (plain phnsw_search_batch_device only:
+                               // callers that chain other kernels on the results must not be
+                               // overtaken)
 };
 
 // the three kernel variants (search_seq.cu, search_tree.cu, search_pq.cu)

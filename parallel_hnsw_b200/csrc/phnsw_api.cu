@@ -246,10 +246,16 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64, stream));
   }
   const uint32_t max_slots = (uint32_t)ix->sm_count * kMaxWarps;
-  if (ws.slots < slots || ws.ovf_cap != ix->ovf_cap || ws.vlog_cap != ix->vlog_cap ||
+  // Batch overlap: only launches that fill the machine take part (then at most two launches are
+  // resident at a time: the next one cannot have started all its CTAs before every CTA of the
+  // previous one has left), each on its own scratch set and work counter.
+  const bool overlap = ix->batch_overlap && c.allow_overlap && !pq8 && c.mode == 0 && grid == (uint32_t)ix->sm_count &&
+                       w == wmax && !c.out_selfhit;
+  const uint32_t need_slots = overlap ? 2 * max_slots : slots;
+  if (ws.slots < need_slots || ws.ovf_cap != ix->ovf_cap || ws.vlog_cap != ix->vlog_cap ||
       ws.bitmap_words < need_words || ws.cap_pad < cap_pad) {
     PH_CUDA(cudaStreamSynchronize(stream));
-    uint32_t ns = std::max(ws.slots, std::max(slots, max_slots));
+    uint32_t ns = std::max(ws.slots, std::max(need_slots, max_slots));
     uint32_t ncp = std::max(ws.cap_pad, cap_pad);
     // the bitmap grows in steps so that a build (layers of increasing size) reallocates rarely
     uint32_t nbw = std::max(ws.bitmap_words, need_words);
@@ -268,7 +274,24 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     ws.bitmap_words = nbw;
     ws.cap_pad = ncp;
   }
-  PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 4, stream));  // work counter; status is sticky until sync
+  uint32_t counter_idx = 0, next_idx = 0, slot_base = 0, overlap_mode = 0;
+  if (overlap) {
+    // counters 2..4 rotate; the first launch of a chain starts from a stream-ordered memset, the
+    // others find their counter zeroed by the launch before them
+    if (!ws.chained) {
+      PH_CUDA(cudaMemsetAsync(ws.ctrl.as<uint32_t>() + 2, 0, 12, stream));
+      ws.chain_seq = 0;
+    }
+    counter_idx = 2 + (uint32_t)(ws.chain_seq % 3);
+    next_idx = 2 + (uint32_t)((ws.chain_seq + 1) % 3);
+    slot_base = (uint32_t)(ws.chain_seq & 1) * max_slots;
+    overlap_mode = ws.chained ? 2u : 1u;
+    ws.chained = true;
+    ws.chain_seq++;
+  } else {
+    ws.chained = false;
+    PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 4, stream));  // work counter; status is sticky until sync
+  }
 
   SearchArgs a;
   memset(&a, 0, sizeof(a));
@@ -305,7 +328,10 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.out_selfhit = c.out_selfhit;
   a.selfhit_eps = c.selfhit_eps;
   a.stats_stride = (uint32_t)ix->layers.size();
-  a.work_counter = ws.ctrl.as<unsigned int>();
+  a.work_counter = ws.ctrl.as<unsigned int>() + counter_idx;
+  a.next_counter = ws.ctrl.as<unsigned int>() + next_idx;
+  a.overlap = overlap_mode;
+  a.slot_base = slot_base;
   a.status = ws.ctrl.as<uint32_t>() + 1;
   a.ovf = ws.ovf.as<uint64_t>();
   a.ovf_cap = ix->ovf_cap;
@@ -864,6 +890,13 @@ phnsw_status phnsw_index_set_sum_order(phnsw_index *ix, int order) {
   return PHNSW_OK;
 }
 int phnsw_index_sum_order(const phnsw_index *ix) { return ix ? ix->sum_order : 0; }
+phnsw_status phnsw_index_set_batch_overlap(phnsw_index *ix, int on) {
+  PH_ENTRY();
+  if (!ix) return PHNSW_ERR_INVALID;
+  ix->batch_overlap = on ? 1 : 0;
+  return PHNSW_OK;
+}
+int phnsw_index_batch_overlap(const phnsw_index *ix) { return ix ? ix->batch_overlap : 0; }
 uint64_t phnsw_index_vector_count(const phnsw_index *ix) {  // lib.rs:592-594 (bottom layer)
   return ix && !ix->layers.empty() ? ix->layers.back().node_count : 0;
 }
@@ -962,6 +995,7 @@ phnsw_status phnsw_search_batch_device(const phnsw_index *ix, const float *queri
   c.out_counts = out_counts;
   c.out_nd = out_ndist;
   c.out_ne = out_nexp;
+  c.allow_overlap = true;
   return launch_search(ix, c, (cudaStream_t)cuda_stream);
 }
 

@@ -99,6 +99,15 @@ struct SearchArgs {
                            // query vector must sit in the leading run of |d| < 1e-5 results
   uint32_t stats_stride;
   unsigned int *work_counter;
+  // Batch overlap (phnsw_index_set_batch_overlap): the launch carries the programmatic-dependent-
+  // launch attribute, so its CTAs may start while the previous search launch of the stream is
+  // still draining its last queries.  The kernel then zeroes the NEXT launch's work counter
+  // (three rotate), lets its dependents be scheduled at once, and waits for the previous grid
+  // before it exits, so completion stays in stream order.  slot_base selects one of the two
+  // per-warp scratch sets (two launches may be resident at the same time).
+  unsigned int *next_counter;
+  uint32_t overlap;
+  uint32_t slot_base;
   uint32_t *status;
   uint64_t *ovf;           // per-warp frontier spill, ovf_cap keys each
   uint32_t ovf_cap;
@@ -189,6 +198,12 @@ __host__ __device__ inline uint32_t variant_lut_floats(int pq, uint32_t pq_table
 }
 
 #ifdef __CUDACC__
+
+#ifndef PHNSW_SCAN_UNROLL
+#define PHNSW_SCAN_UNROLL 1
+#endif
+#define PH_STR_(x) #x
+#define PH_UNROLL(n) _Pragma(PH_STR_(unroll n))
 
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint64_t kHiMask = 0xFFFFFFFF00000000ull;
@@ -1133,6 +1148,7 @@ struct WarpSearch {
         uint32_t A = 0, B = 0;
         uint64_t best = kEmptyKey;
         uint32_t bs = 0;
+        PH_UNROLL(PHNSW_SCAN_UNROLL)
         for (uint32_t s = lane; s < len; s += 32) {
           uint64_t k = pool[s];
           uint64_t km = k & kFlagMask64;
@@ -1654,7 +1670,17 @@ __global__ void __launch_bounds__(((TREE && !PQ) || PQ == 2 ? kTreeWarps : kSeqW
                                         variant_lut_floats(PQ, a.pq_table, a.pq_Q, a.pq_K),
                                         WarpSearch<METRIC, PQ, TREE>::kStageBytes);
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
-  WarpSearch<METRIC, PQ, TREE> ws(a, smem, blockIdx.x * warps_per_cta + warp, lane);
+  if (a.overlap) {
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        *a.next_counter = 0u;
+        __threadfence();
+      }
+      __syncthreads();  // the store is out before this CTA lets the dependents go
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  WarpSearch<METRIC, PQ, TREE> ws(a, smem, a.slot_base + blockIdx.x * warps_per_cta + warp, lane);
   if (lane == 0) {
     for (int s = 0; s < kMaxStages; s++) mbar_init(&ws.mbar[s], 1);
     mbar_fence_init();
@@ -1681,6 +1707,8 @@ __global__ void __launch_bounds__(((TREE && !PQ) || PQ == 2 ? kTreeWarps : kSeqW
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);
   if (lane == 0 && st) atomicOr(a.status, st);
+  // completion in stream order: this grid is not done before the one it was allowed to overtake
+  if (a.overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 #endif  // __CUDACC__

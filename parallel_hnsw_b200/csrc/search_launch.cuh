@@ -3,6 +3,7 @@
 #pragma once
 #include "internal.h"
 #include <mutex>
+#include <string.h>
 
 namespace phnsw {
 
@@ -23,6 +24,20 @@ static cudaError_t launch_moded(const SearchArgs &a, int grid, int block, size_t
       if (e != cudaSuccess) return e;
       if (dev < 16) configured[dev] = smem;
     }
+  }
+  if (a.overlap == 2) {  // chained behind another search launch: programmatic dependent launch
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, search_kernel<METRIC, PQ, TREE, MODE>, a);
   }
   search_kernel<METRIC, PQ, TREE, MODE><<<grid, block, smem, stream>>>(a);
   return cudaGetLastError();

@@ -253,6 +253,16 @@ class Hnsw:
     def sum_order(self):
         return int(N.lib().phnsw_index_sum_order(self._h))
 
+    def set_batch_overlap(self, on=True):
+        """Back-to-back search_device calls on one stream may overlap their ragged ends
+        (programmatic dependent launch; include/phnsw.h phnsw_index_set_batch_overlap states the
+        contract on the inputs).  Off by default."""
+        N.check(N.lib().phnsw_index_set_batch_overlap(self._h, 1 if on else 0))
+        return self
+
+    def batch_overlap(self):
+        return bool(N.lib().phnsw_index_batch_overlap(self._h))
+
     def __len__(self):
         return self.vector_count()
 

@@ -64,6 +64,56 @@ def test_concurrent_host_searches_equal_serial_results(ph, small):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("order", ["SUM_SEQUENTIAL", "SUM_TREE"])
+def test_batch_overlap_gives_the_same_results(ph, small, order):
+    """phnsw_index_set_batch_overlap: back-to-back launches on one stream chained as programmatic
+    dependent launches (rotating work counters, two scratch sets) return exactly what the plain
+    launches return, also when small batches (which do not take part) are interleaved."""
+    import torch
+    rows, comp, gh, oh = small
+    gh.set_sum_order(getattr(ph, order))
+    dev = torch.device("cuda", 0)
+    sp = ph.SearchParameters(80, 80, 2)
+    sizes = [4000, 4000, 300, 4000, 4000, 4000, 50, 4000]
+    qs = [torch.from_numpy(random_normed(n, 64, 500 + i)).to(dev) for i, n in enumerate(sizes)]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run_all():
+        outs = []
+        for q in qs:
+            oi = torch.empty((q.shape[0], 10), dtype=torch.int64, device=dev)
+            od = torch.empty((q.shape[0], 10), dtype=torch.float32, device=dev)
+            oc = torch.empty((q.shape[0],), dtype=torch.int32, device=dev)
+            gh.search_device(q, sp, oi, od, oc, stream=st)
+            outs.append((oi, od, oc))
+        gh.sync(st)
+        return [(a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()) for a, b, c in outs]
+    try:
+        plain = run_all()
+        gh.set_batch_overlap(True)
+        assert gh.batch_overlap()
+        for _ in range(3):
+            got = run_all()
+            for g, p in zip(got, plain):
+                assert np.array_equal(g[0], p[0]) and np.array_equal(g[2], p[2])
+                assert np.array_equal(g[1].view(np.uint32), p[1].view(np.uint32))
+        # errors still surface: a NaN query inside a chained launch
+        bad = qs[0].clone()
+        bad[7, 3] = float("nan")
+        oi = torch.empty((4000, 10), dtype=torch.int64, device=dev)
+        od = torch.empty((4000, 10), dtype=torch.float32, device=dev)
+        oc = torch.empty((4000,), dtype=torch.int32, device=dev)
+        gh.search_device(qs[1], sp, oi, od, oc, stream=st)
+        gh.search_device(bad, sp, oi, od, oc, stream=st)
+        with pytest.raises(ph.PhnswError):
+            gh.sync(st)
+        got = run_all()
+        assert np.array_equal(got[3][0], plain[3][0])
+    finally:
+        gh.set_batch_overlap(False)
+        gh.set_sum_order(ph.SUM_SEQUENTIAL)
+
+
 def test_out_of_range_stored_ids_are_loud(ph, small):
     rows, comp, gh, oh = small
     ids = np.array([3, 6000, 5], dtype=np.uint64)

@@ -23,6 +23,7 @@ ap.add_argument("--tag", default="")
 ap.add_argument("--no-improve", action="store_true")
 ap.add_argument("--order", type=int, nargs="+", default=[0], help="0 sequential, 1 tree")
 ap.add_argument("--streams", type=int, default=1)
+ap.add_argument("--overlap", action="store_true", help="phnsw_index_set_batch_overlap")
 ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one launch "
                 "(ncu --profile-from-start off)")
 args = ap.parse_args()
@@ -33,6 +34,8 @@ gh = ph.Hnsw.generate(comp, seed=1, improve=not args.no_improve)
 torch.cuda.synchronize()
 tb = time.time() - t
 dev = torch.device("cuda:0")
+if args.overlap:
+    gh.set_batch_overlap(True)
 k = 10
 sp = ph.SearchParameters(args.ef, args.ef, 2)
 st = torch.cuda.current_stream().cuda_stream
