@@ -167,6 +167,12 @@ int phnsw_index_sum_order(const phnsw_index *ix);
  * default.  No reference analogue (the crate is synchronous). */
 phnsw_status phnsw_index_set_batch_overlap(phnsw_index *ix, int on);
 int phnsw_index_batch_overlap(const phnsw_index *ix);
+/* Every stream a search was issued on keeps its own per-query scratch (frontier spill, visited
+ * bitmaps, staging buffers: ~0.8 GB at 1M vectors) until the index is destroyed.  A caller that
+ * creates and retires streams releases the scratch of a retired stream here (synchronises that
+ * stream), or of all streams (`all` != 0, synchronises the device).  No search on the affected
+ * stream(s) may be in flight from another thread.  No reference analogue. */
+phnsw_status phnsw_index_release_workspace(const phnsw_index *ix, void *cuda_stream, int all);
 phnsw_status phnsw_index_layer_info(const phnsw_index *ix, uint64_t layer_from_top,
                                     uint64_t *node_count, uint64_t *neighborhood_size);
 /* copy one layer out as u64 (the exact content of layer.nodes.N / layer.neighbors.N) */

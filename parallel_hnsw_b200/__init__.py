@@ -4,11 +4,11 @@ from .hnsw import (BigComparator, BuildParameters, COS_CLAMP, COS_HALF, EMPTY, F
                    L2_SQRT, ONE_MINUS_DOT, PhnswError, Pq8Comparator, PqBuildParameters,
                    QuantizedHnsw, assign_last_stats, pq8_train,
                    SearchParameters, SUM_SEQUENTIAL, SUM_TREE, ADC_TABLE_F32, ADC_TABLE_Q8,
-                   calculate_partitions, device_count, merge_topk_device)
+                   calculate_partitions, device_count, release_build_memory, merge_topk_device)
 
 __all__ = ["BigComparator", "BuildParameters", "COS_CLAMP", "COS_HALF", "EMPTY", "FLT_MAX", "Hnsw",
            "L2_SQRT", "ONE_MINUS_DOT", "PhnswError", "Pq8Comparator", "PqBuildParameters",
            "QuantizedHnsw", "assign_last_stats", "pq8_train",
            "SearchParameters", "SUM_SEQUENTIAL", "SUM_TREE", "ADC_TABLE_F32", "ADC_TABLE_Q8",
-           "calculate_partitions",
+           "calculate_partitions", "release_build_memory",
            "device_count", "merge_topk_device"]

@@ -19,6 +19,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -106,14 +107,17 @@ static bool write_all(const std::string &path, const void *buf, size_t len) {
 static bool read_all(const std::string &path, std::vector<char> &out) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) return false;
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  out.resize((size_t)sz + 1);
+  long sz = -1;
+  if (fseek(f, 0, SEEK_END) == 0) sz = ftell(f);
+  // the documents read this way are small JSON files: anything else is not one of ours
+  if (sz < 0 || sz > (64L << 20) || fseek(f, 0, SEEK_SET) != 0) {
+    fclose(f);
+    errno = sz < 0 ? errno : EFBIG;
+    return false;
+  }
+  out.assign((size_t)sz + 1, 0);
   size_t r = sz ? fread(out.data(), 1, (size_t)sz, f) : 0;
   fclose(f);
-  out[(size_t)sz] = 0;
-  out.resize((size_t)sz + 1);
   return r == (size_t)sz;
 }
 
@@ -320,7 +324,24 @@ phnsw_status io_load_store(const std::string &path, int device, phnsw_store **ou
     set_error("load: %s has an unknown header", path.c_str());
     return PHNSW_ERR_FORMAT;
   }
-  std::vector<float> rows((size_t)hdr[2] * hdr[3]);
+  // dim * count comes from the file: check it against the file's own size before allocating
+  struct stat sb;
+  const bool sized = fstat(fileno(f), &sb) == 0;
+  const unsigned __int128 need = (unsigned __int128)hdr[2] * hdr[3] * 4 + sizeof hdr;
+  if (!sized || hdr[2] > (1ull << 20) || need > (unsigned __int128)(uint64_t)sb.st_size) {
+    fclose(f);
+    set_error("load: %s is truncated (header names %llu x %llu floats)", path.c_str(),
+              (unsigned long long)hdr[3], (unsigned long long)hdr[2]);
+    return PHNSW_ERR_IO;
+  }
+  std::vector<float> rows;
+  try {
+    rows.resize((size_t)hdr[2] * hdr[3]);
+  } catch (const std::exception &) {
+    fclose(f);
+    set_error("load: out of host memory for %s", path.c_str());
+    return PHNSW_ERR_IO;
+  }
   size_t got = rows.empty() ? 0 : fread(rows.data(), 4, rows.size(), f);
   fclose(f);
   if (got != rows.size()) {
@@ -354,6 +375,12 @@ phnsw_status io_load_graph(const std::string &d, phnsw_store *s, phnsw_index **o
     size_t len = 0;
     ~Mapping() { if (p) munmap(p, len); }
   };
+  // sizes come from the files: bound them before anything is allocated from them (the crate
+  // builds at most a few tens of layers: node counts shrink by `order` per layer)
+  if (L > 64) {
+    set_error("load: %s/meta names %llu layers (at most 64 supported)", dir, (unsigned long long)L);
+    return PHNSW_ERR_FORMAT;
+  }
   std::vector<Mapping> maps(2 * L);
   std::vector<phnsw_layer_desc> descs(L);
   for (uint64_t i = 0; i < L; i++) {
@@ -367,9 +394,14 @@ phnsw_status io_load_graph(const std::string &d, phnsw_store *s, phnsw_index **o
       set_error("load: %s/layer.meta.%s is not a valid LayerMeta document", dir, n.c_str());
       return PHNSW_ERR_FORMAT;
     }
+    if (nc >= 0x7FFFFFFFull || M > 64) {  // 32-bit node ids on the device; rows of at most 64
+      set_error("load: %s/layer.meta.%s: node_count %llu / neighborhood_size %llu out of range", dir,
+                n.c_str(), (unsigned long long)nc, (unsigned long long)M);
+      return PHNSW_ERR_FORMAT;
+    }
     const uint64_t *ptr[2] = {nullptr, nullptr};
     for (int which = 0; which < 2; which++) {
-      const size_t want = (size_t)(which ? nc * M : nc) * 8;
+      const size_t want = (size_t)(which ? nc * M : nc) * 8;  // < 2^31 * 64 * 8: no overflow
       std::string p = d + (which ? "/layer.neighbors." : "/layer.nodes.") + n;
       int fd = open(p.c_str(), O_RDONLY);
       struct stat sb;
@@ -478,10 +510,16 @@ phnsw_status phnsw_index_load(const char *dir, int device, phnsw_store **store_o
     return PHNSW_ERR_IO;
   }
   phnsw_store *s = nullptr;
-  phnsw_status rc = io_load_store(d + "/comparator", device, &s);
-  if (rc != PHNSW_OK) return rc;
+  phnsw_status rc;
   phnsw_index *ix = nullptr;
-  rc = io_load_graph(d, s, &ix);
+  try {  // nothing may unwind across the C ABI
+    rc = io_load_store(d + "/comparator", device, &s);
+    if (rc != PHNSW_OK) return rc;
+    rc = io_load_graph(d, s, &ix);
+  } catch (const std::exception &e) {
+    set_error("load: %s", e.what());
+    rc = PHNSW_ERR_IO;
+  }
   if (rc != PHNSW_OK) {
     phnsw_store_destroy(s);
     return rc;

@@ -31,14 +31,15 @@ phnsw_status cuda_fail(cudaError_t e, const char *what) {
 
 // ------------------------------------------------------------------ small kernels
 // K6: u64 on-disk ids (serialize.rs layout) -> u32 in HBM; !0 -> 0xFFFFFFFF
+// (only in neighbour lists: `allow_empty`; a node's VectorId is never the empty marker)
 __global__ void compact_u64_kernel(const uint64_t *__restrict__ in, uint32_t *__restrict__ out,
-                                   size_t n, uint64_t limit, uint32_t *bad) {
+                                   size_t n, uint64_t limit, uint32_t *bad, bool allow_empty) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     uint64_t v = in[i];
     uint32_t o;
-    if (v == ~0ull) o = kEmpty32;
+    if (v == ~0ull && allow_empty) o = kEmpty32;
     else if (v >= limit) { o = kEmpty32; atomicOr(bad, 1u); }
     else o = (uint32_t)v;
     out[i] = o;
@@ -455,9 +456,12 @@ phnsw_status index_push_layer_device(phnsw_index *ix, uint64_t node_count, uint6
         neighbors, (uint32_t)node_count, (uint32_t)M, flags);
   }
   uint32_t hf[3];
-  PH_CUDA(cudaMemcpy(hf, flags, 12, cudaMemcpyDeviceToHost));
+  {
+    cudaError_t ec = cudaMemcpy(hf, flags, 12, cudaMemcpyDeviceToHost);
+    cudaFree(flags);
+    if (ec != cudaSuccess) return cuda_fail(ec, "index_push_layer: flag read-back");
+  }
   l.row_dups = hf[2] != 0;
-  cudaFree(flags);
   if (hf[1]) {
     set_error("layer nodes are not strictly ascending VectorIds (Layer.nodes, lib.rs:85-91)");
     return PHNSW_ERR_GRAPH;
@@ -787,10 +791,10 @@ phnsw_status phnsw_index_from_layers(phnsw_store *s, uint64_t layer_count,
     if (e == cudaSuccess) e = cudaMalloc(&d_nb, std::max<size_t>(nn, 1) * 4);
     if (e == cudaSuccess) e = cudaMemcpy(tmp, L.nodes, L.node_count * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-      compact_u64_kernel<<<grid_for(L.node_count), 256>>>(tmp, d_nodes, L.node_count, s->n, bad);
+      compact_u64_kernel<<<grid_for(L.node_count), 256>>>(tmp, d_nodes, L.node_count, s->n, bad, false);
       if (nn) {
         e = cudaMemcpy(tmp, L.neighbors, nn * 8, cudaMemcpyHostToDevice);
-        compact_u64_kernel<<<grid_for(nn), 256>>>(tmp, d_nb, nn, L.node_count, bad);
+        compact_u64_kernel<<<grid_for(nn), 256>>>(tmp, d_nb, nn, L.node_count, bad, true);
       }
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -897,6 +901,25 @@ phnsw_status phnsw_index_set_batch_overlap(phnsw_index *ix, int on) {
   return PHNSW_OK;
 }
 int phnsw_index_batch_overlap(const phnsw_index *ix) { return ix ? ix->batch_overlap : 0; }
+phnsw_status phnsw_index_release_workspace(const phnsw_index *ix, void *cuda_stream, int all) {
+  PH_ENTRY();
+  if (!ix) return PHNSW_ERR_INVALID;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  std::lock_guard<std::mutex> hg(ix->host_mu);
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (all) {
+    PH_CUDA(cudaDeviceSynchronize());
+    for (auto &kv : ix->ws) kv.second.release();
+    ix->ws.clear();
+    return PHNSW_OK;
+  }
+  auto it = ix->ws.find((cudaStream_t)cuda_stream);
+  if (it == ix->ws.end()) return PHNSW_OK;
+  PH_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  it->second.release();
+  ix->ws.erase(it);
+  return PHNSW_OK;
+}
 uint64_t phnsw_index_vector_count(const phnsw_index *ix) {  // lib.rs:592-594 (bottom layer)
   return ix && !ix->layers.empty() ? ix->layers.back().node_count : 0;
 }

@@ -263,6 +263,11 @@ class Hnsw:
     def batch_overlap(self):
         return bool(N.lib().phnsw_index_batch_overlap(self._h))
 
+    def release_workspace(self, stream=None):
+        """Free the per-query scratch kept for `stream` (None: for every stream)."""
+        N.check(N.lib().phnsw_index_release_workspace(self._h, C.c_void_p(stream or 0),
+                                                      1 if stream is None else 0))
+
     def __len__(self):
         return self.vector_count()
 
@@ -573,6 +578,12 @@ class Pq8Comparator(BigComparator):
 
     def adc_table(self):
         return int(N.lib().phnsw_pq8_store_adc_table(self._h))
+
+
+def release_build_memory(device=0):
+    """Hand the construction temporaries cached in the library's memory pool back to the driver
+    (include/phnsw.h phnsw_release_build_memory)."""
+    N.check(N.lib().phnsw_release_build_memory(int(device)))
 
 
 def PqBuildParameters():

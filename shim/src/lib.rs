@@ -5,7 +5,10 @@
 //! `AbstractVector` (src/types.rs:41-75), `ProgressMonitor` (src/progress.rs:12-29),
 //! `BigComparator` (src/bigvec.rs:36-57), `Hnsw::{generate, search, search_upto, knn,
 //! threshold_nn, improve_index, promote_at_layer, extend_layer, discover_unreachable_vectors,
-//! stochastic_recall, serialize, deserialize}` (src/lib.rs:653-1699).
+//! stochastic_recall, serialize, deserialize}` (src/lib.rs:653-1699), `PqBuildParameters`
+//! (src/parameters.rs:66-71), `HnswQuantizer::{quantize, reconstruct}` and `QuantizedHnsw::{new,
+//! search, vector_count, quantizer, serialize, deserialize}` (src/pq.rs:61-82, 120-477), plus the
+//! device-only ADC view (`AdcIndex`, no crate analogue).
 //!
 //! NOT COMPILED in this repository's environment (no Rust toolchain); `ffi.rs` is generated from
 //! the header and checked by `tests/test_rust_shim.py`, this file is reviewed by hand against it.
@@ -132,6 +135,13 @@ impl BigComparator {
         check_or_panic(unsafe { phnsw_store_compare(self.store.0, a.as_ptr(), b.as_ptr(), a.len() as u64, out.as_mut_ptr()) });
         out
     }
+    /// Comparator::lookup (src/lib.rs:55-59) for a batch of stored ids
+    pub fn lookup(&self, ids: &[VectorId]) -> Vec<Vec<f32>> {
+        let raw: Vec<u64> = ids.iter().map(|v| v.0 as u64).collect();
+        let mut out = vec![0f32; ids.len() * self.dim];
+        check_or_panic(unsafe { phnsw_store_get_rows(self.store.0, raw.as_ptr(), raw.len() as u64, out.as_mut_ptr()) });
+        out.chunks(self.dim.max(1)).map(|c| c.to_vec()).collect()
+    }
 }
 
 struct IndexHandle(*mut phnsw_index);
@@ -206,6 +216,17 @@ impl Hnsw {
         self.search_batch(&[v], sp, upto_layer_from_top).pop().unwrap()
     }
 
+    /// `layers.last().nodes`: the VectorId of every bottom-layer node, in node order
+    fn bottom_layer_nodes(&self) -> Vec<u64> {
+        let (mut nc, mut m) = (0u64, 0u64);
+        let bottom = self.layer_count() as u64 - 1;
+        check_or_panic(unsafe { phnsw_index_layer_info(self.index.0, bottom, &mut nc, &mut m) });
+        let mut nodes = vec![0u64; nc as usize];
+        let mut nb = vec![0u64; (nc * m) as usize];
+        check_or_panic(unsafe { phnsw_index_export_layer(self.index.0, bottom, nodes.as_mut_ptr(), nb.as_mut_ptr()) });
+        nodes
+    }
+
     /// src/lib.rs:905-928: rows follow bottom-layer node order
     pub fn knn(&self, k: usize, probe_depth: usize) -> impl ParallelIterator<Item = (VectorId, Vec<(VectorId, f32)>)> {
         let n = self.vector_count();
@@ -231,11 +252,14 @@ impl Hnsw {
         check_or_panic(unsafe {
             phnsw_threshold_nn(self.index.0, threshold, probe_depth as u64, initial_search_depth as u64, &mut off, &mut ids, &mut ds)
         });
+        // rows follow bottom-layer node order: row i belongs to `layer.nodes[i]` (src/lib.rs:939-960),
+        // which is not `i` for an index built over a subset of the store
+        let nodes = self.bottom_layer_nodes();
         let out = unsafe {
             let off = std::slice::from_raw_parts(off, n + 1);
             (0..n).map(|i| {
                 let (a, b) = (off[i] as usize, off[i + 1] as usize);
-                (VectorId(i), (a..b).map(|j| (VectorId(*ids.add(j) as usize), *ds.add(j))).collect())
+                (VectorId(nodes[i] as usize), (a..b).map(|j| (VectorId(*ids.add(j) as usize), *ds.add(j))).collect())
             }).collect()
         };
         unsafe {
@@ -296,5 +320,170 @@ impl Hnsw {
         check(unsafe { phnsw_index_load(dir.as_ptr(), device, &mut s, &mut ix) })?;
         let dim = unsafe { phnsw_store_dim(s) } as usize;
         Ok(Self { comparator: BigComparator { store: Arc::new(StoreHandle(s)), dim }, index: IndexHandle(ix), seed: 0 })
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Product quantisation: src/pq.rs.  The crate's const generics (SIZE, CENTROID_SIZE,
+// QUANTIZED_SIZE) become run-time sizes read back from the handle; codes are `u16` per
+// sub-vector as in src/pq.rs:20.
+pub type PqBuildParameters = phnsw_pq_build_params;
+
+impl Default for phnsw_pq_build_params {
+    fn default() -> Self {
+        let mut bp = std::mem::MaybeUninit::<phnsw_pq_build_params>::uninit();
+        unsafe {
+            phnsw_default_pq_build_params(bp.as_mut_ptr());
+            bp.assume_init()
+        }
+    }
+}
+
+struct PqHandle(*mut phnsw_pq);
+unsafe impl Send for PqHandle {}
+unsafe impl Sync for PqHandle {}
+impl Drop for PqHandle {
+    fn drop(&mut self) { unsafe { phnsw_pq_destroy(self.0) } }
+}
+
+/// src/pq.rs:61-82 `HnswQuantizer`: a borrowed view of the quantizer half of a `QuantizedHnsw`
+pub struct HnswQuantizer<'a> {
+    pq: &'a PqHandle,
+}
+
+impl<'a> HnswQuantizer<'a> {
+    pub fn centroid_count(&self) -> usize { unsafe { phnsw_pq_centroid_count(self.pq.0) as usize } }
+    pub fn centroid_size(&self) -> usize { unsafe { phnsw_pq_centroid_size(self.pq.0) as usize } }
+    pub fn quantized_size(&self) -> usize { unsafe { phnsw_pq_quantized_size(self.pq.0) as usize } }
+    /// `Quantizer::quantize` (src/pq.rs:133-146) for a batch: one code per sub-vector, each the
+    /// nearest centroid found by an HNSW search over the centroid index
+    pub fn quantize(&self, vecs: &[Vec<f32>]) -> Vec<Vec<u16>> {
+        let q = self.quantized_size();
+        let flat: Vec<f32> = vecs.iter().flat_map(|v| v.iter().copied()).collect();
+        let mut codes = vec![0u16; vecs.len() * q];
+        check_or_panic(unsafe { phnsw_pq_quantize(self.pq.0, flat.as_ptr(), vecs.len() as u64, codes.as_mut_ptr()) });
+        codes.chunks(q.max(1)).map(|c| c.to_vec()).collect()
+    }
+    /// `Quantizer::reconstruct` (src/pq.rs:148-152): the concatenated centroids
+    pub fn reconstruct(&self, codes: &[Vec<u16>]) -> Vec<Vec<f32>> {
+        let size = self.quantized_size() * self.centroid_size();
+        let flat: Vec<u16> = codes.iter().flat_map(|c| c.iter().copied()).collect();
+        let mut out = vec![0f32; codes.len() * size];
+        check_or_panic(unsafe { phnsw_pq_reconstruct(self.pq.0, flat.as_ptr(), codes.len() as u64, out.as_mut_ptr()) });
+        out.chunks(size.max(1)).map(|c| c.to_vec()).collect()
+    }
+}
+
+/// src/pq.rs:120-131 `QuantizedHnsw`: centroid index + quantizer + index over the codes + the
+/// full-precision comparator used for the re-rank
+pub struct QuantizedHnsw {
+    pq: PqHandle,
+    comparator: BigComparator,
+}
+
+impl QuantizedHnsw {
+    /// src/pq.rs:287-344.  `centroid_metric` / `quantized_metric` select the distance bodies the
+    /// crate's tests plug in as CentroidComparator / QuantizedComparator (2 = src/pq.rs:499-505,
+    /// 3 = src/pq.rs:481-497).
+    pub fn new(number_of_centroids: usize, centroid_size: usize, comparator: BigComparator, centroid_metric: c_int,
+               quantized_metric: c_int, bp: PqBuildParameters, seed: u64, mut progress: &mut dyn ProgressMonitor) -> Self {
+        let mut pq = ptr::null_mut();
+        check_or_panic(unsafe {
+            phnsw_pq_build(comparator.store.0, number_of_centroids as u64, centroid_size as u64, centroid_metric,
+                           quantized_metric, &bp, seed, Some(progress_trampoline),
+                           &mut progress as *mut &mut dyn ProgressMonitor as *mut c_void, &mut pq)
+        });
+        Self { pq: PqHandle(pq), comparator }
+    }
+    pub fn vector_count(&self) -> usize { self.comparator.len() }
+    pub fn quantizer(&self) -> HnswQuantizer<'_> { HnswQuantizer { pq: &self.pq } }
+    pub fn full_comparator(&self) -> &BigComparator { &self.comparator }
+    /// the stored codes, one row of `quantized_size` u16 per vector (the QuantizedComparator's data)
+    pub fn codes(&self) -> Vec<Vec<u16>> {
+        let q = self.quantizer().quantized_size();
+        let mut codes = vec![0u16; self.vector_count() * q];
+        check_or_panic(unsafe { phnsw_pq_codes(self.pq.0, codes.as_mut_ptr()) });
+        codes.chunks(q.max(1)).map(|c| c.to_vec()).collect()
+    }
+    /// src/pq.rs:346-364 for a batch: quantise, search the code graph, re-rank every hit with the
+    /// full comparator, sort by (distance, id)
+    pub fn search_batch(&self, vs: &[AbstractVector], sp: SearchParameters) -> Vec<Vec<(VectorId, f32)>> {
+        let nq = vs.len();
+        let ef = sp.number_of_candidates as usize;
+        let (mut out_ids, mut out_ds, mut cnt) = (vec![0u64; nq * ef], vec![0f32; nq * ef], vec![0u32; nq]);
+        let stored = vs.iter().all(|v| matches!(v, AbstractVector::Stored(_)));
+        if stored {
+            let ids: Vec<u64> = vs.iter().map(|v| match v { AbstractVector::Stored(i) => i.0 as u64, _ => unreachable!() }).collect();
+            check_or_panic(unsafe {
+                phnsw_pq_search_batch(self.pq.0, ptr::null(), ids.as_ptr(), nq as u64, &sp, ef as u64,
+                                      out_ids.as_mut_ptr(), out_ds.as_mut_ptr(), cnt.as_mut_ptr())
+            });
+        } else {
+            // a mixed batch is looked up on the host first (Comparator::lookup_abstract, src/lib.rs:61-67)
+            let flat: Vec<f32> = vs.iter().flat_map(|v| match v {
+                AbstractVector::Unstored(x) => x.to_vec(),
+                AbstractVector::Stored(i) => self.comparator.lookup(&[*i]).pop().unwrap(),
+            }).collect();
+            check_or_panic(unsafe {
+                phnsw_pq_search_batch(self.pq.0, flat.as_ptr(), ptr::null(), nq as u64, &sp, ef as u64,
+                                      out_ids.as_mut_ptr(), out_ds.as_mut_ptr(), cnt.as_mut_ptr())
+            });
+        }
+        (0..nq).map(|q| (0..cnt[q] as usize).map(|i| (VectorId(out_ids[q * ef + i] as usize), out_ds[q * ef + i])).collect()).collect()
+    }
+    pub fn search(&self, v: AbstractVector, sp: SearchParameters) -> Vec<(VectorId, f32)> {
+        self.search_batch(&[v], sp).pop().unwrap()
+    }
+    /// src/pq.rs:433-476: `quantizer/`, `hnsw/`, `comparator/`, `pq_build_parameters.json`
+    pub fn serialize<P: AsRef<Path>>(&self, path: P) -> Result<(), Error> {
+        let dir = CString::new(path.as_ref().to_string_lossy().as_bytes()).map_err(|e| Error::Io(e.to_string()))?;
+        check(unsafe { phnsw_pq_save(self.pq.0, dir.as_ptr()) })
+    }
+    pub fn deserialize<P: AsRef<Path>>(path: P, device: c_int) -> Result<Self, Error> {
+        let dir = CString::new(path.as_ref().to_string_lossy().as_bytes()).map_err(|e| Error::Io(e.to_string()))?;
+        let (mut s, mut pq) = (ptr::null_mut(), ptr::null_mut());
+        check(unsafe { phnsw_pq_load(dir.as_ptr(), device, &mut s, &mut pq) })?;
+        let dim = unsafe { phnsw_store_dim(s) } as usize;
+        Ok(Self { pq: PqHandle(pq), comparator: BigComparator { store: Arc::new(StoreHandle(s)), dim } })
+    }
+}
+
+/// Device-only asymmetric-distance view (no crate analogue; BASELINE.json north_star kernel 2):
+/// u8 codes + one k-means codebook, searched with per-query tables in shared memory and
+/// re-ranked exactly (the second half of src/pq.rs:346-364) in one call.
+pub struct AdcIndex {
+    codes: Arc<StoreHandle>,
+    index: IndexHandle,
+    full: BigComparator,
+}
+
+impl AdcIndex {
+    /// `graph`: an index built over `full` (its layers are reused over the codes)
+    pub fn new(graph: &Hnsw, full: BigComparator, number_of_centroids: usize, centroid_size: usize,
+               kmeans_iters: usize, seed: u64, quantised_tables: bool) -> Result<Self, Error> {
+        let mut codebook = vec![0f32; number_of_centroids * centroid_size];
+        let mut k = 0u64;
+        check(unsafe {
+            phnsw_pq8_train(full.store.0, number_of_centroids as u64, centroid_size as u64, kmeans_iters as u64, seed,
+                            codebook.as_mut_ptr(), &mut k)
+        })?;
+        let mut s = ptr::null_mut();
+        check(unsafe { phnsw_pq8_store_create(full.store.0, codebook.as_ptr(), k, centroid_size as u64, &mut s) })?;
+        let codes = Arc::new(StoreHandle(s));
+        check(unsafe { phnsw_pq8_store_set_adc_table(codes.0, if quantised_tables { 1 } else { 0 }) })?;
+        let mut ix = ptr::null_mut();
+        check(unsafe { phnsw_index_rebind(graph.index.0, codes.0, &mut ix) })?;
+        Ok(Self { codes, index: IndexHandle(ix), full })
+    }
+    /// ADC walk + exact re-rank of the first `rerank_k` hits (0 = all candidates), ascending (d, id)
+    pub fn search_batch(&self, queries: &[Vec<f32>], sp: SearchParameters, rerank_k: usize, k: usize) -> Vec<Vec<(VectorId, f32)>> {
+        let nq = queries.len();
+        let flat: Vec<f32> = queries.iter().flat_map(|v| v.iter().copied()).collect();
+        let (mut out_ids, mut out_ds, mut cnt) = (vec![0u64; nq * k], vec![0f32; nq * k], vec![0u32; nq]);
+        check_or_panic(unsafe {
+            phnsw_pq8_search_batch(self.index.0, self.full.store.0, flat.as_ptr(), nq as u64, &sp, rerank_k as u64, k as u64,
+                                   out_ids.as_mut_ptr(), out_ds.as_mut_ptr(), cnt.as_mut_ptr())
+        });
+        (0..nq).map(|q| (0..cnt[q] as usize).map(|i| (VectorId(out_ids[q * k + i] as usize), out_ds[q * k + i])).collect()).collect()
     }
 }

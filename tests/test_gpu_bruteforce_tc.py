@@ -81,3 +81,38 @@ def test_small_problems_stay_on_the_exact_scan(ph):
     comp = ph.BigComparator(rows, ph.COS_HALF)
     comp.bruteforce_knn(rows[:10], 5)
     assert comp.bruteforce_last_stats()["path"] == "cuda"
+
+
+@pytest.mark.parametrize("metric_name,dim,n", [("COS_HALF", 64, 40000), ("L2_SQRT", 128, 36000)])
+def test_tensor_path_against_the_oracle_directly(ph, oracle, metric_name, dim, n):
+    """Above the 32 768-row threshold the ground truth comes from the tcgen05 filter + exact
+    re-rank: checked here against the CPU oracle itself (compare_all = the crate's comparator
+    over every stored vector, sorted by (d, id)), not only against the CUDA-core scan."""
+    metric = getattr(ph, metric_name)
+    rows = (random_normed(n, dim, 31) if metric_name != "L2_SQRT"
+            else clustered(n, dim, 32, n_clusters=128, spread=0.4))
+    comp = ph.BigComparator(rows, metric)
+    oh = oracle.Hnsw.from_layers(getattr(oracle, metric_name), rows, [])
+    vs = np.arange(n, dtype=np.uint64)
+    picks = [0, 1, 17, 4095, 4096, 20000, 32767, 32768, n - 1]
+    k = 10
+    old = os.environ.get("PHNSW_BRUTEFORCE")
+    try:
+        os.environ["PHNSW_BRUTEFORCE"] = "tensor"
+        gi, gd = comp.bruteforce_knn(rows[picks], k + 1)
+        assert comp.bruteforce_last_stats()["path"] == "tensor"
+    finally:
+        if old is None:
+            os.environ.pop("PHNSW_BRUTEFORCE", None)
+        else:
+            os.environ["PHNSW_BRUTEFORCE"] = old
+    gi, gd = np.asarray(gi.cpu() if hasattr(gi, "cpu") else gi), np.asarray(gd.cpu() if hasattr(gd, "cpu") else gd)
+    for r, v in enumerate(picks):
+        oi, od = oh.compare_all(v, vs)          # self excluded, ascending (d, id)
+        keep = gi[r] != v                        # drop the query's own row from the device list
+        g_ids, g_ds = gi[r][keep][:k], gd[r][keep][:k]
+        assert np.array_equal(g_ids.astype(np.uint64), oi[:k]), (v, g_ids, oi[:k])
+        if metric_name == "L2_SQRT":             # sqrt vs powf(0.5): documented 2e-7 bound
+            assert np.all(np.abs(g_ds.astype(np.float64) - od[:k]) <= 2e-7 * od[:k] + 1e-30)
+        else:
+            assert np.array_equal(g_ds.view(np.uint32), od[:k].view(np.uint32))

@@ -265,3 +265,77 @@ def test_sharded_call_world2_nccl(ph, tmp_path):
         assert [p[1] for p in pairs] == ids[0][qi].tolist()
         assert np.array_equal(np.array([p[0] for p in pairs], np.float32).view(np.uint32),
                               ds[0][qi].view(np.uint32))
+
+
+def test_corrupt_index_directories_are_loud(ph, small, tmp_path):
+    """Sizes and ids read from disk are checked before anything is allocated or indexed with
+    them: absurd layer counts, node counts, a truncated comparator file, and the empty marker
+    (!0) in a nodes file all come back as status codes, never as an abort or a wild access."""
+    import json
+    import shutil
+    rows, comp, gh, oh = small
+    good = str(tmp_path / "good")
+    gh.serialize(good)
+    ph.Hnsw.deserialize(good).close()
+
+    def variant(name, edit):
+        d = str(tmp_path / name)
+        shutil.copytree(good, d)
+        edit(d)
+        with pytest.raises(ph.PhnswError) as e:
+            ph.Hnsw.deserialize(d)
+        return e.value.status
+
+    def huge_layer_count(d):
+        m = json.load(open(os.path.join(d, "meta")))
+        m["layer_count"] = 1 << 40
+        json.dump(m, open(os.path.join(d, "meta"), "w"))
+
+    def huge_node_count(d):
+        p = os.path.join(d, "layer.meta.0")
+        m = json.load(open(p))
+        m["node_count"] = (1 << 61) + 5
+        json.dump(m, open(p, "w"))
+
+    def truncated_comparator(d):
+        p = os.path.join(d, "comparator")
+        sz = os.path.getsize(p)
+        with open(p, "r+b") as f:
+            f.truncate(sz // 2)
+
+    def empty_marker_in_nodes(d):
+        p = os.path.join(d, "layer.nodes.0")
+        a = np.fromfile(p, dtype=np.uint64)
+        a[-1] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        a.tofile(p)
+
+    assert variant("layers", huge_layer_count) != 0
+    assert variant("nodes", huge_node_count) != 0
+    assert variant("trunc", truncated_comparator) != 0
+    assert variant("marker", empty_marker_in_nodes) != 0
+    # and the library is still usable afterwards
+    g = ph.Hnsw.deserialize(good)
+    a = g.search(rows[:5], max_out=3)
+    b = gh.search(rows[:5], max_out=3)
+    assert np.array_equal(a[0], b[0])
+    g.close()
+
+
+def test_release_scratch_and_build_memory(ph, small):
+    import torch
+    rows, comp, gh, oh = small
+    want = gh.search(rows[:50], max_out=5)
+    s = torch.cuda.Stream()
+    dev = torch.device("cuda", 0)
+    q = torch.from_numpy(rows[:50]).to(dev)
+    oi = torch.empty((50, 5), dtype=torch.int64, device=dev)
+    od = torch.empty((50, 5), dtype=torch.float32, device=dev)
+    oc = torch.empty((50,), dtype=torch.int32, device=dev)
+    gh.search_device(q, ph.SearchParameters(), oi, od, oc, stream=s.cuda_stream)
+    gh.sync(s.cuda_stream)
+    gh.release_workspace(s.cuda_stream)      # one stream
+    gh.release_workspace()                   # all of them
+    ph.release_build_memory(0)
+    got = gh.search(rows[:50], max_out=5)    # scratch comes back on demand
+    assert np.array_equal(got[0], want[0]) and np.array_equal(oi.cpu().numpy().astype(np.uint64), want[0])
+    ph.Hnsw.generate(ph.BigComparator(rows[:2000], ph.COS_HALF), seed=3).close()

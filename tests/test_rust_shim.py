@@ -56,3 +56,76 @@ def test_wrapper_calls_match_the_declarations():
         args = _call_args(src, m.end() - 1)
         assert len(args) == arity[name], (name, len(args), arity[name])
     assert src.count("{") == src.count("}") and src.count("(") == src.count(")")
+
+
+_RUST_SIZES = {"u64": (8, 8), "u32": (4, 4), "u16": (2, 2), "u8": (1, 1), "c_int": (4, 4), "f32": (4, 4),
+               "f64": (8, 8), "usize": (8, 8)}
+
+
+def _rust_structs():
+    """{name: [(field, rust type)]} of every `#[repr(C)] pub struct` in the generated ffi.rs;
+    a struct without repr(C) is a failure (Rust may reorder its fields)."""
+    src = open(os.path.join(ROOT, "shim", "src", "ffi.rs")).read()
+    out = {}
+    for m in re.finditer(r"((?:#\[[^\]]*\]\s*)*)pub struct (\w+)\s*\{(.*?)\}", src, flags=re.S):
+        attrs, name, body = m.group(1), m.group(2), m.group(3)
+        fields = [(f.group(1), f.group(2).strip()) for f in re.finditer(r"pub (\w+):\s*([^,\n]+),", body)]
+        if fields:  # opaque handles are `{ _private: [u8; 0] }`
+            assert "#[repr(C)]" in attrs, "%s has fields but no #[repr(C)]" % name
+            out[name] = fields
+    return out
+
+
+def _rust_layout(name, structs, memo):
+    """(size, align, [(field, offset)]) under the repr(C) rules (natural alignment, declaration
+    order) -- what rustc lays out for the generated declarations."""
+    if name in memo:
+        return memo[name]
+    off, align, fields = 0, 1, []
+    for fname, t in structs[name]:
+        if t.startswith("*") or t.startswith("Option<") or t == "phnsw_progress_fn":
+            sz, al = 8, 8
+        elif t in _RUST_SIZES:
+            sz, al = _RUST_SIZES[t]
+        else:
+            sz, al, _ = _rust_layout(t, structs, memo)
+        off = (off + al - 1) // al * al
+        fields.append((fname, off))
+        off += sz
+        align = max(align, al)
+    size = (off + align - 1) // align * align
+    memo[name] = (size, align, fields)
+    return memo[name]
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """Field names, order, offsets and sizes of every struct that crosses the ABI: the C side is
+    asked (gcc, offsetof / sizeof on include/phnsw.h), the Rust side is computed from the
+    #[repr(C)] declarations in ffi.rs."""
+    import gen_rust_ffi
+    _, c_structs, _, _ = gen_rust_ffi.parse(open(gen_rust_ffi.HEADER).read())
+    rs = _rust_structs()
+    assert {n for n, _ in c_structs} == set(rs), (sorted(n for n, _ in c_structs), sorted(rs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "phnsw.h"', "int main(void) {"]
+    for name, fields in c_structs:
+        assert [f for _, f in fields] == [f for f, _ in rs[name]], name   # names and order
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (name, name))
+        for _, f in fields:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    c_out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    want = {}
+    for ln in c_out:
+        p = ln.split()
+        if len(p) == 3:
+            want[(p[0], p[1])] = int(p[2])
+    memo = {}
+    for name in rs:
+        size, _, fields = _rust_layout(name, rs, memo)
+        assert want[(name, "size")] == size, (name, want[(name, "size")], size)
+        for f, off in fields:
+            assert want[(name, f)] == off, (name, f, want[(name, f)], off)
