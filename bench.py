@@ -760,7 +760,7 @@ def headline_line(ctx, v):
         ms_local = sharded_info["ms_local"] / args.steps
         out["recall_at_10"] = sharded_info["recall_merged"]
         out["gpu_launches"] = 2 * args.steps
-        out["sharded"] = {
+        out["sharded_step"] = {
             "what": "N > 1: one sub-index of %d vectors per GPU (%d vectors in all), every rank searches "
                     "the same %d-query batch; one library call per step (phnsw_search_batch_sharded): "
                     "ncclBroadcast(queries) -> K1 (epilogue writes global-id records into the exchange "
@@ -816,9 +816,9 @@ def finish(ctx, out, blocks, sweep):
             out["config3"] = r
         torch.cuda.empty_cache()
     if "sharded" in blocks:
-        r = guarded("sharded", lambda: run_config4(ctx))
+        r = guarded("config4", lambda: run_config4(ctx))
         if rank == 0:
-            out["sharded"] = r
+            out["config4"] = r
         torch.cuda.empty_cache()
     if "config5" in blocks:
         r = guarded("config5", lambda: run_config5(ctx))
