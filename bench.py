@@ -997,7 +997,8 @@ def run_config3(ctx):
                     "search ef=%d, exact re-rank of %d ADC hits" % (n, args.ef, rerank_k),
         "queries_per_step": nq,
         "value": nq / (ms_adc * 1e-3), "unit": "queries/s", "ms_per_step": ms_adc,
-        "what": "phnsw_pq8_search_batch_device: ADC walk + exact re-rank inside the timed region",
+        "what": "phnsw_pq8_search_batch_device: ADC walk + exact re-rank inside the timed region "
+                "(one kernel: the warp that finished a query's walk re-ranks it)",
         "adc_table": args.adc_table + (" (per-query tables quantised to u8 by a pre-pass kernel, "
                                        "24 KB per query in flight, integer sums)" if table == ph.ADC_TABLE_Q8
                                        else " (exact f32 entries)"),

@@ -19,6 +19,8 @@
 // One CTA per query: phase A computes the f32 entries into shared memory, phase B the per-row
 // minima / maxima, phase C quantises and writes the blob the traversal kernel pulls with one
 // bulk copy: [4*ceil(Q/4) x K u8 (rows >= Q zero), padded to 16 B][bias f32][delta f32][8 B pad].
+#include <string.h>
+
 #include "internal.h"
 
 namespace phnsw {

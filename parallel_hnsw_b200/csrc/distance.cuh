@@ -12,6 +12,7 @@ constexpr int kScoreRows = 32;
 constexpr int kScoreChunk = 128;
 constexpr int kScoreStride = kScoreChunk + 4;
 
+#ifdef __CUDACC__
 template <int METRIC>
 struct RowScorer {
   const float *rows;
@@ -126,5 +127,7 @@ struct RowScorer {
     __syncwarp();
   }
 };
+
+#endif  // __CUDACC__
 
 }  // namespace phnsw

@@ -161,6 +161,11 @@ struct SearchCall {
   uint32_t *out_counts = nullptr, *out_nd = nullptr, *out_ne = nullptr, *out_selfhit = nullptr;
   uint32_t selfhit_eps = 0;  // out_selfhit by search::match_within_epsilon
   uint64_t id_offset = 0;    // added to every emitted VectorId (sharded search)
+  // quantised ADC only: re-rank the first rr_k hits against rr_store inside the walk kernel when
+  // it fits (launch_search reports through *rr_fused whether it did)
+  const phnsw_store *rr_store = nullptr;
+  uint32_t rr_k = 0;
+  bool *rr_fused = nullptr;
   bool allow_overlap = false;  // batch overlap may apply (plain phnsw_search_batch_device only:
                                // callers that chain other kernels on the results must not be
                                // overtaken)

@@ -291,8 +291,24 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     ws.chain_seq++;
   } else {
     ws.chained = false;
-    PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 4, stream));  // work counter; status is sticky until sync
   }
+  // Quantised ADC: the table pre-pass of the batch.  (Measured and not kept: issuing it as a
+  // programmatic dependent of the previous batch's walk, on a second table buffer, so that it
+  // fills the SMs that walk has left -- 8.42 against 8.44 ms per 10 000-query batch at 1M x 1536:
+  // with ~10 queries per resident warp the ragged end is too short to matter.)
+  uint8_t *qlut_dev = nullptr;
+  if (q8) {
+    const uint32_t blob = adc_q8_blob_bytes(s->pq_Q, s->pq_K);
+    if (ws.qlut.bytes < (size_t)c.nq * blob) {
+      PH_CUDA(cudaStreamSynchronize(stream));
+      PH_CUDA(ws.qlut.reserve((size_t)c.nq * blob));
+    }
+    qlut_dev = ws.qlut.as<uint8_t>();
+    phnsw_status rq = launch_adc_lut_q8(s, c.queries, c.qpitch, c.stored_ids, c.nq, qlut_dev,
+                                        ix->max_smem, stream);
+    if (rq != PHNSW_OK) return rq;
+  }
+  if (!overlap) PH_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 4, stream));  // work counter; status is sticky until sync
 
   SearchArgs a;
   memset(&a, 0, sizeof(a));
@@ -341,16 +357,16 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.vlog = ws.vlog.as<uint32_t>();
   a.vlog_cap = ix->vlog_cap;
   if (q8) {
-    const uint32_t blob = adc_q8_blob_bytes(s->pq_Q, s->pq_K);
-    if (ws.qlut.bytes < (size_t)c.nq * blob) {
-      PH_CUDA(cudaStreamSynchronize(stream));
-      PH_CUDA(ws.qlut.reserve((size_t)c.nq * blob));
-    }
-    phnsw_status rq = launch_adc_lut_q8(s, c.queries, c.qpitch, c.stored_ids, c.nq,
-                                        ws.qlut.as<uint8_t>(), ix->max_smem, stream);
-    if (rq != PHNSW_OK) return rq;
-    a.qlut = ws.qlut.as<uint8_t>();
-    a.qlut_stride = blob;
+    a.qlut = qlut_dev;
+    a.qlut_stride = adc_q8_blob_bytes(s->pq_Q, s->pq_K);
+  }
+  if (c.rr_fused) *c.rr_fused = false;
+  if (q8 && c.rr_store && c.rr_store->rows && c.queries &&
+      adc_q8_rerank_fits(s->pq_Q, s->pq_K, c.rr_store->pitch, c.rr_k) && !getenv("PHNSW_NO_FUSED_RERANK")) {
+    a.rr_rows = c.rr_store->rows;
+    a.rr_pitch = c.rr_store->pitch;
+    a.rr_k = c.rr_k;
+    if (c.rr_fused) *c.rr_fused = true;
   }
   a.saved = ws.saved.as<uint64_t>();
   a.cap_pad = cap_pad_used;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)

@@ -294,6 +294,26 @@ phnsw_status pq8_search_device(const phnsw_index *ix, const phnsw_store *full, c
     return launch_search(ix, c, st);
   }
   const uint32_t hits = (uint32_t)std::min<uint64_t>(ef, rerank_k ? rerank_k : ef);
+  {
+    // first choice: the walk kernel re-ranks each query itself (quantised tables, table area
+    // large enough for the query vector and the row landing zone)
+    bool fused = false;
+    SearchCall f = c;
+    f.rr_store = full;
+    f.rr_k = hits;
+    f.rr_fused = &fused;
+    f.max_out = (uint32_t)max_out;
+    f.out_ids = out_ids;
+    f.out_dists = out_dists;
+    f.out_counts = out_counts;
+    f.id_offset = id_offset;
+    if (cs->adc_table == PHNSW_ADC_TABLE_Q8 &&
+        adc_q8_rerank_fits(cs->pq_Q, cs->pq_K, full->pitch, hits) && !getenv("PHNSW_NO_FUSED_RERANK")) {
+      phnsw_status rf = launch_search(ix, f, st);
+      if (rf != PHNSW_OK || fused) return rf;
+      // (not fused after all: the launch above wrote plain ADC results; fall through and redo)
+    }
+  }
   uint64_t *hi;
   float *hd;
   uint32_t *hc, *status;

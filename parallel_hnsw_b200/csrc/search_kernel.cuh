@@ -35,6 +35,7 @@
 //     form (oracle: orc_pq_merge_flag_closed_form, fuzzed against the literal loop).
 #pragma once
 #include "common.cuh"
+#include "distance.cuh"
 
 namespace phnsw {
 
@@ -128,6 +129,14 @@ struct SearchArgs {
   // (adc_lut.cu): pq_Q x pq_K u8 entries, padded to 16 B, then {bias, delta} f32
   const uint8_t *qlut;
   uint32_t qlut_stride;    // bytes per query blob (adc_q8_blob_bytes)
+  // Fused exact re-rank (PQ == 2 only; QuantizedHnsw::search second half, src/pq.rs:354-363):
+  // when rr_rows is set, the warp that finished a query's ADC walk re-scores its first rr_k
+  // hits against the full-precision rows right away (the table area is free by then and holds
+  // the query vector and the row landing zone), sorts by (d, id) and writes the final top
+  // max_out -- no hit lists through HBM, no second kernel
+  const float *rr_rows;    // full-precision store rows (rr_pitch floats each) or null
+  uint32_t rr_pitch;
+  uint32_t rr_k;
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
   uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
   uint32_t n_vectors;      // rows of the store: stored_ids / exclude are checked against it
@@ -186,6 +195,13 @@ __host__ __device__ inline uint32_t pool_entries(uint32_t cap) {
 __host__ __device__ inline uint32_t adc_q8_blob_bytes(uint32_t Q, uint32_t K) {
   return ((Q + 3) / 4 * 4 * K + 15) / 16 * 16 + 16;  // rows padded to a multiple of four (zeros)
 }
+// the fused re-rank borrows the table area of a finished query: query vector, RowScorer landing
+// zone, hit ids; the sort runs in the 4 KB scratch area (at most 512 keys)
+__host__ __device__ inline bool adc_q8_rerank_fits(uint32_t Q, uint32_t K, uint32_t full_pitch,
+                                                   uint32_t hits) {
+  const uint32_t need = (full_pitch * 4 + 15) / 16 * 16 + kScoreRows * kScoreStride * 4 + hits * 4;
+  return hits >= 1 && hits <= 512 && need <= adc_q8_blob_bytes(Q, K);
+}
 // per-warp query area (floats) and table area (floats) of a kernel variant: the exact ADC walk
 // keeps the query (table entries are built from it), the quantised one only its table blob
 __host__ __device__ inline uint32_t variant_q_floats(int pq, uint32_t dim_pad) {
@@ -201,6 +217,13 @@ __host__ __device__ inline uint32_t variant_lut_floats(int pq, uint32_t pq_table
 
 #ifndef PHNSW_SCAN_UNROLL
 #define PHNSW_SCAN_UNROLL 1
+#endif
+// PHNSW_NO_HINTS: A/B switch for the static branch hints that move rare blocks (duplicate rows,
+// in-walk compaction, frontier spill pops, bad ids) out of the hot loop's fall-through path
+#ifdef PHNSW_NO_HINTS
+#define PH_UNLIKELY(x) (x)
+#else
+#define PH_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
 #define PH_STR_(x) #x
 #define PH_UNROLL(n) _Pragma(PH_STR_(unroll n))
@@ -747,67 +770,108 @@ struct WarpSearch {
   __device__ void compute_distances(const LayerDev &layer, uint32_t nn) {
     if (PQ == 2) {
       // ADC over the query's quantised table (adc_lut.cu; oracle adc_build_lut_q8): a group of
-      // `gl` lanes scores one candidate -- lane t owns the code word t (four sub-spaces; words
-      // t + gl, ... as well when a row has more than 32 words), looks its u8 entries up in
-      // shared memory and the group adds the integers (exact, so the order is free).  The table
-      // has 4 * ceil(Q / 4) rows, the extra ones zero, so a word needs no per-byte guard.  The
-      // code words of the next eight passes are requested before the current eight are summed;
-      // lane c of a batch of 32 keeps candidate c's sum and the batch is finished with one
-      // distance = finalize(bias + delta * sum) per lane.
+      // `gl` lanes scores one candidate -- lane t owns the code word t (four sub-spaces), looks its
+      // u8 entries up in shared memory and the group adds the integers (exact, so the order is
+      // free).  The table has 4 * ceil(Q / 4) rows, the extra ones zero, so a word needs no
+      // per-byte guard.  Lane c of a batch of 32 keeps candidate c's sum and the batch is finished
+      // with one distance = finalize(bias + delta * sum) per lane.  Three bodies, because the hot
+      // loop has to stay small (the profile of a single generic body showed the instruction
+      // fetch of its untaken branches as the top stall): (A) a whole warp per candidate (33-128
+      // sub-spaces: the embedding shape), (B) several candidates per pass (up to 64 sub-spaces:
+      // the 16-code shape), (C) rows of more than 32 code words.
       const uint8_t *tab = (const uint8_t *)lut;
-      const uint32_t K = a.pq_K, W4 = (a.pq_Q + 3) / 4;
-      const uint32_t gl = q8_gl, G = 32 / gl, t = lane & (gl - 1), g = lane / gl;
-      const uint8_t *tb = tab + (size_t)(4 * t) * K;
-      const bool has = t < W4;
-      const uint8_t *base = (const uint8_t *)layer.lrows + (has ? t : 0) * 4;
-      constexpr int R = 8;
+      const uint32_t K = a.pq_K, W4 = (a.pq_Q + 3) / 4, gl = q8_gl;
+      const uint8_t *rows8 = (const uint8_t *)layer.lrows;
       for (uint32_t p0 = 0; p0 < nn; p0 += 32) {
         const uint32_t np = min(32u, nn - p0);
         uint32_t mysum = 0;
-        uint32_t cwn[R];
+        if (gl == 32 && W4 <= 32) {
+          // ---- (A): eight candidates' code words in flight, the next eight requested before
+          // the current eight are summed
+          const bool has = (uint32_t)lane < W4;
+          const uint8_t *tb = tab + (size_t)(4 * (has ? lane : 0)) * K;
+          const uint8_t *base = rows8 + (has ? lane : 0) * 4;
+#ifndef PHNSW_Q8_R
+#define PHNSW_Q8_R 8
+#endif
+          constexpr int R = PHNSW_Q8_R;
+#ifndef PHNSW_Q8_NO_PIPE
+          uint32_t cwn[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const uint32_t c = r * G + g;
-          cwn[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
-        }
-        for (uint32_t c0 = 0; c0 < np; c0 += R * G) {
-          uint32_t cw[R];
+          for (int r = 0; r < R; r++)
+            cwn[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + ((uint32_t)r < np ? r : 0)] * a.cpitch));
+#endif
+          for (uint32_t c0 = 0; c0 < np; c0 += R) {
+            uint32_t cw[R];
+#ifndef PHNSW_Q8_NO_PIPE
 #pragma unroll
-          for (int r = 0; r < R; r++) cw[r] = cwn[r];
-          if (c0 + R * G < np) {
+            for (int r = 0; r < R; r++) cw[r] = cwn[r];
+            if (c0 + R < np) {
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-              const uint32_t c = c0 + R * G + r * G + g;
-              cwn[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            if (c0 + r * G >= np) break;  // warp-uniform
-            uint32_t v = 0;
-            if (has)
-              v = (uint32_t)tb[cw[r] & 255u] + tb[K + ((cw[r] >> 8) & 255u)] +
-                  tb[2 * K + ((cw[r] >> 16) & 255u)] + tb[3 * K + (cw[r] >> 24)];
-            if (W4 > gl) {  // rows of more than 32 code words (Q > 128)
-              const uint32_t c = c0 + r * G + g;
-              const uint8_t *rowp = (const uint8_t *)layer.lrows + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch;
-              for (uint32_t w = t + gl; w < W4; w += gl) {
-                const uint32_t x = __ldg((const uint32_t *)(rowp + 4 * w));
-                const uint8_t *tw = tab + (size_t)(4 * w) * K;
-                v += (uint32_t)tw[x & 255u] + tw[K + ((x >> 8) & 255u)] + tw[2 * K + ((x >> 16) & 255u)] +
-                     tw[3 * K + (x >> 24)];
+              for (int r = 0; r < R; r++) {
+                const uint32_t c = c0 + R + r;
+                cwn[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
               }
             }
-            if (gl == 32) {
-              v = __reduce_add_sync(kFull, v);
+#else
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const uint32_t c = c0 + r;
+              cw[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
+            }
+#endif
+            // every pass of a chunk runs, also past the last candidate (its lane is not read): a
+            // warp-uniform early exit per pass measured 5 % slower than the wasted passes
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#ifdef PHNSW_Q8_BREAK
+              if (c0 + r >= np) break;  // warp-uniform
+#endif
+              uint32_t v = (uint32_t)tb[cw[r] & 255u] + tb[K + ((cw[r] >> 8) & 255u)] +
+                           tb[2 * K + ((cw[r] >> 16) & 255u)] + tb[3 * K + (cw[r] >> 24)];
+              v = __reduce_add_sync(kFull, has ? v : 0u);
               if ((uint32_t)lane == c0 + r) mysum = v;
-            } else {
+            }
+          }
+        } else if (W4 <= gl) {
+          // ---- (B): G = 32 / gl candidates per pass, four passes in flight
+          const uint32_t G = 32 / gl, t = lane & (gl - 1), g = lane / gl;
+          const bool has = t < W4;
+          const uint8_t *tb = tab + (size_t)(4 * (has ? t : 0)) * K;
+          const uint8_t *base = rows8 + (has ? t : 0) * 4;
+          constexpr int R = 4;
+          for (uint32_t c0 = 0; c0 < np; c0 += R * G) {
+            uint32_t cw[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const uint32_t c = c0 + r * G + g;
+              cw[r] = __ldg((const uint32_t *)(base + (size_t)bid[p0 + (c < np ? c : 0)] * a.cpitch));
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              uint32_t v = (uint32_t)tb[cw[r] & 255u] + tb[K + ((cw[r] >> 8) & 255u)] +
+                           tb[2 * K + ((cw[r] >> 16) & 255u)] + tb[3 * K + (cw[r] >> 24)];
+              v = has ? v : 0u;
               for (uint32_t o = gl >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
               // lane L keeps candidate L: it sits in group L - (c0 + r * G) of this pass
               const uint32_t gi = (uint32_t)lane - (c0 + r * G);
               const uint32_t got = __shfl_sync(kFull, v, (gi * gl) & 31u);
               if (gi < G) mysum = got;
             }
+          }
+        } else {
+          // ---- (C): more than 32 code words per row (Q > 128): a warp per candidate, word loop
+          for (uint32_t c = 0; c < np; c++) {
+            const uint8_t *rowp = rows8 + (size_t)bid[p0 + c] * a.cpitch;
+            uint32_t v = 0;
+            for (uint32_t w = lane; w < W4; w += 32) {
+              const uint32_t x = __ldg((const uint32_t *)(rowp + 4 * w));
+              const uint8_t *tw = tab + (size_t)(4 * w) * K;
+              v += (uint32_t)tw[x & 255u] + tw[K + ((x >> 8) & 255u)] + tw[2 * K + ((x >> 16) & 255u)] +
+                   tw[3 * K + (x >> 24)];
+            }
+            v = __reduce_add_sync(kFull, v);
+            if ((uint32_t)lane == c) mysum = v;
           }
         }
         if ((uint32_t)lane < np) {
@@ -1065,7 +1129,7 @@ struct WarpSearch {
       uint32_t next;
       // ovf_min only tracks the duplicate-row keys (the one kind of spilled key that can be
       // below a pool entry); the rest of the list matters once the pool is exhausted
-      if (ovf_n > 0 && (nx_key == kEmptyKey || ovf_min < nx_key)) {
+      if (PH_UNLIKELY(ovf_n > 0 && (nx_key == kEmptyKey || ovf_min < nx_key))) {
         next = key_id(ovf_pop_min());
         nx_valid = true;  // the pool did not change
       } else if (nx_key != kEmptyKey) {
@@ -1092,7 +1156,7 @@ struct WarpSearch {
       uint32_t v1 = __ballot_sync(kFull, n1 != kEmpty32);
       uint32_t valid = v1 ? 64 - __clz(v1) : 32 - __clz(v0);  // __clz(0) == 32
       bool in0 = (uint32_t)lane < valid, in1 = (uint32_t)lane + 32 < valid;
-      if ((in0 && n0 >= layer.node_count) || (in1 && n1 >= layer.node_count)) {
+      if (PH_UNLIKELY((in0 && n0 >= layer.node_count) || (in1 && n1 >= layer.node_count))) {
         stat |= kStatBadNeighbor;  // interior sentinel / out-of-range id: the crate would panic
         in0 = in0 && n0 < layer.node_count;
         in1 = in1 && n1 < layer.node_count;
@@ -1114,7 +1178,7 @@ struct WarpSearch {
         compute_distances(layer, nn);            // lib.rs:199-204 -> bkeys[0..nn)
         const uint64_t *bk = bkeys;
         uint32_t nbu = nn;
-        if (layer.row_dups) {
+        if (PH_UNLIKELY(layer.row_dups)) {
           // a row that lists an id twice yields equal keys: visit_queue is a multiset, so the
           // extra copies stay poppable once more (spill list) while the set takes one
           sort_batch(nn);                        // lib.rs:206
@@ -1194,7 +1258,7 @@ struct WarpSearch {
           uint64_t key = act ? bk[t] : kEmptyKey;
           bool in = act && key < U;
           uint32_t m = __ballot_sync(kFull, in);
-          if (len + __popc(m) > a.cap_pad) {
+          if (PH_UNLIKELY(len + __popc(m) > a.cap_pad)) {
             compact(true);
             nx_valid = false;  // slots moved
             in = act && key < U;
@@ -1257,7 +1321,10 @@ struct WarpSearch {
       // the query's table blob (u8 entries + {bias, delta}) was written by the pre-pass kernel:
       // one bulk (TMA) copy into this warp's table area
       const uint32_t bytes = a.qlut_stride;
-      __syncwarp();  // the previous query's table reads are over
+      // the previous query's table reads are over; its fused re-rank wrote part of this area
+      // with ordinary stores: order them before the bulk (async proxy) copy that overwrites it
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
       if (lane == 0) {
         mbar_arrive_expect_tx(&mbar[0], bytes);
         bulk_g2s(lut, a.qlut + (size_t)q * bytes, bytes, &mbar[0]);
@@ -1532,6 +1599,10 @@ struct WarpSearch {
       }
       if (lane == 0) a.out_selfhit[q] = hit ? 1u : 0u;
     }
+    if (PQ == 2 && a.rr_rows) {
+      rerank_and_emit(q);
+      return;
+    }
     // candidates.iter().collect() (search.rs:139)
     uint32_t n_out = min(len, a.max_out);
     if (a.out_ids) {
@@ -1548,6 +1619,59 @@ struct WarpSearch {
       }
     }
     if (a.out_counts && lane == 0) a.out_counts[q] = n_out;
+  }
+
+  // QuantizedHnsw::search, second half (src/pq.rs:354-363), fused behind the ADC walk: the first
+  // rr_k hits are re-scored with the full-precision comparator (compare_vec(Stored(id), v),
+  // strictly sequential f32 -- the same RowScorer the stand-alone re-rank kernel uses), sorted by
+  // (d, id) and the best max_out written out.
+  __device__ void rerank_and_emit(uint32_t q) {
+    unsigned char *area = (unsigned char *)lut;
+    const uint32_t qb = (a.rr_pitch * 4 + 15) / 16 * 16;
+    float *qv = (float *)area;
+    float *stg = (float *)(area + qb);
+    uint32_t *vids = (uint32_t *)(area + qb + RowScorer<METRIC>::stage_bytes());
+    const uint32_t n = emit_smallest(a.rr_k, [&](uint32_t r, uint64_t k) { vids[r] = (uint32_t)k; });
+    const float *src = a.queries + (size_t)q * a.qpitch;
+    for (uint32_t i = lane; i < a.rr_pitch; i += 32) qv[i] = i < a.qpitch ? src[i] : 0.0f;
+    __syncwarp();
+    float *dd = (float *)pool;  // the pool has been consumed
+    RowScorer<METRIC> sc;
+    sc.rows = a.rr_rows;
+    sc.pitch = a.rr_pitch;
+    sc.dim_pad = a.rr_pitch;
+    sc.qvec = qv;
+    sc.stage = stg;
+    sc.mbar = mbar;
+    sc.ph = ph;
+    sc.lane = lane;
+    sc.score(vids, n, dd);
+    ph = sc.ph;
+    if (sc.nan_seen) stat |= kStatNaN;
+    uint64_t *keys = (uint64_t *)stage;  // 4 KB scratch: up to 512 keys
+    uint32_t P = 32;
+    while (P < n) P <<= 1;
+    for (uint32_t i = lane; i < P; i += 32) keys[i] = i < n ? make_key(dd[i], vids[i]) : kEmptyKey;
+    __syncwarp();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = lane; t < (P >> 1); t += 32) {
+          const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const uint32_t p = i | j;
+          const uint64_t x = keys[i], y = keys[p];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { keys[i] = y; keys[p] = x; }
+        }
+        __syncwarp();
+      }
+    const uint32_t n_out = min(n, a.max_out);
+    for (uint32_t i = lane; i < a.max_out; i += 32) {
+      const uint64_t k = i < n_out ? keys[i] : 0;
+      a.out_ids[(size_t)q * a.max_out + i] = i < n_out ? (uint64_t)(uint32_t)k + a.out_id_offset : ~0ull;
+      a.out_dists[(size_t)q * a.max_out + i] = i < n_out ? key_dist(k) : 3.4028234663852886e38f;
+    }
+    if (a.out_counts && lane == 0) a.out_counts[q] = n_out;
+    __syncwarp();
   }
 
   // Hnsw::knn, src/lib.rs:905-928: bottom layer only, queue of 3k seeded with (self, 0.0)

@@ -164,16 +164,21 @@ def _rerank_reference(oracle, metric, rows, q, hit_ids, k):
     ("COS_HALF", 64, 8, 128, 5000),
     ("COS_HALF", 1536, 16, 256, 2500),   # BASELINE configs[2] shape: 96 codes, 96 KB table
 ])
-def test_adc_search_with_fused_rerank_matches_oracle(ph, oracle, metric_name, dim, cs, K, n):
+@pytest.mark.parametrize("table", [0, 1])
+def test_adc_search_with_fused_rerank_matches_oracle(ph, oracle, metric_name, dim, cs, K, n, table):
+    """table 1 = quantised per-query tables; at the 96 x 256 shape the walk kernel then re-ranks
+    each query itself (the table area holds the query and the row landing zone), at the small
+    shapes the stand-alone re-rank kernel runs -- same results either way."""
     metric = getattr(ph, metric_name)
     rows = clustered(n, dim, 5, n_clusters=64, spread=0.6, normalise=(metric_name != "L2_SQRT"))
     comp = ph.BigComparator(rows, metric)
     cb = ph.pq8_train(comp, K, cs, kmeans_iters=2, seed=7)
-    pq = ph.Pq8Comparator(comp, cb, cs)
+    pq = ph.Pq8Comparator(comp, cb, cs).set_adc_table(table)
     oh = oracle.Hnsw.generate(metric, rows, seed=1, improve=False)
     gh_full = ph.Hnsw.from_layers(comp, oh.layers())
     gh = gh_full.rebind(pq)
     oc = oracle.Hnsw.from_layers_codes(metric, dim, n, oh.layers(), pq.codes(), cb, cs)
+    oracle.attach_pq8(oc, pq.codes(), cb, cs, table=table)
     queries = rows[::29] + np.float32(0.02)
     for ef, rerank_k, k in ((300, 0, 10), (120, 40, 10), (16, 100, 20)):
         sp = ph.SearchParameters(ef, ef, 2)
