@@ -156,11 +156,28 @@ __global__ void __launch_bounds__(kLutThreads)
   // ---- phase C: quantise and write the blob
   const float inv = s_scale[0];
   const uint32_t total = Q * K;
-  for (uint32_t e = tid; e < total; e += kLutThreads) {
-    const uint32_t s = e / K;
-    int v = __float2int_rn(__fmul_rn(__fsub_rn(part[e], lo[s]), inv));
-    v = v < 0 ? 0 : (v > 255 ? 255 : v);
-    blob[e] = (uint8_t)v;
+  if ((K & 3u) == 0) {  // four entries of one row per thread, one 32-bit store
+    for (uint32_t e4 = tid; e4 < total / 4; e4 += kLutThreads) {
+      const uint32_t e = 4 * e4;
+      const float l = lo[e / K];
+      const float4 p4 = *(const float4 *)(part + e);
+      const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        int v = __float2int_rn(__fmul_rn(__fsub_rn(pv[i], l), inv));
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        w |= (uint32_t)v << (8 * i);
+      }
+      ((uint32_t *)blob)[e4] = w;
+    }
+  } else {
+    for (uint32_t e = tid; e < total; e += kLutThreads) {
+      const uint32_t s = e / K;
+      int v = __float2int_rn(__fmul_rn(__fsub_rn(part[e], lo[s]), inv));
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+      blob[e] = (uint8_t)v;
+    }
   }
   const uint32_t tab_bytes = stride - 16;  // rows up to 4 * ceil(Q / 4) and the 16 B padding: zero
   for (uint32_t e = total + tid; e < tab_bytes; e += kLutThreads) blob[e] = 0;
