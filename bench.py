@@ -622,12 +622,14 @@ def main():
             C.c_void_p(hi.data_ptr()), C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr()),
             None, None))
 
+    ms_e2e_sync = None
     if sharded:
         # rank 0: pinned host queries -> H2D -> sharded step (broadcast, search, all-gather,
         # merge) -> D2H of the merged top-k; the other ranks take part in the step
         ms_e2e = timed_e2e_sharded(ctx, sh, gh, queries_h.pin_memory(), dq, sp, 0, args.steps,
                                    args.warmup) * args.steps
     else:
+        # (a) one synchronous phnsw_search_batch per step (Hnsw::search's contract)
         for _ in range(args.warmup):
             e2e_step()
         barrier()
@@ -635,8 +637,35 @@ def main():
         for _ in range(args.steps):
             e2e_step()
         torch.cuda.synchronize()
-        ms_e2e = (time.perf_counter() - t0) * 1e3
+        ms_e2e_sync = (time.perf_counter() - t0) * 1e3
         assert np.array_equal(hi.numpy(), oi.cpu().numpy()), "host path and device path disagree"
+        # (b) the same steps as a server drains a queue of batches: phnsw_search_batch_host_async
+        # per step (pinned host queries read in place, results written straight to pinned host
+        # memory, alternate output buffers), batch overlap on, ONE sync at the end -- every step's
+        # host -> device read and device -> host write is inside the timed region
+        hi2, hd2, hc2 = (torch.empty_like(hi).pin_memory(), torch.empty_like(hd).pin_memory(),
+                         torch.empty_like(hc).pin_memory())
+        q_pin_t = queries_h.pin_memory()
+
+        def e2e_async(i):
+            o = (hi, hd, hc) if i & 1 else (hi2, hd2, hc2)
+            gh.search_host_async(q_pin_t, sp, *o, stream=stream)
+        gh.set_batch_overlap(use_overlap)
+        for i in range(args.warmup):
+            e2e_async(i)
+        gh.sync(stream)
+        hi.zero_()
+        hi2.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_async(i)
+        gh.sync(stream)
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        gh.set_batch_overlap(False)
+        ref_ids = oi.cpu().numpy()
+        assert np.array_equal(hi.numpy(), ref_ids) and np.array_equal(hi2.numpy(), ref_ids), \
+            "asynchronous host path and device path disagree"
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -670,6 +699,7 @@ def headline_line(ctx, v):
          "clocks", "tree", "t_build", "t_gen", "t_gt", "gt_stats", "gh_layers_top_first",
          "sharded_info", "oi", "od"))
     build_times, ms_plain, use_overlap = v["build_times"], v["ms_plain"], v["use_overlap"]
+    ms_e2e_sync = v["ms_e2e_sync"]
     cpu_build = None
     if args.cpu_build:
         sizes = [int(x) for x in args.cpu_build.split(",") if x]
@@ -691,7 +721,14 @@ def headline_line(ctx, v):
         "parity": (main_cpu or {}).get("parity"),
         "e2e": {"value": e2e_qps, "unit": "queries/s",
                 "h2d_bytes_per_step": int(args.nq * args.dim * 4),
-                "d2h_bytes_per_step": int(args.nq * (k * 12 + 4))},
+                "d2h_bytes_per_step": int(args.nq * (k * 12 + 4)),
+                "what": ("phnsw_search_batch_host_async per step from pinned host buffers (read and written "
+                         "in place by the kernel), steps queued on one stream with batch overlap, one "
+                         "sync after the last" if ms_e2e_sync else
+                         "rank 0: pinned host queries -> H2D -> sharded step -> D2H of the merged top-k"),
+                "synchronous_call_per_step": ({"value": world * args.nq * args.steps / (ms_e2e_sync * 1e-3),
+                                               "what": "phnsw_search_batch, one blocking call per step"}
+                                              if ms_e2e_sync else None)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "kernel": "search_kernel<L2_SQRT, %s>" % ("tree" if tree else "sequential"),

@@ -223,6 +223,19 @@ phnsw_status phnsw_search_batch_device(const phnsw_index *ix, const float *queri
                                        uint32_t *out_counts, uint32_t *out_ndist,
                                        uint32_t *out_nexp, void *cuda_stream);
 phnsw_status phnsw_index_sync(const phnsw_index *ix, void *cuda_stream);
+/* The asynchronous form of phnsw_search_batch for HOST buffers: `queries` and the three output
+ * arrays must be page-locked (cudaHostAlloc / cudaHostRegister; PHNSW_ERR_INVALID otherwise);
+ * the kernel reads every query from host memory and writes its results straight back (unified
+ * addressing), nothing is staged and the call returns once the launch is queued on
+ * `cuda_stream`.  The results of a call are complete after phnsw_index_sync(ix, stream) -- or any
+ * later operation on that stream.  This is what a server draining a queue of batches calls: with
+ * phnsw_index_set_batch_overlap the launches of consecutive calls overlap their ragged ends.
+ * No reference analogue (Hnsw::search is synchronous). */
+phnsw_status phnsw_search_batch_host_async(const phnsw_index *ix, const float *queries_pinned,
+                                           uint64_t nq, const phnsw_search_params *sp,
+                                           uint64_t upto_layers_from_top, uint64_t max_out,
+                                           uint64_t *out_ids_pinned, float *out_dists_pinned,
+                                           uint32_t *out_counts_pinned, void *cuda_stream);
 
 /* Hnsw::knn(k, probe_depth) (src/lib.rs:905-928): all-points kNN on the bottom layer;
  * outputs are node_count x k in bottom-layer node order, self removed */

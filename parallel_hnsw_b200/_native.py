@@ -110,6 +110,8 @@ SIGNATURES = {
                                      vp, C.c_uint64, vp, vp, vp, vp, vp]),
     "phnsw_search_batch_device": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams),
                                             C.c_uint64, vp, C.c_uint64, vp, vp, vp, vp, vp, vp]),
+    "phnsw_search_batch_host_async": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(SearchParams), C.c_uint64,
+                                                C.c_uint64, vp, vp, vp, vp]),
     "phnsw_index_sync": (C.c_int, [vp, vp]),
     "phnsw_knn": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
     "phnsw_threshold_nn": (C.c_int, [vp, C.c_float, C.c_uint64, C.c_uint64, C.POINTER(u64p),

@@ -1044,6 +1044,40 @@ phnsw_status phnsw_index_sync(const phnsw_index *ix, void *cuda_stream) {
   return sync_status(ix, (cudaStream_t)cuda_stream);
 }
 
+static bool is_pinned_host(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost && at.devicePointer == p;
+}
+
+phnsw_status phnsw_search_batch_host_async(const phnsw_index *ix, const float *queries_pinned,
+                                           uint64_t nq, const phnsw_search_params *sp,
+                                           uint64_t upto_layers_from_top, uint64_t max_out,
+                                           uint64_t *out_ids_pinned, float *out_dists_pinned,
+                                           uint32_t *out_counts_pinned, void *cuda_stream) {
+  PH_ENTRY();
+  if (!ix || !sp) return PHNSW_ERR_INVALID;
+  if (nq == 0) return PHNSW_OK;
+  if (phnsw_device_count() == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return PHNSW_ERR_NO_DEVICE;
+  }
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  if (!is_pinned_host(queries_pinned) || !is_pinned_host(out_ids_pinned) ||
+      !is_pinned_host(out_dists_pinned) || (out_counts_pinned && !is_pinned_host(out_counts_pinned))) {
+    set_error("search_batch_host_async: queries and outputs must be page-locked host memory with "
+              "unified addressing (cudaHostAlloc / cudaHostRegister)");
+    return PHNSW_ERR_INVALID;
+  }
+  return phnsw_search_batch_device(ix, queries_pinned, nullptr, nq, sp, upto_layers_from_top, nullptr,
+                                   max_out, out_ids_pinned, out_dists_pinned, out_counts_pinned,
+                                   nullptr, nullptr, cuda_stream);
+}
+
 phnsw_status phnsw_search_batch(const phnsw_index *ix, const float *queries,
                                 const uint64_t *stored_ids, uint64_t nq,
                                 const phnsw_search_params *sp, uint64_t upto_layers_from_top,

@@ -63,7 +63,7 @@ def _host(a, dtype):
 def _ptr(a):
     if a is None:
         return None
-    if _is_device(a):
+    if hasattr(a, "data_ptr"):  # torch tensor, device or (pinned) host
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(a.ctypes.data)
 
@@ -354,6 +354,17 @@ class Hnsw:
 
     def sync(self, stream=None):
         N.check(N.lib().phnsw_index_sync(self._h, C.c_void_p(stream or 0)))
+
+    def search_host_async(self, queries_pinned, sp, out_ids, out_dists, out_counts=None, upto=0,
+                          max_out=None, stream=None):
+        """phnsw_search_batch_host_async: every buffer is PAGE-LOCKED host memory (e.g. a torch
+        tensor made with pin_memory()); the kernel reads and writes it in place, the call returns
+        once the launch is queued.  Results are complete after sync(stream)."""
+        max_out = int(max_out or out_ids.shape[1])
+        N.check(N.lib().phnsw_search_batch_host_async(
+            self._h, _ptr(queries_pinned), queries_pinned.shape[0], C.byref(sp), upto, max_out,
+            _ptr(out_ids), _ptr(out_dists), _ptr(out_counts) if out_counts is not None else None,
+            C.c_void_p(stream or 0)))
 
     def adc_search(self, queries, sp=None, rerank=None, rerank_k=0, max_out=None):
         """QuantizedHnsw::search (src/pq.rs:346-364) on an index over a Pq8Comparator, one

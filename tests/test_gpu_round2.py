@@ -114,6 +114,40 @@ def test_batch_overlap_gives_the_same_results(ph, small, order):
         gh.set_sum_order(ph.SUM_SEQUENTIAL)
 
 
+def test_host_async_search_from_pinned_buffers(ph, small):
+    """phnsw_search_batch_host_async: pinned host buffers in place, queued calls on one stream
+    (with and without batch overlap) equal the synchronous host call; pageable buffers are
+    refused."""
+    import torch
+    rows, comp, gh, oh = small
+    sp = ph.SearchParameters(60, 60, 2)
+    st = torch.cuda.current_stream().cuda_stream
+    qs = [torch.from_numpy(random_normed(4000, 64, 900 + i)).pin_memory() for i in range(4)]
+    want = [gh.search(q.numpy(), sp, max_out=10) for q in qs]
+    for overlap in (False, True):
+        gh.set_batch_overlap(overlap)
+        try:
+            outs = []
+            for q in qs:
+                oi = torch.empty((4000, 10), dtype=torch.int64).pin_memory()
+                od = torch.empty((4000, 10), dtype=torch.float32).pin_memory()
+                oc = torch.empty((4000,), dtype=torch.int32).pin_memory()
+                gh.search_host_async(q, sp, oi, od, oc, stream=st)
+                outs.append((oi, od, oc))
+            gh.sync(st)
+            for (oi, od, oc), w in zip(outs, want):
+                assert np.array_equal(oi.numpy().astype(np.uint64), w[0])
+                assert np.array_equal(od.numpy().view(np.uint32), w[1].view(np.uint32))
+                assert np.array_equal(oc.numpy().astype(np.uint32), w[2])
+        finally:
+            gh.set_batch_overlap(False)
+    pageable = torch.from_numpy(random_normed(10, 64, 1))
+    oi = torch.empty((10, 10), dtype=torch.int64).pin_memory()
+    od = torch.empty((10, 10), dtype=torch.float32).pin_memory()
+    with pytest.raises(ph.PhnswError):
+        gh.search_host_async(pageable, sp, oi, od, stream=st)
+
+
 def test_out_of_range_stored_ids_are_loud(ph, small):
     rows, comp, gh, oh = small
     ids = np.array([3, 6000, 5], dtype=np.uint64)
