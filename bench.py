@@ -434,6 +434,18 @@ def main():
         torch.cuda.synchronize()
         build_times.append(time.perf_counter() - t0)
     t_build = float(np.median(build_times[1:]))
+    # one more, untimed, instrumented build: the work counters of every traversal launch of the
+    # build (seed, link and recall searches: 93 % of its kernel time) for build.roofline
+    build_work = None
+    if rank == 0:
+        os.environ["PHNSW_WORK_STATS"] = "1"
+        try:
+            gw = ph.Hnsw.generate(comp, seed=1, improve=not args.no_improve)
+            torch.cuda.synchronize()
+            build_work = gw.work_stats()
+            gw.close()
+        finally:
+            os.environ.pop("PHNSW_WORK_STATS", None)
     L = gh.layer_count()
     layer_M = [gh.get_layer_from_top(i)[2] for i in range(L)] if rank == 0 else None
 
@@ -700,6 +712,7 @@ def headline_line(ctx, v):
          "sharded_info", "oi", "od"))
     build_times, ms_plain, use_overlap = v["build_times"], v["ms_plain"], v["use_overlap"]
     ms_e2e_sync = v["ms_e2e_sync"]
+    build_work = v["build_work"]
     cpu_build = None
     if args.cpu_build:
         sizes = [int(x) for x in args.cpu_build.split(",") if x]
@@ -754,6 +767,24 @@ def headline_line(ctx, v):
                                  if ms_plain else None)},
         "build": {"vectors_per_s": args.n / t_build, "seconds": t_build,
                   "first_build_seconds": build_times[0], "all_build_seconds": build_times,
+                  "roofline": ({
+                      "bound": "hbm",
+                      "what": "algorithmic bytes of the build's traversal launches (SURVEY 8d formula: distance "
+                              "evaluations x 4 dim + expansions x M x 4 + one query row per search), counted by "
+                              "an instrumented, untimed build of the same index; the scoring / fold kernels "
+                              "(7 % of the build's kernel time) are not counted",
+                      "distance_evals": build_work["distance_evals"],
+                      "searches": build_work["queries"], "search_launches": build_work["launches"],
+                      "algorithmic_bytes": build_work["distance_evals"] * args.dim * 4
+                                           + build_work["neighbor_list_bytes"] + build_work["queries"] * args.dim * 4,
+                      "achieved": (build_work["distance_evals"] * args.dim * 4 + build_work["neighbor_list_bytes"]
+                                   + build_work["queries"] * args.dim * 4) / t_build / 1e9,
+                      "peak": peak, "unit": "GB/s",
+                      "frac": (build_work["distance_evals"] * args.dim * 4 + build_work["neighbor_list_bytes"]
+                               + build_work["queries"] * args.dim * 4) / t_build / 1e9 / peak,
+                      "note": "over the WHOLE build wall time (host control flow, layer uploads and the "
+                              "non-traversal kernels included), sequential summation order at 16 warps per SM"}
+                      if build_work else None),
                   "seconds_is": "median of the builds after the first (steady state: construction "
                                 "temporaries cached in the library's memory pool)",
                   "improve_index": not args.no_improve, "data_gen_seconds": t_gen,

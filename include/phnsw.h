@@ -167,6 +167,16 @@ int phnsw_index_sum_order(const phnsw_index *ix);
  * default.  No reference analogue (the crate is synchronous). */
 phnsw_status phnsw_index_set_batch_overlap(phnsw_index *ix, int on);
 int phnsw_index_batch_overlap(const phnsw_index *ix);
+/* Work accounting (instrumentation; SURVEY 8d's algorithmic bytes): while on, every traversal
+ * launch of this index -- the build's seed, link and recall searches included -- also records its
+ * per-query counters and a small kernel adds them into four totals: out4 = {distance
+ * evaluations, neighbour-list bytes (expansions x M x 4 per layer), queries, launches}.
+ * An index created while the environment variable PHNSW_WORK_STATS=1 is set starts with it on
+ * (that is how a whole phnsw_generate is accounted).  Costs two memsets and one small kernel per
+ * launch: not for timed runs.  The crate's counterpart is search_instrumented's distance count
+ * (src/lib.rs:667-673). */
+phnsw_status phnsw_index_set_work_stats(phnsw_index *ix, int on);
+phnsw_status phnsw_index_work_stats(const phnsw_index *ix, uint64_t *out4, int reset);
 /* Every stream a search was issued on keeps its own per-query scratch (frontier spill, visited
  * bitmaps, staging buffers: ~0.8 GB at 1M vectors) until the index is destroyed.  A caller that
  * creates and retires streams releases the scratch of a retired stream here (synchronises that

@@ -80,6 +80,7 @@ struct Workspace {
   DevBuf stage_q, stage_ids, stage_excl, out_ids, out_dists, out_counts, out_nd, out_ne;
   DevBuf hit_ids, hit_dists, hit_counts;  // ADC hits handed from the walk to the re-rank kernel
   DevBuf qlut;                            // quantised ADC tables of the batch (adc_lut.cu)
+  DevBuf ws_nd, ws_ne;                    // per-query counters of a launch under work accounting
   uint32_t slots = 0, ovf_cap = 0, vlog_cap = 0, bitmap_words = 0, cap_pad = 0;
   uint64_t chain_seq = 0;   // batch overlap: launches of the current chain so far
   bool chained = false;     // the last launch on this stream followed the overlap protocol
@@ -87,7 +88,7 @@ struct Workspace {
     ovf.release(); bitmap.release(); vlog.release(); saved.release(); ctrl.release();
     stage_q.release(); stage_ids.release(); stage_excl.release();
     out_ids.release(); out_dists.release(); out_counts.release(); out_nd.release(); out_ne.release();
-    hit_ids.release(); hit_dists.release(); hit_counts.release(); qlut.release();
+    hit_ids.release(); hit_dists.release(); hit_counts.release(); qlut.release(); ws_nd.release(); ws_ne.release();
   }
 };
 
@@ -133,6 +134,12 @@ struct phnsw_index {
   uint32_t vlog_cap = 8192, ovf_cap = 8192;  // per-query device scratch (entries)
   int sum_order = 0;  // PHNSW_SUM_SEQUENTIAL / PHNSW_SUM_TREE: traversal distance summation
   int batch_overlap = 0;  // phnsw_index_set_batch_overlap
+  // work accounting (PHNSW_WORK_STATS=1 at index creation, or phnsw_index_set_work_stats): every
+  // traversal launch also returns its per-query counters and a small kernel adds them up --
+  // distance evaluations, neighbour-list bytes, queries, launches (SURVEY 8d's algorithmic bytes
+  // of a build's searches)
+  int work_stats = 0;
+  unsigned long long *d_work = nullptr;  // device, 4 counters
   uint64_t expect_nodes = 0; // generate: size of the final bottom layer, so that the visited
                              // bitmap is allocated once and not regrown layer by layer
   uint64_t seed = 0;         // seed of the generate call (nested re-top generates derive theirs)

@@ -45,6 +45,32 @@ __global__ void compact_u64_kernel(const uint64_t *__restrict__ in, uint32_t *__
     out[i] = o;
   }
 }
+// work accounting: acc[0] += distance evaluations, acc[1] += neighbour-list bytes (expansions x
+// M x 4 per layer), acc[2] += queries, acc[3] += 1 per launch
+__global__ void work_stats_kernel(const uint32_t *__restrict__ nd, const uint32_t *__restrict__ ne,
+                                  uint32_t nq, uint32_t stride, uint32_t n_layers,
+                                  const LayerDev *__restrict__ layers, unsigned long long *acc) {
+  unsigned long long d = 0, b = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)nq * n_layers;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(i / n_layers), l = (uint32_t)(i - (size_t)q * n_layers);
+    d += nd[(size_t)q * stride + l];
+    b += (unsigned long long)ne[(size_t)q * stride + l] * layers[l].M * 4ull;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (d) atomicAdd(&acc[0], d);
+    if (b) atomicAdd(&acc[1], b);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&acc[2], (unsigned long long)nq);
+    atomicAdd(&acc[3], 1ull);
+  }
+}
 __global__ void expand_u32_kernel(const uint32_t *__restrict__ in, uint64_t *__restrict__ out,
                                   size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,6 +368,19 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.out_counts = c.out_counts;
   a.out_ndist = c.out_nd;
   a.out_nexp = c.out_ne;
+  const bool account = ix->work_stats && ix->d_work && c.mode == 0 && !c.out_nd && !c.out_ne;
+  if (account) {
+    const size_t cb = (size_t)c.nq * ix->layers.size() * 4;
+    if (ws.ws_nd.bytes < cb || ws.ws_ne.bytes < cb) {
+      PH_CUDA(cudaStreamSynchronize(stream));
+      PH_CUDA(ws.ws_nd.reserve(cb));
+      PH_CUDA(ws.ws_ne.reserve(cb));
+    }
+    PH_CUDA(cudaMemsetAsync(ws.ws_nd.p, 0, cb, stream));
+    PH_CUDA(cudaMemsetAsync(ws.ws_ne.p, 0, cb, stream));
+    a.out_ndist = ws.ws_nd.as<uint32_t>();
+    a.out_nexp = ws.ws_ne.as<uint32_t>();
+  }
   a.out_selfhit = c.out_selfhit;
   a.selfhit_eps = c.selfhit_eps;
   a.stats_stride = (uint32_t)ix->layers.size();
@@ -379,6 +418,13 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
                   : tree ? launch_search_tree(s->metric, a, grid, w * 32, smem, stream)
                          : launch_search_seq(s->metric, a, grid, w * 32, smem, stream);
   if (e != cudaSuccess) return cuda_fail(e, "search_kernel launch");
+  if (account) {
+    work_stats_kernel<<<64, 256, 0, stream>>>(ws.ws_nd.as<uint32_t>(), ws.ws_ne.as<uint32_t>(), c.nq,
+                                              (uint32_t)ix->layers.size(), c.n_layers, ix->d_layers,
+                                              ix->d_work);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "work_stats_kernel launch");
+  }
   return PHNSW_OK;
 }
 
@@ -559,6 +605,13 @@ phnsw_status index_create_empty(phnsw_store *s, const phnsw_build_params *bp,
   else phnsw_default_build_params(&ix->bp);
   cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, s->device);
   cudaDeviceGetAttribute(&ix->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+  {
+    const char *e = getenv("PHNSW_WORK_STATS");
+    if (e && atoi(e) != 0) {
+      ix->work_stats = 1;
+      if (cudaMalloc(&ix->d_work, 32) == cudaSuccess) cudaMemset(ix->d_work, 0, 32);
+    }
+  }
 
   *out = ix;
   return PHNSW_OK;
@@ -894,6 +947,7 @@ void phnsw_index_destroy(phnsw_index *ix) {
   cudaDeviceSynchronize();
   for (auto &l : ix->layers) free_layer(l);
   if (ix->d_layers) cudaFree(ix->d_layers);
+  if (ix->d_work) cudaFree(ix->d_work);
   for (auto &kv : ix->ws) kv.second.release();
   store_release(ix->store);
   delete ix;
@@ -917,6 +971,28 @@ phnsw_status phnsw_index_set_batch_overlap(phnsw_index *ix, int on) {
   return PHNSW_OK;
 }
 int phnsw_index_batch_overlap(const phnsw_index *ix) { return ix ? ix->batch_overlap : 0; }
+phnsw_status phnsw_index_set_work_stats(phnsw_index *ix, int on) {
+  PH_ENTRY();
+  if (!ix) return PHNSW_ERR_INVALID;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  if (on && !ix->d_work) {
+    PH_CUDA(cudaMalloc(&ix->d_work, 32));
+    PH_CUDA(cudaMemset(ix->d_work, 0, 32));
+  }
+  ix->work_stats = on ? 1 : 0;
+  return PHNSW_OK;
+}
+phnsw_status phnsw_index_work_stats(const phnsw_index *ix, uint64_t *out4, int reset) {
+  PH_ENTRY();
+  if (!ix || !out4) return PHNSW_ERR_INVALID;
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  if (!ix->d_work) return PHNSW_OK;
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  PH_CUDA(cudaDeviceSynchronize());
+  PH_CUDA(cudaMemcpy(out4, ix->d_work, 32, cudaMemcpyDeviceToHost));
+  if (reset) PH_CUDA(cudaMemset(ix->d_work, 0, 32));
+  return PHNSW_OK;
+}
 phnsw_status phnsw_index_release_workspace(const phnsw_index *ix, void *cuda_stream, int all) {
   PH_ENTRY();
   if (!ix) return PHNSW_ERR_INVALID;

@@ -263,6 +263,18 @@ class Hnsw:
     def batch_overlap(self):
         return bool(N.lib().phnsw_index_batch_overlap(self._h))
 
+    def set_work_stats(self, on=True):
+        N.check(N.lib().phnsw_index_set_work_stats(self._h, 1 if on else 0))
+        return self
+
+    def work_stats(self, reset=False):
+        """{distance_evals, neighbor_list_bytes, queries, launches} of the traversal launches
+        issued on this index while work accounting was on (include/phnsw.h)."""
+        out = (C.c_uint64 * 4)()
+        N.check(N.lib().phnsw_index_work_stats(self._h, out, 1 if reset else 0))
+        return {"distance_evals": int(out[0]), "neighbor_list_bytes": int(out[1]),
+                "queries": int(out[2]), "launches": int(out[3])}
+
     def release_workspace(self, stream=None):
         """Free the per-query scratch kept for `stream` (None: for every stream)."""
         N.check(N.lib().phnsw_index_release_workspace(self._h, C.c_void_p(stream or 0),

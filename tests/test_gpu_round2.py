@@ -148,6 +148,29 @@ def test_host_async_search_from_pinned_buffers(ph, small):
         gh.search_host_async(pageable, sp, oi, od, stream=st)
 
 
+def test_work_accounting_equals_the_per_query_counters(ph, small):
+    """phnsw_index_set_work_stats: the totals a launch adds up are the sums of the per-query
+    counters the same search returns (which the oracle checks elsewhere)."""
+    rows, comp, gh, oh = small
+    q = random_normed(700, 64, 77)
+    sp = ph.SearchParameters(50, 50, 2)
+    ref = gh.search(q, sp, max_out=5, stats=True)
+    M = [gh.get_layer_from_top(i)[2] for i in range(gh.layer_count())]
+    gh.set_work_stats(True)
+    try:
+        gh.work_stats(reset=True)
+        gh.search(q, sp, max_out=5)
+        gh.search(q[:100], sp, max_out=5)
+        w = gh.work_stats(reset=True)
+    finally:
+        gh.set_work_stats(False)
+    nd, ne = ref[3].astype(np.int64), ref[4].astype(np.int64)
+    assert w["distance_evals"] == int(nd.sum() + nd[:100].sum())
+    assert w["neighbor_list_bytes"] == int(((ne * np.array(M)).sum() + (ne[:100] * np.array(M)).sum()) * 4)
+    assert w["queries"] == 800 and w["launches"] == 2
+    assert gh.work_stats() == {"distance_evals": 0, "neighbor_list_bytes": 0, "queries": 0, "launches": 0}
+
+
 def test_out_of_range_stored_ids_are_loud(ph, small):
     rows, comp, gh, oh = small
     ids = np.array([3, 6000, 5], dtype=np.uint64)
