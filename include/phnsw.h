@@ -328,6 +328,13 @@ phnsw_status phnsw_node_distances(const phnsw_index *ix, uint64_t layer_from_top
 phnsw_status phnsw_discover_nodes_to_promote(const phnsw_index *ix, uint64_t layer_from_top,
                                              const uint64_t *supers, uint64_t n_supers,
                                              uint64_t **out_nodes, uint64_t *out_n);
+/* Layer::reachables_from (src/lib.rs:491-508): the literal depth-first walk from `node` over the
+ * layer's neighbourhoods that finds the nodes of `check` (each once, on first sight) with the
+ * distance = parent's distance + position in the parent's neighbourhood + 1.  Outputs hold up to
+ * n_check + 1 entries, entry 0 = (node, 0), in discovery order. */
+phnsw_status phnsw_reachables_from(const phnsw_index *ix, uint64_t layer_from_top, uint64_t node,
+                                   const uint64_t *check, uint64_t n_check, uint64_t *out_nodes,
+                                   uint64_t *out_dist, uint64_t *out_n);
 /* stochastic_recall (src/lib.rs:1463-1505) */
 phnsw_status phnsw_stochastic_recall(const phnsw_index *ix,
                                      const phnsw_optimization_params *op, float *recall_out);

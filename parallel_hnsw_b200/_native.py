@@ -95,6 +95,7 @@ SIGNATURES = {
     "phnsw_index_sum_order": (C.c_int, [vp]),
     "phnsw_release_build_memory": (C.c_int, [C.c_int]),
     "phnsw_index_release_workspace": (C.c_int, [vp, vp, C.c_int]),
+    "phnsw_reachables_from": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, u64p]),
     "phnsw_index_set_work_stats": (C.c_int, [vp, C.c_int]),
     "phnsw_index_work_stats": (C.c_int, [vp, u64p, C.c_int]),
     "phnsw_index_set_batch_overlap": (C.c_int, [vp, C.c_int]),

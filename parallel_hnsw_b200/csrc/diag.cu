@@ -285,6 +285,71 @@ phnsw_status node_distances(const phnsw_index *ix, uint64_t layer_from_top, cons
 
 using namespace phnsw;
 
+namespace phnsw {
+// Layer::reachables_from (src/lib.rs:491-508).  The walk is order dependent by definition: a
+// LIFO stack, `set.remove(n)` on first sight, distance = parent's distance + position + 1 -- the
+// result depends on the order the neighbourhoods are consumed in, so there is exactly one valid
+// schedule.  One warp per start node runs it literally: all lanes fetch the popped node's
+// neighbourhood (one coalesced read), test and clear the `alive` bits of its entries, and lane
+// order IS neighbourhood order, so ranks inside the row come from one ballot.  A batch of start
+// nodes (each with its own `alive` bitmap and stack) runs one warp each.
+__global__ void reachables_kernel(const uint32_t *__restrict__ neighbors, uint32_t node_count,
+                                  uint32_t M, const uint32_t *__restrict__ starts, uint32_t n_starts,
+                                  uint32_t *alive /* n_starts x words, bit set = still to find */,
+                                  uint32_t words, uint32_t *stack /* n_starts x cap x 2 */,
+                                  uint32_t cap, uint32_t *out_nodes, uint32_t *out_dist,
+                                  uint32_t *out_count) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_starts) return;
+  uint32_t *al = alive + (size_t)w * words;
+  uint32_t *st = stack + (size_t)w * cap * 2;
+  uint32_t *on = out_nodes + (size_t)w * cap, *od = out_dist + (size_t)w * cap;
+  uint32_t sp = 0, m = 0;
+  const uint32_t start = starts[w];
+  if (lane == 0) {
+    on[0] = start; od[0] = 0;
+    st[0] = start; st[1] = 0;
+  }
+  m = 1; sp = 1;
+  __syncwarp();
+  while (sp) {
+    sp--;
+    const uint32_t cur = st[2 * sp], dist = st[2 * sp + 1];
+    __syncwarp();
+    if (cur >= node_count) continue;
+    // neighbourhood with trailing sentinels trimmed (lib.rs:114-125)
+    uint32_t valid = 0;
+    for (uint32_t b = 0; b < M; b += 32) {
+      const uint32_t v = b + lane < M ? neighbors[(size_t)cur * M + b + lane] : kEmpty32;
+      const uint32_t mk = __ballot_sync(0xffffffffu, v != kEmpty32);
+      if (mk) valid = b + 32 - __clz(mk);
+    }
+    for (uint32_t b = 0; b < valid; b += 32) {
+      const uint32_t k = b + lane;
+      const uint32_t nb = k < valid ? neighbors[(size_t)cur * M + k] : kEmpty32;
+      // set.remove(n): a row may list an id twice -- only its first occurrence finds it alive
+      bool hit = nb < node_count && ((al[nb >> 5] >> (nb & 31)) & 1u);
+      // lanes without a hit vote with a value no NodeId can take (node_count < 2^32 - 32)
+      const uint32_t same = __match_any_sync(0xffffffffu, hit ? nb : kEmpty32 - lane);
+      hit = hit && lane == (uint32_t)(__ffs(same) - 1);
+      const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        atomicAnd(&al[nb >> 5], ~(1u << (nb & 31)));
+        const uint32_t r = __popc(hm & ((1u << lane) - 1));
+        if (sp + r < cap && m + r < cap) {
+          st[2 * (sp + r)] = nb; st[2 * (sp + r) + 1] = dist + k + 1;
+          on[m + r] = nb; od[m + r] = dist + k + 1;
+        }
+      }
+      sp += __popc(hm);
+      m += __popc(hm);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) out_count[w] = m < cap ? m : cap;
+}
+}  // namespace phnsw
+
 extern "C" {
 
 phnsw_status phnsw_node_distances(const phnsw_index *ix, uint64_t layer_from_top,
@@ -334,6 +399,51 @@ phnsw_status phnsw_discover_nodes_to_promote(const phnsw_index *ix, uint64_t lay
     memcpy(*out_nodes, out.data(), out.size() * 8);
   }
   *out_n = out.size();
+  return PHNSW_OK;
+}
+
+phnsw_status phnsw_reachables_from(const phnsw_index *ix, uint64_t layer_from_top, uint64_t node,
+                                   const uint64_t *check, uint64_t n_check, uint64_t *out_nodes,
+                                   uint64_t *out_dist, uint64_t *out_n) {
+  PH_ENTRY();
+  if (!ix || layer_from_top >= ix->layers.size() || (n_check && !check) || !out_nodes || !out_dist || !out_n)
+    return PHNSW_ERR_INVALID;
+  *out_n = 0;
+  if (phnsw_device_count() == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return PHNSW_ERR_NO_DEVICE;
+  }
+  const LayerStore &l = ix->layers[layer_from_top];
+  PH_CUDA(cudaSetDevice(ix->store->device));
+  const uint32_t nc = (uint32_t)l.node_count, words = (nc + 31) / 32 + 1, cap = (uint32_t)n_check + 1;
+  std::vector<uint32_t> alive(words, 0u);
+  for (uint64_t i = 0; i < n_check; i++)
+    if (check[i] < nc) alive[check[i] >> 5] |= 1u << (check[i] & 31);
+  uint32_t *d = nullptr;
+  const size_t total = (size_t)words + 1 + (size_t)cap * 4 + 1;
+  PH_CUDA(cudaMalloc(&d, total * 4));
+  uint32_t *d_alive = d, *d_start = d + words, *d_stack = d_start + 1, *d_on = d_stack + (size_t)cap * 2,
+           *d_od = d_on + cap, *d_cnt = d_od + cap;
+  const uint32_t start = node >= nc ? kEmpty32 : (uint32_t)node;
+  cudaError_t e = cudaMemcpy(d_alive, alive.data(), (size_t)words * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_start, &start, 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    reachables_kernel<<<1, 32>>>(l.neighbors, nc, (uint32_t)l.M, d_start, 1, d_alive, words, d_stack, cap,
+                                 d_on, d_od, d_cnt);
+    e = cudaGetLastError();
+  }
+  std::vector<uint32_t> hn(cap), hd(cap);
+  uint32_t cnt = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(hn.data(), d_on, (size_t)cap * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(hd.data(), d_od, (size_t)cap * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "reachables_from");
+  for (uint32_t i = 0; i < cnt; i++) {
+    out_nodes[i] = i == 0 ? node : hn[i];
+    out_dist[i] = hd[i];
+  }
+  *out_n = cnt;
   return PHNSW_OK;
 }
 

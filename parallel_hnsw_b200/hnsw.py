@@ -491,6 +491,17 @@ class Hnsw:
             N.lib().phnsw_free(C.cast(p, C.c_void_p))
         return out
 
+    def reachables_from(self, layer_from_top, node, check):
+        """Layer::reachables_from (src/lib.rs:491-508) -> [(NodeId, index distance)] in the
+        crate's discovery order, entry 0 = (node, 0)."""
+        check = _host(np.atleast_1d(np.asarray(check, dtype=np.uint64)), np.uint64)
+        on = np.empty(check.size + 1, dtype=np.uint64)
+        od = np.empty(check.size + 1, dtype=np.uint64)
+        n = C.c_uint64()
+        N.check(N.lib().phnsw_reachables_from(self._h, layer_from_top, node, _ptr(check), check.size,
+                                              _ptr(on), _ptr(od), C.byref(n)))
+        return list(zip(on[:n.value].tolist(), od[:n.value].tolist()))
+
     def improve_index_with_promotion(self, build_parameters=None, seed=1, progress=None):
         """Hnsw::improve_index (src/lib.rs:1664-1685) with the seed sequence of the nested
         re-top generates restarted from `seed` (improve_index continues the index's own)."""

@@ -63,3 +63,22 @@ def test_built_index_all_layers(ph, oracle):
         assert np.array_equal(gh.supers_for_layer(layer_id), oh.supers_for_layer(layer_id))
         g, o = gh.node_distances_for_layer(layer_id), oh.node_distances_for_layer(layer_id)
         assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]), layer_id
+
+
+def test_reachables_from_matches_oracle(ph, oracle):
+    """Layer::reachables_from (lib.rs:491-508): the literal depth-first walk, discovery order and
+    parent-distance + position + 1 distances included; rows with duplicate ids, sentinels,
+    neighbourhoods wider than a warp, check ids outside the layer."""
+    gh, oh = _pair(ph, oracle, [[1, E], [2, E], [3, E], [E, E], [0, E]], 2)
+    assert gh.reachables_from(0, 0, [1, 2, 3, 4]) == [(0, 0), (1, 1), (2, 2), (3, 3)]
+    assert gh.reachables_from(0, 3, [0, 1]) == [(3, 0)]
+    rng = np.random.default_rng(9)
+    for n, M in [(200, 6), (3000, 8), (500, 48), (400, 70)]:
+        nb = rng.integers(0, n, size=(n, M)).astype(np.uint64)
+        cut = rng.integers(0, M + 1, size=n)
+        nb[np.arange(M)[None, :] >= cut[:, None]] = EMPTY
+        gh, oh = _pair(ph, oracle, nb, M)
+        for start in rng.integers(0, n, size=4).tolist():
+            check = np.concatenate([rng.choice(n, n // 2, replace=False), [n + 5, n]]).astype(np.uint64)
+            assert gh.reachables_from(0, start, check) == oh.reachables_from(0, start, check), (n, M)
+        assert gh.reachables_from(0, 0, []) == oh.reachables_from(0, 0, []) == [(0, 0)]
