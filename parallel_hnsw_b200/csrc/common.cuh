@@ -99,6 +99,18 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
   return __ldcg((const unsigned long long *)p);
 }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) { return __ldcg(p); }
+// a vector row's 16 bytes: read once per distance, never again by this SM
+__device__ __forceinline__ float4 ld_row4(const float4 *p) {
+#ifdef PHNSW_ROWS_NO_L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -149,7 +149,7 @@ constexpr uint32_t kSmallLayerNodes = 8192;  // layers up to this size keep thei
                                              // in a 1 KB shared-memory bitmap
 struct WarpSmemLayout {
   uint32_t off_q, off_lut, off_stage, off_pool, off_bkeys, off_bsorted, off_bid, off_mbar, off_vsm,
-      total;
+      off_layer, total;
 };
 // bytes of the landing zone / scratch area: the sequential-order and ADC variants land rows
 // in it; the tree-order variant reads rows straight into registers and only needs scratch for
@@ -168,6 +168,7 @@ __host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uin
   l.off_bkeys = o;   o += kMaxBatch * 8;
   l.off_bid = o;     o += kMaxBatch * 4;
   l.off_mbar = o;    o += kMaxStages * 8;
+  l.off_layer = o;   o += (uint32_t)((sizeof(LayerDev) + 15) / 16 * 16);
   if (stage_bytes == kScratchBytesTree) {
     // the tree variant lands no rows: its 4 KB scratch area also holds the sorted batch of the
     // duplicate-row path and the small-layer visited bitmap (histogram of the radix select in
@@ -216,7 +217,7 @@ __host__ __device__ inline uint32_t variant_lut_floats(int pq, uint32_t pq_table
 #ifdef __CUDACC__
 
 #ifndef PHNSW_SCAN_UNROLL
-#define PHNSW_SCAN_UNROLL 1
+#define PHNSW_SCAN_UNROLL 2
 #endif
 // PHNSW_NO_HINTS: A/B switch for the static branch hints that move rare blocks (duplicate rows,
 // in-walk compaction, frontier spill pops, bad ids) out of the hot loop's fall-through path
@@ -227,6 +228,19 @@ __host__ __device__ inline uint32_t variant_lut_floats(int pq, uint32_t pq_table
 #endif
 #define PH_STR_(x) #x
 #define PH_UNROLL(n) _Pragma(PH_STR_(unroll n))
+// loops outside the per-expansion path (compaction, layer hand-over, spill pops) are kept
+// rolled: unrolled four times by default they are 2-3x the code, and the walk already runs
+// ~48 KB of warm SASS against a 32 KB instruction cache
+#ifdef PHNSW_COLD_UNROLLED
+#define PH_COLD_LOOP
+#else
+#define PH_COLD_LOOP _Pragma("unroll 1")
+#endif
+#ifdef PHNSW_COLD_UNROLLED2
+#define PH_COLD_LOOP2
+#else
+#define PH_COLD_LOOP2 _Pragma("unroll 1")
+#endif
 
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint64_t kHiMask = 0xFFFFFFFF00000000ull;
@@ -279,6 +293,7 @@ struct WarpSearch {
   uint32_t *bm;
   uint32_t *vlog;
   uint32_t *vsm;       // shared-memory visited bitmap of a small layer (vis_small)
+  LayerDev *ldesc;     // this warp's copy of the descriptor of the layer being walked
   bool vis_small;
   uint64_t *saved;
   const int lane;
@@ -310,6 +325,7 @@ struct WarpSearch {
     bid = (uint32_t *)(smem + l.off_bid);
     mbar = (uint64_t *)(smem + l.off_mbar);
     vsm = (uint32_t *)(smem + l.off_vsm);
+    ldesc = (LayerDev *)(smem + l.off_layer);
     vis_small = false;
     ovf = a.ovf + (size_t)slot * a.ovf_cap;
     bm = a.bitmap + (size_t)slot * a.bitmap_words;
@@ -325,6 +341,23 @@ struct WarpSearch {
     ovf_min = kEmptyKey;
   }
 
+  // The descriptor of the layer being walked is copied into this warp's shared memory: the hot
+  // loop reads neighbors / lrows / node_count / M once per expansion, and from global memory
+  // those loads (the compiler cannot keep them in registers across the bitmap stores) sit in
+  // an L1 that the row stream keeps flushing -- 5 % of the tree variant's stall samples were on
+  // them (profiles/r02_ncu_search_kernel_tree_*).
+  __device__ __forceinline__ const LayerDev &stage_layer(const LayerDev *g) {
+#ifdef PHNSW_NO_LAYER_SMEM
+    return *g;
+#else
+    __syncwarp();
+    if ((uint32_t)lane < sizeof(LayerDev) / 4)
+      ((uint32_t *)ldesc)[lane] = __ldg((const uint32_t *)g + lane);
+    __syncwarp();
+    return *ldesc;
+#endif
+  }
+
   // ------------------------------------------------------------------ visited bitmap
   // clear every bit set since the last reset (by replaying the log, or the whole bitmap if the
   // log overflowed)
@@ -335,8 +368,10 @@ struct WarpSearch {
   __device__ void visited_reset(uint32_t next_layer_nodes = 0xffffffffu) {
     __syncwarp();
     if (vlog_over) {
+      PH_COLD_LOOP2
       for (uint32_t w = lane; w < a.bitmap_words; w += 32) bm[w] = 0u;
     } else {
+      PH_COLD_LOOP2
       for (uint32_t i0 = 0; i0 < vlog_n; i0 += 256) {  // 8 independent loads in flight per lane
         uint32_t id[8];
 #pragma unroll
@@ -354,6 +389,7 @@ struct WarpSearch {
     vis_small = next_layer_nodes <= kSmallLayerNodes;
     if (vis_small) {
       uint4 *z = (uint4 *)vsm;
+      PH_COLD_LOOP2
       for (uint32_t w = lane; w < kSmallLayerNodes / 128; w += 32) z[w] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncwarp();
@@ -400,6 +436,7 @@ struct WarpSearch {
     __syncwarp();
     uint64_t best = kEmptyKey;
     uint32_t bi = 0;
+    PH_COLD_LOOP
     for (uint32_t i = lane; i < ovf_n; i += 32) {
       uint64_t k = ld_cg_u64(&ovf[i]);
       if (k < best) { best = k; bi = i; }
@@ -413,6 +450,7 @@ struct WarpSearch {
     ovf_n--;
     __syncwarp();
     uint64_t nb = kEmptyKey;
+    PH_COLD_LOOP
     for (uint32_t i = lane; i < ovf_n; i += 32) {
       uint64_t k = ld_cg_u64(&ovf[i]);
       nb = k < nb ? k : nb;
@@ -425,6 +463,7 @@ struct WarpSearch {
   __device__ void rescan_max() {
     uint64_t best = 0;
     uint32_t bs = 0;
+    PH_COLD_LOOP
     for (uint32_t s = lane; s < len; s += 32) {
       uint64_t k = pool[s] & kFlagMask64;
       if (k >= best) { best = k; bs = s; }
@@ -438,6 +477,7 @@ struct WarpSearch {
   __device__ uint64_t scan_min_unexpanded(uint32_t *slot) {
     uint64_t best = kEmptyKey;
     uint32_t bs = 0;
+    PH_COLD_LOOP
     for (uint32_t s = lane; s < len; s += 32) {
       uint64_t k = pool[s];
       if (!((uint32_t)k & kFlagExpanded) && k < best) { best = k; bs = s; }
@@ -458,6 +498,7 @@ struct WarpSearch {
     uint32_t *hist = (uint32_t *)stage;
     const uint64_t first = pool[0] & kFlagMask64;
     uint64_t diff = 0;
+    PH_COLD_LOOP
     for (uint32_t s = lane; s < len; s += 32) diff |= (pool[s] & kFlagMask64) ^ first;
     diff = ((uint64_t)__reduce_or_sync(kFull, (uint32_t)(diff >> 32)) << 32) |
            __reduce_or_sync(kFull, (uint32_t)diff);
@@ -474,6 +515,7 @@ struct WarpSearch {
       for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
       __syncwarp();
       const uint32_t sh = 8 * d;
+      PH_COLD_LOOP
       for (uint32_t s = lane; s < len; s += 32) {
         uint64_t km = pool[s] & kFlagMask64;
         if ((km & pmask) == prefix) atomicAdd(&hist[(uint32_t)(km >> sh) & 255u], 1u);
@@ -514,6 +556,7 @@ struct WarpSearch {
 #endif
       if (cnt == 1) {  // a single key carries this prefix: that is the tail
         uint64_t mine = 0;
+        PH_COLD_LOOP
         for (uint32_t s = lane; s < len; s += 32) {
           uint64_t km = pool[s] & kFlagMask64;
           if ((km & pmask) == prefix) mine = km;
@@ -529,6 +572,7 @@ struct WarpSearch {
     // unique; up to slack_half more after an early stop)
     const uint32_t old_len = len;
     uint32_t w = 0;
+    PH_COLD_LOOP
     for (uint32_t r0 = 0; r0 < old_len; r0 += 32) {
       uint32_t i = r0 + lane;
       bool act = i < old_len;
@@ -567,11 +611,14 @@ struct WarpSearch {
     while (P < len) P <<= 1;
     __syncwarp();
     if (P > kSortScratch) {  // too large for the scratch area: selection sort in place
+      PH_COLD_LOOP2
       for (uint32_t s = lane; s < len; s += 32) pool[s] &= kFlagMask64;
       __syncwarp();
+      PH_COLD_LOOP2
       for (uint32_t i = 0; i + 1 < len; i++) {
         uint64_t best = kEmptyKey;
         uint32_t bs = i;
+        PH_COLD_LOOP2
         for (uint32_t s = i + lane; s < len; s += 32) {
           uint64_t k = pool[s];
           if (k < best) { best = k; bs = s; }
@@ -584,10 +631,12 @@ struct WarpSearch {
       }
       return;
     }
+    PH_COLD_LOOP2
     for (uint32_t s = lane; s < P; s += 32) scr[s] = s < len ? (pool[s] & kFlagMask64) : kEmptyKey;
     __syncwarp();
     for (uint32_t k = 2; k <= P; k <<= 1)
       for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        PH_COLD_LOOP2
         for (uint32_t t = lane; t < (P >> 1); t += 32) {
           uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
           uint32_t p = i | j;
@@ -597,6 +646,7 @@ struct WarpSearch {
         }
         __syncwarp();
       }
+    PH_COLD_LOOP2
     for (uint32_t s = lane; s < len; s += 32) pool[s] = scr[s];
     __syncwarp();
   }
@@ -704,7 +754,7 @@ struct WarpSearch {
       for (int r = 1; r < 8; r++) id[r] = j0 + r < nn ? id[r] : id[0];  // stale slots: reuse row 0
       float4 x[8];
 #pragma unroll
-      for (int r = 0; r < 8; r++) x[r] = __ldg(base + (size_t)id[r] * pitch4);
+      for (int r = 0; r < 8; r++) x[r] = ld_row4(base + (size_t)id[r] * pitch4);
       float acc[8];
 #pragma unroll
       for (int r = 0; r < 8; r++) {
@@ -1216,6 +1266,7 @@ struct WarpSearch {
         const uint64_t b0 = warp_min_key(mine0 < mine1 ? mine0 : mine1);
         // ---- one pass over the pool: rank of b0 (merge()'s return flag in closed form, see
         // oracle orc_pq_merge_flag_closed_form) and the next node to pop
+#ifdef PHNSW_TWO_COUNTS
         const uint32_t b0hi = (uint32_t)(b0 >> 32);
         uint32_t A = 0, B = 0;
         uint64_t best = kEmptyKey;
@@ -1233,11 +1284,31 @@ struct WarpSearch {
         nx_key = warp_min_key(best);
         nx_slot = __shfl_sync(kFull, bs, __ffs(__ballot_sync(kFull, best == nx_key)) - 1);
         nx_valid = true;
-        // full: the candidate set holds `cap` entries; its tail is the cap-th smallest key.
-        // b0 < tail  <=>  fewer than cap keys are below b0; tail and b0 tie on the distance
-        // <=>  b0 is not below the tail but fewer than cap keys have a smaller distance.
         const bool full = len >= cap;
         did = !full || A < cap || (nn >= 2 && B < cap);
+#else
+        // full: the candidate set holds `cap` entries; its tail is the cap-th smallest key.
+        // b0 < tail  <=>  A = #{keys < b0} < cap; tail and b0 tie on the distance (the quirk,
+        // batches of two or more)  <=>  B = #{keys with a smaller distance} < cap.  B <= A, so
+        // one count decides: against the distance alone for a batch of two or more (A < cap
+        // implies B < cap), against the whole key for a batch of one.
+        const uint64_t bx = nn >= 2 ? (b0 & kHiMask) : b0;
+        uint32_t A = 0;
+        uint64_t best = kEmptyKey;
+        uint32_t bs = 0;
+#pragma unroll kScanUnroll
+        for (uint32_t s = lane; s < len; s += 32) {
+          uint64_t k = pool[s];
+          uint64_t km = k & kFlagMask64;
+          A += km < bx;
+          if (!((uint32_t)k & kFlagExpanded) && km < best) { best = km; bs = s; }
+        }
+        A = __reduce_add_sync(kFull, A);
+        nx_key = warp_min_key(best);
+        nx_slot = __shfl_sync(kFull, bs, __ffs(__ballot_sync(kFull, best == nx_key)) - 1);
+        nx_valid = true;
+        did = len < cap || A < cap;
+#endif
         if (did || probe > 1) {  // the walk continues: request the next row now
           uint64_t i0 = mine0 < U ? mine0 : kEmptyKey, i1 = mine1 < U ? mine1 : kEmptyKey;
           uint64_t pk = warp_min_key(i0 < i1 ? i0 : i1);
@@ -1341,6 +1412,7 @@ struct WarpSearch {
     if (PQ) {
       if (a.queries) {
         const float *src = a.queries + (size_t)q * a.qpitch;
+        PH_COLD_LOOP2
         for (uint32_t i = lane; i < a.dim_pad; i += 32) qvec[i] = i < a.qpitch ? src[i] : 0.0f;
       } else {  // Stored: the query is the reconstruction of its own codes
         uint32_t vid;
@@ -1380,6 +1452,7 @@ struct WarpSearch {
     const float *src;
     if (a.queries) {
       src = a.queries + (size_t)q * a.qpitch;
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < a.dim_pad; i += 32) qvec[i] = i < a.qpitch ? src[i] : 0.0f;
     } else {
       uint32_t vid;
@@ -1389,6 +1462,7 @@ struct WarpSearch {
         vid = l.nodes ? l.nodes[a.q_offset + q] : a.q_offset + q;
       }
       src = a.rows + (size_t)vid * a.pitch;
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < a.dim_pad; i += 32) qvec[i] = src[i];
     }
     __syncwarp();
@@ -1397,6 +1471,7 @@ struct WarpSearch {
   // outputs of a skipped query: no results
   __device__ void emit_nothing(uint32_t q) {
     if (a.out_ids)
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < a.max_out; i += 32) {
         a.out_ids[(size_t)q * a.max_out + i] = ~0ull;
         a.out_dists[(size_t)q * a.max_out + i] = 3.4028234663852886e38f;
@@ -1412,10 +1487,12 @@ struct WarpSearch {
     uint32_t n = min(want, len);
     if (n > 24) {
       sort_pool();
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < n; i += 32) f(i, pool[i]);
       __syncwarp();
       return n;
     }
+    PH_COLD_LOOP2
     for (uint32_t r = 0; r < n; r++) {
       uint32_t slot;
       uint64_t k = scan_min_unexpanded(&slot);
@@ -1447,6 +1524,7 @@ struct WarpSearch {
       const bool was_full = len == cap;
       bool mine = false;
       uint32_t myslot = 0;
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < len; i += 32)
         if ((uint32_t)pool[i] == excl) { mine = true; myslot = i; }
       uint32_t mm = __ballot_sync(kFull, mine);
@@ -1455,6 +1533,7 @@ struct WarpSearch {
       if (lane == 0) pool[s] = pool[len - 1];
       len--;
       uint64_t add = kEmptyKey;
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < old_len; i += 32) {
         uint64_t k = ld_cg_u64(&saved[i]);
         if ((uint32_t)k == excl || (was_full && k > pmax_v)) add = k < add ? k : add;
@@ -1472,6 +1551,7 @@ struct WarpSearch {
     // then merge the incoming candidates that are not already there
     sort_pool();
     uint32_t w = 0;
+    PH_COLD_LOOP2
     for (uint32_t i0 = 0; i0 < len; i0 += 32) {
       uint32_t i = i0 + lane;
       bool act = i < len;
@@ -1488,6 +1568,7 @@ struct WarpSearch {
     const uint32_t sorted_len = len;
     // pass 1: compact the incoming candidates that are absent from the returned set
     uint32_t n_abs = 0;
+    PH_COLD_LOOP2
     for (uint32_t i0 = 0; i0 < old_len; i0 += 32) {
       uint32_t i = i0 + lane;
       bool act = i < old_len;
@@ -1522,7 +1603,7 @@ struct WarpSearch {
     uint32_t nd_l = 0, ne_l = 0;
     // entry vector = first node of the top layer (search.rs:9-11, 101-111)
     {
-      const LayerDev &top = a.layers[0];
+      const LayerDev &top = stage_layer(&a.layers[0]);
       if (lane == 0) bid[0] = 0;
       __syncwarp();
       compute_distances(top, 1);
@@ -1534,12 +1615,13 @@ struct WarpSearch {
       __syncwarp();
     }
     for (uint32_t li = 0; li < a.n_layers; li++) {
-      const LayerDev &layer = a.layers[li];
+      const LayerDev &layer = stage_layer(&a.layers[li]);
       const uint32_t count = (li == a.n_layers - 1) ? cap : a.upper_count;
       const uint32_t old_len = len;
       // keep the incoming candidates (VectorId keys) for the merge at search.rs:136, and
       // map VectorId -> NodeId for this layer (lib.rs:258-262)
       visited_reset(layer.node_count);
+      PH_COLD_LOOP
       for (uint32_t i0 = 0; i0 < old_len; i0 += 32) {
         uint32_t i = i0 + lane;
         bool act = i < old_len;
@@ -1570,6 +1652,7 @@ struct WarpSearch {
         pmax_v = (pmax & kHiMask) | (layer.nodes ? __ldg(&layer.nodes[pn]) : pn);
       }
       bool hit = false;
+      PH_COLD_LOOP
       for (uint32_t i = lane; i < len; i += 32) {
         uint64_t k = pool[i];
         uint32_t node = key_id(k);
@@ -1585,6 +1668,7 @@ struct WarpSearch {
       const uint32_t self = (uint32_t)a.stored_ids[q];
       bool hit = false;
       float dmin = 3.4028234663852886e38f;
+      PH_COLD_LOOP2
       for (uint32_t i = lane; i < len; i += 32) {
         const uint64_t k = pool[i];
         const float d = key_dist(k);
@@ -1613,6 +1697,7 @@ struct WarpSearch {
         oi[r] = (uint64_t)(uint32_t)k + idoff;
         od[r] = key_dist(k);
       });
+      PH_COLD_LOOP2
       for (uint32_t i = n_out + lane; i < a.max_out; i += 32) {
         oi[i] = ~0ull;
         od[i] = 3.4028234663852886e38f;
@@ -1655,6 +1740,7 @@ struct WarpSearch {
     __syncwarp();
     for (uint32_t k = 2; k <= P; k <<= 1)
       for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        PH_COLD_LOOP2
         for (uint32_t t = lane; t < (P >> 1); t += 32) {
           const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
           const uint32_t p = i | j;
@@ -1665,6 +1751,7 @@ struct WarpSearch {
         __syncwarp();
       }
     const uint32_t n_out = min(n, a.max_out);
+    PH_COLD_LOOP2
     for (uint32_t i = lane; i < a.max_out; i += 32) {
       const uint64_t k = i < n_out ? keys[i] : 0;
       a.out_ids[(size_t)q * a.max_out + i] = i < n_out ? (uint64_t)(uint32_t)k + a.out_id_offset : ~0ull;
@@ -1676,7 +1763,7 @@ struct WarpSearch {
 
   // Hnsw::knn, src/lib.rs:905-928: bottom layer only, queue of 3k seeded with (self, 0.0)
   __device__ void run_knn(uint32_t q) {
-    const LayerDev &layer = a.layers[a.n_layers - 1];
+    const LayerDev &layer = stage_layer(&a.layers[a.n_layers - 1]);
     uint32_t nd_l = 0, ne_l = 0;
     const uint32_t node = a.q_offset + q;
     visited_reset();
@@ -1690,6 +1777,7 @@ struct WarpSearch {
     // .filter(|(n,_)| *n != node).take(k): drop self from the pool, then emit the k smallest
     bool mine = false;
     uint32_t myslot = 0;
+    PH_COLD_LOOP2
     for (uint32_t i = lane; i < len; i += 32) {
       uint64_t k = pool[i] & kFlagMask64;
       pool[i] = k;
@@ -1710,6 +1798,7 @@ struct WarpSearch {
       oi[r] = layer.nodes ? layer.nodes[nid] : nid;
       od[r] = key_dist(k);
     });
+    PH_COLD_LOOP2
     for (uint32_t i = n_out + lane; i < a.max_out; i += 32) {
       oi[i] = ~0ull;
       od[i] = 3.4028234663852886e38f;
@@ -1721,7 +1810,7 @@ struct WarpSearch {
   // call starts with all current candidates unexpanded), doubling the capacity while the
   // last distance is still under the threshold and the queue grew.
   __device__ void run_threshold(uint32_t q) {
-    const LayerDev &layer = a.layers[a.n_layers - 1];
+    const LayerDev &layer = stage_layer(&a.layers[a.n_layers - 1]);
     uint32_t nd_l = 0, ne_l = 0;
     const uint32_t node = a.q_offset + q;
     if (lane == 0) pool[0] = make_key(0.0f, node);
@@ -1732,6 +1821,7 @@ struct WarpSearch {
     while (last < a.threshold && len > last_size) {
       last_size = len;
       visited_reset();
+      PH_COLD_LOOP2
       for (uint32_t i0 = 0; i0 < len; i0 += 32) {
         uint32_t i = i0 + lane;
         bool act = i < len;
