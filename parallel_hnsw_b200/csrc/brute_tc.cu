@@ -141,11 +141,15 @@ __device__ __forceinline__ void split8(const float4 &f0, const float4 &f1, float
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    // two values per conversion (cvt.rn.bf16x2.f32: the first operand lands in the low half);
+    // a bf16 widens to f32 by a shift, so the remainder costs one subtraction per value
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hh);
+    const float r0 = v[2 * i] - __uint_as_float(hb << 16);
+    const float r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t *>(&ll);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -166,6 +170,8 @@ struct FilterArgs {
   uint32_t *cand;         // nq x cap row ids
   uint32_t *cnt;          // nq
   uint32_t cap;
+  uint32_t skip_zero;     // 1: products whose low-part operand is all zero are not issued
+  uint32_t *mma_groups;   // number of 4 x K16 product groups issued (statistics)
 };
 
 // dynamic shared memory: [A: nkb x (qh tile, ql tile)] [ring: stages x (xh tile, xl tile)]
@@ -188,6 +194,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
   uint64_t *tfull = empty + 8;
   uint64_t *tempty = tfull + 2;
   uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+  // "is any low part of this operand tile non-zero": one word per query k-block, one byte per
+  // producer warp and stage.  Data whose values are exact in bf16 (SIFT's integers 0..218,
+  // anything on an 8-bit grid) has x_lo = q_lo = 0, and then two of the three split products are
+  // exactly zero -- they are not issued.  Nothing is approximated: a skipped product is 0.
+  uint32_t *qnz = tmem_slot + 4;               // [4]
+  unsigned char *xnz = (unsigned char *)(qnz + 4);  // [8 stages][4 warps]
 
   const uint32_t q0 = blockIdx.x * kM;
   const uint64_t n_begin = (uint64_t)blockIdx.y * a.rows_per_cta;
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
       mbar_init(&tempty[b], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_fence_init();
+    for (int i = 0; i < 4; i++) qnz[i] = a.skip_zero ? 0u : 1u;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -212,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  __syncthreads();
   // ---- the resident A operand: -2 * q, bf16 high / low parts, all threads
   for (uint32_t idx = threadIdx.x; idx < nkb * kM * 8; idx += blockDim.x) {
     const uint32_t kb = idx / (kM * 8), rem = idx - kb * (kM * 8), r = rem >> 3, c = rem & 7;
@@ -229,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
     split8(f0, f1, -2.0f, hi, lo);
     *(uint4 *)(smA + (size_t)(kb * 2) * kTileA + sw128(r, c)) = hi;
     *(uint4 *)(smA + (size_t)(kb * 2 + 1) * kTileA + sw128(r, c)) = lo;
+    if ((lo.x | lo.y | lo.z | lo.w) & 0x7FFF7FFFu) atomicOr(&qnz[kb & 3], 1u);
   }
   fence_async_smem();
   tc_fence_before();
@@ -251,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
       const uint64_t row0 = n_begin + (uint64_t)t * kN;
       unsigned char *xh = smB + (size_t)(s * 2) * kTileB, *xl = xh + kTileB;
       const uint32_t d0 = kb * kKB + pc * 8;
+      uint32_t nz = a.skip_zero ? 0u : 1u;
 #pragma unroll 1
       for (uint32_t half = 0; half < (uint32_t)NT / 128; half++) {  // 128 rows per pass
         float4 f0[8], f1[8];
@@ -270,7 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
           const uint32_t off = sw128(half * 128 + pr + 16 * i, pc);
           *(uint4 *)(xh + off) = hi;
           *(uint4 *)(xl + off) = lo;
+          nz |= (lo.x | lo.y | lo.z | lo.w) & 0x7FFF7FFFu;
         }
+      }
+      {
+        const bool any = __any_sync(0xffffffffu, nz != 0u);
+        if (lane == 0) xnz[s * 4 + ((warp - kFirstProducer) & 3)] = any ? 1 : 0;
       }
       if (kb == 0) {  // row term of this tile (rows past the end never pass)
         for (uint32_t r = p; r < (uint32_t)NT; r += 128) {
@@ -285,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
   } else if (warp == kEpiWarps) {
     // ================= MMA issuer
     const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
+    uint32_t issued = 0;
     for (uint32_t t = 0; t < T; t++) {
       const uint32_t b = t & 1u;
       mbar_wait(&tempty[b], ((t >> 1) & 1u) ^ 1u);
@@ -294,6 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
         mbar_wait(&full[s], (it / S) & 1u);
         tc_fence_after();
         if (lane == 0) {
+          const bool x_lo = *(volatile uint32_t *)(xnz + s * 4) != 0u;
+          const bool q_lo = *(volatile uint32_t *)&qnz[kb & 3] != 0u;
+          issued += 1u + (x_lo ? 1u : 0u) + (q_lo ? 1u : 0u);
           const uint64_t qh = umma_desc(a_base + (kb * 2) * kTileA);
           const uint64_t ql = umma_desc(a_base + (kb * 2 + 1) * kTileA);
           const uint64_t xh = umma_desc(b_base + (s * 2) * kTileB);
@@ -302,16 +327,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_filter_kernel(const FilterArgs
 #pragma unroll
           for (uint32_t k = 0; k < 4; k++)  // 4 x K16 = 64 dims; +32 B per step = +2 in the desc
             umma_bf16(d, qh + 2 * k, xh + 2 * k, kIdesc, (kb | k) != 0);
+          if (x_lo) {
 #pragma unroll
-          for (uint32_t k = 0; k < 4; k++) umma_bf16(d, qh + 2 * k, xl + 2 * k, kIdesc, 1u);
+            for (uint32_t k = 0; k < 4; k++) umma_bf16(d, qh + 2 * k, xl + 2 * k, kIdesc, 1u);
+          }
+          if (q_lo) {
 #pragma unroll
-          for (uint32_t k = 0; k < 4; k++) umma_bf16(d, ql + 2 * k, xh + 2 * k, kIdesc, 1u);
+            for (uint32_t k = 0; k < 4; k++) umma_bf16(d, ql + 2 * k, xh + 2 * k, kIdesc, 1u);
+          }
           umma_commit(&empty[s]);                      // the stage is free once these complete
           if (kb == nkb - 1) umma_commit(&tfull[b]);   // ... and the accumulator is ready
         }
         __syncwarp();
       }
     }
+    if (lane == 0 && a.mma_groups) atomicAdd(a.mma_groups, issued);
   } else {
     // ================= epilogue: warps w and w + 4 own TMEM lanes 32 (w % 4) .. + 31 (one query
     // per lane) and half of the tile's columns each.  The slot of a passing row comes from a
@@ -830,7 +860,7 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
   if (e == cudaSuccess) e = cudaMalloc(&thr, nq * 4);
   if (e == cudaSuccess) e = cudaMalloc(&topk, nq * k * 8);
   if (e == cudaSuccess) e = cudaMalloc(&cand, nq * (size_t)cap * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&cnt, (nq + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&cnt, (nq + 2) * 4);
   auto cleanup = [&]() {
     if (w) cudaFree(w);
     if (thr) cudaFree(thr);
@@ -851,7 +881,7 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
     tc_row_term_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(s->rows, s->pitch, s->n, l2, c, w);
     tc_threshold_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(
         dq, (uint32_t)s->dim, (uint32_t)s->dim, (uint32_t)nq, topk, (uint32_t)k, s->metric, c, thr);
-    cudaMemsetAsync(cnt, 0, (nq + 1) * 4, st);
+    cudaMemsetAsync(cnt, 0, (nq + 2) * 4, st);
     FilterArgs a;
     a.rows = s->rows;
     a.pitch = s->pitch;
@@ -867,6 +897,8 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
     a.cand = cand;
     a.cnt = cnt;
     a.cap = cap;
+    a.skip_zero = getenv("PHNSW_TC_NO_SKIP") ? 0u : 1u;  // developer A/B switch
+    a.mma_groups = cnt + nq + 1;
     const uint32_t qblocks = (uint32_t)((nq + kM - 1) / kM);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -881,8 +913,9 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
     tc_filter_kernel<128><<<dim3(qblocks, splits), threads, smem, st>>>(a);
     cudaEventRecord(ev1, st);
     tc_max_u32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cnt, (uint32_t)nq, cnt + nq);
-    uint32_t mx = 0;
-    e = cudaMemcpyAsync(&mx, cnt + nq, 4, cudaMemcpyDeviceToHost, st);
+    uint32_t mxg[2] = {0, 0};
+    uint32_t &mx = mxg[0];
+    e = cudaMemcpyAsync(mxg, cnt + nq, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) rc = cuda_fail(e, "tc_filter_kernel");
@@ -910,8 +943,8 @@ phnsw_status bruteforce_knn_tc(const phnsw_store *s, const float *dq, uint64_t n
     if (rc == PHNSW_OK) cudaEventElapsedTime(&ms, ev0, ev1);
     g_stats.path = *done ? 1 : 0;
     g_stats.filter_ms = ms;
-    g_stats.filter_flops = 2.0 * 3.0 * (double)qblocks * kM * (double)((s->n + NT - 1) / NT * NT) *
-                           (double)(nkb * kKB);
+    // flops of the products actually issued: a group = 4 x (M128 N128 K16)
+    g_stats.filter_flops = 2.0 * (double)mxg[1] * (double)kM * (double)NT * (double)kKB;
     g_stats.max_candidates = mx;
     g_stats.candidate_cap = cap;
     g_stats.prefix_rows = n_prefix;

@@ -781,14 +781,20 @@ struct WarpSearch {
     const uint32_t nchunks = (fl4 + 31) / 32;
     const float4 *q4p = (const float4 *)qvec;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 *lrows4 = (const float4 *)layer.lrows + lane;
+    const uint32_t pitch4 = a.pitch / 4;
     for (uint32_t j0 = 0; j0 < nn; j0 += RB) {
-      const float4 *rp[RB];
-      bool valid[RB];
+      // Row addresses are rebuilt from the node ids at every chunk (one IMAD.WIDE per load)
+      // instead of being carried as eight 64-bit pointers: the chunk loop then fits the 80
+      // registers of 24 resident warps in every metric variant.  The empty asm keeps the compiler
+      // from hoisting the products back out of the loop.
+      uint32_t nd[RB];
+      uint32_t vmask = 0;
 #pragma unroll
       for (int r = 0; r < RB; r++) {
-        valid[r] = j0 + r < nn;
-        uint32_t node = bid[valid[r] ? j0 + r : j0];
-        rp[r] = (const float4 *)(layer.lrows + (size_t)node * a.pitch) + lane;
+        const bool ok = j0 + r < nn;
+        vmask |= ok ? 1u << r : 0u;
+        nd[r] = bid[ok ? j0 + r : j0];
       }
       float acc[RB];
 #pragma unroll
@@ -798,7 +804,12 @@ struct WarpSearch {
         const float4 q4 = in ? q4p[c * 32 + lane] : zero;
         float4 x[RB];
 #pragma unroll
-        for (int r = 0; r < RB; r++) x[r] = (in && valid[r]) ? __ldg(rp[r] + c * 32) : zero;
+        for (int r = 0; r < RB; r++) {
+#ifndef PHNSW_TREE_ROW_POINTERS
+          asm volatile("" : "+r"(nd[r]));
+#endif
+          x[r] = (in && ((vmask >> r) & 1u)) ? __ldg(lrows4 + (size_t)nd[r] * pitch4 + c * 32) : zero;
+        }
 #pragma unroll
         for (int r = 0; r < RB; r++) acc[r] = tree_accum(acc[r], x[r], q4);
       }
@@ -1212,8 +1223,24 @@ struct WarpSearch {
         in1 = in1 && n1 < layer.node_count;
       }
       // ---- drop already visited ones (lib.rs:198); duplicates inside the row both pass
+#ifndef PHNSW_VIS_BRANCHY
+      // both bitmap words requested back to back with no per-lane branch (lanes outside the row
+      // read word 0); the second half only exists for neighbourhoods wider than a warp
+      const uint32_t t0 = in0 ? n0 : 0u, t1 = in1 ? n1 : 0u;
+      uint32_t w0, w1 = 0u;
+      if (vis_small) {
+        w0 = vsm[t0 >> 5];
+        w1 = vsm[t1 >> 5];
+      } else {
+        w0 = ld_cg_u32(&bm[t0 >> 5]);
+        if (v1) w1 = ld_cg_u32(&bm[t1 >> 5]);
+      }
+      bool u0 = in0 && !((w0 >> (t0 & 31)) & 1u);
+      bool u1 = in1 && !((w1 >> (t1 & 31)) & 1u);
+#else
       bool u0 = in0 && !visited_test(n0);
       bool u1 = in1 && !visited_test(n1);
+#endif
       uint32_t m0 = __ballot_sync(kFull, u0);
       uint32_t m1 = __ballot_sync(kFull, u1);
       uint32_t nn = __popc(m0) + __popc(m1);

@@ -116,3 +116,38 @@ def test_tensor_path_against_the_oracle_directly(ph, oracle, metric_name, dim, n
             assert np.all(np.abs(g_ds.astype(np.float64) - od[:k]) <= 2e-7 * od[:k] + 1e-30)
         else:
             assert np.array_equal(g_ds.view(np.uint32), od[:k].view(np.uint32))
+
+
+def test_zero_low_parts_are_not_multiplied(ph):
+    """Operands that are exact in bf16 (integers below 256: SIFT) have all-zero low parts; the
+    filter then issues one of the three split products (two when only one side is exact) and
+    returns the same bits as with every product issued (PHNSW_TC_NO_SKIP)."""
+    n, nq, dim, k = 40000, 256, 128, 10
+    rows = clustered(n, dim, 41, n_clusters=256, spread=0.3, integer=True)
+    qi = clustered(nq, dim, 42, n_clusters=256, spread=0.3, integer=True)
+    qf = (qi + np.float32(0.123)).astype(np.float32)
+    comp = ph.BigComparator(rows, ph.L2_SQRT)
+    old = {v: os.environ.get(v) for v in ("PHNSW_BRUTEFORCE", "PHNSW_TC_NO_SKIP")}
+    try:
+        os.environ["PHNSW_BRUTEFORCE"] = "tensor"
+        os.environ["PHNSW_TC_NO_SKIP"] = "1"
+        full_i = comp.bruteforce_knn(qi, k)
+        full_flops = comp.bruteforce_last_stats()["filter_flops"]
+        full_f = comp.bruteforce_knn(qf, k)
+        del os.environ["PHNSW_TC_NO_SKIP"]
+        skip_i = comp.bruteforce_knn(qi, k)
+        st_i = comp.bruteforce_last_stats()
+        skip_f = comp.bruteforce_knn(qf, k)
+        st_f = comp.bruteforce_last_stats()
+    finally:
+        for v, x in old.items():
+            if x is None:
+                os.environ.pop(v, None)
+            else:
+                os.environ[v] = x
+    assert st_i["path"] == "tensor" and st_f["path"] == "tensor"
+    assert st_i["filter_flops"] * 3 == full_flops        # q_hi . x_hi only
+    assert st_f["filter_flops"] * 3 == full_flops * 2    # + q_lo . x_hi
+    for a, b in ((full_i, skip_i), (full_f, skip_f)):
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
