@@ -223,9 +223,14 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     if (force) pq_table = atoi(force) != 0;
   }
   const int variant = q8 ? 2 : (pq8 ? 1 : 0);
+  // landing zone of the sequential f32 variant: shallow for rows of one chunk (more resident
+  // warps), deep for rows of several chunks; the exact ADC variant lands 32 code rows in it
+  const uint32_t landing_rows =
+      (variant == 0 && s->pitch <= (uint32_t)kChunk) ? (uint32_t)kLandingRowsSmall : (uint32_t)kLandingRows;
   WarpSmemLayout lay = warp_smem_layout(variant_q_floats(variant, s->pitch), cap_pad,
                                         variant_lut_floats(variant, pq_table, s->pq_Q, s->pq_K),
-                                        (tree || q8) ? kScratchBytesTree : kLandingBytes);
+                                        (tree || q8) ? kScratchBytesTree
+                                                     : landing_rows * (uint32_t)kRowStride * 4u);
   const size_t avail = (size_t)ix->max_smem;
   if (lay.total > avail) {
     set_error("search: per-query shared memory %u B exceeds %zu B (dim %llu, capacity %u)",
@@ -408,6 +413,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     if (c.rr_fused) *c.rr_fused = true;
   }
   a.saved = ws.saved.as<uint64_t>();
+  a.landing_rows = landing_rows;
   a.cap_pad = cap_pad_used;  // also the stride of `saved` (the workspace holds >= slots * cap_pad)
   a.n_vectors = (uint32_t)s->n;
   a.out_id_offset = c.id_offset;

@@ -44,6 +44,13 @@ namespace phnsw {
 #endif
 constexpr int kLandingRows = PHNSW_LANDING_ROWS;  // landing-zone rows per warp (1 stage x R rows
                                                   // when a row is one chunk, else 2 x R/2)
+// ... and for rows of a single chunk (<= 128 floats) in the sequential f32 variant: a smaller
+// zone lets 20 warps stay resident instead of 16 (build of 1M x 128: 0.89 -> 0.84 s); rows of
+// several chunks keep the deep zone (8 rows at 1536 floats: -25 %)
+#ifndef PHNSW_LANDING_ROWS_SMALL
+#define PHNSW_LANDING_ROWS_SMALL 8
+#endif
+constexpr int kLandingRowsSmall = PHNSW_LANDING_ROWS_SMALL;
 constexpr int kChunk = 128;               // floats of a row staged per bulk copy (512 B)
 constexpr int kRowStride = kChunk + 4;    // +16 B pad: conflict-free LDS.128 across rows
 constexpr int kMaxStages = 2;
@@ -51,7 +58,10 @@ constexpr int kMaxBatch = 64;             // max neighbourhood size handled by o
 #ifndef PHNSW_TREE_WARPS
 #define PHNSW_TREE_WARPS 24
 #endif
-constexpr int kSeqWarps = 16;                 // resident warps per SM, sequential / ADC variants
+#ifndef PHNSW_SEQ_WARPS
+#define PHNSW_SEQ_WARPS 20
+#endif
+constexpr int kSeqWarps = PHNSW_SEQ_WARPS;    // resident warps per SM, sequential / ADC variants
 constexpr int kTreeWarps = PHNSW_TREE_WARPS;  // ... tree variant (no landing zone)
 constexpr int kMaxWarps = kTreeWarps > kSeqWarps ? kTreeWarps : kSeqWarps;
 
@@ -139,6 +149,7 @@ struct SearchArgs {
   uint32_t rr_k;
   uint64_t *saved;         // per-warp copy of the incoming candidates, cap_pad keys each
   uint32_t cap_pad;        // pool entries per warp in shared memory (see pool_entries())
+  uint32_t landing_rows;   // rows of the landing zone (sequential f32 / exact ADC variants)
   uint32_t n_vectors;      // rows of the store: stored_ids / exclude are checked against it
   uint64_t out_id_offset;  // added to every emitted VectorId (sharded search: shard-local ->
                            // global ids straight from the kernel epilogue); empty slots stay !0
@@ -269,9 +280,11 @@ __device__ __forceinline__ uint64_t warp_max_key(uint64_t v) {
 //           sequential order to a few ulp.
 template <int METRIC, int PQ, int TREE>
 struct WarpSearch {
-  static constexpr uint32_t kStageBytes =
-      ((TREE && !PQ) || PQ == 2) ? kScratchBytesTree : kLandingBytes;
-  static constexpr uint32_t kSortScratch = kStageBytes / 8;  // u64 keys the scratch can hold
+  // the tree-order and quantised-ADC variants land no rows: a fixed 4 KB scratch area
+  static constexpr bool kScratchOnly = (TREE && !PQ) || PQ == 2;
+  __host__ __device__ static uint32_t stage_bytes_of(uint32_t landing_rows) {
+    return kScratchOnly ? kScratchBytesTree : landing_rows * kRowStride * 4;
+  }
   // pool scan unroll factor.  Measured, both ways: at 24 warps per SM (f32 tree order) 2 / 4
   // give +1 % / -1 %; at 7 warps per SM (quantised ADC at 96 x 256) 4 is 8 % SLOWER than 1 --
   // the hot loop is ~47 KB of SASS against a 32 KB L1.5 instruction cache, extra code costs more
@@ -315,7 +328,7 @@ struct WarpSearch {
       : a(args), lane(lane_) {
     WarpSmemLayout l = warp_smem_layout(variant_q_floats(PQ, a.dim_pad), a.cap_pad,
                                         variant_lut_floats(PQ, a.pq_table, a.pq_Q, a.pq_K),
-                                        kStageBytes);
+                                        stage_bytes_of(a.landing_rows));
     qvec = (float *)(smem + l.off_q);
     lut = (float *)(smem + l.off_lut);
     stage = (float *)(smem + l.off_stage);
@@ -610,7 +623,7 @@ struct WarpSearch {
     uint32_t P = 32;
     while (P < len) P <<= 1;
     __syncwarp();
-    if (P > kSortScratch) {  // too large for the scratch area: selection sort in place
+    if (P > stage_bytes_of(a.landing_rows) / 8) {  // too large for the scratch area: selection sort in place
       PH_COLD_LOOP2
       for (uint32_t s = lane; s < len; s += 32) pool[s] &= kFlagMask64;
       __syncwarp();
@@ -1032,10 +1045,11 @@ struct WarpSearch {
     if (a.dim_pad <= (uint32_t)kChunk) {  // one bulk copy per row: no chunk pipeline needed
       const uint32_t fl4 = a.dim_pad / 4;
       const float4 q4 = (uint32_t)lane < fl4 ? ((const float4 *)qvec)[lane] : make_float4(0, 0, 0, 0);
-      for (uint32_t p0 = 0; p0 < nn; p0 += kLandingRows) {
+      const uint32_t LR = a.landing_rows;
+      for (uint32_t p0 = 0; p0 < nn; p0 += LR) {
         const uint32_t j = p0 + lane;
-        const bool active = (uint32_t)lane < (uint32_t)kLandingRows && j < nn;
-        const uint32_t rows_p = min((uint32_t)kLandingRows, nn - p0);
+        const bool active = (uint32_t)lane < LR && j < nn;
+        const uint32_t rows_p = min(LR, nn - p0);
         uint32_t node = 0;
         if (lane == 0) mbar_arrive_expect_tx(&mbar[0], rows_p * a.dim_pad * 4);
         __syncwarp();  // also orders the previous readers of the landing zone before the refill
@@ -1081,7 +1095,7 @@ struct WarpSearch {
     }
     const uint32_t nchunks = (a.dim_pad + kChunk - 1) / kChunk;
     const uint32_t S = nchunks > 1 ? 2u : 1u;
-    const uint32_t R = kLandingRows / S;
+    const uint32_t R = a.landing_rows / S;
     const uint32_t npass = (nn + R - 1) / R;
     const uint32_t ntiles = npass * nchunks;
     uint32_t vec_issue = 0;
@@ -1917,7 +1931,7 @@ __global__ void __launch_bounds__(((TREE && !PQ) || PQ == 2 ? kTreeWarps : kSeqW
   const uint32_t warps_per_cta = blockDim.x >> 5;
   WarpSmemLayout lay = warp_smem_layout(variant_q_floats(PQ, a.dim_pad), a.cap_pad,
                                         variant_lut_floats(PQ, a.pq_table, a.pq_Q, a.pq_K),
-                                        WarpSearch<METRIC, PQ, TREE>::kStageBytes);
+                                        WarpSearch<METRIC, PQ, TREE>::stage_bytes_of(a.landing_rows));
   unsigned char *smem = smem_raw + (size_t)warp * lay.total;
   if (a.overlap) {
     if (blockIdx.x == 0) {

@@ -30,7 +30,12 @@ def gen(m):
 
 rows, q = gen(n), gen(nq)
 comp = ph.BigComparator(rows, ph.COS_HALF)
+import time
+torch.cuda.synchronize()
+t0 = time.time()
 gh = ph.Hnsw.generate(comp, seed=1)
+torch.cuda.synchronize()
+print('PROBE-COS %s build %.2f s' % (tag, time.time() - t0), flush=True)
 sp = ph.SearchParameters(300, 300, 2)
 dev = torch.device("cuda:0")
 oi = torch.empty((nq, k), dtype=torch.int64, device=dev)
