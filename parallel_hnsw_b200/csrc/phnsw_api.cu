@@ -418,11 +418,41 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   a.n_vectors = (uint32_t)s->n;
   a.out_id_offset = c.id_offset;
 
-  const size_t smem = (size_t)lay.total * w;
-  cudaError_t e = q8     ? launch_search_pq8q(s->metric, a, grid, w * 32, smem, stream)
-                  : pq8  ? launch_search_pq(s->metric, a, grid, w * 32, smem, stream)
-                  : tree ? launch_search_tree(s->metric, a, grid, w * 32, smem, stream)
-                         : launch_search_seq(s->metric, a, grid, w * 32, smem, stream);
+  // CTA shape.  The warps of a query batch are independent, so a launch that fills the machine
+  // may be cut into several CTAs per SM.  With batch overlap that pays: a CTA leaves when its
+  // last warp runs out of queries and the next launch's CTAs move in CTA by CTA, so the finer
+  // the CTAs, the less of an SM waits for its slowest warp (24 warps as 8 CTAs of 3: 3.34 ->
+  // 3.11 ms per 10 000-query step; plain launches lose 1 % and keep one CTA per SM).  Every CTA
+  // costs 1 KB of reserved shared memory, which bounds their number.
+  uint32_t wc = w;
+  {
+    static const char *env = getenv("PHNSW_CTA_WARPS");  // developer knob: warps per CTA
+    const size_t spare = (size_t)ix->max_smem + 1024 > (size_t)lay.total * w
+                             ? (size_t)ix->max_smem + 1024 - (size_t)lay.total * w : 0;
+    if (env) {
+      const uint32_t want = (uint32_t)atoi(env);
+      if (want >= 1 && want < w && w % want == 0 && grid == (uint32_t)ix->sm_count && w == wmax &&
+          (size_t)(w / want) * 1024 <= spare)
+        wc = want;
+    } else if (overlap) {
+      for (uint32_t k = 2; k <= w / 2; k++)  // CTAs per SM: the most that fit, two warps or more each
+        if (w % k == 0 && (size_t)k * 1024 <= spare) wc = w / k;
+    }
+  }
+  const uint32_t ctas = grid * (w / wc);
+  size_t smem = (size_t)lay.total * wc;
+  if (wc < w) {
+    // The overlap protocol (two scratch sets, three rotating work counters) rests on "a launch
+    // fills the machine": the launch after next cannot start before this one has left.  Small
+    // CTAs must therefore fill an SM exactly -- each asks for its share of the SM's shared
+    // memory, so that one more CTA than the launch's k per SM can never be resident.
+    const size_t share = (((size_t)ix->max_smem + 1024) / (w / wc) - 1024) / 128 * 128;
+    if (share > smem) smem = share;
+  }
+  cudaError_t e = q8     ? launch_search_pq8q(s->metric, a, ctas, wc * 32, smem, stream)
+                  : pq8  ? launch_search_pq(s->metric, a, ctas, wc * 32, smem, stream)
+                  : tree ? launch_search_tree(s->metric, a, ctas, wc * 32, smem, stream)
+                         : launch_search_seq(s->metric, a, ctas, wc * 32, smem, stream);
   if (e != cudaSuccess) return cuda_fail(e, "search_kernel launch");
   if (account) {
     work_stats_kernel<<<64, 256, 0, stream>>>(ws.ws_nd.as<uint32_t>(), ws.ws_ne.as<uint32_t>(), c.nq,

@@ -114,6 +114,43 @@ def test_batch_overlap_gives_the_same_results(ph, small, order):
         gh.set_sum_order(ph.SUM_SEQUENTIAL)
 
 
+@pytest.mark.parametrize("order,ef", [("SUM_SEQUENTIAL", 24), ("SUM_TREE", 24), ("SUM_TREE", 200)])
+def test_long_overlap_chains_never_share_scratch(ph, small, order, ef):
+    """Twelve machine-filling launches back to back on one stream.  The overlap protocol has two
+    scratch sets and three work counters, i.e. it relies on the launch after next not starting
+    before this one has left -- which small CTAs (several per SM under overlap) only guarantee
+    because each asks for its full share of the SM's shared memory.  Small candidate sets make
+    the CTAs small: the case where a third launch could otherwise slip in."""
+    import torch
+    rows, comp, gh, oh = small
+    gh.set_sum_order(getattr(ph, order))
+    dev = torch.device("cuda", 0)
+    sp = ph.SearchParameters(ef, ef, 2)
+    qs = [torch.from_numpy(random_normed(6000, 64, 700 + i)).to(dev) for i in range(12)]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run_all():
+        outs = []
+        for q in qs:
+            oi = torch.empty((q.shape[0], 10), dtype=torch.int64, device=dev)
+            od = torch.empty((q.shape[0], 10), dtype=torch.float32, device=dev)
+            oc = torch.empty((q.shape[0],), dtype=torch.int32, device=dev)
+            gh.search_device(q, sp, oi, od, oc, stream=st)
+            outs.append((oi, od, oc))
+        gh.sync(st)
+        return [(a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()) for a, b, c in outs]
+    try:
+        plain = run_all()
+        gh.set_batch_overlap(True)
+        for _ in range(3):
+            for g, p in zip(run_all(), plain):
+                assert np.array_equal(g[0], p[0]) and np.array_equal(g[2], p[2])
+                assert np.array_equal(g[1].view(np.uint32), p[1].view(np.uint32))
+    finally:
+        gh.set_batch_overlap(False)
+        gh.set_sum_order(ph.SUM_SEQUENTIAL)
+
+
 def test_host_async_search_from_pinned_buffers(ph, small):
     """phnsw_search_batch_host_async: pinned host buffers in place, queued calls on one stream
     (with and without batch overlap) equal the synchronous host call; pageable buffers are
