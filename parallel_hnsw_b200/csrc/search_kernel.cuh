@@ -177,17 +177,19 @@ __host__ __device__ inline WarpSmemLayout warp_smem_layout(uint32_t dim_pad, uin
   l.off_stage = o;   o += stage_bytes;
   l.off_pool = o;    o += cap_pad * 8;
   l.off_bkeys = o;   o += kMaxBatch * 8;
-  l.off_bid = o;     o += kMaxBatch * 4;
   l.off_mbar = o;    o += kMaxStages * 8;
   l.off_layer = o;   o += (uint32_t)((sizeof(LayerDev) + 15) / 16 * 16);
   if (stage_bytes == kScratchBytesTree) {
     // the tree variant lands no rows: its 4 KB scratch area also holds the sorted batch of the
-    // duplicate-row path and the small-layer visited bitmap (histogram of the radix select in
-    // [0, 1 KB), sorted batch in [1 KB, 1.5 KB), bitmap in [3 KB, 4 KB); the pool sort uses the
-    // whole area, but only after a layer's walk is over), which keeps 24 warps resident
+    // duplicate-row path, the ids of the batch being scored and the small-layer visited bitmap
+    // (histogram of the radix select in [0, 1 KB), sorted batch in [1 KB, 1.5 KB), batch ids in
+    // [1.5 KB, 1.75 KB), bitmap in [3 KB, 4 KB); the pool sort uses the whole area, but only
+    // after a layer's walk is over), which keeps 24 warps resident -- as up to twelve CTAs
     l.off_bsorted = l.off_stage + 1024;
+    l.off_bid = l.off_stage + 1536;
     l.off_vsm = l.off_stage + 3072;
   } else {
+    l.off_bid = o;     o += kMaxBatch * 4;
     l.off_bsorted = o; o += kMaxBatch * 8;
     l.off_vsm = o;     o += kSmallLayerNodes / 8;
   }
