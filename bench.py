@@ -503,8 +503,19 @@ def main():
     alt = (torch.empty_like(oi), torch.empty_like(od), torch.empty_like(oc))
     step_no = [0]
 
+    # N > 1: the pipelined sharded step (phnsw_search_batch_sharded_queued): every rank holds the
+    # batch, the shard search of a step runs on `stream` chained behind the previous step's (batch
+    # overlap), its all-gather + merge on the library's side stream on rotating exchange
+    # buffers; four rotating result buffers, one phnsw_comm_flush before the closing event --
+    # the flush (all exchanges and merges complete) is inside the timed region
+    ring = [(mi, md)] + [(torch.empty_like(mi), torch.empty_like(md)) for _ in range(3)]
+    queued = sharded and not args.no_overlap
+
     def step():
-        if sharded:
+        if queued:
+            step_no[0] += 1
+            sh.search_queued(dq, sp, k, stream=stream, out=ring[step_no[0] & 3])
+        elif sharded:
             sh.search(dq, sp, k, src=0, stream=stream, out=(mi, md))
         else:
             # consecutive steps write different output buffers (two launches may be in flight
@@ -516,10 +527,12 @@ def main():
     # back-to-back batches on one stream: the library may start a launch on the SMs the previous
     # one has already left (phnsw_index_set_batch_overlap; same results, checked below).  The
     # plain launches are timed right after as `no_batch_overlap`.
-    use_overlap = (not sharded) and (not args.no_overlap)
+    use_overlap = not args.no_overlap
     gh.set_batch_overlap(use_overlap)
     for _ in range(args.warmup):
         step()
+    if queued:
+        sh.flush(stream)
     gh.sync(stream)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -532,6 +545,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    if queued:
+        sh.flush(stream)
     e1.record()
     barrier()
     if args.profile_range:
@@ -542,7 +557,28 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     gh.set_batch_overlap(False)
     ms_plain = None
-    if use_overlap:
+    ms_blocking = None
+    if queued:
+        # beside it: the blocking call per step (broadcast of the batch from rank 0 inside the
+        # step, everything on one stream, no overlap between steps), same barriers
+        q_last = ring[step_no[0] & 3]
+        q_ids, q_ds = q_last[0].clone(), q_last[1].clone()
+        for _ in range(args.warmup):
+            sh.search(dq, sp, k, src=0, stream=stream, out=(mi, md))
+        gh.sync(stream)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        b0.record()
+        for _ in range(args.steps):
+            sh.search(dq, sp, k, src=0, stream=stream, out=(mi, md))
+        b1.record()
+        barrier()
+        gh.sync(stream)
+        tb = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        ms_blocking = float(tb[0]) / args.steps
+        assert torch.equal(q_ids, mi) and torch.equal(q_ds, md), "pipelined sharded step changed the results"
+    if use_overlap and not sharded:
         ov_ids, ov_ds = oi.clone(), od.clone()
         for _ in range(args.warmup):
             step()
@@ -574,10 +610,27 @@ def main():
         tl = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
         dist.all_reduce(tl, op=dist.ReduceOp.MAX)
         ms_local = float(tl[0])
+        # ... and with batch overlap between the steps (what the pipelined step competes with)
+        gh.set_batch_overlap(use_overlap)
+        for i_ in range(args.warmup + args.steps + 1):
+            if i_ == args.warmup:
+                gh.sync(stream)
+                barrier()
+                r0.record()
+            o_ = (oi, od, oc) if i_ & 1 else alt
+            gh.search_device(dq, sp, *o_, stream=stream)
+        r1.record()
+        barrier()
+        gh.sync(stream)
+        gh.set_batch_overlap(False)
+        tl = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        ms_local_ov = float(tl[0]) / (args.steps + 1)
         merged_np = mi.cpu().numpy()
         sharded_info = {
             "recall_merged": recall_at_k(merged_np, gt_global, k),
-            "ms_local": ms_local,
+            "ms_local": ms_local, "ms_blocking": ms_blocking, "queued": queued,
+            "ms_local_overlap": ms_local_ov,
             # every merged entry that names a vector of this rank's shard must be this rank's own
             # result for that query, and every merged list ascending by (distance, id)
             "merged": merged_np, "merged_d": md.cpu().numpy()}
@@ -753,8 +806,8 @@ def headline_line(ctx, v):
         "cpu_baseline": (main_cpu or {}).get("cpu_baseline"),
         "clocks": clocks,
         "sum_order": args.sum_order,
-        "parallelism": ("sharded x%d (one sub-index per GPU, queries broadcast, NCCL all-gather + merge "
-                        "inside the step)" % world) if world > 1 else "single GPU",
+        "parallelism": ("sharded x%d (one sub-index per GPU, one NCCL all-gather + merge per step, "
+                        "steps pipelined)" % world) if world > 1 else "single GPU",
         "layers_top_first": gh_layers_top_first,
         "batch_overlap": {
             "on": bool(use_overlap),
@@ -839,18 +892,30 @@ def headline_line(ctx, v):
         out["gpu_launches"] = 2 * args.steps
         out["sharded_step"] = {
             "what": "N > 1: one sub-index of %d vectors per GPU (%d vectors in all), every rank searches "
-                    "the same %d-query batch; one library call per step (phnsw_search_batch_sharded): "
-                    "ncclBroadcast(queries) -> K1 (epilogue writes global-id records into the exchange "
-                    "buffer) -> one ncclAllGather -> merge.  `value` = (query, shard) searches per "
+                    "the same %d-query batch.  Headline = the PIPELINED step "
+                    "(phnsw_search_batch_sharded_queued, one call per step + one phnsw_comm_flush inside "
+                    "the timed region): K1 of step i + 1 (epilogue writes global-id records into a "
+                    "rotating exchange buffer) overlaps the end of step i's, one ncclAllGather + merge "
+                    "per step on the library's side stream.  `value` = (query, shard) searches per "
                     "second over all ranks = N x merged queries/s" % (args.n, args.n * world, args.nq),
+            "pipelined": bool(sharded_info["queued"]),
             "merged_queries_per_s": args.nq / (kernel_ms * 1e-3),
             "vectors_total": args.n * world,
             "recall_at_10_merged_vs_exact_over_all_shards": sharded_info["recall_merged"],
             "recall_at_10_rank0_shard_alone": recall,
-            "without_exchange": {"value": world * args.nq / (ms_local * 1e-3), "ms_per_step": ms_local,
-                                 "what": "the same shards searched with no broadcast / all-gather / merge "
-                                         "(N independent replicas of the per-GPU workload), max over ranks"},
-            "exchange_overhead_frac": kernel_ms / ms_local - 1.0,
+            "blocking_call_per_step": ({
+                "value": world * args.nq / (sharded_info["ms_blocking"] * 1e-3),
+                "ms_per_step": sharded_info["ms_blocking"],
+                "what": "phnsw_search_batch_sharded: ncclBroadcast(queries) -> K1 -> ncclAllGather -> "
+                        "merge on one stream, nothing of step i + 1 starts before step i is merged "
+                        "(same results, asserted in-run)"} if sharded_info["ms_blocking"] else None),
+            "without_exchange": {"value": world * args.nq / (sharded_info["ms_local_overlap"] * 1e-3),
+                                 "ms_per_step": sharded_info["ms_local_overlap"],
+                                 "plain_launches_ms_per_step": ms_local,
+                                 "what": "the same shards searched with no all-gather / merge, back-to-back "
+                                         "with batch overlap (N independent replicas of the per-GPU "
+                                         "workload), max over ranks"},
+            "exchange_overhead_frac": kernel_ms / sharded_info["ms_local_overlap"] - 1.0,
             "exchange_bytes_per_rank_per_step": int(args.nq * k * 12),
             "merge_parity": {"merged_entries_of_rank0_shard_match_frac": float(np.mean(ok_rows)),
                              "merged_ascending_frac": float(np.mean(asc))}}

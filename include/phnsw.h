@@ -516,6 +516,21 @@ phnsw_status phnsw_search_batch_sharded(phnsw_comm *c, const phnsw_index *ix,
                                         uint64_t rerank_k, uint64_t k, uint64_t id_offset, int root,
                                         uint64_t *out_ids_device, float *out_dists_device,
                                         void *cuda_stream);
+/* The same step for a server that drains a queue of batches: calls are PIPELINED.  The shard
+ * search of a call is issued on `cuda_stream` and may overlap the end of the previous call's
+ * search (phnsw_index_set_batch_overlap); its all-gather and merge run on the communicator's own
+ * high-priority stream behind it, on one of four rotating exchange buffers.  Every rank must hold
+ * the query batch already (no broadcast), the index must be an f32 index, and
+ *   - queries_device of a call must stay untouched until the call after next has been issued,
+ *   - out_ids_device / out_dists_device of a call are complete on `cuda_stream` only after
+ *     phnsw_comm_flush (which makes `cuda_stream` wait for every queued exchange; no host wait).
+ * Results are those of phnsw_search_batch_sharded bit for bit. */
+phnsw_status phnsw_search_batch_sharded_queued(phnsw_comm *c, const phnsw_index *ix,
+                                               const float *queries_device, uint64_t nq,
+                                               const phnsw_search_params *sp, uint64_t k,
+                                               uint64_t id_offset, uint64_t *out_ids_device,
+                                               float *out_dists_device, void *cuda_stream);
+phnsw_status phnsw_comm_flush(phnsw_comm *c, void *cuda_stream);
 
 #ifdef __cplusplus
 }

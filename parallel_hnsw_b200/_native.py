@@ -183,6 +183,9 @@ SIGNATURES = {
     "phnsw_comm_allreduce_sum_f32": (C.c_int, [vp, vp, C.c_uint64, vp]),
     "phnsw_search_batch_sharded": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.POINTER(SearchParams),
                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]),
+    "phnsw_search_batch_sharded_queued": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(SearchParams),
+                                                    C.c_uint64, C.c_uint64, vp, vp, vp]),
+    "phnsw_comm_flush": (C.c_int, [vp, vp]),
 }
 COMM_ID_BYTES = 128
 

@@ -135,12 +135,26 @@ __global__ void merge_slices_kernel(const unsigned char *__restrict__ buf, uint6
 
 using namespace phnsw;
 
+constexpr int kQueueMax = 8;  // exchange buffers of the pipelined step (kQueueDepth in use)
+static int queue_depth() {
+  static const char *e = getenv("PHNSW_QUEUE_DEPTH");  // developer knob
+  const int d = e ? atoi(e) : 4;
+  return d < 2 ? 2 : (d > kQueueMax ? kQueueMax : d);
+}
+
 struct phnsw_comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, device = 0;
   std::mutex mu;
   DevBuf gather;   // nranks slices
   DevBuf counts;   // nq u32 (per-query result counts of the local search; not exchanged)
+  // pipelined step (phnsw_search_batch_sharded_queued): the exchange of call i runs on `side`
+  // behind the search of call i while the search of call i + 1 is already under way
+  cudaStream_t side = nullptr;
+  cudaEvent_t searched[kQueueMax] = {};
+  cudaEvent_t done[kQueueMax] = {};
+  DevBuf qgather[kQueueMax], qcounts[kQueueMax];
+  uint64_t qseq = 0;
 };
 
 extern "C" {
@@ -207,6 +221,13 @@ void phnsw_comm_destroy(phnsw_comm *c) {
   if (c->comm) nccl_api().CommDestroy(c->comm);
   c->gather.release();
   c->counts.release();
+  for (int i = 0; i < kQueueMax; i++) {
+    c->qgather[i].release();
+    c->qcounts[i].release();
+    if (c->searched[i]) cudaEventDestroy(c->searched[i]);
+    if (c->done[i]) cudaEventDestroy(c->done[i]);
+  }
+  if (c->side) cudaStreamDestroy(c->side);
   delete c;
 }
 
@@ -298,6 +319,92 @@ phnsw_status phnsw_search_batch_sharded(phnsw_comm *c, const phnsw_index *ix,
       out_dists_device);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "merge_slices_kernel");
+  return PHNSW_OK;
+}
+
+phnsw_status phnsw_search_batch_sharded_queued(phnsw_comm *c, const phnsw_index *ix,
+                                               const float *queries_device, uint64_t nq,
+                                               const phnsw_search_params *sp, uint64_t k,
+                                               uint64_t id_offset, uint64_t *out_ids_device,
+                                               float *out_dists_device, void *cuda_stream) {
+  PH_ENTRY();
+  if (!c || !ix || !sp || !queries_device || !out_ids_device || !out_dists_device || k == 0 ||
+      nq > 0xFFFFFFF0ull || ix->store->is_pq8()) {
+    set_error("search_batch_sharded_queued: bad arguments (f32 indexes only)");
+    return PHNSW_ERR_INVALID;
+  }
+  if (ix->store->device != c->device) {
+    set_error("search_batch_sharded_queued: the index lives on device %d, the communicator on %d",
+              ix->store->device, c->device);
+    return PHNSW_ERR_INVALID;
+  }
+  if (sp->number_of_candidates == 0 || sp->number_of_candidates > 65536 || sp->probe_depth == 0) {
+    set_error("search_batch_sharded_queued: number_of_candidates / probe_depth must be positive");
+    return PHNSW_ERR_INVALID;
+  }
+  if (nq == 0) return PHNSW_OK;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PH_CUDA(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->side) {
+    int lo = 0, hi = 0;
+    PH_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PH_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < kQueueMax; i++) {
+      PH_CUDA(cudaEventCreateWithFlags(&c->searched[i], cudaEventDisableTiming));
+      PH_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+    }
+  }
+  const int kQueueDepth = queue_depth();
+  const int slot = (int)(c->qseq % kQueueDepth);
+  // the buffer's previous use (four calls ago) has to be over: a host-side wait, which in a
+  // running pipeline never blocks -- a stream-side wait between two searches would serialise them
+  if (c->qseq >= (uint64_t)kQueueDepth) PH_CUDA(cudaEventSynchronize(c->done[slot]));
+  const uint64_t slice = slice_bytes(nq, k), doff = slice_dist_offset(nq, k);
+  PH_CUDA(c->qgather[slot].reserve(slice * c->nranks));
+  PH_CUDA(c->qcounts[slot].reserve(nq * 4));
+  unsigned char *buf = c->qgather[slot].as<unsigned char>();
+  unsigned char *mine = buf + (uint64_t)c->rank * slice;
+  SearchCall sc;
+  sc.mode = 0;
+  sc.queries = queries_device;
+  sc.qpitch = (uint32_t)ix->store->dim;
+  sc.nq = (uint32_t)nq;
+  sc.cap = (uint32_t)sp->number_of_candidates;
+  sc.upper = (uint32_t)std::min<uint64_t>(sp->upper_layer_candidate_count, 0xFFFFFFFFull);
+  sc.probe = (uint32_t)std::min<uint64_t>(sp->probe_depth, 0xFFFFFFFFull);
+  sc.n_layers = (uint32_t)ix->layers.size();
+  sc.max_out = (uint32_t)k;
+  sc.out_ids = (uint64_t *)mine;
+  sc.out_dists = (float *)(mine + doff);
+  sc.out_counts = c->qcounts[slot].as<uint32_t>();
+  sc.id_offset = id_offset;
+  sc.allow_overlap = true;  // nothing on `st` reads this call's results: the exchange is on `side`
+  phnsw_status rc = launch_search(ix, sc, st);
+  if (rc != PHNSW_OK) return rc;
+  PH_CUDA(cudaEventRecord(c->searched[slot], st));
+  PH_CUDA(cudaStreamWaitEvent(c->side, c->searched[slot], 0));
+  if (c->nranks > 1)
+    PH_NCCL(nccl_api().AllGather(mine, buf, slice, ncclChar, c->comm, c->side));
+  merge_slices_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, c->side>>>(
+      buf, slice, doff, (uint32_t)c->nranks, (uint32_t)nq, (uint32_t)k, out_ids_device,
+      out_dists_device);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "merge_slices_kernel");
+  PH_CUDA(cudaEventRecord(c->done[slot], c->side));
+  c->qseq++;
+  return PHNSW_OK;
+}
+
+phnsw_status phnsw_comm_flush(phnsw_comm *c, void *cuda_stream) {
+  PH_ENTRY();
+  if (!c) return PHNSW_ERR_INVALID;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->side || c->qseq == 0) return PHNSW_OK;
+  PH_CUDA(cudaSetDevice(c->device));
+  // the side stream runs the exchanges in order: waiting for the last one covers them all
+  PH_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream,
+                              c->done[(c->qseq - 1) % queue_depth()], 0));
   return PHNSW_OK;
 }
 

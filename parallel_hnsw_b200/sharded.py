@@ -114,3 +114,26 @@ class ShardedHnsw:
             C.c_void_p(queries.data_ptr()), nq, C.byref(sp), rerank_k, k, self.id_offset, src,
             C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), C.c_void_p(st)))
         return out
+
+    def search_queued(self, queries, sp, k, stream=None, out=None):
+        """The pipelined step (phnsw_search_batch_sharded_queued): every rank already holds
+        `queries`; this call's shard search may overlap the end of the previous call's, its
+        all-gather and merge run on the communicator's own stream.  `out` is complete on the
+        stream only after flush(); `queries` must stay untouched until the call after next."""
+        dev = queries.device
+        nq = queries.shape[0]
+        st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.int64, device=dev),
+                   torch.empty((nq, k), dtype=torch.float32, device=dev))
+        N.check(N.lib().phnsw_search_batch_sharded_queued(
+            self.comm._h, self.hnsw._h, C.c_void_p(queries.data_ptr()), nq, C.byref(sp), k,
+            self.id_offset, C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+            C.c_void_p(st)))
+        return out
+
+    def flush(self, stream=None):
+        """Make `stream` wait for every queued exchange (phnsw_comm_flush)."""
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        N.check(N.lib().phnsw_comm_flush(self.comm._h, C.c_void_p(st)))
+

@@ -313,6 +313,36 @@ def test_sharded_call_single_rank_equals_plain_search(ph, small):
     sh.comm.close()
 
 
+def test_queued_sharded_calls_single_rank(ph, small):
+    """phnsw_search_batch_sharded_queued at nranks = 1: ten pipelined calls (search on the caller's
+    stream with batch overlap, merge on the communicator's stream, four rotating buffers) return
+    what the blocking call returns."""
+    import torch
+    from parallel_hnsw_b200.sharded import ShardedHnsw
+    rows, comp, gh, oh = small
+    sp = ph.SearchParameters(50, 50, 2)
+    sh = ShardedHnsw(gh, 5000, rank=0, world=1)
+    qs = [torch.from_numpy(random_normed(5000, 64, 300 + i)).cuda() for i in range(10)]
+    st = torch.cuda.current_stream().cuda_stream
+    want = []
+    for q in qs:
+        ids, ds = sh.search(q, sp, 10, src=-1)
+        gh.sync(st)
+        want.append((ids.cpu().numpy(), ds.cpu().numpy()))
+    for overlap in (False, True):
+        gh.set_batch_overlap(overlap)
+        try:
+            outs = [sh.search_queued(q, sp, 10) for q in qs]
+            sh.flush()
+            gh.sync(st)
+            for (ids, ds), (wi, wd) in zip(outs, want):
+                assert np.array_equal(ids.cpu().numpy(), wi)
+                assert np.array_equal(ds.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+        finally:
+            gh.set_batch_overlap(False)
+    sh.comm.close()
+
+
 def _shard_worker(rank, world, port, tmp):
     import torch
     import torch.distributed as dist
@@ -338,6 +368,15 @@ def _shard_worker(rank, world, port, tmp):
     np.save(os.path.join(tmp, "ds_%d.npy" % rank), ds.cpu().numpy())
     np.save(os.path.join(tmp, "lid_%d.npy" % rank), local[0].astype(np.int64) + rank * n)
     np.save(os.path.join(tmp, "ld_%d.npy" % rank), local[1])
+    # the pipelined form: six queued calls with batch overlap on, same bits as the blocking call
+    gh.set_batch_overlap(True)
+    outs = [sh.search_queued(q, sp, 10) for _ in range(6)]
+    sh.flush()
+    gh.sync(torch.cuda.current_stream().cuda_stream)
+    for qi_, qd_ in outs:
+        assert np.array_equal(qi_.cpu().numpy(), ids.cpu().numpy()), "queued ids"
+        assert np.array_equal(qd_.cpu().numpy().view(np.uint32), ds.cpu().numpy().view(np.uint32))
+    gh.set_batch_overlap(False)
     dist.barrier()
     sh.comm.close()
     dist.destroy_process_group()

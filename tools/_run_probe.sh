@@ -1,8 +1,9 @@
 cd /root/repo
-python -m pytest tests -x -q -m gpu > gpurun_out/r02_tests27.log 2>&1; tail -2 gpurun_out/r02_tests27.log
-for cw in auto 3 2 auto; do
-  if [ $cw = auto ]; then unset PHNSW_CTA_WARPS; else export PHNSW_CTA_WARPS=$cw; fi
-  timeout 300 python tools/probe_k1.py --order 1 --overlap --tag "cta${cw}_overlap" 2>&1 | grep PROBE
-done | tee gpurun_out/r02_probe37.log
-unset PHNSW_CTA_WARPS
-timeout 300 python tools/probe_k1.py --order 1 0 --tag "plain" 2>&1 | grep PROBE | tee -a gpurun_out/r02_probe37.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --blocks none --cpu-build "" --builds 2 > gpurun_out/r02_bench_n2_v2.json 2> gpurun_out/r02_bench_n2_v2.err
+tail -3 gpurun_out/r02_bench_n2_v2.err | cut -c1-300
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench_n2_v2.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['recall_at_10'])
+print(json.dumps(d['sharded_step'],indent=1)[:2500])
+PY

@@ -24,6 +24,7 @@ ap.add_argument("--no-improve", action="store_true")
 ap.add_argument("--order", type=int, nargs="+", default=[0], help="0 sequential, 1 tree")
 ap.add_argument("--streams", type=int, default=1)
 ap.add_argument("--overlap", action="store_true", help="phnsw_index_set_batch_overlap")
+ap.add_argument("--record-events", action="store_true", help="record an event after every launch")
 ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around one launch "
                 "(ncu --profile-from-start off)")
 args = ap.parse_args()
@@ -55,9 +56,12 @@ for order, nq in [(o, n) for o in args.order for n in args.nq]:
         torch.cuda.profiler.stop()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.streams == 1:
+        evs = [torch.cuda.Event() for _ in range(args.reps)]
         e0.record()
-        for _ in range(args.reps):
+        for r_ in range(args.reps):
             gh.search_device(dq, sp, oi, od, oc, stream=st)
+            if args.record_events:
+                evs[r_].record()
         e1.record()
         gh.sync(st)
     else:
