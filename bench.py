@@ -485,6 +485,22 @@ def main():
     gh.sync(stream)
     ms_seq = s0.elapsed_time(s1) / seq_steps
     seq_ids = oi.cpu().numpy().astype(np.uint64)
+    # ... and the same order with back-to-back batches overlapped (alternate output buffers)
+    ms_seq_ov = None
+    if not args.no_overlap:
+        seq_alt = (torch.empty_like(oi), torch.empty_like(od), torch.empty_like(oc))
+        gh.set_batch_overlap(True)
+        for i_ in range(args.warmup + seq_steps * 2):
+            if i_ == args.warmup:
+                gh.sync(stream)
+                s0.record()
+            gh.search_device(dq, sp, *((oi, od, oc) if i_ & 1 else seq_alt), stream=stream)
+        s1.record()
+        gh.sync(stream)
+        gh.set_batch_overlap(False)
+        ms_seq_ov = s0.elapsed_time(s1) / (seq_steps * 2)
+        assert np.array_equal(seq_alt[0].cpu().numpy().astype(np.uint64), seq_ids), \
+            "sequential order: overlapped launches changed the results"
     gh.set_sum_order(ph.SUM_TREE if tree else ph.SUM_SEQUENTIAL)
     gh.search_device(dq, sp, oi, od, oc, stream=stream, out_ndist=nd, out_nexp=ne)
     gh.sync(stream)
@@ -758,6 +774,7 @@ def main():
 def headline_line(ctx, v):
     """The headline JSON object (rank 0), built before the secondary blocks run."""
     args, world, k, peaks = ctx["args"], ctx["world"], ctx["k"], ctx["peaks"]
+    ms_seq_ov = v.get("ms_seq_ov")
     (ndist, nexp, layer_M, ms_dev, ms_e2e, ms_seq, ms_pipe, recall, main_cpu, clocks, tree, t_build,
      t_gen, t_gt, gt_stats, gh_layers_top_first, sharded_info, oi, od) = (v[x] for x in (
          "ndist", "nexp", "layer_M", "ms_dev", "ms_e2e", "ms_seq", "ms_pipe", "recall", "main_cpu",
@@ -844,6 +861,8 @@ def headline_line(ctx, v):
                   "cpu_baseline_build": cpu_build},
         "sequential_order": {"value": world * args.nq / (ms_seq * 1e-3), "unit": "queries/s",
                              "ms_per_step": ms_seq,
+                             "with_batch_overlap": ({"value": world * args.nq / (ms_seq_ov * 1e-3),
+                                                     "ms_per_step": ms_seq_ov} if ms_seq_ov else None),
                              "note": "same kernel with PHNSW_SUM_SEQUENTIAL (the crate's loop bit for bit)"},
         "two_streams": {"value": world * args.nq / (ms_pipe * 1e-3), "unit": "queries/s",
                         "ms_per_step": ms_pipe,
