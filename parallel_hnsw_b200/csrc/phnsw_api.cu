@@ -449,10 +449,18 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     const size_t share = (((size_t)ix->max_smem + 1024) / (w / wc) - 1024) / 128 * 128;
     if (share > smem) smem = share;
   }
-  cudaError_t e = q8     ? launch_search_pq8q(s->metric, a, ctas, wc * 32, smem, stream)
-                  : pq8  ? launch_search_pq(s->metric, a, ctas, wc * 32, smem, stream)
-                  : tree ? launch_search_tree(s->metric, a, ctas, wc * 32, smem, stream)
-                         : launch_search_seq(s->metric, a, ctas, wc * 32, smem, stream);
+  auto launch = [&](uint32_t nctas, uint32_t warps, size_t bytes) {
+    return q8     ? launch_search_pq8q(s->metric, a, nctas, warps * 32, bytes, stream)
+           : pq8  ? launch_search_pq(s->metric, a, nctas, warps * 32, bytes, stream)
+           : tree ? launch_search_tree(s->metric, a, nctas, warps * 32, bytes, stream)
+                  : launch_search_seq(s->metric, a, nctas, warps * 32, bytes, stream);
+  };
+  cudaError_t e = launch(ctas, wc, smem);
+  if (e == cudaErrorInvalidConfiguration && wc < w) {
+    // the device would not keep all small CTAs resident: one CTA per SM (same slots, same results)
+    cudaGetLastError();
+    e = launch(grid, w, (size_t)lay.total * w);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "search_kernel launch");
   if (account) {
     work_stats_kernel<<<64, 256, 0, stream>>>(ws.ws_nd.as<uint32_t>(), ws.ws_ne.as<uint32_t>(), c.nq,

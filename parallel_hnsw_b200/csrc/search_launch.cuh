@@ -25,6 +25,28 @@ static cudaError_t launch_moded(const SearchArgs &a, int grid, int block, size_t
       if (dev < 16) configured[dev] = smem;
     }
   }
+  // several CTAs per SM (batch overlap): the protocol needs every CTA of the launch resident at
+  // once, so ask for the largest shared-memory carve-out and check what the device grants; the
+  // caller falls back to one CTA per SM on cudaErrorInvalidConfiguration
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > 0 && grid > sms) {
+    static std::mutex omu;
+    static int ok_block[16] = {0}, ok_per_sm[16] = {0};
+    static size_t ok_smem[16] = {0};
+    std::lock_guard<std::mutex> g(omu);
+    const int per_sm = (grid + sms - 1) / sms;
+    if (dev >= 16 || ok_block[dev] != block || ok_smem[dev] != smem || ok_per_sm[dev] < per_sm) {
+      cudaFuncSetAttribute(search_kernel<METRIC, PQ, TREE, MODE>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+      int nb = 0;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &nb, search_kernel<METRIC, PQ, TREE, MODE>, block, smem);
+      if (e != cudaSuccess || nb < per_sm) return cudaErrorInvalidConfiguration;
+      if (dev < 16) { ok_block[dev] = block; ok_smem[dev] = smem; ok_per_sm[dev] = nb; }
+    }
+  }
   if (a.overlap == 2) {  // chained behind another search launch: programmatic dependent launch
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
