@@ -748,7 +748,7 @@ struct WarpSearch {
     const float4 q4 = in ? ((const float4 *)qvec)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 *base = (const float4 *)layer.lrows + (in ? lane : 0);
     const uint32_t pitch4 = a.pitch / 4;
-#ifndef PHNSW_NO_L2_PREFETCH
+#if !defined(PHNSW_NO_L2_PREFETCH) && !defined(PHNSW_PREFETCH_ALL_EARLY)
     // DRAM-resident layer (identity node map = the bottom layer): the rows of the later batches
     // are pulled into L2 while the first batch is in flight -- one prefetch instruction covers
     // eight rows (lane l touches 128-byte line l & 3 of row l >> 2); no registers, no barrier
@@ -1266,6 +1266,25 @@ struct WarpSearch {
       *n_dist += nn;
       bool did = false;
       if (nn > 0) {
+#ifndef PHNSW_NO_PREFETCH_BATCH0
+        // DRAM-resident layer: the first row batch starts towards L2 before the visited marks
+        // are written (one prefetch per lane covers eight rows of up to four lines; the later
+        // batches follow at the head of compute_distances_tree1): +2 %, no registers
+        if (TREE && !PQ && !layer.nodes) {
+#ifdef PHNSW_PREFETCH_ALL_EARLY
+          for (uint32_t j0 = 0; j0 < nn; j0 += 8) {
+            const uint32_t j = j0 + ((uint32_t)lane >> 2);
+#else
+          {
+            const uint32_t j = (uint32_t)lane >> 2;
+#endif
+            if (j < nn && (uint32_t)(lane & 3) * 32 < a.dim_pad) {
+              const float *p = layer.lrows + (size_t)bid[j] * a.pitch + (lane & 3) * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+          }
+        }
+#endif
         visited_set(u0, n0);                     // lib.rs:209 (order is immaterial)
         if (m1) visited_set(u1, n1);
         compute_distances(layer, nn);            // lib.rs:199-204 -> bkeys[0..nn)
