@@ -302,6 +302,40 @@ impl Hnsw {
         unsafe { phnsw_free(p as *mut c_void) };
         out
     }
+    /// Layer::node_distances, src/lib.rs:425-489 -> (hops, index_sum) per NodeId of the layer;
+    /// usize::MAX marks a node the walk never reached
+    pub fn node_distances(&self, layer_from_top: usize, supers: &[VectorId]) -> (Vec<usize>, Vec<usize>) {
+        let (mut nc, mut m) = (0u64, 0u64);
+        check_or_panic(unsafe { phnsw_index_layer_info(self.index.0, layer_from_top as u64, &mut nc, &mut m) });
+        let sup: Vec<u64> = supers.iter().map(|v| v.0 as u64).collect();
+        let (mut hops, mut isum) = (vec![0u64; nc as usize], vec![0u64; nc as usize]);
+        check_or_panic(unsafe {
+            phnsw_node_distances(self.index.0, layer_from_top as u64, sup.as_ptr(), sup.len() as u64,
+                                 hops.as_mut_ptr(), isum.as_mut_ptr())
+        });
+        (hops.into_iter().map(|x| x as usize).collect(), isum.into_iter().map(|x| x as usize).collect())
+    }
+    /// Layer::discover_nodes_to_promote, src/lib.rs:510-536
+    pub fn discover_nodes_to_promote(&self, layer_from_top: usize, supers: &[VectorId]) -> Vec<usize> {
+        let sup: Vec<u64> = supers.iter().map(|v| v.0 as u64).collect();
+        let (mut p, mut n) = (ptr::null_mut::<u64>(), 0u64);
+        check_or_panic(unsafe {
+            phnsw_discover_nodes_to_promote(self.index.0, layer_from_top as u64, sup.as_ptr(), sup.len() as u64, &mut p, &mut n)
+        });
+        let out = (0..n as usize).map(|i| unsafe { *p.add(i) } as usize).collect();
+        if n > 0 { unsafe { phnsw_free(p as *mut c_void) }; }
+        out
+    }
+    /// Layer::reachables_from, src/lib.rs:491-508 -> (NodeId, index distance) in discovery order
+    pub fn reachables_from(&self, layer_from_top: usize, node: usize, check: &[usize]) -> Vec<(usize, usize)> {
+        let chk: Vec<u64> = check.iter().map(|&v| v as u64).collect();
+        let (mut on, mut od, mut n) = (vec![0u64; chk.len() + 1], vec![0u64; chk.len() + 1], 0u64);
+        check_or_panic(unsafe {
+            phnsw_reachables_from(self.index.0, layer_from_top as u64, node as u64, chk.as_ptr(), chk.len() as u64,
+                                  on.as_mut_ptr(), od.as_mut_ptr(), &mut n)
+        });
+        (0..n as usize).map(|i| (on[i] as usize, od[i] as usize)).collect()
+    }
     /// src/lib.rs:1501-1505
     pub fn stochastic_recall(&self, op: OptimizationParameters) -> f32 {
         let mut r = 0f32;
@@ -487,3 +521,53 @@ impl AdcIndex {
         (0..nq).map(|q| (0..cnt[q] as usize).map(|i| (VectorId(out_ids[q * k + i] as usize), out_ds[q * k + i])).collect()).collect()
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Several GPUs (no analogue in the crate: one index, rayon in one process): one sub-index per
+// rank, the exchange inside the library (csrc/sharded.cu).  All buffers are device pointers and
+// every call is asynchronous on `stream`.
+pub struct CommHandle(*mut phnsw_comm);
+unsafe impl Send for CommHandle {}
+impl Drop for CommHandle {
+    fn drop(&mut self) { unsafe { phnsw_comm_destroy(self.0) } }
+}
+
+pub struct ShardedHnsw {
+    comm: CommHandle,
+    shard: Hnsw,
+    id_offset: u64,
+}
+
+impl ShardedHnsw {
+    /// rank 0 creates the id and hands it to the other ranks over the host's own channel
+    pub fn unique_id() -> Result<[u8; 128], Error> {
+        let mut id = [0u8; 128];
+        check(unsafe { phnsw_comm_unique_id(id.as_mut_ptr() as *mut c_void, id.len() as u64) })?;
+        Ok(id)
+    }
+    pub fn new(shard: Hnsw, id_offset: u64, nranks: c_int, rank: c_int, unique_id: &[u8; 128], device: c_int) -> Result<Self, Error> {
+        let mut c = ptr::null_mut();
+        check(unsafe { phnsw_comm_init(nranks, rank, unique_id.as_ptr() as *const c_void, device, &mut c) })?;
+        Ok(Self { comm: CommHandle(c), shard, id_offset })
+    }
+    /// broadcast (root >= 0) -> shard search -> one all-gather -> merge, all on `stream`
+    pub fn search_batch_device(&self, queries_device: *mut f32, nq: usize, sp: SearchParameters, k: usize, root: c_int,
+                               out_ids_device: *mut u64, out_dists_device: *mut f32, stream: *mut c_void) -> Result<(), Error> {
+        check(unsafe {
+            phnsw_search_batch_sharded(self.comm.0, self.shard.index.0, ptr::null(), queries_device, nq as u64, &sp, 0,
+                                       k as u64, self.id_offset, root, out_ids_device, out_dists_device, stream)
+        })
+    }
+    /// the pipelined form: results are complete on `stream` after `flush`
+    pub fn search_batch_queued(&self, queries_device: *const f32, nq: usize, sp: SearchParameters, k: usize,
+                               out_ids_device: *mut u64, out_dists_device: *mut f32, stream: *mut c_void) -> Result<(), Error> {
+        check(unsafe {
+            phnsw_search_batch_sharded_queued(self.comm.0, self.shard.index.0, queries_device, nq as u64, &sp, k as u64,
+                                              self.id_offset, out_ids_device, out_dists_device, stream)
+        })
+    }
+    pub fn flush(&self, stream: *mut c_void) -> Result<(), Error> {
+        check(unsafe { phnsw_comm_flush(self.comm.0, stream) })
+    }
+}
+
