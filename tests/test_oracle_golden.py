@@ -127,6 +127,38 @@ def test_pq_merge_closed_form_fuzz(oracle):
         assert all(int(x) == E for x in d[n:])
 
 
+def test_pq_merge_flag_is_one_rank_count(oracle):
+    """What the traversal kernel evaluates per expansion (search_kernel.cuh, closest_nodes): with
+    A = #{queue keys below the batch head by (priority, id)} and B = #{queue keys with a smaller
+    priority}, merge's flag on a full queue is A < cap, or -- the walk-off-the-end quirk, batches
+    of two or more -- B < cap.  B <= A, so ONE count decides: B for a batch of two or more, A for
+    a batch of one.  Checked against the literal loop of priority_queue.rs:70-144."""
+    rng = np.random.default_rng(11)
+    for trial in range(20000):
+        cap = int(rng.integers(1, 9))
+        fill = int(rng.integers(0, cap + 1))
+        levels = int(rng.integers(1, 5))
+        pool = rng.permutation(40)[: fill + 8].astype(np.uint64)
+        qi = pool[:fill]
+        qp = rng.integers(0, levels, size=fill).astype(np.float32) * np.float32(0.25)
+        order = np.lexsort((qi, qp))
+        d = np.full(cap, EMPTY, dtype=np.uint64)
+        p = np.full(cap, FMAX, dtype=np.float32)
+        d[:fill], p[:fill] = qi[order], qp[order]
+        nb = int(rng.integers(1, 8))
+        bi = pool[fill:fill + nb]
+        bp = rng.integers(0, levels + 1, size=nb).astype(np.float32) * np.float32(0.25)
+        o = np.lexsort((bi, bp))
+        bi, bp = bi[o], bp[o]
+        A = sum(1 for i in range(fill) if (p[i], d[i]) < (bp[0], bi[0]))
+        B = sum(1 for i in range(fill) if p[i] < bp[0])
+        assert B <= A
+        one = (fill < cap) or ((B if nb >= 2 else A) < cap)
+        two = (fill < cap) or A < cap or (nb >= 2 and B < cap)
+        flag = oracle.pq_merge(d, p, bi, bp)
+        assert flag == one == two, (trial, cap, fill, nb, A, B)
+
+
 # ---- src/lib.rs:2476-2512 test_final_idx ----
 def test_final_idx(oracle):
     assert oracle.final_neighbor_idx(10, [E] * 10, 0) == 0
