@@ -425,10 +425,16 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
   // 3.11 ms per 10 000-query step; plain launches lose 1 % and keep one CTA per SM).  Every CTA
   // costs 1 KB of reserved shared memory, which bounds their number.
   uint32_t wc = w;
+  // shared memory of one SM (all resident CTAs together, each charged 1 KB on top of its own)
+  size_t sm_smem = (size_t)ix->max_smem + 1024;
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device) == cudaSuccess && v > 0)
+      sm_smem = (size_t)v;
+  }
   {
     static const char *env = getenv("PHNSW_CTA_WARPS");  // developer knob: warps per CTA
-    const size_t spare = (size_t)ix->max_smem + 1024 > (size_t)lay.total * w
-                             ? (size_t)ix->max_smem + 1024 - (size_t)lay.total * w : 0;
+    const size_t spare = sm_smem > (size_t)lay.total * w ? sm_smem - (size_t)lay.total * w : 0;
     if (env) {
       const uint32_t want = (uint32_t)atoi(env);
       if (want >= 1 && want < w && w % want == 0 && grid == (uint32_t)ix->sm_count && w == wmax &&
@@ -446,7 +452,7 @@ phnsw_status launch_search(const phnsw_index *ix, const SearchCall &c, cudaStrea
     // fills the machine": the launch after next cannot start before this one has left.  Small
     // CTAs must therefore fill an SM exactly -- each asks for its share of the SM's shared
     // memory, so that one more CTA than the launch's k per SM can never be resident.
-    const size_t share = (((size_t)ix->max_smem + 1024) / (w / wc) - 1024) / 128 * 128;
+    const size_t share = (sm_smem / (w / wc) - 1024) / 128 * 128;
     if (share > smem) smem = share;
   }
   auto launch = [&](uint32_t nctas, uint32_t warps, size_t bytes) {
