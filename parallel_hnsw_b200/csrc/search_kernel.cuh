@@ -1183,6 +1183,292 @@ struct WarpSearch {
     __syncwarp();
   }
 
+#ifndef PHNSW_POOL_SCAN
+  // ------------------------------------------------------------------ closest_nodes (block minima)
+  // lib.rs:175-248 on `layer`; pool[0..len) holds NodeId keys (len <= cap), all unexpanded,
+  // all marked in the visited bitmap.  On return the pool is exact again (len <= cap).
+  __device__ void closest_nodes(const LayerDev &layer, uint32_t probe, uint32_t *n_dist,
+                                uint32_t *n_exp) {
+    ovf_n = 0;
+    ovf_min = kEmptyKey;
+    U = kEmptyKey;
+    const uint32_t M = layer.M;
+    const uint32_t lt = (1u << lane) - 1;
+    // BLOCK MINIMA.  The pool is cut into at most 32 blocks of 2^bsh slots; lane b keeps the
+    // smallest unexpanded key of block b.  A pop is one warp-wide minimum over the lanes plus a
+    // rescan of the one block it came from (mark it, find that block's next best); an append
+    // touches the one or two blocks the new keys land in.  No pass over the whole pool per
+    // expansion -- together with the pivot count below this replaces the 330-key scan.
+    uint32_t bsh = 5;
+    while ((a.cap_pad >> bsh) > 32) bsh++;
+    uint64_t bmk = kEmptyKey;
+    bool blk_valid = false;
+    // the smallest unexpanded pool entry, carried from one expansion to the next
+    uint64_t nx_key = kEmptyKey;
+    bool nx_valid = false;
+    // PIVOT COUNT.  merge()'s flag on a full queue is A(bx) = #{keys below bx} < cap.  P is a key
+    // with CP = #{pool keys below P} known exactly (kept up to date by the appends; compactions
+    // only remove keys above their threshold).  bx <= P and CP < cap  =>  A(bx) <= CP < cap: the
+    // flag is raised without looking at the pool.  Otherwise the pool is counted and (bx, A)
+    // becomes the new pivot.
+    uint64_t P = 0;
+    uint32_t CP = 0;
+    // neighbour row of the node that will most likely be popped next, requested while the
+    // current expansion is still being merged (hides one dependent HBM round trip)
+    uint32_t pf_id = kEmpty32, pf_n0 = kEmpty32, pf_n1 = kEmpty32;
+    while (true) {
+      // ---- pop the smallest (d,id) among all discovered, unexpanded nodes
+      if (PH_UNLIKELY(!blk_valid)) {  // layer start, or a compaction moved the slots
+        bmk = kEmptyKey;
+        PH_COLD_LOOP
+        for (uint32_t b = 0; (b << bsh) < len; b++) {
+          const uint32_t e = min(len, (b + 1) << bsh);
+          uint64_t best = kEmptyKey;
+          PH_COLD_LOOP
+          for (uint32_t s = (b << bsh) + lane; s < e; s += 32) {
+            const uint64_t k = pool[s];
+            if (!((uint32_t)k & kFlagExpanded) && k < best) best = k;
+          }
+          best = warp_min_key(best);
+          if ((uint32_t)lane == b) bmk = best;
+        }
+        blk_valid = true;
+        nx_valid = false;
+      }
+      if (!nx_valid) nx_key = warp_min_key(bmk);
+      uint32_t next;
+      // ovf_min only tracks the duplicate-row keys (the one kind of spilled key that can be
+      // below a pool entry); the rest of the list matters once the pool is exhausted
+      if (PH_UNLIKELY(ovf_n > 0 && (nx_key == kEmptyKey || ovf_min < nx_key))) {
+        next = key_id(ovf_pop_min());
+        nx_valid = true;  // the pool did not change
+      } else if (nx_key != kEmptyKey) {
+        // the block it lives in: mark it, and find that block's next unexpanded key
+        const uint32_t b = __ffs(__ballot_sync(kFull, bmk == nx_key)) - 1;
+        const uint32_t e = min(len, (b + 1) << bsh);
+        uint64_t best = kEmptyKey;
+        for (uint32_t s = (b << bsh) + lane; s < e; s += 32) {
+          const uint64_t k = pool[s];
+          if (k == nx_key) pool[s] = k | (uint64_t)kFlagExpanded;
+          else if (!((uint32_t)k & kFlagExpanded) && k < best) best = k;
+        }
+        best = warp_min_key(best);
+        if ((uint32_t)lane == b) bmk = best;
+        next = key_id(nx_key);
+        nx_valid = false;
+        __syncwarp();
+      } else {
+        break;  // frontier exhausted
+      }
+      (*n_exp)++;
+      // ---- neighbours of `next`, trailing sentinels trimmed (lib.rs:114-125, 144-148)
+      uint32_t n0, n1;
+      if (next == pf_id) {
+        n0 = pf_n0;
+        n1 = pf_n1;
+      } else {
+        const uint32_t *row = layer.neighbors + (size_t)next * M;
+        n0 = lane < M ? __ldg(&row[lane]) : kEmpty32;
+        n1 = lane + 32 < M ? __ldg(&row[lane + 32]) : kEmpty32;
+      }
+      pf_id = kEmpty32;
+      uint32_t v0 = __ballot_sync(kFull, n0 != kEmpty32);
+      uint32_t v1 = __ballot_sync(kFull, n1 != kEmpty32);
+      uint32_t valid = v1 ? 64 - __clz(v1) : 32 - __clz(v0);  // __clz(0) == 32
+      bool in0 = (uint32_t)lane < valid, in1 = (uint32_t)lane + 32 < valid;
+      if (PH_UNLIKELY((in0 && n0 >= layer.node_count) || (in1 && n1 >= layer.node_count))) {
+        stat |= kStatBadNeighbor;  // interior sentinel / out-of-range id: the crate would panic
+        in0 = in0 && n0 < layer.node_count;
+        in1 = in1 && n1 < layer.node_count;
+      }
+      // ---- drop already visited ones (lib.rs:198); duplicates inside the row both pass
+#ifndef PHNSW_VIS_BRANCHY
+      // both bitmap words requested back to back with no per-lane branch (lanes outside the row
+      // read word 0); the second half only exists for neighbourhoods wider than a warp
+      const uint32_t t0 = in0 ? n0 : 0u, t1 = in1 ? n1 : 0u;
+      uint32_t w0, w1 = 0u;
+      if (vis_small) {
+        w0 = vsm[t0 >> 5];
+        w1 = vsm[t1 >> 5];
+      } else {
+        w0 = ld_cg_u32(&bm[t0 >> 5]);
+        if (v1) w1 = ld_cg_u32(&bm[t1 >> 5]);
+      }
+      bool u0 = in0 && !((w0 >> (t0 & 31)) & 1u);
+      bool u1 = in1 && !((w1 >> (t1 & 31)) & 1u);
+#else
+      bool u0 = in0 && !visited_test(n0);
+      bool u1 = in1 && !visited_test(n1);
+#endif
+      uint32_t m0 = __ballot_sync(kFull, u0);
+      uint32_t m1 = __ballot_sync(kFull, u1);
+      uint32_t nn = __popc(m0) + __popc(m1);
+      if (u0) bid[__popc(m0 & lt)] = n0;
+      if (u1) bid[__popc(m0) + __popc(m1 & lt)] = n1;
+      __syncwarp();
+      *n_dist += nn;
+      bool did = false;
+      if (nn > 0) {
+#ifndef PHNSW_NO_PREFETCH_BATCH0
+        // DRAM-resident layer: the first row batch starts towards L2 before the visited marks
+        // are written (one prefetch per lane covers eight rows of up to four lines; the later
+        // batches follow at the head of compute_distances_tree1): +2 %, no registers
+        if (TREE && !PQ && !layer.nodes) {
+#ifdef PHNSW_PREFETCH_ALL_EARLY
+          for (uint32_t j0 = 0; j0 < nn; j0 += 8) {
+            const uint32_t j = j0 + ((uint32_t)lane >> 2);
+#else
+          {
+            const uint32_t j = (uint32_t)lane >> 2;
+#endif
+            if (j < nn && (uint32_t)(lane & 3) * 32 < a.dim_pad) {
+              const float *p = layer.lrows + (size_t)bid[j] * a.pitch + (lane & 3) * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+          }
+        }
+#endif
+        visited_set(u0, n0);                     // lib.rs:209 (order is immaterial)
+        if (m1) visited_set(u1, n1);
+        compute_distances(layer, nn);            // lib.rs:199-204 -> bkeys[0..nn)
+        const uint64_t *bk = bkeys;
+        uint32_t nbu = nn;
+        if (PH_UNLIKELY(layer.row_dups)) {
+          // a row that lists an id twice yields equal keys: visit_queue is a multiset, so the
+          // extra copies stay poppable once more (spill list) while the set takes one
+          sort_batch(nn);                        // lib.rs:206
+          bk = bsorted;
+          bool dup = false;
+          for (uint32_t j0 = 0; j0 < nn; j0 += 32) {
+            uint32_t j = j0 + lane;
+            dup |= (j > 0 && j < nn && bsorted[j] == bsorted[j - 1]);
+          }
+          if (__any_sync(kFull, dup)) {
+            __syncwarp();
+            if (lane == 0) {
+              uint32_t w = 1;
+              for (uint32_t j = 1; j < nn; j++) {
+                uint64_t k = bsorted[j];
+                if (k == bsorted[w - 1]) {
+                  if (ovf_n < a.ovf_cap) ovf[ovf_n++] = k; else stat |= kStatOverflowFrontier;
+                  ovf_min = k < ovf_min ? k : ovf_min;
+                } else {
+                  bsorted[w++] = k;
+                }
+              }
+              nbu = w;
+            }
+            nbu = __shfl_sync(kFull, nbu, 0);
+            ovf_n = __shfl_sync(kFull, ovf_n, 0);
+            ovf_min = __shfl_sync(kFull, ovf_min, 0);
+            stat |= __shfl_sync(kFull, stat, 0);
+            __syncwarp();
+          }
+        }
+        // smallest new key (lib.rs:206 sorts; only the head of that order matters here)
+        uint64_t mine0 = (uint32_t)lane < nbu ? bk[lane] : kEmptyKey;
+        uint64_t mine1 = (uint32_t)lane + 32 < nbu ? bk[lane + 32] : kEmptyKey;
+        const uint64_t b0 = warp_min_key(mine0 < mine1 ? mine0 : mine1);
+        // ---- one pass over the pool: rank of b0 (merge()'s return flag in closed form, see
+        // oracle orc_pq_merge_flag_closed_form) and the next node to pop
+        // full: the candidate set holds `cap` entries; its tail is the cap-th smallest key.
+        // b0 < tail  <=>  A = #{keys < b0} < cap; tail and b0 tie on the distance (the quirk,
+        // batches of two or more)  <=>  B = #{keys with a smaller distance} < cap.  B <= A, so
+        // one count decides: against the distance alone for a batch of two or more, against the
+        // whole key for a batch of one.
+        const uint64_t bx = nn >= 2 ? (b0 & kHiMask) : b0;
+        if (len < cap || (bx <= P && CP < cap)) {
+          did = true;
+        } else {
+          uint32_t A = 0;
+#pragma unroll 2
+          for (uint32_t s = lane; s < len; s += 32) A += (pool[s] & kFlagMask64) < bx;
+          A = __reduce_add_sync(kFull, A);
+          P = bx;
+          CP = A;
+          did = A < cap;
+        }
+        if (did || probe > 1) {  // the walk continues: request the next row now
+          uint64_t i0 = mine0 < U ? mine0 : kEmptyKey, i1 = mine1 < U ? mine1 : kEmptyKey;
+          uint64_t pk = warp_min_key(i0 < i1 ? i0 : i1);
+          // the next pop from the pool: the best of what is there and of what is about to join
+          const uint64_t om = warp_min_key(bmk);
+          nx_key = pk < om ? pk : om;
+          nx_valid = true;  // (a compaction inside the merge takes it back)
+          pk = ovf_min < nx_key ? ovf_min : nx_key;
+          if (pk != kEmptyKey) {
+            pf_id = key_id(pk);
+            const uint32_t *prow = layer.neighbors + (size_t)pf_id * M;
+            pf_n0 = lane < M ? __ldg(&prow[lane]) : kEmpty32;
+            pf_n1 = lane + 32 < M ? __ldg(&prow[lane + 32]) : kEmpty32;
+          }
+        }
+        // ---- merge (lib.rs:211-226): keys under the bound join the pool, the rest can never
+        // enter the candidate set and go straight to the frontier spill list
+        for (uint32_t t0 = 0; t0 < nbu; t0 += 32) {
+          uint32_t t = t0 + lane;
+          bool act = t < nbu;
+          uint64_t key = act ? bk[t] : kEmptyKey;
+          bool in = act && key < U;
+          uint32_t m = __ballot_sync(kFull, in);
+          if (PH_UNLIKELY(len + __popc(m) > a.cap_pad)) {
+            compact(true);
+            blk_valid = false;  // slots moved: block minima and the carried pop are rebuilt
+            nx_valid = false;
+            if (P > U) { P = 0; CP = 0; }  // keys below P were dropped: the count is void
+            in = act && key < U;
+            m = __ballot_sync(kFull, in);
+          }
+          const uint32_t cnt = __popc(m);
+          uint32_t pos = len + __popc(m & lt);
+          if (in) pool[pos] = key;
+          CP += __popc(__ballot_sync(kFull, in && key < P));
+          if (blk_valid && cnt) {  // the one or two blocks the new keys land in
+            const uint32_t bA = len >> bsh, bB = (len + cnt - 1) >> bsh;
+            const uint64_t kA = warp_min_key(in && (pos >> bsh) == bA ? key : kEmptyKey);
+            if ((uint32_t)lane == bA && kA < bmk) bmk = kA;
+            if (PH_UNLIKELY(bB != bA)) {
+              const uint64_t kB = warp_min_key(in && (pos >> bsh) == bB ? key : kEmptyKey);
+              if ((uint32_t)lane == bB && kB < bmk) bmk = kB;
+            }
+          }
+          len += cnt;
+          ovf_append(act && !in, key);
+          __syncwarp();
+        }
+      }
+      if (!did) {                                // lib.rs:233-238: cumulative, never reset
+        if (--probe == 0) break;
+      }
+#ifndef PHNSW_NO_VIS_PREFETCH
+      // the neighbour row of the next pop was requested before the merge and has arrived by
+      // now: pull the visited-bitmap words of its entries towards L2 (HBM-resident bitmaps only)
+      if (pf_id != kEmpty32 && !vis_small) {
+        if (pf_n0 < layer.node_count) asm volatile("prefetch.global.L2 [%0];" ::"l"(&bm[pf_n0 >> 5]));
+        if (pf_n1 < layer.node_count) asm volatile("prefetch.global.L2 [%0];" ::"l"(&bm[pf_n1 >> 5]));
+      }
+#endif
+#ifndef PHNSW_NO_CODE_PREFETCH
+      // quantised ADC: the code rows of that row's entries as well (the bottom layer's codes are
+      // DRAM-resident; a row may straddle two 128-byte lines)
+      if (PQ == 2 && pf_id != kEmpty32 && !layer.nodes) {
+        if (pf_n0 < layer.node_count) {
+          const uint8_t *p = a.codes + (size_t)pf_n0 * a.cpitch;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          if (a.cpitch & 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + a.cpitch - 1));
+        }
+        if (pf_n1 < layer.node_count) {
+          const uint8_t *p = a.codes + (size_t)pf_n1 * a.cpitch;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          if (a.cpitch & 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + a.cpitch - 1));
+        }
+      }
+#endif
+    }
+    compact(false);
+  }
+
+#else
   // ------------------------------------------------------------------ closest_nodes
   // lib.rs:175-248 on `layer`; pool[0..len) holds NodeId keys (len <= cap), all unexpanded,
   // all marked in the visited bitmap.  On return the pool is exact again (len <= cap).
@@ -1442,6 +1728,7 @@ struct WarpSearch {
     compact(false);
   }
 
+#endif
   // ------------------------------------------------------------------ whole-query drivers
   // false: the query names a stored vector that does not exist (the crate panics on an unknown
   // VectorId); the status word is raised and the query is skipped
